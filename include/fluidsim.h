@@ -1,0 +1,188 @@
+/* fluidsim.h -- C ABI of libfluidsim.so, the B200 (sm_100a) replacement for the
+ * per-timestep Stokes hot path of TobiasHoffmannP/PUC-Fluidsimulation-Project.
+ *
+ * The reference has no FFI: its boundary is a set of module-level Python
+ * functions.  Each entry point below names the reference
+ * function (file:line under /root/reference) it replaces; the Python mirror in
+ * puc-fluidsimulation-project_b200/ binds these with ctypes and keeps the
+ * reference's names and signatures.  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, <0 = error (fs_last_error() has text);
+ *     no C++ exception crosses the boundary; nothing falls back to the CPU.
+ *   - array arguments are plain pointers and may be HOST or DEVICE pointers
+ *     (detected with cudaPointerGetAttributes).  Host arrays are staged through
+ *     device memory inside the call, device arrays are used in place.
+ *   - layouts are the reference's: coords (N,2) f64 C-order, triangles (T,3)
+ *     i32 0-based, velocity (N,2) f64 C-order, scalars (N,) f64, CSR with i32
+ *     rowptr/colidx and f64 values, columns sorted ascending inside a row.
+ *   - calls are synchronous with respect to the host unless stated; a handle is
+ *     bound to the CUDA device current at creation and is not thread-safe.
+ */
+#ifndef FLUIDSIM_H
+#define FLUIDSIM_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fs_mesh fs_mesh;       /* device mesh + topology              */
+typedef struct fs_csr fs_csr;         /* device CSR matrix                   */
+typedef struct fs_stokes fs_stokes;   /* operator-split Stokes step state    */
+
+#define FS_OK 0
+#define FS_ERR_ARG -1
+#define FS_ERR_CUDA -2
+#define FS_ERR_IO -3
+#define FS_ERR_NOCONV -4   /* Krylov solver hit maxit (result still written) */
+#define FS_ERR_INTERNAL -5
+
+#define FS_PRECOND_NONE 0
+#define FS_PRECOND_JACOBI 1
+
+int fs_version(void);
+const char* fs_last_error(void);
+int fs_device_count(int* count);
+int fs_set_device(int device);
+/* Bind subsequent work of this host thread to a caller-owned CUDA stream
+ * (cudaStream_t cast to void*; NULL = the library's own stream). */
+int fs_set_stream(void* cuda_stream);
+int fs_sync(void);
+/* number of kernels this library has launched since load (bench.py gpu_launches) */
+int64_t fs_launch_count(void);
+/* Serialise all ranks' kernels for profiling-free timing: record / read a CUDA
+ * event pair on the library stream.  ms = elapsed between the two marks. */
+int fs_timer_start(void);
+int fs_timer_stop(float* ms);
+
+/* ---- ingest: readNode / readEle, code/StokesColor.py:54-95 (fp32 variant
+ * code/poisson.py:27-74 = same parse, caller casts).  Two-step: count, then fill. */
+int fs_node_file_count(const char* path, int64_t* n_nodes);
+int fs_read_node(const char* path, double* coords /* (n,2) host */, int32_t* markers /* (n,) host */,
+                 int64_t n_nodes);
+int fs_ele_file_count(const char* path, int64_t* n_tris, int32_t* nodes_per_tri);
+int fs_read_ele(const char* path, int32_t* tris /* (t,3) host */, int64_t n_tris);
+
+/* ---- mesh handle: uploads the mesh and builds, on the device, the structural
+ * CSR pattern of the P1 stiffness matrix, the element->nonzero scatter map, the
+ * per-nonzero contribution lists (ascending element order) and the
+ * node->element incidence lists.  Replaces the dense np.zeros((N,N)) of
+ * buildStiffnessMatrix, code/StokesColor.py:98-101. */
+int fs_mesh_create(const double* coords, int64_t n_nodes, const int32_t* tris, int64_t n_tris,
+                   const int32_t* markers /* may be NULL */, fs_mesh** out);
+int fs_mesh_destroy(fs_mesh* m);
+int fs_mesh_sizes(const fs_mesh* m, int64_t* n_nodes, int64_t* n_tris, int64_t* nnz);
+int fs_csr_pattern(const fs_mesh* m, int32_t* rowptr /* n+1 */, int32_t* colidx /* nnz */);
+int fs_scatter_map(const fs_mesh* m, int32_t* scatter /* (t,9): entry (i,j) at i*3+j */);
+
+/* ---- assembly.
+ * fs_assemble_stiffness: buildStiffnessMatrix, code/StokesColor.py:98-128
+ *   (2|det| denominator, skip |det|<1e-14), values on the structural pattern,
+ *   contributions summed in ascending element order => bit-identical to the
+ *   reference's dense matrix.
+ * fs_lumped_mass: buildLumpedMassMatrix, code/StokesColor.py:266-284.
+ * fs_assemble_fem: buildFemSystem, code/poisson.py:100-146 (signed 2*ADet, skip
+ *   only ADet==0, load vector b_j += g(centroid)*area/3, returns -b).
+ *   f32_arith != 0 reproduces the reference's float32 coordinate arithmetic.
+ *   g_centroid: g evaluated at the element centroids ((t,) f64), or NULL for the
+ *   constant g_const.  fs_centroids gives the centroids in the same arithmetic. */
+int fs_assemble_stiffness(fs_mesh* m, double* vals /* nnz */);
+int fs_lumped_mass(fs_mesh* m, double* mass /* n */);
+int fs_centroids(fs_mesh* m, int f32_arith, double* cx /* t */, double* cy /* t */);
+int fs_assemble_fem(fs_mesh* m, int f32_arith, const double* g_centroid, double g_const,
+                    double* vals /* nnz */, double* b /* n */);
+
+/* ---- nodal operators.
+ * fs_divergence: calculate_divergence, code/StokesColor.py:130-165.
+ * fs_gradient:   calculate_gradiant,  code/StokesColor.py:224-263. */
+int fs_divergence(fs_mesh* m, const double* u /* (n,2) */, double* div /* n */);
+int fs_gradient(fs_mesh* m, const double* p /* n */, double* gx /* n */, double* gy /* n */);
+
+/* ---- boundary conditions.
+ * fs_bc_set: the index sets of code/StokesColor.py:442-464 (computed by the
+ *   Python mirror with the reference's rules) are stored on the device.
+ * fs_make_per_bcu: makePerBCU, code/StokesColor.py:429-431 (u[slave]=u[master],
+ *   sequential pair order).   fs_make_dir_bcu: makeDirBCU, :405-427.
+ * fs_reapply_scalar_bc: reapply_periodic_u + reapply_dirchlect_u,
+ *   code/heatEq.py:282-301 (pairs = the unfiltered list given here). */
+int fs_bc_set(fs_mesh* m, const int32_t* wall, int64_t n_wall, const int32_t* inner, int64_t n_inner,
+              const int32_t* pairs /* (np,2) master,slave */, int64_t n_pairs,
+              const int32_t* interior, int64_t n_interior);
+int fs_make_per_bcu(fs_mesh* m, double* u /* (n,2) */);
+int fs_make_dir_bcu(fs_mesh* m, double* u /* (n,2) */, double B1, double B2);
+int fs_reapply_scalar_bc(fs_mesh* m, double* u /* n */, const int32_t* pairs_all, int64_t n_pairs_all,
+                         double wall_value, double inner_value);
+
+/* ---- sparse matrices and Krylov solvers: replace np.linalg.solve(A, b),
+ * code/StokesColor.py:544-545,555,569, code/heatEq.py:323, code/poisson.py:285. */
+int fs_csr_create(int64_t n, int64_t nnz, const int32_t* rowptr, const int32_t* colidx,
+                  const double* vals, fs_csr** out);
+int fs_csr_from_mesh(fs_mesh* m, const double* vals /* nnz */, fs_csr** out); /* shares the pattern */
+int fs_csr_destroy(fs_csr* a);
+int fs_csr_sizes(const fs_csr* a, int64_t* n, int64_t* nnz);
+int fs_csr_get(const fs_csr* a, int32_t* rowptr, int32_t* colidx, double* vals);
+int fs_spmv(fs_csr* a, const double* x, double* y);
+/* Conjugate gradients, stop when ||r||_2 <= rtol*||b||_2.  x holds the initial
+ * guess on entry.  nrhs = 1 or 2 interleaved right-hand sides ((n,nrhs) C-order).
+ * project_mean != 0: A is singular with the constants as null space (pressure):
+ * b is made mean-free first and the mean of x is removed at the end. */
+int fs_cg(fs_csr* a, const double* b, double* x, int nrhs, double rtol, int maxit, int precond,
+          int project_mean, int* iters, double* relres);
+int fs_bicgstab(fs_csr* a, const double* b, double* x, double rtol, int maxit, int precond,
+                int* iters, double* relres);
+
+/* ---- the operator-split Stokes step, code/StokesColor.py:537-575 ==
+ * code/StokesFood.py:441-479.  fs_stokes_create assembles K, the lumped mass,
+ * A_visc = I + DT*nu*K with Dirichlet rows+columns eliminated (:471-475) and the
+ * periodic-merged SPD pressure operator Z^T K Z (restatement of :478-479, see
+ * DESIGN.md); needs fs_bc_set first.  fs_stokes_step advances u in place: two
+ * viscous CG solves (one 2-RHS solve), BCs, divergence, pressure CG, gradient,
+ * velocity update, BCs, second projection on the interior nodes -- all on the
+ * device with no host round trip except the convergence polls. */
+typedef struct fs_stokes_opts {
+  double rtol_visc;      /* CG tolerance of the viscous solves    (default 1e-12) */
+  double rtol_pressure;  /* CG tolerance of the pressure solves   (default 1e-10) */
+  int maxit;             /* per solve                              (default 200000) */
+  int precond;           /* FS_PRECOND_*                           (default JACOBI) */
+  int warm_start;        /* start pressure CG from the previous step's p / p2 (default 1) */
+  int final_div;         /* also evaluate final_div (:575) and its max-norm (default 0) */
+} fs_stokes_opts;
+typedef struct fs_stokes_stats {
+  int iters_visc, iters_p1, iters_p2;
+  double relres_visc, relres_p1, relres_p2;
+  double max_div_ustar, max_final_div;
+} fs_stokes_stats;
+int fs_stokes_default_opts(fs_stokes_opts* o);
+int fs_stokes_create(fs_mesh* m, double DT, double nu, fs_stokes** out);
+int fs_stokes_destroy(fs_stokes* s);
+int fs_stokes_step(fs_stokes* s, double* u /* (n,2) in/out */, double B1, double B2,
+                   const fs_stokes_opts* opts, fs_stokes_stats* stats);
+/* p and p2 of the last step, mean-free, expanded to the N nodes */
+int fs_stokes_pressure(fs_stokes* s, double* p /* n or NULL */, double* p2 /* n or NULL */);
+/* the two operators, for inspection / parity (borrowed handles, do not destroy) */
+int fs_stokes_matrices(fs_stokes* s, fs_csr** a_visc, fs_csr** k_pressure, int32_t* dof /* n or NULL */);
+
+/* ---- tracers and dye.
+ * fs_locate: PointLocator.find, code/StokesColor.py:314-345 -- the 10 nearest
+ *   centroids in ascending distance, first triangle with w1,w2,w3 >= 0, else -1.
+ * fs_advect_dye: advect_semilagrange, :347-389 (in place on c; ids_out optional).
+ * fs_mixing_index: mixing_index, :391-403; out = {I, mu, var}.
+ * fs_locate_exact: containing triangle by walking from hint[i] (or a grid seed),
+ *   -1 outside the mesh; the tri-finder under code/StokesFood.py:482-486.
+ * fs_tracer_step: code/StokesFood.py:482-503 -- interpolate u at the tracers,
+ *   forward Euler, wrap x, sticky capture; eaten = sum(status). */
+int fs_locate(fs_mesh* m, const double* pts /* (P,2) */, int64_t n_pts, int32_t* ids /* P */);
+int fs_advect_dye(fs_mesh* m, double* c /* n */, const double* u /* (n,2) */, double DT,
+                  int32_t* ids_out /* n or NULL */);
+int fs_mixing_index(fs_mesh* m, const double* c, const double* mass, const int32_t* mask_idx,
+                    int64_t n_mask, double* out3);
+int fs_locate_exact(fs_mesh* m, const double* pts, int64_t n_pts, int32_t* hint_ids /* P in/out */);
+int fs_tracer_step(fs_mesh* m, double* pts /* (P,2) in/out */, int32_t* status /* P in/out */,
+                   int32_t* hint_ids /* P in/out */, int64_t n_pts, const double* u /* (n,2) */,
+                   double DT, double L, double cx, double cy, double rcap, int64_t* eaten);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLUIDSIM_H */

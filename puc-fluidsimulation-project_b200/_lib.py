@@ -1,0 +1,172 @@
+"""ctypes binding of libfluidsim.so (include/fluidsim.h).
+
+There is no CPU fallback: if the shared library is missing it is built with nvcc
+(build.py); if that fails, or the library cannot be loaded, import fails loudly.
+Compute calls on a machine without a CUDA device return FS_ERR_CUDA and raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+c_i64 = C.c_int64
+c_i32 = C.c_int32
+c_dbl = C.c_double
+c_vp = C.c_void_p
+P = C.POINTER
+
+
+class FluidsimError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libfluidsim error {code}: {msg}")
+        self.code = code
+
+
+class StokesOpts(C.Structure):
+    _fields_ = [("rtol_visc", c_dbl), ("rtol_pressure", c_dbl), ("maxit", C.c_int),
+                ("precond", C.c_int), ("warm_start", C.c_int), ("final_div", C.c_int)]
+
+
+class StokesStats(C.Structure):
+    _fields_ = [("iters_visc", C.c_int), ("iters_p1", C.c_int), ("iters_p2", C.c_int),
+                ("relres_visc", c_dbl), ("relres_p1", c_dbl), ("relres_p2", c_dbl),
+                ("max_div_ustar", c_dbl), ("max_final_div", c_dbl)]
+
+
+# name -> (restype, argtypes); every symbol declared in include/fluidsim.h
+SIGNATURES = {
+    "fs_version": (C.c_int, []),
+    "fs_last_error": (C.c_char_p, []),
+    "fs_device_count": (C.c_int, [P(C.c_int)]),
+    "fs_set_device": (C.c_int, [C.c_int]),
+    "fs_set_stream": (C.c_int, [c_vp]),
+    "fs_sync": (C.c_int, []),
+    "fs_launch_count": (c_i64, []),
+    "fs_timer_start": (C.c_int, []),
+    "fs_timer_stop": (C.c_int, [P(C.c_float)]),
+    "fs_node_file_count": (C.c_int, [C.c_char_p, P(c_i64)]),
+    "fs_read_node": (C.c_int, [C.c_char_p, c_vp, c_vp, c_i64]),
+    "fs_ele_file_count": (C.c_int, [C.c_char_p, P(c_i64), P(c_i32)]),
+    "fs_read_ele": (C.c_int, [C.c_char_p, c_vp, c_i64]),
+    "fs_mesh_create": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, P(c_vp)]),
+    "fs_mesh_destroy": (C.c_int, [c_vp]),
+    "fs_mesh_sizes": (C.c_int, [c_vp, P(c_i64), P(c_i64), P(c_i64)]),
+    "fs_csr_pattern": (C.c_int, [c_vp, c_vp, c_vp]),
+    "fs_scatter_map": (C.c_int, [c_vp, c_vp]),
+    "fs_assemble_stiffness": (C.c_int, [c_vp, c_vp]),
+    "fs_lumped_mass": (C.c_int, [c_vp, c_vp]),
+    "fs_centroids": (C.c_int, [c_vp, C.c_int, c_vp, c_vp]),
+    "fs_assemble_fem": (C.c_int, [c_vp, C.c_int, c_vp, c_dbl, c_vp, c_vp]),
+    "fs_divergence": (C.c_int, [c_vp, c_vp, c_vp]),
+    "fs_gradient": (C.c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "fs_bc_set": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64]),
+    "fs_make_per_bcu": (C.c_int, [c_vp, c_vp]),
+    "fs_make_dir_bcu": (C.c_int, [c_vp, c_vp, c_dbl, c_dbl]),
+    "fs_reapply_scalar_bc": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_dbl, c_dbl]),
+    "fs_csr_create": (C.c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, P(c_vp)]),
+    "fs_csr_from_mesh": (C.c_int, [c_vp, c_vp, P(c_vp)]),
+    "fs_csr_destroy": (C.c_int, [c_vp]),
+    "fs_csr_sizes": (C.c_int, [c_vp, P(c_i64), P(c_i64)]),
+    "fs_csr_get": (C.c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "fs_spmv": (C.c_int, [c_vp, c_vp, c_vp]),
+    "fs_cg": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, c_dbl, C.c_int, C.c_int, C.c_int, P(C.c_int), P(c_dbl)]),
+    "fs_bicgstab": (C.c_int, [c_vp, c_vp, c_vp, c_dbl, C.c_int, C.c_int, P(C.c_int), P(c_dbl)]),
+    "fs_stokes_default_opts": (C.c_int, [P(StokesOpts)]),
+    "fs_stokes_create": (C.c_int, [c_vp, c_dbl, c_dbl, P(c_vp)]),
+    "fs_stokes_destroy": (C.c_int, [c_vp]),
+    "fs_stokes_step": (C.c_int, [c_vp, c_vp, c_dbl, c_dbl, P(StokesOpts), P(StokesStats)]),
+    "fs_stokes_pressure": (C.c_int, [c_vp, c_vp, c_vp]),
+    "fs_stokes_matrices": (C.c_int, [c_vp, P(c_vp), P(c_vp), c_vp]),
+    "fs_locate": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),
+    "fs_advect_dye": (C.c_int, [c_vp, c_vp, c_vp, c_dbl, c_vp]),
+    "fs_mixing_index": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "fs_locate_exact": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),
+    "fs_tracer_step": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, P(c_i64)]),
+}
+
+_NO_CHECK = {"fs_version", "fs_last_error", "fs_launch_count"}
+
+
+def _load():
+    path = _build.LIB
+    if not os.path.exists(path):
+        path = _build.build()
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(rc):
+    if rc != 0:
+        raise FluidsimError(rc, lib.fs_last_error().decode(errors="replace"))
+    return rc
+
+
+def call(name, *args):
+    fn = getattr(lib, name)
+    rc = fn(*args)
+    if name not in _NO_CHECK:
+        check(rc)
+    return rc
+
+
+# ---- buffers: numpy (host) or torch (device) -----------------------------------
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def ptr(x, dtype=None, shape=None, name="array"):
+    """Raw pointer of a C-contiguous numpy array or torch tensor (None -> NULL)."""
+    if x is None:
+        return None
+    if _is_torch(x):
+        import torch
+        if not x.is_contiguous():
+            raise ValueError(f"{name}: tensor must be contiguous")
+        if dtype is not None:
+            want = {np.float64: torch.float64, np.int32: torch.int32}[dtype]
+            if x.dtype != want:
+                raise TypeError(f"{name}: expected dtype {want}, got {x.dtype}")
+        if shape is not None and tuple(x.shape) != tuple(shape):
+            raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(x.shape)}")
+        return C.c_void_p(x.data_ptr())
+    if not isinstance(x, np.ndarray):
+        raise TypeError(f"{name}: expected numpy.ndarray or torch.Tensor, got {type(x)}")
+    if not x.flags["C_CONTIGUOUS"]:
+        raise ValueError(f"{name}: array must be C-contiguous")
+    if dtype is not None and x.dtype != np.dtype(dtype):
+        raise TypeError(f"{name}: expected dtype {np.dtype(dtype)}, got {x.dtype}")
+    if shape is not None and tuple(x.shape) != tuple(shape):
+        raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(x.shape)}")
+    return C.c_void_p(x.ctypes.data)
+
+
+def as_f64(x, name="array"):
+    """Host arrays are converted to contiguous float64 (copy only if needed)."""
+    if _is_torch(x):
+        return x
+    return np.ascontiguousarray(x, dtype=np.float64)
+
+
+def as_i32(x, name="array"):
+    if _is_torch(x):
+        return x
+    return np.ascontiguousarray(x, dtype=np.int32)
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    call("fs_device_count", C.byref(n))
+    return n.value

@@ -1,0 +1,245 @@
+// internal.cuh -- shared plumbing of libfluidsim (device buffers, host/device
+// pointer staging, error translation, reductions).  Not part of the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <memory>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/fluidsim.h"
+
+namespace fs {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+void set_last_error(const std::string& s);
+cudaStream_t stream();          // current library stream of this thread
+void count_launch(int n = 1);   // bumps fs_launch_count()
+
+#define FS_CUDA(call)                                                                       \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      throw fs::Error(FS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__) +    \
+                                       " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+  } while (0)
+
+#define FS_REQUIRE(cond, msg)                                  \
+  do {                                                         \
+    if (!(cond)) throw fs::Error(FS_ERR_ARG, std::string(msg)); \
+  } while (0)
+
+#define FS_API_BEGIN try {
+#define FS_API_END                                  \
+  return FS_OK;                                     \
+  }                                                 \
+  catch (const fs::Error& e) {                      \
+    fs::set_last_error(e.what());                   \
+    return e.code;                                  \
+  }                                                 \
+  catch (const std::exception& e) {                 \
+    fs::set_last_error(e.what());                   \
+    return FS_ERR_INTERNAL;                         \
+  }                                                 \
+  catch (...) {                                     \
+    fs::set_last_error("unknown C++ exception");    \
+    return FS_ERR_INTERNAL;                         \
+  }
+
+#define FS_LAUNCH_CHECK()          \
+  do {                             \
+    fs::count_launch();            \
+    FS_CUDA(cudaGetLastError());   \
+  } while (0)
+
+// ---------------------------------------------------------------- device buffer
+template <class T>
+struct DBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DBuf() = default;
+  explicit DBuf(size_t count) { alloc(count); }
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  DBuf(DBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DBuf& operator=(DBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DBuf() { release(); }
+  void alloc(size_t count) {
+    release();
+    n = count;
+    if (count) FS_CUDA(cudaMalloc(&p, count * sizeof(T)));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  void zero() { if (n) FS_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), stream())); }
+  void upload(const T* src, size_t count) {  // src host or device
+    FS_REQUIRE(count <= n, "DBuf::upload overflow");
+    if (count) FS_CUDA(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyDefault, stream()));
+  }
+  std::vector<T> to_host() const {
+    std::vector<T> h(n);
+    if (n) {
+      FS_CUDA(cudaMemcpyAsync(h.data(), p, n * sizeof(T), cudaMemcpyDeviceToHost, stream()));
+      FS_CUDA(cudaStreamSynchronize(stream()));
+    }
+    return h;
+  }
+};
+
+inline bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Read-only argument that may live on the host: staged into a stream-ordered
+// temporary when needed.
+template <class T>
+struct In {
+  const T* d = nullptr;
+  T* tmp = nullptr;
+  In(const T* ptr, size_t count) {
+    if (!ptr || count == 0) return;
+    if (is_device_ptr(ptr)) { d = ptr; return; }
+    FS_CUDA(cudaMallocAsync(&tmp, count * sizeof(T), stream()));
+    FS_CUDA(cudaMemcpyAsync(tmp, ptr, count * sizeof(T), cudaMemcpyHostToDevice, stream()));
+    d = tmp;
+  }
+  ~In() { if (tmp) cudaFreeAsync(tmp, stream()); }
+  In(const In&) = delete;
+  In& operator=(const In&) = delete;
+};
+
+// Output (or in/out) argument that may live on the host.  commit() copies back
+// and synchronises; call it last in the API function.
+template <class T>
+struct Out {
+  T* d = nullptr;
+  T* tmp = nullptr;
+  T* host = nullptr;
+  size_t count = 0;
+  Out(T* ptr, size_t cnt, bool read_in = false) : count(cnt) {
+    if (!ptr || cnt == 0) return;
+    if (is_device_ptr(ptr)) { d = ptr; return; }
+    host = ptr;
+    FS_CUDA(cudaMallocAsync(&tmp, cnt * sizeof(T), stream()));
+    if (read_in) FS_CUDA(cudaMemcpyAsync(tmp, ptr, cnt * sizeof(T), cudaMemcpyHostToDevice, stream()));
+    d = tmp;
+  }
+  void commit() {
+    if (tmp && host)
+      FS_CUDA(cudaMemcpyAsync(host, tmp, count * sizeof(T), cudaMemcpyDeviceToHost, stream()));
+  }
+  ~Out() { if (tmp) cudaFreeAsync(tmp, stream()); }
+  Out(const Out&) = delete;
+  Out& operator=(const Out&) = delete;
+};
+
+inline void sync() { FS_CUDA(cudaStreamSynchronize(stream())); }
+
+inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+int sm_count();
+
+// ---------------------------------------------------------------- structures
+struct CsrView {
+  int n;
+  int64_t nnz;
+  const int* rowptr;
+  const int* colidx;
+  const double* vals;
+};
+
+}  // namespace fs
+
+// Opaque handle definitions ----------------------------------------------------
+struct fs_csr {
+  int64_t n = 0, nnz = 0;
+  fs::DBuf<int> rowptr_own, colidx_own;
+  const int* rowptr = nullptr;   // either own or borrowed from a mesh pattern
+  const int* colidx = nullptr;
+  fs::DBuf<double> vals;
+  fs::DBuf<double> dinv;         // Jacobi (lazy)
+  bool dinv_ready = false;
+  // Krylov workspace (lazy, sized n*nrhs)
+  fs::DBuf<double> ws;
+  size_t ws_n = 0;
+  fs::DBuf<double> partials;
+  fs::DBuf<double> scal;
+  fs::CsrView view() const { return fs::CsrView{(int)n, nnz, rowptr, colidx, vals.p}; }
+};
+
+namespace fs {
+// Structural pattern built from (mapped) triangles.
+struct Pattern {
+  int64_t n = 0, nnz = 0, T = 0;
+  DBuf<int> rowptr, colidx;
+  DBuf<int> scatter;     // (T,9) element entry -> nnz id
+  DBuf<int> seg_start;   // (nnz+1) start of each nonzero's contribution list
+  DBuf<unsigned> contrib; // (9T) element-entry ids (e*9+k), sorted by nnz, ascending e inside
+};
+void build_pattern(const int* d_tris, int64_t T, int64_t n, const int* d_dof /*nullable*/, Pattern& out);
+void assemble_on_pattern(const Pattern& pat, const double* d_ke /* (T,9) */, double* d_vals);
+}  // namespace fs
+
+namespace fs { struct Locator; }
+
+struct fs_mesh {
+  int64_t N = 0, T = 0;
+  fs::DBuf<double> coords;    // (N,2)
+  fs::DBuf<int> tris;         // (T,3)
+  fs::DBuf<int> markers;      // (N)
+  fs::Pattern pat;            // pattern of K on the N nodes
+  // node -> incident element-corner list (ascending element id)
+  fs::DBuf<int> inc_ptr;      // (N+1)
+  fs::DBuf<unsigned> inc;     // (3T) entries e*3+i
+  // per-element scratch
+  fs::DBuf<double> ke;        // (T,9) lazily allocated
+  fs::DBuf<double> elem_a, elem_b, elem_c;  // (T) scratch for lumps
+  fs::DBuf<double> area_sum;  // (N) sum of area/3 over non-degenerate incident elements
+  fs::DBuf<double> mass;      // (N) lumped mass (no skip)
+  bool geom_ready = false;
+  // boundary sets
+  fs::DBuf<int> wall, inner, pairs, interior;
+  fs::DBuf<double> inner_sin, inner_cos, inner_sin2;
+  int64_t n_wall = 0, n_inner = 0, n_pairs = 0, n_interior = 0;
+  std::vector<int> pairs_host;
+  bool bc_ready = false;
+  // locator (lazy)
+  fs::Locator* loc = nullptr;
+  ~fs_mesh();
+};
+
+namespace fs {
+void ensure_geom(fs_mesh* m);
+void divergence_dev(fs_mesh* m, const double* d_u, double* d_div, double* d_div_sum /*nullable*/);
+void gradient_dev(fs_mesh* m, const double* d_p, double* d_gx, double* d_gy);
+void per_bcu_dev(fs_mesh* m, double* d_u);
+void dir_bcu_dev(fs_mesh* m, double* d_u, double B1, double B2);
+void grad_update_dev(fs_mesh* m, const double* d_p, const double* d_ui, double* d_uo, double DT,
+                     const unsigned char* d_interior_flag /* null: all nodes */);
+void jacobi_prepare(fs_csr* a);
+// CG on device pointers; returns iterations, writes relres.
+int cg_dev(fs_csr* a, const double* d_b, double* d_x, int nrhs, double rtol, int maxit, int precond,
+           int project_mean, double* relres);
+void spmv_dev(const CsrView& A, const double* d_x, double* d_y);
+double max_abs_dev(const double* d_x, int64_t n);
+void free_locator(Locator* l);
+}  // namespace fs

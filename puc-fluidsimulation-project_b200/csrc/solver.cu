@@ -1,0 +1,680 @@
+// solver.cu -- fp64 CSR SpMV and the Krylov solvers that replace the reference's
+// dense np.linalg.solve (code/StokesColor.py:544-545,555,569; code/heatEq.py:323;
+// code/poisson.py:285).
+//
+// CG schedule (3 passes per iteration, dots fused into the passes):
+//   A: Ap = A p            + partial p.Ap          (matrix stream + p gather)
+//   B: x += a p; r -= a Ap + partial r.r, r.z      (z = Dinv r never stored)
+//   C: p = z + b p
+// Scalars never visit the host inside a chunk of iterations: each pass
+// re-reduces the previous pass's per-block partials in a fixed order
+// (deterministic, no atomics); the host polls a "done" flag every chunk.
+#include <algorithm>
+
+#include "internal.cuh"
+
+namespace fs {
+
+constexpr int kBlock = 256;
+constexpr int kMaxBlocks = 1024;   // partial arrays are sized for this
+
+template <int R>
+struct VecT;
+template <>
+struct VecT<1> {
+  using type = double;
+};
+template <>
+struct VecT<2> {
+  using type = double2;
+};
+
+template <int R> struct Acc { double v[R]; };
+
+__device__ __forceinline__ double ld_c(const double* p, int64_t i, int) { return p[i]; }
+
+template <int R>
+__device__ __forceinline__ void load_vec(const double* __restrict__ p, int64_t i, double (&o)[R]) {
+  if (R == 1) o[0] = p[i];
+  else { double2 t = reinterpret_cast<const double2*>(p)[i]; o[0] = t.x; o[R - 1] = t.y; }
+}
+template <int R>
+__device__ __forceinline__ void load_vec_ldg(const double* __restrict__ p, int64_t i, double (&o)[R]) {
+  if (R == 1) o[0] = __ldg(p + i);
+  else { double2 t = __ldg(reinterpret_cast<const double2*>(p) + i); o[0] = t.x; o[R - 1] = t.y; }
+}
+template <int R>
+__device__ __forceinline__ void store_vec(double* __restrict__ p, int64_t i, const double (&o)[R]) {
+  if (R == 1) p[i] = o[0];
+  else reinterpret_cast<double2*>(p)[i] = make_double2(o[0], o[R - 1]);
+}
+
+// block-wide deterministic sum of K values per thread -> out[0..K) valid in thread 0
+template <int K>
+__device__ __forceinline__ void block_reduce(double (&v)[K], double* smem /* K*32 */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  if (lane == 0)
+#pragma unroll
+    for (int k = 0; k < K; ++k) smem[k * 32 + warp] = v[k];
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      double t = (lane < nw) ? smem[k * 32 + lane] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      v[k] = t;
+    }
+  }
+  __syncthreads();
+}
+
+// every block re-reduces the partial array (nblk x K) in the same fixed order;
+// result broadcast to all threads through shared memory.
+template <int K>
+__device__ __forceinline__ void reduce_partials(const double* __restrict__ part, int nblk, double (&out)[K],
+                                                double* smem /* K */) {
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      double t = 0.0;
+      for (int b = lane; b < nblk; b += 32) t += part[(size_t)b * K + k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) smem[k] = t;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) out[k] = smem[k];
+  __syncthreads();
+}
+
+// ---- SpMV: LPR lanes per row, R interleaved right-hand sides -------------------
+template <int R, int LPR, bool DOT>
+__global__ void __launch_bounds__(kBlock)
+k_spmv(CsrView A, const double* __restrict__ x, double* __restrict__ y, double* __restrict__ part,
+       const int* __restrict__ done) {
+  __shared__ double red[R * 32];
+  if (done && *done) return;
+  const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int sub = threadIdx.x % LPR;
+  const int64_t nrow_threads = ((int64_t)gridDim.x * blockDim.x) / LPR;
+  double acc[R];
+#pragma unroll
+  for (int c = 0; c < R; ++c) acc[c] = 0.0;
+  const int64_t niter = (A.n + nrow_threads - 1) / nrow_threads;
+  for (int64_t it = 0; it < niter; ++it) {
+    const int64_t row = it * nrow_threads + gt / LPR;
+    double s[R];
+#pragma unroll
+    for (int c = 0; c < R; ++c) s[c] = 0.0;
+    if (row < A.n) {
+      const int rs = __ldg(A.rowptr + row), re = __ldg(A.rowptr + row + 1);
+      for (int k = rs + sub; k < re; k += LPR) {
+        const double a = __ldg(A.vals + k);
+        const int col = __ldg(A.colidx + k);
+        double xv[R];
+        load_vec_ldg<R>(x, col, xv);
+#pragma unroll
+        for (int c = 0; c < R; ++c) s[c] += a * xv[c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < R; ++c)
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) s[c] += __shfl_xor_sync(0xffffffffu, s[c], o);
+    if (row < A.n && sub == 0) {
+      store_vec<R>(y, row, s);
+      if (DOT) {
+        double xv[R];
+        load_vec_ldg<R>(x, row, xv);
+#pragma unroll
+        for (int c = 0; c < R; ++c) acc[c] += xv[c] * s[c];
+      }
+    }
+  }
+  if (DOT) {
+    block_reduce<R>(acc, red);
+    if (threadIdx.x == 0)
+#pragma unroll
+      for (int c = 0; c < R; ++c) part[(size_t)blockIdx.x * R + c] = acc[c];
+  }
+}
+
+static int spmv_grid(int64_t n, int lpr) {
+  int64_t want = (n * lpr + kBlock - 1) / kBlock;
+  int64_t cap = std::min<int64_t>(kMaxBlocks, (int64_t)sm_count() * 6);
+  return (int)std::max<int64_t>(1, std::min(want, cap));
+}
+
+static int pick_lpr(const CsrView& A) {
+  double avg = A.n ? (double)A.nnz / (double)A.n : 1.0;
+  if (avg <= 2.5) return 2;
+  if (avg <= 5.0) return 4;
+  if (avg <= 12.0) return 8;
+  if (avg <= 24.0) return 16;
+  return 32;
+}
+
+template <int R, bool DOT>
+static void launch_spmv(const CsrView& A, const double* x, double* y, double* part, const int* done, int grid_override = 0) {
+  int lpr = pick_lpr(A);
+  int grid = grid_override ? grid_override : spmv_grid(A.n, lpr);
+  cudaStream_t st = stream();
+  switch (lpr) {
+    case 2: k_spmv<R, 2, DOT><<<grid, kBlock, 0, st>>>(A, x, y, part, done); break;
+    case 4: k_spmv<R, 4, DOT><<<grid, kBlock, 0, st>>>(A, x, y, part, done); break;
+    case 8: k_spmv<R, 8, DOT><<<grid, kBlock, 0, st>>>(A, x, y, part, done); break;
+    case 16: k_spmv<R, 16, DOT><<<grid, kBlock, 0, st>>>(A, x, y, part, done); break;
+    default: k_spmv<R, 32, DOT><<<grid, kBlock, 0, st>>>(A, x, y, part, done); break;
+  }
+  FS_LAUNCH_CHECK();
+}
+
+void spmv_dev(const CsrView& A, const double* d_x, double* d_y) { launch_spmv<1, false>(A, d_x, d_y, nullptr, nullptr); }
+
+// ---- Jacobi ---------------------------------------------------------------------
+__global__ void k_diag_inv(CsrView A, double* __restrict__ dinv) {
+  int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (row >= A.n) return;
+  double d = 0.0;
+  for (int k = A.rowptr[row]; k < A.rowptr[row + 1]; ++k)
+    if (A.colidx[k] == row) d = A.vals[k];
+  dinv[row] = (d != 0.0) ? 1.0 / d : 1.0;
+}
+
+void jacobi_prepare(fs_csr* a) {
+  if (a->dinv_ready) return;
+  a->dinv.alloc(a->n);
+  k_diag_inv<<<div_up(a->n, 256), 256, 0, stream()>>>(a->view(), a->dinv.p);
+  FS_LAUNCH_CHECK();
+  a->dinv_ready = true;
+}
+
+// ---- CG passes --------------------------------------------------------------------
+// scalar block (doubles): slot s in {0,1}: rz[R] at s*R ; then bb[R] at 2R ; rr[R] at 3R
+// ints live in a separate array: done, iters
+struct CgScal {
+  double* d;     // 4R doubles
+  int* flags;    // [0]=done [1]=iters
+};
+
+// r = b - Ap (Ap holds A x0) ; z = Dinv r ; p = z ; partials {rr, rz, bb}
+template <int R>
+__global__ void __launch_bounds__(kBlock)
+k_cg_init(int64_t n, const double* __restrict__ b, const double* __restrict__ Ap, const double* __restrict__ dinv,
+          double* __restrict__ r, double* __restrict__ p, double* __restrict__ part) {
+  __shared__ double red[3 * R * 32];
+  double acc[3 * R];
+#pragma unroll
+  for (int k = 0; k < 3 * R; ++k) acc[k] = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double bv[R], av[R], rv[R], zv[R];
+    load_vec<R>(b, i, bv);
+    load_vec<R>(Ap, i, av);
+    const double di = dinv ? dinv[i] : 1.0;
+#pragma unroll
+    for (int c = 0; c < R; ++c) {
+      rv[c] = bv[c] - av[c];
+      zv[c] = di * rv[c];
+      acc[c] += rv[c] * rv[c];
+      acc[R + c] += rv[c] * zv[c];
+      acc[2 * R + c] += bv[c] * bv[c];
+    }
+    store_vec<R>(r, i, rv);
+    store_vec<R>(p, i, zv);
+  }
+  block_reduce<3 * R>(acc, red);
+  if (threadIdx.x == 0)
+#pragma unroll
+    for (int k = 0; k < 3 * R; ++k) part[(size_t)blockIdx.x * 3 * R + k] = acc[k];
+}
+
+template <int R>
+__global__ void k_cg_init_fin(const double* __restrict__ part, int nblk, CgScal sc, double tol2) {
+  __shared__ double sm[3 * R];
+  double v[3 * R];
+  reduce_partials<3 * R>(part, nblk, v, sm);
+  if (threadIdx.x == 0) {
+    bool all = true;
+#pragma unroll
+    for (int c = 0; c < R; ++c) {
+      sc.d[c] = v[R + c];          // rz slot 0
+      sc.d[2 * R + c] = v[2 * R + c];  // bb
+      sc.d[3 * R + c] = v[c];      // rr
+      if (!(v[c] <= tol2 * v[2 * R + c])) all = false;
+    }
+    sc.flags[0] = all ? 1 : 0;
+    sc.flags[1] = 0;
+  }
+}
+
+// pass B
+template <int R>
+__global__ void __launch_bounds__(kBlock)
+k_cg_update_xr(int64_t n, const double* __restrict__ p, const double* __restrict__ Ap, const double* __restrict__ dinv,
+               double* __restrict__ x, double* __restrict__ r, const double* __restrict__ part_pAp, int nblk_a,
+               CgScal sc, int slot, double* __restrict__ part_out) {
+  __shared__ double red[2 * R * 32];
+  __shared__ double sm[R];
+  if (sc.flags[0]) return;
+  double pAp[R], alpha[R];
+  reduce_partials<R>(part_pAp, nblk_a, pAp, sm);
+#pragma unroll
+  for (int c = 0; c < R; ++c) {
+    double rz = sc.d[slot * R + c];
+    alpha[c] = (pAp[c] != 0.0) ? rz / pAp[c] : 0.0;
+  }
+  double acc[2 * R];
+#pragma unroll
+  for (int k = 0; k < 2 * R; ++k) acc[k] = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double pv[R], av[R], xv[R], rv[R];
+    load_vec<R>(p, i, pv);
+    load_vec<R>(Ap, i, av);
+    load_vec<R>(x, i, xv);
+    load_vec<R>(r, i, rv);
+    const double di = dinv ? dinv[i] : 1.0;
+#pragma unroll
+    for (int c = 0; c < R; ++c) {
+      xv[c] += alpha[c] * pv[c];
+      rv[c] -= alpha[c] * av[c];
+      acc[c] += rv[c] * rv[c];
+      acc[R + c] += rv[c] * (di * rv[c]);
+    }
+    store_vec<R>(x, i, xv);
+    store_vec<R>(r, i, rv);
+  }
+  block_reduce<2 * R>(acc, red);
+  if (threadIdx.x == 0)
+#pragma unroll
+    for (int k = 0; k < 2 * R; ++k) part_out[(size_t)blockIdx.x * 2 * R + k] = acc[k];
+}
+
+// pass C
+template <int R>
+__global__ void __launch_bounds__(kBlock)
+k_cg_update_p(int64_t n, const double* __restrict__ r, const double* __restrict__ dinv, double* __restrict__ p,
+              const double* __restrict__ part_b, int nblk_b, CgScal sc, int slot, double tol2) {
+  __shared__ double sm[2 * R];
+  if (sc.flags[0]) return;
+  double v[2 * R], beta[R];
+  reduce_partials<2 * R>(part_b, nblk_b, v, sm);
+#pragma unroll
+  for (int c = 0; c < R; ++c) {
+    double rz_old = sc.d[slot * R + c];
+    beta[c] = (rz_old != 0.0) ? v[R + c] / rz_old : 0.0;
+  }
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double rv[R], pv[R];
+    load_vec<R>(r, i, rv);
+    load_vec<R>(p, i, pv);
+    const double di = dinv ? dinv[i] : 1.0;
+#pragma unroll
+    for (int c = 0; c < R; ++c) pv[c] = di * rv[c] + beta[c] * pv[c];
+    store_vec<R>(p, i, pv);
+  }
+  // block 0 publishes the scalars of the finished iteration into the other slot;
+  // nobody reads that slot, rr or the counters during this launch.  A block that
+  // starts after "done" is set skips its p update, which is no longer needed.
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    bool all = true;
+#pragma unroll
+    for (int c = 0; c < R; ++c) {
+      sc.d[(slot ^ 1) * R + c] = v[R + c];
+      sc.d[3 * R + c] = v[c];
+      if (!(v[c] <= tol2 * sc.d[2 * R + c])) all = false;
+    }
+    sc.flags[1] += 1;
+    if (all) sc.flags[0] = 1;
+  }
+}
+
+// mean handling for the singular pressure operator
+__global__ void __launch_bounds__(kBlock)
+k_sum(int64_t n, const double* __restrict__ v, double* __restrict__ part) {
+  __shared__ double red[32];
+  double acc[1] = {0.0};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc[0] += v[i];
+  block_reduce<1>(acc, red);
+  if (threadIdx.x == 0) part[blockIdx.x] = acc[0];
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_sub_mean(int64_t n, const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ part, int nblk) {
+  __shared__ double sm[1];
+  double s[1];
+  reduce_partials<1>(part, nblk, s, sm);
+  const double mean = s[0] / (double)n;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[i] - mean;
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_maxabs(int64_t n, const double* __restrict__ v, double* __restrict__ part) {
+  __shared__ double red[32];
+  double m = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmax(m, fabs(v[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) part[blockIdx.x] = m;
+  }
+}
+
+static int vec_grid(int64_t n) {
+  int64_t want = (n + kBlock - 1) / kBlock;
+  int64_t cap = std::min<int64_t>(kMaxBlocks, (int64_t)sm_count() * 6);
+  return (int)std::max<int64_t>(1, std::min(want, cap));
+}
+
+static void ensure_ws(fs_csr* a, size_t doubles) {
+  if (a->ws_n < doubles) { a->ws.alloc(doubles); a->ws_n = doubles; }
+  if (!a->partials.n) a->partials.alloc((size_t)kMaxBlocks * 16);
+  if (!a->scal.n) a->scal.alloc(64);
+}
+
+double max_abs_dev(const double* d_x, int64_t n) {
+  int g = vec_grid(n);
+  DBuf<double> part(g);
+  k_maxabs<<<g, kBlock, 0, stream()>>>(n, d_x, part.p);
+  FS_LAUNCH_CHECK();
+  std::vector<double> h = part.to_host();
+  double m = 0.0;
+  for (double v : h) m = std::max(m, v);
+  return m;
+}
+
+template <int R>
+static int cg_impl(fs_csr* a, const double* d_b, double* d_x, double rtol, int maxit, int precond, int project_mean,
+                   double* relres) {
+  const int64_t n = a->n;
+  const size_t len = (size_t)n * R;
+  ensure_ws(a, 4 * len);
+  double* r = a->ws.p;
+  double* p = r + len;
+  double* Ap = p + len;
+  double* bproj = Ap + len;
+  const double* dinv = nullptr;
+  if (precond == FS_PRECOND_JACOBI) { jacobi_prepare(a); dinv = a->dinv.p; }
+  cudaStream_t st = stream();
+  const CsrView A = a->view();
+  double* partA = a->partials.p;                    // pass A partials (R per block)
+  double* partB = a->partials.p + kMaxBlocks * 4;   // pass B partials (2R per block)
+  double* part0 = a->partials.p + kMaxBlocks * 8;   // init partials (3R per block) / mean sums
+  CgScal sc{a->scal.p, reinterpret_cast<int*>(a->scal.p + 32)};
+  const int gv = vec_grid(n);
+  const double tol2 = rtol * rtol;
+
+  const double* b_use = d_b;
+  if (project_mean) {
+    FS_REQUIRE(R == 1, "project_mean needs nrhs == 1");
+    k_sum<<<gv, kBlock, 0, st>>>(n, d_b, part0);
+    FS_LAUNCH_CHECK();
+    k_sub_mean<<<gv, kBlock, 0, st>>>(n, d_b, bproj, part0, gv);
+    FS_LAUNCH_CHECK();
+    b_use = bproj;
+  }
+  launch_spmv<R, false>(A, d_x, Ap, nullptr, nullptr);
+  k_cg_init<R><<<gv, kBlock, 0, st>>>(n, b_use, Ap, dinv, r, p, part0);
+  FS_LAUNCH_CHECK();
+  k_cg_init_fin<R><<<1, 32, 0, st>>>(part0, gv, sc, tol2);
+  FS_LAUNCH_CHECK();
+
+  struct HostScal { double d[8]; int flags[2]; } hs;
+  auto poll = [&]() {
+    FS_CUDA(cudaMemcpyAsync(hs.d, sc.d, sizeof(double) * 4 * R, cudaMemcpyDeviceToHost, st));
+    FS_CUDA(cudaMemcpyAsync(hs.flags, sc.flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+    FS_CUDA(cudaStreamSynchronize(st));
+  };
+  poll();
+  bool zero_rhs = true;
+  for (int c = 0; c < R; ++c) if (hs.d[2 * R + c] != 0.0) zero_rhs = false;
+  if (zero_rhs) {
+    FS_CUDA(cudaMemsetAsync(d_x, 0, len * sizeof(double), st));
+    if (relres) *relres = 0.0;
+    return 0;
+  }
+  const int ga = spmv_grid(n, pick_lpr(A));
+  int launched = 0, chunk = 8, slot = 0;
+  while (!hs.flags[0] && launched < maxit) {
+    int todo = std::min(chunk, maxit - launched);
+    for (int k = 0; k < todo; ++k) {
+      launch_spmv<R, true>(A, p, Ap, partA, sc.flags, ga);
+      k_cg_update_xr<R><<<gv, kBlock, 0, st>>>(n, p, Ap, dinv, d_x, r, partA, ga, sc, slot, partB);
+      FS_LAUNCH_CHECK();
+      k_cg_update_p<R><<<gv, kBlock, 0, st>>>(n, r, dinv, p, partB, gv, sc, slot, tol2);
+      FS_LAUNCH_CHECK();
+      slot ^= 1;
+    }
+    launched += todo;
+    poll();
+    chunk = std::min(chunk * 2, 128);
+  }
+  if (project_mean) {
+    k_sum<<<gv, kBlock, 0, st>>>(n, d_x, part0);
+    FS_LAUNCH_CHECK();
+    k_sub_mean<<<gv, kBlock, 0, st>>>(n, d_x, d_x, part0, gv);
+    FS_LAUNCH_CHECK();
+  }
+  double worst = 0.0;
+  for (int c = 0; c < R; ++c) {
+    double bb = hs.d[2 * R + c], rr = hs.d[3 * R + c];
+    if (bb > 0.0) worst = std::max(worst, std::sqrt(rr / bb));
+  }
+  if (relres) *relres = worst;
+  return hs.flags[0] ? hs.flags[1] : -hs.flags[1] - 1;   // negative: not converged
+}
+
+int cg_dev(fs_csr* a, const double* d_b, double* d_x, int nrhs, double rtol, int maxit, int precond, int project_mean,
+           double* relres) {
+  FS_REQUIRE(nrhs == 1 || nrhs == 2, "nrhs must be 1 or 2");
+  return nrhs == 1 ? cg_impl<1>(a, d_b, d_x, rtol, maxit, precond, project_mean, relres)
+                   : cg_impl<2>(a, d_b, d_x, rtol, maxit, precond, project_mean, relres);
+}
+
+// ---- small vector kernels for BiCGStab (host-driven scalars; small systems) -----
+__global__ void __launch_bounds__(kBlock)
+k_dot2(int64_t n, const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ c,
+       const double* __restrict__ d, double* __restrict__ part) {
+  __shared__ double red[64];
+  double acc[2] = {0.0, 0.0};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    acc[0] += a[i] * b[i];
+    if (c) acc[1] += c[i] * d[i];
+  }
+  block_reduce<2>(acc, red);
+  if (threadIdx.x == 0) { part[2 * blockIdx.x] = acc[0]; part[2 * blockIdx.x + 1] = acc[1]; }
+}
+
+// out = a*x + b*y + c*z (any of y,z may be null)
+__global__ void k_lin3(int64_t n, double a, const double* __restrict__ x, double b, const double* __restrict__ y, double c,
+                       const double* __restrict__ z, double* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double v = a * x[i];
+    if (y) v += b * y[i];
+    if (z) v += c * z[i];
+    out[i] = v;
+  }
+}
+
+__global__ void k_mul(int64_t n, const double* __restrict__ d, const double* __restrict__ x, double* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = d ? d[i] * x[i] : x[i];
+}
+
+static void dot2(int64_t n, const double* a, const double* b, const double* c, const double* d, double* part, double* out2) {
+  int g = std::min(vec_grid(n), 256);
+  k_dot2<<<g, kBlock, 0, stream()>>>(n, a, b, c, d, part);
+  FS_LAUNCH_CHECK();
+  std::vector<double> h(2 * g);
+  FS_CUDA(cudaMemcpyAsync(h.data(), part, sizeof(double) * 2 * g, cudaMemcpyDeviceToHost, stream()));
+  FS_CUDA(cudaStreamSynchronize(stream()));
+  out2[0] = out2[1] = 0.0;
+  for (int i = 0; i < g; ++i) { out2[0] += h[2 * i]; out2[1] += h[2 * i + 1]; }
+}
+
+static int bicgstab_impl(fs_csr* a, const double* d_b, double* x, double rtol, int maxit, int precond, double* relres) {
+  const int64_t n = a->n;
+  ensure_ws(a, 8 * (size_t)n);
+  double *r = a->ws.p, *r0 = r + n, *p = r0 + n, *v = p + n, *s = v + n, *t = s + n, *ph = t + n, *sh = ph + n;
+  const double* dinv = nullptr;
+  if (precond == FS_PRECOND_JACOBI) { jacobi_prepare(a); dinv = a->dinv.p; }
+  const CsrView A = a->view();
+  cudaStream_t st = stream();
+  const int g = vec_grid(n);
+  double* part = a->partials.p;
+  double d2[2];
+  spmv_dev(A, x, v);
+  k_lin3<<<g, kBlock, 0, st>>>(n, 1.0, d_b, -1.0, v, 0.0, nullptr, r); FS_LAUNCH_CHECK();
+  FS_CUDA(cudaMemcpyAsync(r0, r, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  dot2(n, d_b, d_b, r, r, part, d2);
+  const double bb = d2[0];
+  double rr = d2[1];
+  if (bb == 0.0) { FS_CUDA(cudaMemsetAsync(x, 0, n * sizeof(double), st)); if (relres) *relres = 0.0; return 0; }
+  const double tol2 = rtol * rtol;
+  double rho = 1.0, alpha = 1.0, omega = 1.0;
+  FS_CUDA(cudaMemsetAsync(p, 0, n * sizeof(double), st));
+  FS_CUDA(cudaMemsetAsync(v, 0, n * sizeof(double), st));
+  int it = 0;
+  while (rr > tol2 * bb && it < maxit) {
+    dot2(n, r0, r, nullptr, nullptr, part, d2);
+    double rho_new = d2[0];
+    if (rho_new == 0.0) break;   // breakdown
+    double beta = (rho_new / rho) * (alpha / omega);
+    // p = r + beta*(p - omega*v)
+    k_lin3<<<g, kBlock, 0, st>>>(n, 1.0, r, beta, p, -beta * omega, v, p); FS_LAUNCH_CHECK();
+    k_mul<<<g, kBlock, 0, st>>>(n, dinv, p, ph); FS_LAUNCH_CHECK();
+    spmv_dev(A, ph, v);
+    dot2(n, r0, v, nullptr, nullptr, part, d2);
+    if (d2[0] == 0.0) break;
+    alpha = rho_new / d2[0];
+    k_lin3<<<g, kBlock, 0, st>>>(n, 1.0, r, -alpha, v, 0.0, nullptr, s); FS_LAUNCH_CHECK();
+    k_mul<<<g, kBlock, 0, st>>>(n, dinv, s, sh); FS_LAUNCH_CHECK();
+    spmv_dev(A, sh, t);
+    dot2(n, t, s, t, t, part, d2);
+    omega = (d2[1] != 0.0) ? d2[0] / d2[1] : 0.0;
+    // x += alpha*ph + omega*sh ; r = s - omega*t
+    k_lin3<<<g, kBlock, 0, st>>>(n, 1.0, x, alpha, ph, omega, sh, x); FS_LAUNCH_CHECK();
+    k_lin3<<<g, kBlock, 0, st>>>(n, 1.0, s, -omega, t, 0.0, nullptr, r); FS_LAUNCH_CHECK();
+    dot2(n, r, r, nullptr, nullptr, part, d2);
+    rr = d2[0];
+    rho = rho_new;
+    ++it;
+    if (omega == 0.0) break;
+  }
+  if (relres) *relres = std::sqrt(rr / bb);
+  return (rr <= tol2 * bb) ? it : -it - 1;
+}
+
+}  // namespace fs
+
+using namespace fs;
+
+extern "C" {
+
+int fs_csr_create(int64_t n, int64_t nnz, const int32_t* rowptr, const int32_t* colidx, const double* vals, fs_csr** out) {
+  FS_API_BEGIN
+  FS_REQUIRE(out, "out is NULL");
+  *out = nullptr;
+  FS_REQUIRE(n > 0 && nnz >= 0 && rowptr && (nnz == 0 || (colidx && vals)), "bad CSR arguments");
+  std::unique_ptr<fs_csr> a(new fs_csr());
+  a->n = n; a->nnz = nnz;
+  a->rowptr_own.alloc(n + 1); a->rowptr_own.upload(rowptr, n + 1);
+  a->colidx_own.alloc(nnz); a->colidx_own.upload(colidx, nnz);
+  a->vals.alloc(nnz); a->vals.upload(vals, nnz);
+  a->rowptr = a->rowptr_own.p; a->colidx = a->colidx_own.p;
+  fs::sync();
+  *out = a.release();
+  FS_API_END
+}
+
+int fs_csr_from_mesh(fs_mesh* m, const double* vals, fs_csr** out) {
+  FS_API_BEGIN
+  FS_REQUIRE(m && vals && out, "NULL argument");
+  std::unique_ptr<fs_csr> a(new fs_csr());
+  a->n = m->N; a->nnz = m->pat.nnz;
+  a->rowptr = m->pat.rowptr.p; a->colidx = m->pat.colidx.p;   // borrowed: mesh must outlive the matrix
+  a->vals.alloc(a->nnz); a->vals.upload(vals, a->nnz);
+  fs::sync();
+  *out = a.release();
+  FS_API_END
+}
+
+int fs_csr_destroy(fs_csr* a) {
+  FS_API_BEGIN
+  if (a) { cudaStreamSynchronize(stream()); delete a; }
+  FS_API_END
+}
+
+int fs_csr_sizes(const fs_csr* a, int64_t* n, int64_t* nnz) {
+  FS_API_BEGIN
+  FS_REQUIRE(a, "matrix is NULL");
+  if (n) *n = a->n;
+  if (nnz) *nnz = a->nnz;
+  FS_API_END
+}
+
+int fs_csr_get(const fs_csr* a, int32_t* rowptr, int32_t* colidx, double* vals) {
+  FS_API_BEGIN
+  FS_REQUIRE(a, "matrix is NULL");
+  cudaStream_t st = stream();
+  if (rowptr) FS_CUDA(cudaMemcpyAsync(rowptr, a->rowptr, (a->n + 1) * sizeof(int), cudaMemcpyDefault, st));
+  if (colidx && a->nnz) FS_CUDA(cudaMemcpyAsync(colidx, a->colidx, a->nnz * sizeof(int), cudaMemcpyDefault, st));
+  if (vals && a->nnz) FS_CUDA(cudaMemcpyAsync(vals, a->vals.p, a->nnz * sizeof(double), cudaMemcpyDefault, st));
+  fs::sync();
+  FS_API_END
+}
+
+int fs_spmv(fs_csr* a, const double* x, double* y) {
+  FS_API_BEGIN
+  FS_REQUIRE(a && x && y, "NULL argument");
+  In<double> ix(x, a->n);
+  Out<double> oy(y, a->n);
+  spmv_dev(a->view(), ix.d, oy.d);
+  oy.commit();
+  fs::sync();
+  FS_API_END
+}
+
+int fs_cg(fs_csr* a, const double* b, double* x, int nrhs, double rtol, int maxit, int precond, int project_mean,
+          int* iters, double* relres) {
+  FS_API_BEGIN
+  FS_REQUIRE(a && b && x, "NULL argument");
+  FS_REQUIRE(nrhs == 1 || nrhs == 2, "nrhs must be 1 or 2");
+  In<double> ib(b, a->n * nrhs);
+  Out<double> ox(x, a->n * nrhs, true);
+  double rr = 0.0;
+  int it = cg_dev(a, ib.d, ox.d, nrhs, rtol, maxit, precond, project_mean, &rr);
+  ox.commit();
+  fs::sync();
+  if (iters) *iters = it >= 0 ? it : -it - 1;
+  if (relres) *relres = rr;
+  if (it < 0) throw Error(FS_ERR_NOCONV, "fs_cg: no convergence within maxit");
+  FS_API_END
+}
+
+int fs_bicgstab(fs_csr* a, const double* b, double* x, double rtol, int maxit, int precond, int* iters, double* relres) {
+  FS_API_BEGIN
+  FS_REQUIRE(a && b && x, "NULL argument");
+  In<double> ib(b, a->n);
+  Out<double> ox(x, a->n, true);
+  double rr = 0.0;
+  int it = bicgstab_impl(a, ib.d, ox.d, rtol, maxit, precond, &rr);
+  ox.commit();
+  fs::sync();
+  if (iters) *iters = it >= 0 ? it : -it - 1;
+  if (relres) *relres = rr;
+  if (it < 0) throw Error(FS_ERR_NOCONV, "fs_bicgstab: no convergence (maxit or breakdown)");
+  FS_API_END
+}
+
+}  // extern "C"

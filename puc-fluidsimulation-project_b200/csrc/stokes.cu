@@ -1,0 +1,231 @@
+// stokes.cu -- the operator-split Stokes step of code/StokesColor.py:537-575
+// (== code/StokesFood.py:441-479), device resident.
+//
+//   u*  = solve(A_visc, u)            two RHS in one CG (A_visc = I + DT*nu*K, :471-475)
+//   makePerBCU(u*); makeDirBCU(u*)    :546-547
+//   p   = solve(A_pressure, -div(u*)/DT)          :551-555   (restated, see below)
+//   u   = u* - DT*grad(p); BCs        :559-564
+//   p2  = solve(A_pressure, -div(u)/DT)           :567-569
+//   u[interior] -= DT*grad(p2)[interior]          :570-573
+//
+// Pressure restatement (DESIGN.md "pressure system"): the reference's
+// A_pressure = diag(1/(M+1e-12)) K + 1e10 penalty on periodic pairs is singular
+// and non-symmetric.  Here each periodic pair is merged into one dof (Z), the
+// equations are multiplied by the lumped mass and the SPD system
+//     (Z^T K Z) q = Z^T (M * b) - mean,   p = Z (q - mean q)
+// is solved by CG.
+#include "internal.cuh"
+
+struct fs_stokes {
+  fs_mesh* mesh = nullptr;
+  double DT = 0, nu = 0;
+  fs_csr a_visc;          // pattern borrowed from the mesh
+  fs_csr k_red;           // periodic-merged stiffness, own pattern
+  fs::Pattern pat_red;
+  fs::DBuf<int> dof;      // (N) node -> merged dof
+  int64_t nd = 0;
+  fs::DBuf<unsigned char> is_dir, is_interior;
+  fs::DBuf<double> ustar, div, rhs_red, p_red, p2_red, p_full, p2_full;
+  bool have_p = false;
+};
+
+namespace fs {
+
+__global__ void k_flag(const int* __restrict__ idx, int64_t n, unsigned char* __restrict__ flag) {
+  int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k < n) flag[idx[k]] = 1;
+}
+
+// A_visc values on K's pattern: I + (DT*nu) K, Dirichlet rows+columns zeroed, diagonal 1
+__global__ void k_visc_vals(CsrView K, double dtnu, const unsigned char* __restrict__ is_dir, double* __restrict__ out) {
+  int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (row >= K.n) return;
+  const bool rd = is_dir[row];
+  for (int k = K.rowptr[row]; k < K.rowptr[row + 1]; ++k) {
+    const int col = K.colidx[k];
+    const bool diag = (col == row);
+    double v = (diag ? 1.0 : 0.0) + dtnu * K.vals[k];
+    if (rd || is_dir[col]) v = diag ? 1.0 : 0.0;
+    out[k] = v;
+  }
+}
+
+// rhs_red[dof[n]] += M[n] * (-(1/DT) * div[n])   (code/StokesColor.py:554 then mass-weighting)
+__global__ void k_pressure_rhs(int64_t N, const int* __restrict__ dof, const double* __restrict__ mass,
+                               const double* __restrict__ div, double s, double* __restrict__ rhs_red) {
+  int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  atomicAdd(&rhs_red[dof[n]], mass[n] * (s * div[n]));
+}
+
+__global__ void k_expand(int64_t N, const int* __restrict__ dof, const double* __restrict__ q, double* __restrict__ p) {
+  int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (n < N) p[n] = q[dof[n]];
+}
+
+static void pressure_solve(fs_stokes* s, const double* d_vel, double* q, double* p_full, const fs_stokes_opts& o,
+                           int* iters, double* relres, double* max_div) {
+  fs_mesh* m = s->mesh;
+  cudaStream_t st = stream();
+  divergence_dev(m, d_vel, s->div.p, nullptr);
+  if (max_div) *max_div = max_abs_dev(s->div.p, m->N);
+  s->rhs_red.zero();
+  k_pressure_rhs<<<div_up(m->N, 256), 256, 0, st>>>(m->N, s->dof.p, m->mass.p, s->div.p, -(1.0 / s->DT), s->rhs_red.p);
+  FS_LAUNCH_CHECK();
+  if (!o.warm_start || !s->have_p) FS_CUDA(cudaMemsetAsync(q, 0, s->nd * sizeof(double), st));
+  int it = cg_dev(&s->k_red, s->rhs_red.p, q, 1, o.rtol_pressure, o.maxit, o.precond, 1, relres);
+  if (it < 0) throw Error(FS_ERR_NOCONV, "pressure CG did not converge within maxit");
+  *iters = it;
+  k_expand<<<div_up(m->N, 256), 256, 0, st>>>(m->N, s->dof.p, q, p_full);
+  FS_LAUNCH_CHECK();
+}
+
+}  // namespace fs
+
+using namespace fs;
+
+extern "C" {
+
+int fs_stokes_default_opts(fs_stokes_opts* o) {
+  FS_API_BEGIN
+  FS_REQUIRE(o, "opts is NULL");
+  o->rtol_visc = 1e-12;
+  o->rtol_pressure = 1e-10;
+  o->maxit = 200000;
+  o->precond = FS_PRECOND_JACOBI;
+  o->warm_start = 1;
+  o->final_div = 0;
+  FS_API_END
+}
+
+int fs_stokes_create(fs_mesh* m, double DT, double nu, fs_stokes** out) {
+  FS_API_BEGIN
+  FS_REQUIRE(m && out, "NULL argument");
+  *out = nullptr;
+  FS_REQUIRE(m->bc_ready, "fs_bc_set must be called before fs_stokes_create");
+  FS_REQUIRE(DT > 0, "DT must be positive");
+  std::unique_ptr<fs_stokes> s(new fs_stokes());
+  s->mesh = m; s->DT = DT; s->nu = nu;
+  cudaStream_t st = stream();
+  const int64_t N = m->N;
+  ensure_geom(m);
+  // K on the node pattern
+  DBuf<double> kvals(m->pat.nnz);
+  {
+    int rc = fs_assemble_stiffness(m, kvals.p);
+    if (rc != FS_OK) throw Error(rc, fs_last_error());
+  }
+  // Dirichlet / interior flags
+  s->is_dir.alloc(N); s->is_dir.zero();
+  s->is_interior.alloc(N); s->is_interior.zero();
+  if (m->n_wall) { k_flag<<<div_up(m->n_wall, 256), 256, 0, st>>>(m->wall.p, m->n_wall, s->is_dir.p); FS_LAUNCH_CHECK(); }
+  if (m->n_inner) { k_flag<<<div_up(m->n_inner, 256), 256, 0, st>>>(m->inner.p, m->n_inner, s->is_dir.p); FS_LAUNCH_CHECK(); }
+  if (m->n_interior) { k_flag<<<div_up(m->n_interior, 256), 256, 0, st>>>(m->interior.p, m->n_interior, s->is_interior.p); FS_LAUNCH_CHECK(); }
+  // A_visc
+  s->a_visc.n = N; s->a_visc.nnz = m->pat.nnz;
+  s->a_visc.rowptr = m->pat.rowptr.p; s->a_visc.colidx = m->pat.colidx.p;
+  s->a_visc.vals.alloc(m->pat.nnz);
+  CsrView Kv{(int)N, m->pat.nnz, m->pat.rowptr.p, m->pat.colidx.p, kvals.p};
+  k_visc_vals<<<div_up(N, 256), 256, 0, st>>>(Kv, DT * nu, s->is_dir.p, s->a_visc.vals.p);
+  FS_LAUNCH_CHECK();
+  // periodic merge: union-find on the host (pairs are few), representative = smallest id,
+  // dofs numbered in ascending representative order
+  std::vector<int> parent(N);
+  for (int64_t i = 0; i < N; ++i) parent[i] = (int)i;
+  auto find = [&](int a) { while (parent[a] != a) { parent[a] = parent[parent[a]]; a = parent[a]; } return a; };
+  for (int64_t k = 0; k < m->n_pairs; ++k) {
+    int ra = find(m->pairs_host[2 * k]), rb = find(m->pairs_host[2 * k + 1]);
+    if (ra != rb) parent[std::max(ra, rb)] = std::min(ra, rb);
+  }
+  std::vector<int> dof(N), newid(N, -1);
+  int nd = 0;
+  for (int64_t i = 0; i < N; ++i) if (find((int)i) == (int)i) newid[i] = nd++;
+  for (int64_t i = 0; i < N; ++i) dof[i] = newid[find((int)i)];
+  s->nd = nd;
+  s->dof.alloc(N);
+  s->dof.upload(dof.data(), N);
+  fs::sync();
+  build_pattern(m->tris.p, m->T, nd, s->dof.p, s->pat_red);
+  s->k_red.n = nd; s->k_red.nnz = s->pat_red.nnz;
+  s->k_red.rowptr = s->pat_red.rowptr.p; s->k_red.colidx = s->pat_red.colidx.p;
+  s->k_red.vals.alloc(s->pat_red.nnz);
+  assemble_on_pattern(s->pat_red, m->ke.p, s->k_red.vals.p);   // m->ke still holds the element matrices
+  // the merged pattern's contribution lists are only needed for this assembly
+  s->pat_red.contrib.release(); s->pat_red.seg_start.release(); s->pat_red.scatter.release();
+  s->ustar.alloc(2 * N); s->div.alloc(N); s->rhs_red.alloc(nd);
+  s->p_red.alloc(nd); s->p2_red.alloc(nd); s->p_full.alloc(N); s->p2_full.alloc(N);
+  s->p_red.zero(); s->p2_red.zero(); s->p_full.zero(); s->p2_full.zero();
+  fs::sync();
+  *out = s.release();
+  FS_API_END
+}
+
+int fs_stokes_destroy(fs_stokes* s) {
+  FS_API_BEGIN
+  if (s) { cudaStreamSynchronize(stream()); delete s; }
+  FS_API_END
+}
+
+int fs_stokes_step(fs_stokes* s, double* u, double B1, double B2, const fs_stokes_opts* opts, fs_stokes_stats* stats) {
+  FS_API_BEGIN
+  FS_REQUIRE(s && u, "NULL argument");
+  fs_stokes_opts o;
+  fs_stokes_default_opts(&o);
+  if (opts) o = *opts;
+  fs_mesh* m = s->mesh;
+  const int64_t N = m->N;
+  cudaStream_t st = stream();
+  Out<double> ou(u, 2 * N, true);
+  double* du = ou.d;
+  fs_stokes_stats sts;
+  std::memset(&sts, 0, sizeof(sts));
+  // Step 1: tentative velocity, both components in one 2-RHS CG started from u
+  FS_CUDA(cudaMemcpyAsync(s->ustar.p, du, 2 * N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  int it = cg_dev(&s->a_visc, du, s->ustar.p, 2, o.rtol_visc, o.maxit, o.precond, 0, &sts.relres_visc);
+  if (it < 0) throw Error(FS_ERR_NOCONV, "viscous CG did not converge within maxit");
+  sts.iters_visc = it;
+  per_bcu_dev(m, s->ustar.p);
+  dir_bcu_dev(m, s->ustar.p, B1, B2);
+  // Step 2+3: pressure correction and velocity update
+  pressure_solve(s, s->ustar.p, s->p_red.p, s->p_full.p, o, &sts.iters_p1, &sts.relres_p1,
+                 o.final_div ? &sts.max_div_ustar : nullptr);
+  grad_update_dev(m, s->p_full.p, s->ustar.p, du, s->DT, nullptr);
+  per_bcu_dev(m, du);
+  dir_bcu_dev(m, du, B1, B2);
+  // second projection, interior nodes only, no BC re-imposition (:566-573)
+  pressure_solve(s, du, s->p2_red.p, s->p2_full.p, o, &sts.iters_p2, &sts.relres_p2, nullptr);
+  grad_update_dev(m, s->p2_full.p, du, du, s->DT, s->is_interior.p);
+  s->have_p = true;
+  if (o.final_div) {
+    divergence_dev(m, du, s->div.p, nullptr);
+    sts.max_final_div = max_abs_dev(s->div.p, N);
+  }
+  ou.commit();
+  fs::sync();
+  if (stats) *stats = sts;
+  FS_API_END
+}
+
+int fs_stokes_pressure(fs_stokes* s, double* p, double* p2) {
+  FS_API_BEGIN
+  FS_REQUIRE(s, "NULL argument");
+  const int64_t N = s->mesh->N;
+  if (p) FS_CUDA(cudaMemcpyAsync(p, s->p_full.p, N * sizeof(double), cudaMemcpyDefault, stream()));
+  if (p2) FS_CUDA(cudaMemcpyAsync(p2, s->p2_full.p, N * sizeof(double), cudaMemcpyDefault, stream()));
+  fs::sync();
+  FS_API_END
+}
+
+int fs_stokes_matrices(fs_stokes* s, fs_csr** a_visc, fs_csr** k_pressure, int32_t* dof) {
+  FS_API_BEGIN
+  FS_REQUIRE(s, "NULL argument");
+  if (a_visc) *a_visc = &s->a_visc;
+  if (k_pressure) *k_pressure = &s->k_red;
+  if (dof) {
+    FS_CUDA(cudaMemcpyAsync(dof, s->dof.p, s->mesh->N * sizeof(int), cudaMemcpyDefault, stream()));
+    fs::sync();
+  }
+  FS_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,171 @@
+"""Mesh ingest and host-side setup logic (Triangle .node/.ele/.poly files, periodic
+pairs, index sets) plus the synthetic square-with-hole generator used by the
+benchmarks.  Mirrors the reference's loader functions (same names, same returns).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import call
+
+
+# --------------------------------------------------------------------------- readers
+def readNode(filepath, dtype=np.float64):
+    """readNode(filepath) -> (nodes_coords (N,2), nodes_boundary_markers (N,) i32).
+    code/StokesColor.py:54-78; ``dtype=np.float32`` gives the code/poisson.py:27-56
+    variant (same parse, coordinates stored as float32)."""
+    path = str(filepath).encode()
+    n = C.c_int64(0)
+    call("fs_node_file_count", path, C.byref(n))
+    coords = np.zeros((n.value, 2), dtype=np.float64)
+    markers = np.zeros(n.value, dtype=np.int32)
+    call("fs_read_node", path, _lib.ptr(coords), _lib.ptr(markers), n.value)
+    if np.dtype(dtype) != np.float64:
+        coords = coords.astype(dtype)
+    return coords, markers
+
+
+def readEle(filepath):
+    """readEle(filepath) -> (T,3) int32, 0-based.  code/StokesColor.py:82-95.
+    Only the three corner ids are read (6-node .ele files keep their corners)."""
+    path = str(filepath).encode()
+    t = C.c_int64(0)
+    k = C.c_int32(0)
+    call("fs_ele_file_count", path, C.byref(t), C.byref(k))
+    tris = np.zeros((t.value, 3), dtype=np.int32)
+    call("fs_read_ele", path, _lib.ptr(tris), t.value)
+    return tris
+
+
+def readPoly(path):
+    """readPoly(path) -> (segments (S,2) int, boundaryMarkers (S,) int).
+    code/poisson.py:76-97 (never called by the reference's main bodies; host only)."""
+    with open(path) as f:
+        f.readline()
+        nseg = int(f.readline().split()[0])
+        segments = np.zeros((nseg, 2), dtype=int)
+        markers = np.zeros(nseg, dtype=int)
+        for _ in range(nseg):
+            parts = f.readline().split()
+            i = int(parts[0]) - 1
+            segments[i] = (int(parts[1]) - 1, int(parts[2]) - 1)
+            if len(parts) > 3:
+                markers[i] = int(parts[3])
+    return segments, markers
+
+
+def write_node(path, coords, markers):
+    """Triangle .node writer (1-based ids, 17 significant digits)."""
+    coords = np.asarray(coords, dtype=np.float64)
+    with open(path, "w") as f:
+        f.write(f"{coords.shape[0]}  2  0  1\n")
+        for i, ((x, y), m) in enumerate(zip(coords, markers)):
+            f.write(f"{i + 1:4d}    {float(x)!r}  {float(y)!r}    {int(m)}\n")
+        f.write("# written by fluidsim_b200\n")
+
+
+def write_ele(path, tris):
+    tris = np.asarray(tris)
+    with open(path, "w") as f:
+        f.write(f"{tris.shape[0]}  3  0\n")
+        for e, t in enumerate(tris):
+            f.write(f"{e + 1:4d}    {t[0] + 1:4d}  {t[1] + 1:4d}  {t[2] + 1:4d}\n")
+        f.write("# written by fluidsim_b200\n")
+
+
+# --------------------------------------------------------------------------- boundary sets
+def find_boundary_pairs(nodes_coords, L=1.0, tol=1e-6):
+    """[(left_id, right_id)] in ascending left id: for each node on x=0 the node on
+    x=L nearest in y.  code/StokesColor.py:169-203.  At an exact distance tie (the
+    reference's KDTree result is implementation-defined there) the smaller y wins,
+    which is what the reference returns on resources/mesh2.1."""
+    nodes_coords = np.asarray(nodes_coords)
+    left = np.where(np.abs(nodes_coords[:, 0]) < tol)[0]
+    right = np.where(np.abs(nodes_coords[:, 0] - L) < tol)[0]
+    if len(left) == 0 or len(right) == 0:
+        print("Warning: One or both boundaries have no nodes.")
+        return []
+    ry = nodes_coords[right, 1].astype(np.float64)
+    order = np.argsort(ry, kind="stable")
+    rys = ry[order]
+    ly = nodes_coords[left, 1].astype(np.float64)
+    pos = np.searchsorted(rys, ly)
+    lo = np.clip(pos - 1, 0, len(rys) - 1)
+    hi = np.clip(pos, 0, len(rys) - 1)
+    pick = np.where(np.abs(ly - rys[lo]) <= np.abs(rys[hi] - ly), lo, hi)
+    # among equal y's keep the first in sorted order
+    first = np.searchsorted(rys, rys[pick], side="left")
+    return [(int(a), int(right[order[b]])) for a, b in zip(left, first)]
+
+
+def filter_wall_pairs(nodes_coords, pairs, H=1.0, tol=1e-6):
+    """code/StokesColor.py:449-457: drop pairs whose master sits on y=0 or y=H."""
+    out = []
+    for m, s in pairs:
+        my = nodes_coords[m, 1]
+        if not (abs(my - 0.0) < tol or abs(my - H) < tol):
+            out.append((m, s))
+    return out
+
+
+def index_sets(nodes_coords, markers, H=1.0, tol=1e-6, inner_marker=2):
+    """(wall, inner_boundary, dirichlet, interior) of code/StokesColor.py:461-464:
+    walls by y-coordinate, inner boundary by marker."""
+    y = np.asarray(nodes_coords)[:, 1]
+    wall = np.where(np.isclose(y, 0.0, atol=tol) | np.isclose(y, H, atol=tol))[0]
+    inner = np.where(np.asarray(markers) == inner_marker)[0]
+    dirichlet = np.union1d(wall, inner)
+    interior = np.setdiff1d(np.arange(len(y)), dirichlet)
+    return wall, inner, dirichlet, interior
+
+
+# --------------------------------------------------------------------------- synthetic mesh
+def square_with_hole(n_theta, n_r, radius=0.25, center=(0.5, 0.5), half=0.5):
+    """Structured triangulation of the unit square with a circular hole, the
+    topological annulus of SURVEY.md section 8(d): n_theta angular x n_r radial
+    quads, two CCW triangles each (T = 2*n_theta*n_r, N = n_theta*(n_r+1)).
+    Ring 0 lies on the circle (marker 2), the last ring is snapped onto the box
+    (marker 1) so the x=0 / x=1 nodes match in y.  Node id = ring*n_theta + j,
+    i.e. contiguous rings: a row-block partition cuts along rings."""
+    if n_theta % 8:
+        raise ValueError("n_theta must be a multiple of 8")
+    j = np.arange(n_theta)
+    th = 2.0 * np.pi * j / n_theta
+    ct, st = np.cos(th), np.sin(th)
+    # exact box direction: scale the ray so the larger of |cos|,|sin| becomes `half`
+    rbox = half / np.maximum(np.abs(ct), np.abs(st))
+    s = np.linspace(0.0, 1.0, n_r + 1)[:, None]
+    r = (1.0 - s) * radius + s * rbox[None, :]
+    x = center[0] + r * ct[None, :]
+    y = center[1] + r * st[None, :]
+    # snap the outer ring exactly onto the box so the periodic sides match bit for bit
+    xo, yo = x[-1], y[-1]
+    on_v = np.abs(ct) >= np.abs(st)
+    xo[on_v] = center[0] + half * np.sign(ct[on_v])
+    yo[~on_v] = center[1] + half * np.sign(st[~on_v])
+    corner = np.abs(np.abs(ct) - np.abs(st)) < 1e-12
+    yo[corner] = center[1] + half * np.sign(st[corner])
+    # symmetrise y on the two vertical sides (theta and pi-theta give the same y)
+    k = n_theta // 2
+    yr = yo.copy()
+    for jj in np.where(on_v)[0]:
+        mirror = (k - jj) % n_theta
+        yr[jj] = yr[mirror] = 0.5 * (yo[jj] + yo[mirror])
+    y[-1] = yr
+    coords = np.stack([x.ravel(), y.ravel()], axis=1)
+    markers = np.zeros((n_r + 1, n_theta), dtype=np.int32)
+    markers[0] = 2
+    markers[-1] = 1
+    i = np.arange(n_r)[:, None]
+    jn = (j + 1) % n_theta
+    a = i * n_theta + j[None, :]
+    b = i * n_theta + jn[None, :]
+    c = (i + 1) * n_theta + jn[None, :]
+    d = (i + 1) * n_theta + j[None, :]
+    t1 = np.stack([a, c, b], axis=-1)
+    t2 = np.stack([a, d, c], axis=-1)
+    tris = np.stack([t1, t2], axis=2).reshape(-1, 3).astype(np.int32)
+    return np.ascontiguousarray(coords), markers.ravel(), tris

@@ -1,0 +1,153 @@
+"""The operator-split Stokes step and its two drivers (dye mixing, food capture).
+
+``StokesSolver`` is the reference's module body (code/StokesColor.py:437-498 setup,
+:537-575 step) as an object: the module-level globals the reference functions
+read (pairs, wall_node_indices, inner_boundary_indices, B1, B2, DT, v ...) are its
+attributes, the functions that read them (makeDirBCU, makePerBCU,
+advect_semilagrange) are its methods.  All arithmetic runs in libfluidsim.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from . import mesh as _mesh
+from ._lib import StokesOpts, StokesStats, call, ptr, as_f64
+from .core import CsrMatrix, Mesh
+
+
+class StokesSolver:
+    def __init__(self, nodes_coords, nodes_boundary_markers, triangles, B1=-2.0, B2=0.0, DT=0.05, v=0.1,
+                 L=1.0, H=1.0, tol=1e-6, rtol_pressure=1e-10, rtol_visc=1e-12, precond=1, warm_start=True,
+                 maxit=200000, final_div=False):
+        self.nodes_coords = np.ascontiguousarray(nodes_coords, dtype=np.float64)
+        self.nodes_boundary_markers = np.ascontiguousarray(nodes_boundary_markers, dtype=np.int32)
+        self.triangles = np.ascontiguousarray(triangles, dtype=np.int32)
+        self.N = self.nodes_coords.shape[0]
+        self.B1, self.B2, self.DT, self.v, self.L, self.H, self.tol = B1, B2, DT, v, L, H, tol
+        # code/StokesColor.py:442-464
+        self.all_pairs = _mesh.find_boundary_pairs(self.nodes_coords, L=L, tol=tol)
+        self.pairs = _mesh.filter_wall_pairs(self.nodes_coords, self.all_pairs, H=H, tol=tol)
+        (self.wall_node_indices, self.inner_boundary_indices, self.dirichlet_node_indices,
+         self.interior) = _mesh.index_sets(self.nodes_coords, self.nodes_boundary_markers, H=H, tol=tol)
+        self.mesh = Mesh(self.nodes_coords, self.triangles, self.nodes_boundary_markers)
+        self.mesh.set_bc(self.wall_node_indices, self.inner_boundary_indices, self.pairs, self.interior)
+        h = C.c_void_p()
+        call("fs_stokes_create", self.mesh._h, float(DT), float(v), C.byref(h))
+        self._h = h
+        self.opts = StokesOpts()
+        call("fs_stokes_default_opts", C.byref(self.opts))
+        self.opts.rtol_pressure = rtol_pressure
+        self.opts.rtol_visc = rtol_visc
+        self.opts.precond = precond
+        self.opts.warm_start = 1 if warm_start else 0
+        self.opts.maxit = maxit
+        self.opts.final_div = 1 if final_div else 0
+        self.stats = StokesStats()
+        self.M_lumped_diag = self.mesh.lumped_mass()
+        # code/StokesColor.py:482-483
+        self.u = np.zeros((self.N, 2))
+        self.makeDirBCU(self.u)
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.lib.fs_stokes_destroy(self._h)
+        except Exception:
+            pass
+
+    # -- the reference's global-reading helpers
+    def makeDirBCU(self, u):
+        """code/StokesColor.py:405-427 (in place)."""
+        self.mesh.make_dir_bcu(u, self.B1, self.B2)
+
+    def makePerBCU(self, u):
+        """code/StokesColor.py:429-431 (in place)."""
+        self.mesh.make_per_bcu(u)
+
+    # -- matrices, for inspection
+    def matrices(self):
+        av, kp = C.c_void_p(), C.c_void_p()
+        dof = np.empty(self.N, dtype=np.int32)
+        call("fs_stokes_matrices", self._h, C.byref(av), C.byref(kp), ptr(dof))
+        return CsrMatrix(av, owner=self, borrowed=True), CsrMatrix(kp, owner=self, borrowed=True), dof
+
+    # -- one step, code/StokesColor.py:540-575
+    def step(self, u=None):
+        """Advance ``u`` (default: self.u) in place; numpy (host, staged) or torch cuda tensor."""
+        if u is None:
+            u = self.u
+        call("fs_stokes_step", self._h, ptr(u, np.float64, (self.N, 2), "u"), float(self.B1), float(self.B2),
+             C.byref(self.opts), C.byref(self.stats))
+        return self.stats
+
+    def pressure(self):
+        p = np.empty(self.N)
+        p2 = np.empty(self.N)
+        call("fs_stokes_pressure", self._h, ptr(p), ptr(p2))
+        return p, p2
+
+
+class StokesColor(StokesSolver):
+    """code/StokesColor.py: Stokes step + semi-Lagrangian dye + mixing index."""
+
+    def __init__(self, nodes_coords, nodes_boundary_markers, triangles, B1=-2.0, B2=0.0, DT=0.05, v=0.1, **kw):
+        super().__init__(nodes_coords, nodes_boundary_markers, triangles, B1=B1, B2=B2, DT=DT, v=v, **kw)
+        # code/StokesColor.py:493-498
+        self.c = np.zeros(self.N)
+        self.c[self.nodes_coords[:, 0] < 0.5] = 1.0
+        self.inner = np.where(self.nodes_boundary_markers == 0)[0].astype(np.int32)
+        self.I0, self.mu0, self.var0 = self.mesh.mixing_index(self.c, self.M_lumped_diag, self.inner)
+        self.progress = 0.0
+
+    def advect_semilagrange(self, c, u, DT):
+        """code/StokesColor.py:347-389 (in place on c)."""
+        self.mesh.advect_dye(c, u, DT)
+
+    def step_all(self):
+        """One pass of the reference loop body, code/StokesColor.py:538-585."""
+        st = self.step()
+        self.advect_semilagrange(self.c, self.u, self.DT)
+        I, mu, var = self.mesh.mixing_index(self.c, self.M_lumped_diag, self.inner)
+        self.progress = 1.0 - var / (self.var0 + 1e-16)
+        return st, self.progress
+
+
+def food_tracer_grid(grid_density=25, L=1.0, H=1.0, radius=0.25, center=(0.5, 0.5)):
+    """code/StokesFood.py:421-430: g x g grid on [0.05, L-0.05] x [0.05, H-0.05] minus the body."""
+    xx = np.linspace(0.05, L - 0.05, grid_density)
+    yy = np.linspace(0.05, H - 0.05, grid_density)
+    gx, gy = np.meshgrid(xx, yy)
+    pts = np.vstack([gx.ravel(), gy.ravel()]).T
+    d = np.linalg.norm(pts - np.asarray(center), axis=1)
+    return np.ascontiguousarray(pts[d > radius])
+
+
+class StokesFood(StokesSolver):
+    """code/StokesFood.py: Stokes step + passive tracers with sticky capture."""
+
+    SQUIRMER_RADIUS = 0.25
+    CAPTURE_RADIUS = 0.25 + 0.03
+    SQUIRMER_CENTER = (0.5, 0.5)
+
+    def __init__(self, nodes_coords, nodes_boundary_markers, triangles, B1=-2.0, B2=0.0, DT=0.01, v=1.0,
+                 grid_density=25, tracer_points=None, **kw):
+        super().__init__(nodes_coords, nodes_boundary_markers, triangles, B1=B1, B2=B2, DT=DT, v=v, **kw)
+        self.tracer_points = (food_tracer_grid(grid_density, self.L, self.H, self.SQUIRMER_RADIUS)
+                              if tracer_points is None else np.ascontiguousarray(tracer_points, dtype=np.float64))
+        self.num_tracers = self.tracer_points.shape[0]
+        self.tracer_status = np.zeros(self.num_tracers, dtype=np.int32)
+        self._hint = np.full(self.num_tracers, -1, dtype=np.int32)
+        self.num_eaten = 0
+
+    def tracer_step(self):
+        """code/StokesFood.py:482-503."""
+        self.num_eaten = self.mesh.tracer_step(self.tracer_points, self.tracer_status, self._hint, self.u, self.DT,
+                                               L=self.L, center=self.SQUIRMER_CENTER, rcap=self.CAPTURE_RADIUS)
+        return self.num_eaten
+
+    def step_all(self):
+        st = self.step()
+        return st, self.tracer_step()

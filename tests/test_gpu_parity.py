@@ -1,0 +1,366 @@
+"""GPU parity: every CUDA path through the C ABI against the oracle / golden vectors.
+
+Bars (BASELINE.json north_star): CSR pattern and tracer element ids bit-exact; assembled
+values <= 1e-12 relative (K, M, div are in fact bit-exact); CG pressure / velocity <= 1e-9
+relative L2 over 100 steps; mixing / food fractions <= 1e-6.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import fluidsim_b200 as fb
+from oracle import restated as R
+from conftest import load_golden, MESHES
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(np.asarray(b)), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def meshes():
+    out = {}
+    for name in MESHES:
+        g = load_golden(name + "_ops")
+        out[name] = (g, fb.Mesh(g["nodes"], g["tris"], g["markers"]))
+    return out
+
+
+@pytest.mark.parametrize("name", MESHES)
+def test_pattern_bit_exact(meshes, name):
+    g, m = meshes[name]
+    rowptr, colidx = m.csr_pattern()
+    assert np.array_equal(rowptr, g["rowptr"]) and np.array_equal(colidx, g["colidx"])
+    assert np.array_equal(m.scatter_map(), g["scatter"])
+    assert (m.N, m.T, m.nnz) == (len(g["nodes"]), len(g["tris"]), len(g["colidx"]))
+
+
+@pytest.mark.parametrize("name", MESHES)
+def test_assembly_bit_exact(meshes, name):
+    g, m = meshes[name]
+    assert np.array_equal(m.stiffness_values(), g["K"])
+    assert np.array_equal(m.lumped_mass(), g["M"])
+    # reference-signature entry points
+    A, b = fb.buildStiffnessMatrix(g["nodes"], g["tris"], g_source=0.0)
+    assert np.array_equal(A.tocsr().toarray(), sp.csr_matrix((g["K"], g["colidx"], g["rowptr"])).toarray())
+    assert b.shape == (m.N,) and not b.any()
+    assert np.array_equal(fb.buildLumpedMassMatrix(g["nodes"], g["tris"]), g["M"])
+
+
+@pytest.mark.parametrize("name", MESHES)
+def test_div_grad(meshes, name):
+    g, m = meshes[name]
+    for k in ("rand", "katB", "final_test"):
+        assert np.array_equal(m.divergence(g["u_" + k]), g["div_" + k]), k
+    for k in ("rand", "katA"):
+        gx, gy = m.gradient(g["p_" + k])
+        assert np.abs(gx - g["gx_" + k]).max() <= 1e-13 * np.abs(g["gx_" + k]).max()
+        assert np.abs(gy - g["gy_" + k]).max() <= 1e-13 * np.abs(g["gy_" + k]).max()
+    assert np.array_equal(fb.calculate_divergence(g["nodes"], g["tris"], g["u_rand"]), g["div_rand"])
+    gx, gy = fb.calculate_gradiant(g["nodes"], g["tris"], g["p_rand"])
+    assert np.abs(gx - g["gx_rand"]).max() <= 1e-13 * np.abs(g["gx_rand"]).max()
+
+
+def test_device_pointers_equal_host_pointers(meshes):
+    import torch
+    g, m = meshes["mesh5_1"]
+    u = torch.from_numpy(g["u_rand"]).cuda()
+    d = m.divergence(u)
+    assert d.is_cuda and np.array_equal(d.cpu().numpy(), g["div_rand"])
+    gx, gy = m.gradient(torch.from_numpy(g["p_rand"]).cuda())
+    hx, hy = m.gradient(g["p_rand"])
+    assert np.array_equal(gx.cpu().numpy(), hx) and np.array_equal(gy.cpu().numpy(), hy)
+
+
+@pytest.mark.parametrize("name", MESHES)
+def test_adjointness(meshes, name):
+    """scripts/stokes_report.py:532-591 (Test E)."""
+    g, m = meshes[name]
+    rng = np.random.default_rng(0)
+    interior = g["markers"] == 0
+    p = rng.standard_normal(m.N) * interior
+    u = rng.standard_normal((m.N, 2)) * interior[:, None]
+    gx, gy = m.gradient(p)
+    d = m.divergence(u)
+    M = g["M"]
+    lhs = np.sum(M * (gx * u[:, 0] + gy * u[:, 1]))
+    rhs = -np.sum(M * p * d)
+    assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), abs(rhs))
+
+
+@pytest.mark.parametrize("name", MESHES)
+def test_boundary_conditions(meshes, name):
+    g, m = meshes[name]
+    m.set_bc(g["wall"], g["inner_b"], g["pairs"], g["interior"])
+    for (B1, B2), uin, uout in zip(g["bc_B"], g["bc_in"], g["bc_out"]):
+        u = uin.copy()
+        m.make_per_bcu(u)
+        m.make_dir_bcu(u, B1, B2)
+        # device libm sin/cos/atan2 vs numpy's: a few ulp on values of size <= 7
+        assert np.abs(u - uout).max() <= 1e-14
+
+
+@pytest.mark.parametrize("name", MESHES)
+def test_locator_ids_bit_exact(meshes, name):
+    g, m = meshes[name]
+    ids = m.locate(g["loc_pts"])
+    assert np.array_equal(ids, g["loc_ids"])
+    loc = fb.PointLocator(g["nodes"], g["tris"])
+    for k in (0, 17, 4242):
+        x, y = g["loc_pts"][k]
+        want = None if g["loc_ids"][k] < 0 else int(g["loc_ids"][k])
+        assert loc.find(x, y) == want
+    assert m.locate(np.zeros((0, 2))).shape == (0,)
+
+
+@pytest.mark.parametrize("name", MESHES)
+def test_dye_advection_and_mixing(meshes, name):
+    g, m = meshes[name]
+    c = g["dye_c0"].copy()
+    m.advect_dye(c, g["dye_u"], 0.05)
+    assert np.array_equal(c, g["dye_c1"])
+    mask = np.where(g["markers"] == 0)[0].astype(np.int32)
+    mi = m.mixing_index(c, g["M"], mask)
+    assert np.allclose(mi, g["dye_mix"], rtol=1e-12)
+    mi_all = m.mixing_index(c, g["M"], None)
+    assert np.allclose(mi_all, R.mixing_index(c, g["M"]), rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", MESHES)
+def test_exact_locate(meshes, name):
+    g, m = meshes[name]
+    pts = g["loc_pts"][:6000]
+    want = R.locate_exact(g["nodes"], g["tris"], pts)
+    got = m.locate_exact(pts)
+    assert np.array_equal(got < 0, want < 0)
+    # same triangle, or (point on a shared edge) another triangle that also contains it
+    diff = np.where(got != want)[0]
+    for i in diff:
+        w = R.interp_p1(g["nodes"], g["tris"], np.ones(m.N), pts[i:i + 1], np.array([got[i]]))
+        assert np.isfinite(w).all()
+    assert len(diff) <= 5
+    # a walk seeded with a far-away triangle still arrives
+    hint = np.full(len(pts), 0, dtype=np.int32)
+    got2 = m.locate_exact(pts, hint)
+    assert np.array_equal(got2 < 0, want < 0) and (got2 != want).sum() <= 5
+
+
+@pytest.mark.parametrize("name", MESHES)
+def test_stokes_matrices(meshes, name):
+    g, _ = meshes[name]
+    s = fb.StokesSolver(g["nodes"], g["markers"], g["tris"], B1=-2.0, B2=0.0, DT=0.05, v=0.1)
+    av, kp, dof = s.matrices()
+    assert np.array_equal(av.arrays()[2], g["avisc_color"])
+    ps = R.PressureSystem(g["nodes"], g["tris"], [tuple(p) for p in g["pairs"]])
+    assert np.array_equal(dof, ps.dof)
+    rp, ci, v = kp.arrays()
+    assert np.array_equal(rp, ps.rowptr) and np.array_equal(ci, ps.colidx) and np.array_equal(v, ps.vals)
+    assert np.array_equal(s.u, g["bc_out"][0] * 0 + s.u)   # finite
+    u0 = np.zeros((s.N, 2))
+    R.make_dir_bcu(u0, g["nodes"], g["wall"], g["inner_b"], -2.0, 0.0)
+    assert np.abs(s.u - u0).max() <= 1e-14
+
+
+def test_spmv_cg_bicgstab(meshes):
+    g, m = meshes["mesh_fine_1"]
+    K = sp.csr_matrix((g["K"], g["colidx"], g["rowptr"]), shape=(m.N, m.N))
+    A = m.matrix(g["K"])
+    x = np.random.default_rng(5).standard_normal(m.N)
+    y = A @ x
+    assert np.abs(y - K @ x).max() <= 1e-12 * np.abs(K @ x).max()
+    # SPD system: I + K
+    S = (sp.eye(m.N) + K).tocsr()
+    Sd = fb.CsrMatrix.from_scipy(S)
+    b = np.random.default_rng(6).standard_normal(m.N)
+    xs, it, rr = Sd.cg(b, rtol=1e-13)
+    import scipy.sparse.linalg as spla
+    assert rel(xs, spla.spsolve(S.tocsc(), b)) <= 1e-11 and 0 < it < 2000
+    # two right-hand sides at once
+    b2 = np.random.default_rng(7).standard_normal((m.N, 2))
+    x2, it2, _ = Sd.cg(b2, rtol=1e-13)
+    ref2 = np.stack([spla.spsolve(S.tocsc(), b2[:, 0]), spla.spsolve(S.tocsc(), b2[:, 1])], axis=1)
+    assert rel(x2, ref2) <= 1e-11
+    # zero right-hand side and exact initial guess
+    x0, it0, _ = Sd.cg(np.zeros(m.N))
+    assert it0 == 0 and not x0.any()
+    x1, it1, _ = Sd.cg(b, x0=xs, rtol=1e-9)
+    assert it1 == 0
+    # non-symmetric: BiCGStab
+    Nn = (S + sp.diags(np.linspace(0, 1, m.N - 1), 1)).tocsr()
+    xb, itb, _ = fb.CsrMatrix.from_scipy(Nn).bicgstab(b, rtol=1e-13)
+    assert rel(xb, spla.spsolve(Nn.tocsc(), b)) <= 1e-10
+    # the singular pressure operator with mean projection
+    with pytest.raises(fb.FluidsimError):
+        Sd.cg(b, rtol=1e-30, maxit=3)
+
+
+def _run_traj(cls, name, traj, steps, **kw):
+    g = load_golden(name + "_ops")
+    t = load_golden(f"{name}_traj_{traj}")
+    sim = cls(g["nodes"], g["markers"], g["tris"], B1=float(t["B1"]), B2=float(t["B2"]), DT=float(t["DT"]),
+              v=float(t["v"]), rtol_pressure=1e-12, rtol_visc=1e-13, **kw)
+    return g, t, sim
+
+
+def test_stokes_color_100_steps_vs_restated_oracle():
+    """Config 3 (mesh5.1, pusher B1=-2 B2=-5): u, p <= 1e-9 rel L2, mixing progress <= 1e-6."""
+    g, t, sim = _run_traj(fb.StokesColor, "mesh5_1", "color_pusher", 100)
+    prog = []
+    worst_u = worst_p = 0.0
+    for s in range(100):
+        st, pr = sim.step_all()
+        prog.append(pr)
+        if s in t["snap"]:
+            p, p2 = sim.pressure()
+            worst_u = max(worst_u, rel(sim.u, t[f"res_u_{s}"]))
+            worst_p = max(worst_p, rel(p, t[f"res_p_{s}"]), rel(p2, t[f"res_p2_{s}"]))
+            assert np.abs(sim.c - t[f"res_c_{s}"]).max() <= 1e-8
+    assert worst_u <= 1e-9, worst_u
+    assert worst_p <= 1e-9, worst_p
+    assert np.abs(np.array(prog) - t["res_progress"]).max() <= 1e-6
+    # distance to the literal reference LU (unpinned boundary): report, bound loosely
+    gap_u = rel(sim.u, t["lit_u_99"])
+    assert gap_u < 5e-3
+    assert np.abs(np.array(prog) - t["lit_progress"]).max() < 1e-3
+
+
+def test_stokes_color_mesh_fine_20_steps():
+    g, t, sim = _run_traj(fb.StokesColor, "mesh_fine_1", "color_puller", 20)
+    prog = []
+    for s in range(20):
+        _, pr = sim.step_all()
+        prog.append(pr)
+        if s in t["snap"]:
+            p, _ = sim.pressure()
+            assert rel(sim.u, t[f"res_u_{s}"]) <= 1e-9
+            assert rel(p, t[f"res_p_{s}"]) <= 1e-9
+    assert np.abs(np.array(prog) - t["res_progress"]).max() <= 1e-6
+
+
+@pytest.mark.parametrize("traj", ["food_pusher", "food_neutral"])
+def test_stokes_food_100_steps(traj):
+    """Config 4 building block: food capture counts equal, tracer positions <= 1e-9."""
+    g, t, sim = _run_traj(fb.StokesFood, "mesh5_1", traj, 100)
+    assert np.array_equal(sim.tracer_points, t["food_pts0"]) and sim.num_tracers == 488
+    eaten = []
+    for s in range(100):
+        _, e = sim.step_all()
+        eaten.append(e)
+        if s in t["snap"]:
+            assert rel(sim.u, t[f"res_u_{s}"]) <= 1e-9
+            a, b = sim.tracer_points, t[f"food_pts_{s}"]
+            assert np.array_equal(np.isnan(a), np.isnan(b))
+            ok = ~np.isnan(b)
+            assert np.abs(a[ok] - b[ok]).max() <= 1e-9
+            assert np.array_equal(sim.tracer_status, t[f"food_status_{s}"])
+    assert np.array_equal(np.array(eaten), t["food_eaten"])
+    assert abs(eaten[-1] / sim.num_tracers - t["food_eaten"][-1] / 488) <= 1e-6
+
+
+def test_warm_start_and_unpreconditioned_agree():
+    g = load_golden("mesh5_1_ops")
+    a = fb.StokesSolver(g["nodes"], g["markers"], g["tris"], B2=-5.0, rtol_pressure=1e-12, warm_start=True, precond=1)
+    b = fb.StokesSolver(g["nodes"], g["markers"], g["tris"], B2=-5.0, rtol_pressure=1e-12, warm_start=False, precond=0)
+    for _ in range(5):
+        sa, sb = a.step(), b.step()
+    assert rel(a.u, b.u) <= 1e-9
+    assert sa.iters_p1 > 0 and sb.iters_p1 > 0
+
+
+def test_stokes_step_on_device_tensor():
+    import torch
+    g = load_golden("mesh5_1_ops")
+    a = fb.StokesSolver(g["nodes"], g["markers"], g["tris"], B2=5.0)
+    b = fb.StokesSolver(g["nodes"], g["markers"], g["tris"], B2=5.0)
+    ud = torch.from_numpy(b.u.copy()).cuda()
+    for _ in range(3):
+        a.step()
+        b.step(ud)
+    assert np.array_equal(a.u, ud.cpu().numpy())
+
+
+@pytest.mark.parametrize("name", MESHES)
+def test_poisson_and_heat(name):
+    """Configs 1 and 2: code/poisson.py on float32 coordinates, code/heatEq.py time loop."""
+    g = load_golden(name + "_poisson")
+    pb = fb.PoissonProblem(g["nodes32"], g["markers"], g["tris"])
+    Ag = sp.csr_matrix((g["A_vals"], g["A_colidx"], g["A_rowptr"]), shape=(pb.N, pb.N)).toarray()
+    assert np.array_equal(pb.A.toarray(), Ag)          # float32 assembly + row surgery bit-exact
+    assert np.allclose(pb.b, g["b"], rtol=1e-6, atol=1e-9)
+    f = pb.solve()
+    assert rel(f, g["f"]) <= 1e-6                      # north_star: fp32-parity tolerance 1e-6
+    assert rel(f, np.linalg.solve(Ag, pb.b)) <= 1e-10
+    A2, b2 = fb.buildFemSystem(g["nodes32"], g["tris"], g_source=lambda x, y: 50 * np.sin(3 * y))
+    assert np.array_equal(A2.arrays()[2], g["fem_vals"])
+    hp = fb.HeatProblem(g["nodes32"], g["markers"], g["tris"], DT=float(g["heat_DT"]))
+    assert np.array_equal(hp.u, g["heat_u_init"])
+    for n in range(int(g["heat_steps"])):
+        hp.step()
+        if n in g["heat_snap"]:
+            assert np.abs(hp.u - g[f"heat_u_{n}"]).max() <= 1e-9, n
+
+
+def test_synthetic_mesh_vs_oracle():
+    """A 131k-triangle structured mesh: everything still bit-exact / 1e-9 against the oracle."""
+    c, mk, t = fb.square_with_hole(512, 128)
+    m = fb.Mesh(c, t, mk)
+    rowptr, colidx, scatter = R.csr_pattern(len(c), t)
+    rp, ci = m.csr_pattern()
+    assert np.array_equal(rp, rowptr) and np.array_equal(ci, colidx)
+    assert np.array_equal(m.scatter_map(), scatter)
+    assert np.array_equal(m.stiffness_values(), R.assemble_stiffness(c, t, rowptr, colidx, scatter))
+    assert np.array_equal(m.lumped_mass(), R.lumped_mass(c, t))
+    u = np.random.default_rng(0).standard_normal((len(c), 2))
+    assert np.array_equal(m.divergence(u), R.divergence(c, t, u))
+    s = fb.StokesSolver(c, mk, t, B1=-2.0, B2=-5.0, DT=0.05, v=0.1, rtol_pressure=1e-12, rtol_visc=1e-13)
+    o = R.RestatedStokes(c, mk, t, B1=-2.0, B2=-5.0, DT=0.05, v=0.1)
+    assert s.pairs == o.pairs
+    for _ in range(2):
+        st = s.step()
+        o.flow_step()
+    p, _ = s.pressure()
+    assert rel(s.u, o.u) <= 1e-9 and rel(p, o.p) <= 1e-9
+    assert st.iters_p1 > 50
+
+
+def test_large_mesh_properties():
+    """1M triangles: size-independent properties (symmetry, null space, linearity, residual)."""
+    c, mk, t = fb.square_with_hole(1024, 512)
+    m = fb.Mesh(c, t, mk)
+    assert m.nnz == m.N + 2 * (m.N + m.T - 0)  # Euler: E = N + T for an annulus (chi = 0)
+    A = m.stiffness()
+    ones = np.ones(m.N)
+    assert np.abs(A @ ones).max() < 1e-9
+    rng = np.random.default_rng(1)
+    x, y = rng.standard_normal(m.N), rng.standard_normal(m.N)
+    ax, ay = A @ x, A @ y
+    assert abs(x @ ay - y @ ax) <= 1e-9 * abs(x @ ay)            # symmetry
+    assert np.abs((A @ (2.0 * x + y)) - (2.0 * ax + ay)).max() <= 1e-9 * np.abs(ax).max()
+    assert np.isclose(m.lumped_mass().sum(), 1.0 - np.pi * 0.0625, rtol=1e-4)
+    # K + M-like shift is SPD: solve and check the true residual
+    rowptr, colidx = m.csr_pattern()
+    vals = m.stiffness_values()
+    rows = np.repeat(np.arange(m.N), np.diff(rowptr))
+    vals[rows == colidx] += 1e-3
+    Sd = m.matrix(vals)
+    b = rng.standard_normal(m.N)
+    xs, it, rr = Sd.cg(b, rtol=1e-10)
+    assert np.linalg.norm(b - (Sd @ xs)) <= 1e-9 * np.linalg.norm(b)
+    ids = m.locate(rng.random((200000, 2)))
+    inside = ids >= 0
+    assert 0.75 < inside.mean() < 0.85                             # 1 - pi/16 of the square is mesh
+
+
+def test_argument_errors():
+    with pytest.raises((ValueError, fb.FluidsimError)):
+        fb.Mesh(np.zeros((3, 3)), np.zeros((1, 3), dtype=np.int32))
+    with pytest.raises(fb.FluidsimError):
+        fb.Mesh(np.zeros((3, 2)), np.array([[0, 1, 7]], dtype=np.int32))
+    g = load_golden("mesh5_1_ops")
+    m = fb.Mesh(g["nodes"], g["tris"])
+    with pytest.raises(ValueError):
+        m.divergence(np.zeros((5, 2)))
+    with pytest.raises(fb.FluidsimError):
+        m.make_dir_bcu(np.zeros((m.N, 2)), 1.0, 0.0)       # fs_bc_set not called
