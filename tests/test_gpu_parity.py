@@ -106,7 +106,21 @@ def test_boundary_conditions(meshes, name):
 def test_locator_ids_bit_exact(meshes, name):
     g, m = meshes[name]
     ids = m.locate(g["loc_pts"])
-    assert np.array_equal(ids, g["loc_ids"])
+    want = g["loc_ids"]
+    # the seeded random cloud: bit-exact, misses (-1) included
+    assert np.array_equal(ids[:20000], want[:20000])
+    # the mesh nodes themselves sit on shared vertices where several centroids are
+    # EXACTLY equidistant; the reference's KDTree breaks such ties by its internal
+    # node order (unpinnable).  Parity there: same id, or an equidistant
+    # candidate that also contains the point.
+    bad = np.where(ids != want)[0]
+    assert len(bad) <= 5 and (bad >= 20000).all()
+    cen = np.mean(g["nodes"][g["tris"]], axis=1)
+    for i in bad:
+        p = g["loc_pts"][i]
+        dg, dw = np.sum((cen[ids[i]] - p) ** 2), np.sum((cen[want[i]] - p) ** 2)
+        assert abs(dg - dw) <= 4e-16 * dw
+        assert R.locate_exact(g["nodes"], g["tris"][ids[i]:ids[i] + 1], p[None, :])[0] == 0
     loc = fb.PointLocator(g["nodes"], g["tris"])
     for k in (0, 17, 4242):
         x, y = g["loc_pts"][k]
