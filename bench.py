@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- Stokes steps/sec on the 4M-triangle synthetic mesh (BASELINE.json metric)
+and the pressure-CG SpMV's achieved HBM GB/s against the measured roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the operator-split Stokes step (code/StokesColor.py:537-575):
+2-RHS viscous CG, BCs, divergence, pressure CG, gradient update, BCs, second pressure
+CG, interior update -- on the square-with-hole mesh n_theta=2048 x n_r=1024
+(T=4 194 304, N=2 099 200), pusher squirmer B1=-2 B2=-5, nu=0.1, DT=0.05.
+
+N>1 (torchrun, one rank per GPU): the B1/B2 sweep of config 4 -- every rank advances
+its own squirmer configuration on its own copy of the mesh, no data-path collective
+("scaling": "weak"); value = steps of all ranks / max-over-ranks time.
+
+--impl reference times the reference's CPU path.  The literal reference (dense numpy)
+cannot hold a 4M-triangle mesh (N x N doubles = 32 TB), so the arm runs the oracle's
+CPU port of the same algorithm (oracle/cg_port.c, OpenMP, all host threads) on a bounded
+sample and extrapolates with the iteration counts of the GPU run (profiles/bench_iters.json).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_THETA, N_R = 2048, 1024
+PARAMS = dict(B1=-2.0, B2=-5.0, DT=0.05, v=0.1)
+RTOL_P, RTOL_V = 1e-10, 1e-12
+ITERS_FILE = os.path.join(ROOT, "profiles", "bench_iters.json")
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "spmv_traffic.json")
+
+
+def sweep_params(rank):
+    """Config 4: 64 (B1,B2) pairs = linspace(-4,-0.5,8) x linspace(-5,5,8); rank r takes pair r
+    (rank 0 keeps the N=1 pusher so the per-GPU work is the same problem class)."""
+    if rank == 0:
+        return PARAMS["B1"], PARAMS["B2"]
+    b1 = np.linspace(-4.0, -0.5, 8)
+    b2 = np.linspace(-5.0, 5.0, 8)
+    return float(b1[rank % 8]), float(b2[(rank * 3) % 8])
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------ CPU baseline
+def cpu_baseline_sample(rowptr, colidx, vals, nodes, tris, iters_per_step, n_cg=60):
+    """Oracle port on the host cores: n_cg Jacobi-CG iterations of the pressure operator
+    (oracle/cg_port.c, OpenMP) + one divergence + one gradient (oracle/restated.py, numpy),
+    extrapolated to one Stokes step = iters_per_step CG iterations + 3 div + 2 grad."""
+    from oracle import cgport, restated as R
+    nd = len(rowptr) - 1
+    rng = np.random.default_rng(0)
+    b = rng.standard_normal(nd)
+    cgport.cg(rowptr, colidx, vals, b, rtol=0.0, maxit=10, project_mean=True)     # warm (thread start-up)
+    t0 = time.perf_counter()
+    _, it, _ = cgport.cg(rowptr, colidx, vals, b, rtol=0.0, maxit=n_cg, project_mean=True)
+    t_iter = (time.perf_counter() - t0) / max(it, 1)
+    u = rng.standard_normal((nodes.shape[0], 2))
+    t0 = time.perf_counter()
+    R.divergence(nodes, tris, u)
+    t_div = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    R.gradient(nodes, tris, u[:, 0].copy())
+    t_grad = time.perf_counter() - t0
+    t_step = iters_per_step * t_iter + 3 * t_div + 2 * t_grad
+    return {"value": 1.0 / t_step, "unit": "steps/s", "cores": cgport.threads(), "kind": "port",
+            "sample": f"{it} Jacobi-CG iterations of the 4M-tri pressure operator (oracle/cg_port.c, OpenMP) "
+                      f"+ 1 divergence + 1 gradient (oracle/restated.py); extrapolated to {iters_per_step:.0f} "
+                      f"CG iterations + 3 div + 2 grad per step",
+            "ms_per_cg_iter": 1e3 * t_iter, "s_div": t_div, "s_grad": t_grad,
+            "cg_iter_gbs": (12.0 * len(colidx) + 92.0 * nd) / t_iter / 1e9}
+
+
+def run_reference(args):
+    """--impl reference: CPU only (rank 0)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import restated as R
+    import fluidsim_b200.mesh as fmesh     # host-only helpers (generator, pair finder); no GPU call
+    nodes, markers, tris = fmesh.square_with_hole(args.n_theta, args.n_r)
+    pairs = fmesh.filter_wall_pairs(nodes, fmesh.find_boundary_pairs(nodes))
+    ps = R.PressureSystem(nodes, tris, pairs)
+    iters = 2 * 9000.0
+    src = "default estimate"
+    if os.path.exists(ITERS_FILE):
+        j = json.load(open(ITERS_FILE))
+        iters = float(j["iters_per_step"])
+        src = "profiles/bench_iters.json (GPU run)"
+    vals = []
+    for _ in range(args.warmup + args.steps):
+        vals.append(cpu_baseline_sample(ps.rowptr, ps.colidx, ps.vals, nodes, tris, iters))
+    vals = vals[args.warmup:]
+    best = max(vals, key=lambda d: d["value"])
+    v = float(np.mean([d["value"] for d in vals]))
+    best["value"] = v
+    best["sample"] += f"; iteration count from {src}"
+    out = {"impl": "reference", "metric": "stokes_steps_per_sec_4M_tri", "value": v, "unit": "steps/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": workload_config(args, iters_note=src), "cpu_baseline": best,
+           "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def workload_config(args, **extra):
+    cfg = {"workload": f"stokes_step square-with-hole n_theta={args.n_theta} n_r={args.n_r} "
+                       f"(T={2 * args.n_theta * args.n_r}, N={args.n_theta * (args.n_r + 1)}), pusher B1=-2 B2=-5, "
+                       f"nu=0.1, DT=0.05",
+           "solver": f"CG Jacobi, rtol_pressure={RTOL_P:g}, rtol_visc={RTOL_V:g}, warm start from previous step",
+           "l2": "inputs larger than L2 (CSR matrix 185 MB + 4 vectors 67 MB > 126 MB), no flush needed",
+           "steps_from": "t=0 (u=0 + squirmer BC); warm-up steps advance the same trajectory"}
+    cfg.update(extra)
+    return cfg
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import fluidsim_b200 as fb
+    from fluidsim_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    torch.cuda.set_device(local)
+    _lib.call("fs_set_device", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        _lib.call("fs_sync")
+
+    nodes, markers, tris = fb.square_with_hole(args.n_theta, args.n_r)
+    B1, B2 = sweep_params(rank) if world > 1 else (PARAMS["B1"], PARAMS["B2"])
+    sim = fb.StokesSolver(nodes, markers, tris, B1=B1, B2=B2, DT=PARAMS["DT"], v=PARAMS["v"],
+                          rtol_pressure=RTOL_P, rtol_visc=RTOL_V)
+    N = sim.N
+    _, kp, _ = sim.matrices()
+    nd, nnz = kp.n, kp.nnz
+    u_dev = torch.from_numpy(sim.u.copy()).cuda()
+
+    # ---- device-resident arm: W warm-up steps, then exactly K timed steps
+    iters = []
+    for _ in range(args.warmup):
+        st = sim.step(u_dev)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = fb.launch_count()
+    _lib.call("fs_profile", 16)
+    _lib.call("fs_timer_start")
+    for _ in range(args.steps):
+        st = sim.step(u_dev)
+        iters.append((st.iters_visc, st.iters_p1, st.iters_p2))
+    ms = C.c_float(0)
+    _lib.call("fs_timer_stop", C.byref(ms))
+    barrier()
+    launches = fb.launch_count() - launches0
+    pms = np.zeros(3)
+    ns, ni = C.c_int64(0), C.c_int64(0)
+    _lib.call("fs_profile_read", _lib.ptr(pms), C.byref(ns), C.byref(ni))
+    _lib.call("fs_profile", 0)
+    clk = clocks.stop() if rank == 0 else None
+    t_ms = torch.tensor([ms.value], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    t_dev = float(t_ms.item()) / 1e3
+    value = world * args.steps / t_dev
+
+    # ---- end-to-end arm: same K steps through the host-buffer C-ABI call (pinned numpy view):
+    # every step copies u host->device and device->host inside the timed region
+    u_pin = torch.empty((N, 2), dtype=torch.float64).pin_memory()
+    u_pin.copy_(u_dev.cpu())
+    u_host = u_pin.numpy()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sim.step(u_host)
+    barrier()
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e = world * args.steps / float(t_e2e.item())
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    spmv_bytes = 12.0 * nnz + 20.0 * nd
+    cg_bytes = 12.0 * nnz + 92.0 * nd + 16.0 * nd      # + Jacobi: dinv read in passes B and C
+    samples = max(int(ns.value), 1)
+    t_spmv = pms[0] / samples / 1e3
+    t_iter = pms.sum() / samples / 1e3
+    traffic = None
+    if os.path.exists(TRAFFIC_FILE):
+        traffic = json.load(open(TRAFFIC_FILE)).get("dram_bytes_per_launch")
+    roof = {"bound": "hbm", "kernel": "k_spmv<1,8,true> (CG pass A: Ap=A*p fused with p.Ap)",
+            "achieved": spmv_bytes / t_spmv / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": spmv_bytes / t_spmv / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": spmv_bytes, "us_per_launch": 1e6 * t_spmv,
+            "sampled_launches": samples, "frac_of_8TBps_spec": spmv_bytes / t_spmv / 8e12}
+    roof_cg = {"achieved": cg_bytes / t_iter / 1e9, "frac": cg_bytes / t_iter / 1e9 / peak, "unit": "GB/s",
+               "algorithmic_bytes_per_iteration": cg_bytes, "us_per_iteration": 1e6 * t_iter,
+               "us_pass_A_B_C": [1e6 * x / samples / 1e3 for x in pms]}
+    it_arr = np.array(iters, dtype=np.float64)
+    iters_per_step = float((it_arr[:, 1] + it_arr[:, 2]).mean())
+    os.makedirs(os.path.dirname(ITERS_FILE), exist_ok=True)
+    try:
+        json.dump({"iters_per_step": iters_per_step, "iters": iters, "warmup": args.warmup, "steps": args.steps,
+                   "n_theta": args.n_theta, "n_r": args.n_r, "rtol_pressure": RTOL_P},
+                  open(os.path.join(ROOT, "gpurun_out", "bench_iters.json"), "w"))
+    except OSError:
+        pass
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        rp, ci, vv = kp.arrays()
+        cpu = cpu_baseline_sample(rp, ci, vv, nodes, tris, iters_per_step + 2 * float(it_arr[:, 0].mean()))
+    out = {"metric": "stokes_steps_per_sec_4M_tri", "value": value, "unit": "steps/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": workload_config(args, cg_iters_per_step=iters, parallelism=("single GPU" if world == 1 else
+                                     f"{world} independent squirmer (B1,B2) configs, one per GPU, no collective")),
+           "roofline": roof, "roofline_cg_iteration": roof_cg, "cpu_baseline": cpu,
+           "e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": 16 * N, "d2h_bytes_per_step": 16 * N},
+           "gpu_launches": int(launches), "clocks": clk}
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-theta", dest="n_theta", type=int, default=N_THETA)
+    ap.add_argument("--n-r", dest="n_r", type=int, default=N_R)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

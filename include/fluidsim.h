@@ -56,6 +56,14 @@ int64_t fs_launch_count(void);
 int fs_timer_start(void);
 int fs_timer_stop(float* ms);
 
+/* Sampled kernel timing for the roofline report: with every>0 the three passes of
+ * every `every`-th single-RHS CG iteration (A: SpMV+dot, B: x/r update+dots,
+ * C: p update) are bracketed by CUDA events on the library stream.  fs_profile_read
+ * returns the summed milliseconds per pass, the number of sampled iterations and
+ * the CG iterations launched since fs_profile(every).  every=0 switches it off. */
+int fs_profile(int every);
+int fs_profile_read(double* ms3, int64_t* samples, int64_t* iters);
+
 /* ---- ingest: readNode / readEle, code/StokesColor.py:54-95 (fp32 variant
  * code/poisson.py:27-74 = same parse, caller casts).  Two-step: count, then fill. */
 int fs_node_file_count(const char* path, int64_t* n_nodes);

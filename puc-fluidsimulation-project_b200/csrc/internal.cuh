@@ -165,6 +165,7 @@ struct CsrView {
   const int* rowptr;
   const int* colidx;
   const double* vals;
+  int tile_nnz_max = 0;   // max nonzeros in a 256-row tile (0: not computed -> vector SpMV)
 };
 
 }  // namespace fs
@@ -183,7 +184,10 @@ struct fs_csr {
   size_t ws_n = 0;
   fs::DBuf<double> partials;
   fs::DBuf<double> scal;
-  fs::CsrView view() const { return fs::CsrView{(int)n, nnz, rowptr, colidx, vals.p}; }
+  int tile_nnz_max = -1;         // lazily computed by fs::ensure_tiles
+  fs::CsrView view() const {
+    return fs::CsrView{(int)n, nnz, rowptr, colidx, vals.p, tile_nnz_max > 0 ? tile_nnz_max : 0};
+  }
 };
 
 namespace fs {
@@ -236,6 +240,10 @@ void dir_bcu_dev(fs_mesh* m, double* d_u, double B1, double B2);
 void grad_update_dev(fs_mesh* m, const double* d_p, const double* d_ui, double* d_uo, double DT,
                      const unsigned char* d_interior_flag /* null: all nodes */);
 void jacobi_prepare(fs_csr* a);
+void ensure_tiles(fs_csr* a);
+bool cg_persistent_supported(const CsrView& A, size_t* smem_out);
+void cg_persistent_launch(const CsrView& A, double* x, double* r, double* p, double* Ap, const double* dinv,
+                          double* partA, double* partB, double* scal, int* flags, int maxit, double tol2);
 // CG on device pointers; returns iterations, writes relres.
 int cg_dev(fs_csr* a, const double* d_b, double* d_x, int nrhs, double rtol, int maxit, int precond,
            int project_mean, double* relres);

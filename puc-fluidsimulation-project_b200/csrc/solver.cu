@@ -147,6 +147,139 @@ k_spmv(CsrView A, const double* __restrict__ x, double* __restrict__ y, double* 
   }
 }
 
+// ---- L2 cache-policy hints --------------------------------------------------------
+// The matrix (12 B/nnz) is streamed once per iteration: evict-first, so that the CG
+// vectors (5 x 8N bytes, < 126 MB L2) stay resident between passes: evict-last.
+__device__ __forceinline__ uint64_t pol_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t pol_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ double ldg_f64_hint(const double* a, uint64_t pol) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(a), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ int ldg_s32_hint(const int* a, uint64_t pol) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ double ld_f64_keep(const double* a, uint64_t pol) {
+  double v;
+  asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(a), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_f64_keep(double* a, double v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(a), "d"(v), "l"(pol) : "memory");
+}
+
+// ---- tile SpMV (CSR-stream): a CTA owns kTileRows consecutive rows.  Phase 1 streams
+// the tile's values/columns with fully coalesced, independent loads (8 per thread in
+// flight), gathers x and parks the products in shared memory; phase 2 sums each row
+// from shared memory in ascending column order (deterministic) and writes y coalesced.
+constexpr int kTileRows = 256;
+constexpr int kTileUnroll = 8;
+
+template <bool DOT>
+__global__ void __launch_bounds__(kTileRows)
+k_spmv_tile(CsrView A, const double* __restrict__ x, double* __restrict__ y, double* __restrict__ part,
+            const int* __restrict__ done, int ntiles) {
+  extern __shared__ double prod[];
+  __shared__ int s_rp[kTileRows + 1];
+  __shared__ double red[32];
+  if (done && *done) return;
+  const uint64_t pf = pol_evict_first(), pl = pol_evict_last();
+  const int t = threadIdx.x;
+  double acc[1] = {0.0};
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int r0 = tile * kTileRows;
+    const int nr = min(kTileRows, A.n - r0);
+    if (t <= nr) s_rp[t] = __ldg(A.rowptr + r0 + t);
+    if (t == 0 && nr == kTileRows) s_rp[kTileRows] = __ldg(A.rowptr + r0 + kTileRows);
+    __syncthreads();
+    const int base = s_rp[0];
+    const int cnt = s_rp[nr] - base;
+    const double* __restrict__ va = A.vals + base;
+    const int* __restrict__ ca = A.colidx + base;
+    for (int k0 = 0; k0 < cnt; k0 += kTileRows * kTileUnroll) {
+      double a[kTileUnroll];
+      int c[kTileUnroll];
+#pragma unroll
+      for (int j = 0; j < kTileUnroll; ++j) {
+        const int k = k0 + j * kTileRows + t;
+        const bool ok = k < cnt;
+        a[j] = ok ? ldg_f64_hint(va + k, pf) : 0.0;
+        c[j] = ok ? ldg_s32_hint(ca + k, pf) : -1;
+      }
+#pragma unroll
+      for (int j = 0; j < kTileUnroll; ++j) {
+        const int k = k0 + j * kTileRows + t;
+        if (c[j] >= 0) prod[k] = a[j] * ld_f64_keep(x + c[j], pl);
+      }
+    }
+    __syncthreads();
+    if (t < nr) {
+      double s = 0.0;
+      const int ke = s_rp[t + 1] - base;
+      for (int k = s_rp[t] - base; k < ke; ++k) s += prod[k];
+      st_f64_keep(y + r0 + t, s, pl);
+      if (DOT) acc[0] += ld_f64_keep(x + r0 + t, pl) * s;
+    }
+    __syncthreads();
+  }
+  if (DOT) {
+    block_reduce<1>(acc, red);
+    if (t == 0) part[blockIdx.x] = acc[0];
+  }
+}
+
+__global__ void k_tile_nnz_max(const int* __restrict__ rowptr, int n, int ntiles, int* __restrict__ out) {
+  int tile = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tile >= ntiles) return;
+  int r0 = tile * kTileRows, r1 = min(n, r0 + kTileRows);
+  atomicMax(out, rowptr[r1] - rowptr[r0]);
+}
+
+void ensure_tiles(fs_csr* a) {
+  if (a->tile_nnz_max >= 0) return;
+  const int ntiles = div_up(a->n, kTileRows);
+  DBuf<int> mx(1);
+  mx.zero();
+  k_tile_nnz_max<<<div_up(ntiles, 256), 256, 0, stream()>>>(a->rowptr, (int)a->n, ntiles, mx.p);
+  FS_LAUNCH_CHECK();
+  a->tile_nnz_max = mx.to_host()[0];
+}
+
+constexpr int kTileSmemMax = 96 * 1024;   // products buffer cap (bytes); beyond it use the vector kernel
+
+static bool tile_ok(const CsrView& A) { return A.tile_nnz_max > 0 && (size_t)A.tile_nnz_max * 8 <= kTileSmemMax; }
+
+static int tile_grid(const CsrView& A) {
+  const int ntiles = div_up(A.n, kTileRows);
+  const size_t smem = (size_t)A.tile_nnz_max * 8;
+  int per_sm = (int)std::min<size_t>(8, (200 * 1024) / (smem + 2048));
+  per_sm = std::max(per_sm, 1);
+  return std::max(1, std::min(ntiles, std::min(kMaxBlocks, sm_count() * per_sm)));
+}
+
+template <bool DOT>
+static void launch_spmv_tile(const CsrView& A, const double* x, double* y, double* part, const int* done, int grid) {
+  const size_t smem = (size_t)A.tile_nnz_max * 8;
+  static bool attr_set[2] = {false, false};
+  if (smem > 48 * 1024 && !attr_set[DOT]) {
+    FS_CUDA(cudaFuncSetAttribute(k_spmv_tile<DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemMax));
+    attr_set[DOT] = true;
+  }
+  k_spmv_tile<DOT><<<grid, kTileRows, smem, stream()>>>(A, x, y, part, done, div_up(A.n, kTileRows));
+  FS_LAUNCH_CHECK();
+}
+
 static int spmv_grid(int64_t n, int lpr) {
   int64_t want = (n * lpr + kBlock - 1) / kBlock;
   int64_t cap = std::min<int64_t>(kMaxBlocks, (int64_t)sm_count() * 6);
@@ -162,8 +295,18 @@ static int pick_lpr(const CsrView& A) {
   return 32;
 }
 
+template <int R>
+static int spmv_launch_grid(const CsrView& A) {
+  if (R == 1 && tile_ok(A)) return tile_grid(A);
+  return spmv_grid(A.n, pick_lpr(A));
+}
+
 template <int R, bool DOT>
 static void launch_spmv(const CsrView& A, const double* x, double* y, double* part, const int* done, int grid_override = 0) {
+  if (R == 1 && tile_ok(A)) {
+    launch_spmv_tile<DOT>(A, x, y, part, done, grid_override ? grid_override : tile_grid(A));
+    return;
+  }
   int lpr = pick_lpr(A);
   int grid = grid_override ? grid_override : spmv_grid(A.n, lpr);
   cudaStream_t st = stream();
@@ -370,6 +513,29 @@ k_maxabs(int64_t n, const double* __restrict__ v, double* __restrict__ part) {
   }
 }
 
+// ---- sampled per-pass timing (bench.py roofline): CUDA events around the three
+// passes of every `every`-th CG iteration, harvested at the convergence polls.
+struct PassProf {
+  int every = 0;
+  std::vector<cudaEvent_t> ev;
+  int used = 0;
+  double ms[3] = {0, 0, 0};
+  long long samples = 0;
+  long long iters = 0;   // CG iterations launched while enabled
+};
+static PassProf g_prof;
+
+static void prof_harvest() {
+  for (int k = 0; k + 3 < g_prof.used; k += 4) {
+    for (int j = 0; j < 3; ++j) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, g_prof.ev[k + j], g_prof.ev[k + j + 1]) == cudaSuccess) g_prof.ms[j] += t;
+    }
+    g_prof.samples += 1;
+  }
+  g_prof.used = 0;
+}
+
 static int vec_grid(int64_t n) {
   int64_t want = (n + kBlock - 1) / kBlock;
   int64_t cap = std::min<int64_t>(kMaxBlocks, (int64_t)sm_count() * 6);
@@ -393,6 +559,16 @@ double max_abs_dev(const double* d_x, int64_t n) {
   return m;
 }
 
+// FS_CG_MODE=multi forces the 3-kernels-per-iteration path (A/B testing); default persistent
+static int cg_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = std::getenv("FS_CG_MODE");
+    mode = (e && std::string(e) == "multi") ? 0 : 1;
+  }
+  return mode;
+}
+
 template <int R>
 static int cg_impl(fs_csr* a, const double* d_b, double* d_x, double rtol, int maxit, int precond, int project_mean,
                    double* relres) {
@@ -405,7 +581,8 @@ static int cg_impl(fs_csr* a, const double* d_b, double* d_x, double rtol, int m
   double* bproj = Ap + len;
   const double* dinv = nullptr;
   if (precond == FS_PRECOND_JACOBI) { jacobi_prepare(a); dinv = a->dinv.p; }
-  cudaStream_t st = stream();
+ cudaStream_t st = stream();
+  ensure_tiles(a);
   const CsrView A = a->view();
   double* partA = a->partials.p;                    // pass A partials (R per block)
   double* partB = a->partials.p + kMaxBlocks * 4;   // pass B partials (2R per block)
@@ -443,20 +620,43 @@ static int cg_impl(fs_csr* a, const double* d_b, double* d_x, double rtol, int m
     if (relres) *relres = 0.0;
     return 0;
   }
-  const int ga = spmv_grid(n, pick_lpr(A));
+  // single-RHS solves run as one persistent cooperative kernel (cg_persistent.cu)
+  if (R == 1 && !hs.flags[0] && cg_mode() == 1 && cg_persistent_supported(A, nullptr)) {
+    cg_persistent_launch(A, d_x, r, p, Ap, dinv, partA, partB, sc.d, sc.flags, maxit, tol2);
+    double tim[4];
+    FS_CUDA(cudaMemcpyAsync(tim, sc.d + 8, sizeof(tim), cudaMemcpyDeviceToHost, st));
+    poll();
+    if (g_prof.every > 0) {
+      for (int j = 0; j < 3; ++j) g_prof.ms[j] += tim[j] * 1e-6;
+      g_prof.samples += (long long)tim[3];
+      g_prof.iters += (long long)tim[3];
+    }
+    maxit = 0;   // skip the multi-kernel loop below
+  }
+  const int ga = spmv_launch_grid<R>(A);
   int launched = 0, chunk = 8, slot = 0;
   while (!hs.flags[0] && launched < maxit) {
     int todo = std::min(chunk, maxit - launched);
     for (int k = 0; k < todo; ++k) {
+      const bool samp = R == 1 && g_prof.every > 0 && ((launched + k) % g_prof.every == 0) &&
+                        g_prof.used + 4 <= (int)g_prof.ev.size();
+      if (samp) cudaEventRecord(g_prof.ev[g_prof.used++], st);
       launch_spmv<R, true>(A, p, Ap, partA, sc.flags, ga);
+      if (samp) cudaEventRecord(g_prof.ev[g_prof.used++], st);
       k_cg_update_xr<R><<<gv, kBlock, 0, st>>>(n, p, Ap, dinv, d_x, r, partA, ga, sc, slot, partB);
       FS_LAUNCH_CHECK();
+      if (samp) cudaEventRecord(g_prof.ev[g_prof.used++], st);
       k_cg_update_p<R><<<gv, kBlock, 0, st>>>(n, r, dinv, p, partB, gv, sc, slot, tol2);
       FS_LAUNCH_CHECK();
+      if (samp) cudaEventRecord(g_prof.ev[g_prof.used++], st);
       slot ^= 1;
     }
     launched += todo;
     poll();
+    if (g_prof.every > 0 && R == 1) {
+      prof_harvest();
+      g_prof.iters = g_prof.iters + todo;
+    }
     chunk = std::min(chunk * 2, 128);
   }
   if (project_mean) {
@@ -528,6 +728,7 @@ static int bicgstab_impl(fs_csr* a, const double* d_b, double* x, double rtol, i
   double *r = a->ws.p, *r0 = r + n, *p = r0 + n, *v = p + n, *s = v + n, *t = s + n, *ph = t + n, *sh = ph + n;
   const double* dinv = nullptr;
   if (precond == FS_PRECOND_JACOBI) { jacobi_prepare(a); dinv = a->dinv.p; }
+  ensure_tiles(a);
   const CsrView A = a->view();
   cudaStream_t st = stream();
   const int g = vec_grid(n);
@@ -580,6 +781,29 @@ static int bicgstab_impl(fs_csr* a, const double* d_b, double* x, double rtol, i
 using namespace fs;
 
 extern "C" {
+
+int fs_profile(int every) {
+  FS_API_BEGIN
+  FS_REQUIRE(every >= 0, "every must be >= 0");
+  g_prof.every = every;
+  g_prof.used = 0;
+  g_prof.ms[0] = g_prof.ms[1] = g_prof.ms[2] = 0.0;
+  g_prof.samples = 0;
+  g_prof.iters = 0;
+  if (every > 0 && g_prof.ev.empty()) {
+    g_prof.ev.resize(4 * 64);
+    for (auto& e : g_prof.ev) FS_CUDA(cudaEventCreate(&e));
+  }
+  FS_API_END
+}
+
+int fs_profile_read(double* ms3, int64_t* samples, int64_t* iters) {
+  FS_API_BEGIN
+  if (ms3) for (int j = 0; j < 3; ++j) ms3[j] = g_prof.ms[j];
+  if (samples) *samples = g_prof.samples;
+  if (iters) *iters = g_prof.iters;
+  FS_API_END
+}
 
 int fs_csr_create(int64_t n, int64_t nnz, const int32_t* rowptr, const int32_t* colidx, const double* vals, fs_csr** out) {
   FS_API_BEGIN
@@ -639,6 +863,7 @@ int fs_spmv(fs_csr* a, const double* x, double* y) {
   FS_REQUIRE(a && x && y, "NULL argument");
   In<double> ix(x, a->n);
   Out<double> oy(y, a->n);
+  ensure_tiles(a);
   spmv_dev(a->view(), ix.d, oy.d);
   oy.commit();
   fs::sync();
