@@ -3,10 +3,11 @@
 // rows for all three passes of an iteration; grid-wide barriers between the passes;
 // convergence is decided on the device, the host is not involved until the end.
 //
-//   pass A  Ap = A p (+ p.Ap)   CSR-stream tiles of 512 rows: the tile's values/columns
-//           are streamed with coalesced evict-first loads that are issued one tile
-//           ahead (register prefetch, in flight while the previous tile is reduced),
-//           products parked in shared memory, rows summed in column order.
+//   pass A  Ap = A p (+ p.Ap)   warp-granular CSR-stream: a warp owns 32-row mini-tiles;
+//           the mini-tile's values/columns are streamed with coalesced evict-first loads
+//           issued one mini-tile ahead (register prefetch, in flight while the previous
+//           one is reduced; row pointers two ahead), products parked in the warp's
+//           shared-memory slice, each lane sums one row in column order.  No block barrier.
 //   pass B  x += a p ; r -= a Ap (+ r.r, r.z with z = Dinv r)
 //   pass C  p = z + b p
 // Dot products: per-CTA partials, re-reduced by every CTA after the barrier in a fixed
@@ -20,8 +21,9 @@ namespace cg = cooperative_groups;
 
 namespace fs {
 
-constexpr int kPT = 512;       // threads per CTA == rows per tile
-constexpr int kPU = 8;         // prefetched nonzeros per thread per tile
+constexpr int kPT = 512;       // threads per CTA == rows per CTA tile (row-block granularity)
+constexpr int kPW = kPT / 32;  // warps per CTA
+constexpr int kPU = 8;         // prefetched nonzeros per lane per 32-row mini-tile (window = 256 nonzeros)
 constexpr int kPVU = 2;        // unroll of the vector passes (64-register budget: 2 CTAs x 512 threads per SM)
 
 __device__ __forceinline__ uint64_t p_evict_first() {
@@ -74,6 +76,7 @@ struct CgPersistArgs {
   int maxit;
   double tol2;
   int ntiles;
+  int wcap;             // shared-memory doubles per warp (>= max nonzeros of a 32-row mini-tile)
 };
 
 template <int K>
@@ -122,10 +125,10 @@ __device__ __forceinline__ void sum_partials(const double* part, int nblk, doubl
 __global__ void __launch_bounds__(kPT, 2) k_cg_persistent(CgPersistArgs a) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ double prod[];
-  __shared__ int s_rp[kPT + 1];
   __shared__ double red[2 * 16];
   __shared__ double sm[2];
   const int t = threadIdx.x, nb = gridDim.x, b = blockIdx.x;
+  const int lane = t & 31, warp = t >> 5;
   const uint64_t pf = p_evict_first(), pl = p_evict_last();
   const int tile0 = (int)(((long long)a.ntiles * b) / nb);
   const int tile1 = (int)(((long long)a.ntiles * (b + 1)) / nb);
@@ -145,48 +148,64 @@ __global__ void __launch_bounds__(kPT, 2) k_cg_persistent(CgPersistArgs a) {
 
   while (it < a.maxit) {
     // ------------------------------------------------------------------ pass A
+    // Warp-granular CSR-stream: every warp owns 32-row mini-tiles (stride 16 inside the
+    // CTA's row block) and needs no block barrier.  Three-deep software pipeline per warp:
+    // row pointers two mini-tiles ahead, the value/column stream one ahead (registers),
+    // gathers + products + row sums on the current one.
     double accA[1] = {0.0};
     {
+      const unsigned full = 0xffffffffu;
+      double* pw = prod + (size_t)warp * a.wcap;
+      const int nmt = (R1 - R0 + 31) >> 5;
       double va[kPU];
       int ca[kPU];
-      int my_rp = 0, base = 0, cnt = 0;
-      auto prefetch = [&](int tile) {
-        const int r0 = tile * kPT;
-        const int nr = min(kPT, a.A.n - r0);
-        base = __ldg(rowptr + r0);
-        cnt = __ldg(rowptr + r0 + nr) - base;
-        my_rp = (t < nr) ? __ldg(rowptr + r0 + t) : base + cnt;
+      auto load_rp = [&](int mt, int& rp, int& rend) {
+        if (mt < nmt) {
+          const int r0 = R0 + (mt << 5);
+          const int nr = min(32, R1 - r0);
+          rp = __ldg(rowptr + r0 + min(lane, nr));
+          rend = __ldg(rowptr + r0 + nr);
+        } else { rp = 0; rend = 0; }
+      };
+      auto stream = [&](int base, int cnt) {
 #pragma unroll
         for (int j = 0; j < kPU; ++j) {
-          const int k = j * kPT + t;
+          const int k = (j << 5) + lane;
           const bool ok = k < cnt;
           va[j] = ok ? ld_stream_f64(vals + base + k, pf) : 0.0;
           ca[j] = ok ? ld_stream_s32(colidx + base + k, pf) : -1;
         }
       };
-      if (tile0 < tile1) prefetch(tile0);
-      for (int tile = tile0; tile < tile1; ++tile) {
-        const int r0 = tile * kPT;
-        const int nr = min(kPT, a.A.n - r0);
-        const int cbase = base, ccnt = cnt;
-        s_rp[t] = my_rp - cbase;
-        if (t == 0) s_rp[kPT] = ccnt;
+      int rpA, endA, rpB, endB;
+      load_rp(warp, rpA, endA);
+      load_rp(warp + kPW, rpB, endB);
+      int baseA = __shfl_sync(full, rpA, 0);
+      int cntA = endA - baseA;
+      stream(baseA, cntA);
+      for (int mt = warp; mt < nmt; mt += kPW) {
 #pragma unroll
         for (int j = 0; j < kPU; ++j)
-          if (ca[j] >= 0) prod[j * kPT + t] = va[j] * ld_vec(a.p + ca[j], pl);
-        // rows longer than the prefetch window (rare): finish the tile without prefetch
-        for (int k = kPU * kPT + t; k < ccnt; k += kPT)
-          prod[k] = ld_stream_f64(vals + cbase + k, pf) * ld_vec(a.p + ld_stream_s32(colidx + cbase + k, pf), pl);
-        __syncthreads();
-        if (tile + 1 < tile1) prefetch(tile + 1);      // in flight while this tile is reduced
-        if (t < nr) {
+          if (ca[j] >= 0) pw[(j << 5) + lane] = va[j] * ld_vec(a.p + ca[j], pl);
+        for (int k = (kPU << 5) + lane; k < cntA; k += 32)   // rows beyond the prefetch window (rare)
+          pw[k] = ld_stream_f64(vals + baseA + k, pf) * ld_vec(a.p + ld_stream_s32(colidx + baseA + k, pf), pl);
+        __syncwarp();
+        int rpC, endC;
+        load_rp(mt + 2 * kPW, rpC, endC);
+        const int baseB = __shfl_sync(full, rpB, 0);
+        const int cntB = endB - baseB;
+        stream(baseB, cntB);                                  // in flight while this mini-tile is reduced
+        int nxt = __shfl_down_sync(full, rpA, 1);
+        if (lane == 31) nxt = endA;
+        const int row = R0 + (mt << 5) + lane;
+        if (row < R1) {
           double s = 0.0;
-          const int ke = s_rp[t + 1];
-          for (int k = s_rp[t]; k < ke; ++k) s += prod[k];
-          st_vec(a.Ap + r0 + t, s, pl);
-          accA[0] += ld_vec(a.p + r0 + t, pl) * s;
+          for (int k = rpA - baseA; k < nxt - baseA; ++k) s += pw[k];
+          st_vec(a.Ap + row, s, pl);
+          accA[0] += ld_vec(a.p + row, pl) * s;
         }
-        __syncthreads();
+        __syncwarp();
+        rpA = rpB; endA = endB; baseA = baseB; cntA = cntB;
+        rpB = rpC; endB = endC;
       }
     }
     blk_reduce<1>(accA, red);
@@ -275,9 +294,9 @@ static int g_persist_blocks_per_sm = -1;
 // Returns false when this matrix cannot use the persistent kernel (tile too large for
 // shared memory, cooperative launch unsupported); the caller then runs the 3-kernel path.
 bool cg_persistent_supported(const CsrView& A, size_t* smem_out) {
-  if (A.tile_nnz_max <= 0) return false;
-  // tile_nnz_max counts 256-row tiles; a 512-row tile holds at most two of them
-  const size_t smem = (size_t)2 * A.tile_nnz_max * sizeof(double);
+  if (A.wtile_nnz_max <= 0) return false;
+  const size_t wcap = ((size_t)A.wtile_nnz_max + 31) / 32 * 32;
+  const size_t smem = (size_t)kPW * wcap * sizeof(double);
   if (smem > 100 * 1024) return false;
   if (g_persist_blocks_per_sm < 0) {
     int dev = 0, coop = 0;
@@ -303,7 +322,8 @@ void cg_persistent_launch(const CsrView& A, double* x, double* r, double* p, dou
   per_sm = std::min(per_sm, 2);
   const int ntiles = div_up(A.n, kPT);
   const int grid = std::max(1, std::min(sm_count() * per_sm, ntiles));
-  CgPersistArgs args{A, x, r, p, Ap, dinv, partA, partB, scal, flags, maxit, tol2, ntiles};
+  const int wcap = (A.wtile_nnz_max + 31) / 32 * 32;
+  CgPersistArgs args{A, x, r, p, Ap, dinv, partA, partB, scal, flags, maxit, tol2, ntiles, wcap};
   void* kargs[] = {&args};
   FS_CUDA(cudaLaunchCooperativeKernel((void*)k_cg_persistent, dim3(grid), dim3(kPT), kargs, smem, stream()));
   count_launch();

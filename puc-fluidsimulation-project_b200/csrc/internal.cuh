@@ -166,6 +166,7 @@ struct CsrView {
   const int* colidx;
   const double* vals;
   int tile_nnz_max = 0;   // max nonzeros in a 256-row tile (0: not computed -> vector SpMV)
+  int wtile_nnz_max = 0;  // max nonzeros in a 32-row (one warp) tile
 };
 
 }  // namespace fs
@@ -185,8 +186,9 @@ struct fs_csr {
   fs::DBuf<double> partials;
   fs::DBuf<double> scal;
   int tile_nnz_max = -1;         // lazily computed by fs::ensure_tiles
+  int wtile_nnz_max = 0;
   fs::CsrView view() const {
-    return fs::CsrView{(int)n, nnz, rowptr, colidx, vals.p, tile_nnz_max > 0 ? tile_nnz_max : 0};
+    return fs::CsrView{(int)n, nnz, rowptr, colidx, vals.p, tile_nnz_max > 0 ? tile_nnz_max : 0, wtile_nnz_max};
   }
 };
 

@@ -239,21 +239,25 @@ k_spmv_tile(CsrView A, const double* __restrict__ x, double* __restrict__ y, dou
   }
 }
 
-__global__ void k_tile_nnz_max(const int* __restrict__ rowptr, int n, int ntiles, int* __restrict__ out) {
+__global__ void k_tile_nnz_max(const int* __restrict__ rowptr, int n, int rows_per_tile, int ntiles, int* __restrict__ out) {
   int tile = blockIdx.x * blockDim.x + threadIdx.x;
   if (tile >= ntiles) return;
-  int r0 = tile * kTileRows, r1 = min(n, r0 + kTileRows);
+  int r0 = tile * rows_per_tile, r1 = min(n, r0 + rows_per_tile);
   atomicMax(out, rowptr[r1] - rowptr[r0]);
 }
 
 void ensure_tiles(fs_csr* a) {
   if (a->tile_nnz_max >= 0) return;
-  const int ntiles = div_up(a->n, kTileRows);
-  DBuf<int> mx(1);
+  DBuf<int> mx(2);
   mx.zero();
-  k_tile_nnz_max<<<div_up(ntiles, 256), 256, 0, stream()>>>(a->rowptr, (int)a->n, ntiles, mx.p);
+  const int nt256 = div_up(a->n, kTileRows), nt32 = div_up(a->n, 32);
+  k_tile_nnz_max<<<div_up(nt256, 256), 256, 0, stream()>>>(a->rowptr, (int)a->n, kTileRows, nt256, mx.p);
   FS_LAUNCH_CHECK();
-  a->tile_nnz_max = mx.to_host()[0];
+  k_tile_nnz_max<<<div_up(nt32, 256), 256, 0, stream()>>>(a->rowptr, (int)a->n, 32, nt32, mx.p + 1);
+  FS_LAUNCH_CHECK();
+  std::vector<int> h = mx.to_host();
+  a->tile_nnz_max = h[0];
+  a->wtile_nnz_max = h[1];
 }
 
 constexpr int kTileSmemMax = 96 * 1024;   // products buffer cap (bytes); beyond it use the vector kernel
