@@ -213,6 +213,9 @@ def run_ours(args):
     for _ in range(args.warmup):
         st = sim.step(u_dev)
     barrier()
+    # snapshot the loop state so that the end-to-end arm repeats exactly the same K steps
+    u_snap = u_dev.clone()
+    warm_snap = sim.get_warm_state()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -240,8 +243,9 @@ def run_ours(args):
     # ---- end-to-end arm: same K steps through the host-buffer C-ABI call (pinned numpy view):
     # every step copies u host->device and device->host inside the timed region
     u_pin = torch.empty((N, 2), dtype=torch.float64).pin_memory()
-    u_pin.copy_(u_dev.cpu())
+    u_pin.copy_(u_snap.cpu())
     u_host = u_pin.numpy()
+    sim.set_warm_state(warm_snap)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -263,17 +267,28 @@ def run_ours(args):
     samples = max(int(ns.value), 1)
     t_spmv = pms[0] / samples / 1e3
     t_iter = pms.sum() / samples / 1e3
-    traffic = None
+    # the dominant kernel (99.7 % of the step, profiles/r01_launch_list_summary.txt) is the persistent
+    # CG kernel: one launch = one whole solve, so bytes and time are both per launch = iterations x
+    # per-iteration figures.  Phase times come from CTA 0's %globaltimer between the grid barriers.
+    n_launch = 2 * args.steps
+    it_per_launch = samples / n_launch
+    traffic_it = None
     if os.path.exists(TRAFFIC_FILE):
-        traffic = json.load(open(TRAFFIC_FILE)).get("dram_bytes_per_launch")
-    roof = {"bound": "hbm", "kernel": "k_spmv<1,8,true> (CG pass A: Ap=A*p fused with p.Ap)",
-            "achieved": spmv_bytes / t_spmv / 1e9, "peak": peak, "unit": "GB/s",
-            "frac": spmv_bytes / t_spmv / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": spmv_bytes, "us_per_launch": 1e6 * t_spmv,
-            "sampled_launches": samples, "frac_of_8TBps_spec": spmv_bytes / t_spmv / 8e12}
-    roof_cg = {"achieved": cg_bytes / t_iter / 1e9, "frac": cg_bytes / t_iter / 1e9 / peak, "unit": "GB/s",
-               "algorithmic_bytes_per_iteration": cg_bytes, "us_per_iteration": 1e6 * t_iter,
-               "us_pass_A_B_C": [1e6 * x / samples / 1e3 for x in pms]}
+        traffic_it = json.load(open(TRAFFIC_FILE)).get("dram_bytes_per_iteration")
+    roof = {"bound": "hbm", "kernel": "k_cg_persistent (pressure PCG: SpMV+dot | x,r update+dots | p update, 3 grid barriers)",
+            "achieved": cg_bytes / t_iter / 1e9, "peak": peak, "unit": "GB/s", "frac": cg_bytes / t_iter / 1e9 / peak,
+            "traffic": None if traffic_it is None else traffic_it * it_per_launch,
+            "peak_source": peak_src, "launches_timed": n_launch, "iterations_per_launch": it_per_launch,
+            "algorithmic_bytes_per_launch": cg_bytes * it_per_launch, "us_per_launch": 1e6 * t_iter * it_per_launch,
+            "algorithmic_bytes_per_iteration": cg_bytes, "us_per_iteration": 1e6 * t_iter,
+            "dram_bytes_per_iteration_ncu": traffic_it, "us_pass_A_B_C": [1e6 * x / samples / 1e3 for x in pms],
+            "frac_of_8TBps_spec": cg_bytes / t_iter / 8e12,
+            "note": "frac can exceed 1: the five CG vectors (84 MB) are kept L2-resident with evict_last hints, so "
+                    "DRAM traffic (ncu, caches left alone) is below the algorithmic bytes"}
+    roof_cg = {"kernel": "k_cg_persistent pass A only: SpMV Ap=A*p fused with p.Ap (the metric's 'pressure-CG SpMV')",
+               "achieved": spmv_bytes / t_spmv / 1e9, "frac": spmv_bytes / t_spmv / 1e9 / peak, "unit": "GB/s",
+               "peak": peak, "algorithmic_bytes_per_pass": spmv_bytes, "us_per_pass": 1e6 * t_spmv,
+               "frac_of_8TBps_spec": spmv_bytes / t_spmv / 8e12}
     it_arr = np.array(iters, dtype=np.float64)
     iters_per_step = float((it_arr[:, 1] + it_arr[:, 2]).mean())
     os.makedirs(os.path.dirname(ITERS_FILE), exist_ok=True)
@@ -292,7 +307,7 @@ def run_ours(args):
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": workload_config(args, cg_iters_per_step=iters, parallelism=("single GPU" if world == 1 else
                                      f"{world} independent squirmer (B1,B2) configs, one per GPU, no collective")),
-           "roofline": roof, "roofline_cg_iteration": roof_cg, "cpu_baseline": cpu,
+           "roofline": roof, "roofline_spmv_pass": roof_cg, "cpu_baseline": cpu,
            "e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": 16 * N, "d2h_bytes_per_step": 16 * N},
            "gpu_launches": int(launches), "clocks": clk}
     print(json.dumps(out))

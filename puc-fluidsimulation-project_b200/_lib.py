@@ -85,6 +85,7 @@ SIGNATURES = {
     "fs_stokes_step": (C.c_int, [c_vp, c_vp, c_dbl, c_dbl, P(StokesOpts), P(StokesStats)]),
     "fs_stokes_pressure": (C.c_int, [c_vp, c_vp, c_vp]),
     "fs_stokes_matrices": (C.c_int, [c_vp, P(c_vp), P(c_vp), c_vp]),
+    "fs_stokes_warm_state": (C.c_int, [c_vp, c_vp, C.c_int]),
     "fs_locate": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),
     "fs_advect_dye": (C.c_int, [c_vp, c_vp, c_vp, c_dbl, c_vp]),
     "fs_mixing_index": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),

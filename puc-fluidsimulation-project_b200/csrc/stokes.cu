@@ -228,4 +228,21 @@ int fs_stokes_matrices(fs_stokes* s, fs_csr** a_visc, fs_csr** k_pressure, int32
   FS_API_END
 }
 
+int fs_stokes_warm_state(fs_stokes* s, double* q, int set) {
+  FS_API_BEGIN
+  FS_REQUIRE(s && q, "NULL argument");
+  const size_t nd = (size_t)s->nd;
+  cudaStream_t st = stream();
+  if (set) {
+    FS_CUDA(cudaMemcpyAsync(s->p_red.p, q, nd * sizeof(double), cudaMemcpyDefault, st));
+    FS_CUDA(cudaMemcpyAsync(s->p2_red.p, q + nd, nd * sizeof(double), cudaMemcpyDefault, st));
+    s->have_p = true;
+  } else {
+    FS_CUDA(cudaMemcpyAsync(q, s->p_red.p, nd * sizeof(double), cudaMemcpyDefault, st));
+    FS_CUDA(cudaMemcpyAsync(q + nd, s->p2_red.p, nd * sizeof(double), cudaMemcpyDefault, st));
+  }
+  fs::sync();
+  FS_API_END
+}
+
 }  // extern "C"

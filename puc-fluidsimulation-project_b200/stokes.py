@@ -83,6 +83,16 @@ class StokesSolver:
              C.byref(self.opts), C.byref(self.stats))
         return self.stats
 
+    def get_warm_state(self):
+        """CG warm-start vectors of the two pressure solves (with ``u`` the full loop state)."""
+        _, kp, _ = self.matrices()
+        q = np.empty(2 * kp.n)
+        call("fs_stokes_warm_state", self._h, ptr(q), 0)
+        return q
+
+    def set_warm_state(self, q):
+        call("fs_stokes_warm_state", self._h, ptr(np.ascontiguousarray(q, dtype=np.float64)), 1)
+
     def pressure(self):
         p = np.empty(self.N)
         p2 = np.empty(self.N)
