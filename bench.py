@@ -41,14 +41,13 @@ ITERS_FILE = os.path.join(ROOT, "profiles", "bench_iters.json")
 TRAFFIC_FILE = os.path.join(ROOT, "profiles", "spmv_traffic.json")
 
 
-def sweep_params(rank):
-    """Config 4: 64 (B1,B2) pairs = linspace(-4,-0.5,8) x linspace(-5,5,8); rank r takes pair r
-    (rank 0 keeps the N=1 pusher so the per-GPU work is the same problem class)."""
+def sweep_params(rank, world):
+    """Config 4: the 64 (B1,B2) pairs of fluidsim_b200.parallel.sweep_configs(), sharded round-robin;
+    rank 0 keeps the N=1 pusher so that its work is the N=1 workload."""
     if rank == 0:
         return PARAMS["B1"], PARAMS["B2"]
-    b1 = np.linspace(-4.0, -0.5, 8)
-    b2 = np.linspace(-5.0, 5.0, 8)
-    return float(b1[rank % 8]), float(b2[(rank * 3) % 8])
+    from fluidsim_b200.parallel import shard_list, sweep_configs
+    return shard_list(sweep_configs(), rank, world)[0]
 
 
 class ClockSampler:
@@ -200,7 +199,7 @@ def run_ours(args):
         _lib.call("fs_sync")
 
     nodes, markers, tris = fb.square_with_hole(args.n_theta, args.n_r)
-    B1, B2 = sweep_params(rank) if world > 1 else (PARAMS["B1"], PARAMS["B2"])
+    B1, B2 = sweep_params(rank, world) if world > 1 else (PARAMS["B1"], PARAMS["B2"])
     sim = fb.StokesSolver(nodes, markers, tris, B1=B1, B2=B2, DT=PARAMS["DT"], v=PARAMS["v"],
                           rtol_pressure=RTOL_P, rtol_visc=RTOL_V)
     N = sim.N

@@ -1,0 +1,109 @@
+"""CPU, world_size 2, gloo: the N>1 host logic -- sweep / tracer sharding with the final count
+reduction, and the row-block partition + halo exchange of the partitioned CG (the SpMV itself is a
+numpy stand-in here; the CUDA kernels are covered by the -m gpu tests)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from fluidsim_b200 import parallel as par
+    from fluidsim_b200.mesh import square_with_hole, find_boundary_pairs, filter_wall_pairs
+    from oracle import restated as R
+    r, w, _, d = par.init_distributed("gloo")
+    assert (r, w) == (rank, world) and d is not None
+    # --- sweeps: 64 configs, no overlap, union complete
+    mine = par.shard_list(par.sweep_configs(), rank, world)
+    got = [None] * world
+    dist.all_gather_object(got, mine)
+    flat = sorted(c for g in got for c in g)
+    assert flat == sorted(par.sweep_configs()) and len(set(flat)) == 64
+    # --- tracer ensemble: shard, count locally, allreduce
+    pts = R.food_tracer_init(25)
+    lo, hi = par.shard_range(len(pts), rank, world)
+    local_eaten = int((np.hypot(pts[lo:hi, 0] - 0.5, pts[lo:hi, 1] - 0.5) <= 0.28).sum())
+    total = par.allreduce(local_eaten, "sum", d)
+    assert total == int((np.hypot(pts[:, 0] - 0.5, pts[:, 1] - 0.5) <= 0.28).sum())
+    assert par.allreduce(float(rank), "max", d) == world - 1
+    # --- partitioned SpMV with halo exchange == global SpMV
+    nodes, markers, tris = square_with_hole(64, 48)
+    pairs = filter_wall_pairs(nodes, find_boundary_pairs(nodes))
+    ps = R.PressureSystem(nodes, tris, pairs)
+    part = par.row_block_partition(ps.rowptr, ps.colidx, rank, world, align=32)
+    lo, hi = part["lo"], part["hi"]
+    a, b = part["nnz_range"]
+    x = np.random.default_rng(0).standard_normal(ps.nd)        # same on both ranks
+    xl = np.concatenate([x[lo:hi], np.zeros(len(part["halo_global"]))])
+    # halo exchange: every rank publishes which global ids it needs; owners answer
+    need = [None] * world
+    dist.all_gather_object(need, part["halo_global"])
+    for peer in range(world):
+        if peer == rank:
+            continue
+        want = need[peer]
+        sel = want[(want >= lo) & (want < hi)]
+        dist.send(torch.from_numpy(x[sel].copy()), dst=peer) if rank < peer else None
+        if rank > peer:
+            buf = torch.empty(len(part["recv_slots"].get(peer, [])), dtype=torch.float64)
+            dist.recv(buf, src=peer)
+            xl[(hi - lo) + part["recv_slots"][peer]] = buf.numpy()
+    for peer in range(world):                                   # second half of the pairwise exchange
+        if peer == rank:
+            continue
+        want = need[peer]
+        sel = want[(want >= lo) & (want < hi)]
+        if rank > peer:
+            dist.send(torch.from_numpy(x[sel].copy()), dst=peer)
+        else:
+            buf = torch.empty(len(part["recv_slots"].get(peer, [])), dtype=torch.float64)
+            dist.recv(buf, src=peer)
+            xl[(hi - lo) + part["recv_slots"][peer]] = buf.numpy()
+    import scipy.sparse as sp
+    Al = sp.csr_matrix((ps.vals[a:b], part["colidx"], part["rowptr"]), shape=(hi - lo, len(xl)))
+    yl = Al @ xl
+    yg = ps.K @ x
+    assert np.array_equal(yl, yg[lo:hi]) or np.abs(yl - yg[lo:hi]).max() < 1e-12 * np.abs(yg).max()
+    # dot product by allreduce
+    assert abs(par.allreduce(float(yl @ xl[:hi - lo]), "sum", d) - float(yg @ x)) < 1e-9 * abs(float(yg @ x))
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, "ok"))
+
+
+def test_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    res = sorted(q.get(timeout=5) for _ in procs)
+    assert res == [(0, "ok"), (1, "ok")]
+
+
+def test_shard_helpers():
+    sys.path.insert(0, ROOT)
+    from fluidsim_b200 import parallel as par
+    for n, w in ((10, 3), (64, 8), (7, 8), (0, 2)):
+        rs = [par.shard_range(n, r, w) for r in range(w)]
+        assert rs[0][0] == 0 and rs[-1][1] == n and all(rs[i][1] == rs[i + 1][0] for i in range(w - 1))
+    assert len(par.sweep_configs()) == 64 and par.sweep_configs()[0] == (-4.0, -5.0)
+    rp = np.arange(0, 4001, 4, dtype=np.int32)
+    ci = np.tile(np.arange(4, dtype=np.int32), 1000)
+    p0 = par.row_block_partition(rp, ci, 0, 2, align=100)
+    p1 = par.row_block_partition(rp, ci, 1, 2, align=100)
+    assert p0["hi"] == p1["lo"] and p1["hi"] == 1000 and p0["lo"] == 0
+    assert len(p0["halo_global"]) == 0 and list(p1["halo_global"]) == [0, 1, 2, 3]
