@@ -33,6 +33,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version at VERSION/INFO)
 
 N_THETA, N_R = 2048, 1024
 PARAMS = dict(B1=-2.0, B2=-5.0, DT=0.05, v=0.1)
