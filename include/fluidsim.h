@@ -175,6 +175,33 @@ int fs_stokes_matrices(fs_stokes* s, fs_csr** a_visc, fs_csr** k_pressure, int32
  * the complete state of the time loop (checkpoint / resume, repeatable benchmarks). */
 int fs_stokes_warm_state(fs_stokes* s, double* q /* 2*n_dof */, int set);
 
+/* ---- partitioned pressure CG, one rank (process) per GPU, peer memory over NVLink.
+ * Replaces the same np.linalg.solve(A_pressure, .) for meshes that are split across GPUs
+ * (SURVEY 8e / BASELINE config 5).  Rank r owns a contiguous block of rows of the SPD
+ * operator; the local CSR slice has its columns renumbered to [0,n_own) (owned) and
+ * [n_own, n_own+n_halo) (external).  The search direction p lives as [own | halo] in a
+ * CUDA-IPC shared allocation: inside the persistent CG kernel every rank stores its
+ * boundary values of p directly into its neighbours' halo slots and the per-iteration dot
+ * products are summed through the same mailboxes in rank order (deterministic); no host
+ * or NCCL call happens inside a solve.  Rendezvous (exchange of the 64-byte IPC handles
+ * and of the halo index lists, and the two scalars of the init) is the caller's job
+ * (torch.distributed in the Python mirror).
+ *   fs_dist_create   local matrix                       fs_dist_ipc_handle  this rank's handle
+ *   fs_dist_connect  all ranks' handles + send list: own row send_row[k] goes to slot
+ *                    send_dst[k] of rank send_peer[k]'s p (sorted by send_row)
+ *   fs_dist_cg_begin x0=0: r=b, p=Dinv b; returns the local (b.b, b.Dinv b)
+ *   fs_dist_cg_run   globally summed (b.b, r.z) in, x_own out; all ranks call it together */
+typedef struct fs_dist fs_dist;
+int fs_dist_create(int rank, int world, int64_t n_own, int64_t n_halo, int64_t nnz, const int32_t* rowptr,
+                   const int32_t* colidx, const double* vals, fs_dist** out);
+int fs_dist_destroy(fs_dist* d);
+int fs_dist_ipc_handle(fs_dist* d, void* handle64 /* 64 bytes, host */);
+int fs_dist_connect(fs_dist* d, const void* all_handles /* world*64 bytes, host */, const int32_t* send_row,
+                    const int32_t* send_peer, const int32_t* send_dst, int64_t n_send /* host arrays */);
+int fs_dist_cg_begin(fs_dist* d, const double* b_own, int precond, double* local_sums2 /* host */);
+int fs_dist_cg_run(fs_dist* d, double bb_global, double rz_global, double* x_own, double rtol, int maxit,
+                   int precond, int* iters, double* relres, double* ns_pass3 /* host, may be NULL */);
+
 /* ---- tracers and dye.
  * fs_locate: PointLocator.find, code/StokesColor.py:314-345 -- the 10 nearest
  *   centroids in ascending distance, first triangle with w1,w2,w3 >= 0, else -1.

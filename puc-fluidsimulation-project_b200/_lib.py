@@ -86,6 +86,12 @@ SIGNATURES = {
     "fs_stokes_pressure": (C.c_int, [c_vp, c_vp, c_vp]),
     "fs_stokes_matrices": (C.c_int, [c_vp, P(c_vp), P(c_vp), c_vp]),
     "fs_stokes_warm_state": (C.c_int, [c_vp, c_vp, C.c_int]),
+    "fs_dist_create": (C.c_int, [C.c_int, C.c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, P(c_vp)]),
+    "fs_dist_destroy": (C.c_int, [c_vp]),
+    "fs_dist_ipc_handle": (C.c_int, [c_vp, c_vp]),
+    "fs_dist_connect": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64]),
+    "fs_dist_cg_begin": (C.c_int, [c_vp, c_vp, C.c_int, c_vp]),
+    "fs_dist_cg_run": (C.c_int, [c_vp, c_dbl, c_dbl, c_vp, c_dbl, C.c_int, C.c_int, P(C.c_int), P(c_dbl), c_vp]),
     "fs_locate": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),
     "fs_advect_dye": (C.c_int, [c_vp, c_vp, c_vp, c_dbl, c_vp]),
     "fs_mixing_index": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
