@@ -144,6 +144,7 @@ struct DistArgs {
   const int* send_peer;                            // destination rank
   const int* send_dst;                             // slot in the destination's p
   const int* send_begin;                           // [grid+1] CTA b pushes entries [send_begin[b], send_begin[b+1])
+  const int* needs_halo;                           // [grid] 1 if CTA b's rows reference a halo column
   unsigned long long red_epoch0, halo_epoch0;      // epochs already consumed by earlier solves
 };
 
@@ -175,25 +176,61 @@ __device__ __forceinline__ void wait_flag(const unsigned long long* a, unsigned 
   }
 }
 
-// all ranks: v[k] (already summed over the local CTAs, identical in every CTA) -> sum over ranks
+// all ranks: v[k] (already summed over the local CTAs, identical in every CTA) -> sum over ranks.
+// Low-latency protocol: every double travels as two 8-byte words {32 data bits | 32-bit epoch};
+// an 8-byte store is atomic, so data and "ready" flag arrive together and no fence or separate
+// flag write is needed.  CTA 0 posts this rank's sums into every rank's mailbox (peer stores),
+// every CTA polls its own mailbox and adds the world's contributions in rank order.
+__device__ __forceinline__ void st_sys_u64(unsigned long long* a, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(a), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* a) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a) : "memory");
+  return v;
+}
+
 template <int K>
 __device__ __forceinline__ void rank_allreduce(const DistArgs& d, double (&v)[K], unsigned long long epoch, double* sm, int* err) {
+  static_assert(K <= 2, "mailbox slot holds two doubles");
   const int t = threadIdx.x;
   const int par = (int)(epoch & 1ull);
+  const unsigned long long e32 = (epoch & 0xffffffffull) << 32;
   if (blockIdx.x == 0 && t < d.world) {
-    double* dst = d.red_peer[t] + ((size_t)par * d.world + d.rank) * 4;
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(d.red_peer[t]) + ((size_t)par * d.world + d.rank) * 4;
 #pragma unroll
-    for (int k = 0; k < K; ++k) st_sys_f64(dst + k, v[k]);
-    __threadfence_system();
-    st_release_sys(d.redflag_peer[t] + (size_t)par * d.world + d.rank, epoch);
+    for (int k = 0; k < K; ++k) {
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(v[k]);
+      st_sys_u64(dst + 2 * k, (bits & 0xffffffffull) | e32);
+      st_sys_u64(dst + 2 * k + 1, (bits >> 32) | e32);
+    }
   }
-  if (t < d.world) wait_flag(d.redflag_local + (size_t)par * d.world + t, epoch, err, 0x200 | t);
+  __shared__ double got[kMaxRanks][2];
+  if (t < d.world) {
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(d.red_local) + ((size_t)par * d.world + t) * 4;
+    unsigned long long w[2 * K];
+    unsigned long long spins = 0;
+    bool ok = false;
+    while (!ok) {
+      ok = true;
+#pragma unroll
+      for (int j = 0; j < 2 * K; ++j) { w[j] = ld_sys_u64(src + j); ok = ok && ((w[j] & 0xffffffff00000000ull) == e32); }
+      if (!ok) {
+        ++spins;
+        if ((spins & 1023ull) == 0 && *(volatile int*)err != 0) break;
+        if (spins > (1ull << 24)) { atomicCAS(err, 0, 0x200 | t); break; }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      got[t][k] = __longlong_as_double((long long)((w[2 * k] & 0xffffffffull) | (w[2 * k + 1] << 32)));
+  }
   __syncthreads();
   if (t == 0) {
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       double s = 0.0;
-      for (int q = 0; q < d.world; ++q) s += ld_sys_f64(d.red_local + ((size_t)par * d.world + q) * 4 + k);
+      for (int q = 0; q < d.world; ++q) s += got[q][k];
       sm[k] = s;
     }
   }
@@ -248,8 +285,10 @@ __global__ void __launch_bounds__(kPT, 2) k_cg_persistent(CgPersistArgs a, DistA
 
   while (it < a.maxit) {
     if (DIST) {
-      if (t < d.n_nbr) wait_flag(d.haloflag_local + d.nbr[t], halo_epoch, a.flags + 2, 0x100 | d.nbr[t]);
-      __syncthreads();
+      if (d.needs_halo[b]) {      // only the CTAs whose rows reference halo columns have to wait
+        if (t < d.n_nbr) wait_flag(d.haloflag_local + d.nbr[t], halo_epoch, a.flags + 2, 0x100 | d.nbr[t]);
+        __syncthreads();
+      }
     }
     // ------------------------------------------------------------------ pass A
     // Warp-granular CSR-stream: every warp owns 32-row mini-tiles (stride 16 inside the
@@ -467,6 +506,16 @@ void cg_persistent_launch(const CsrView& A, double* x, double* r, double* p, dou
   cg_persistent_launch(A, x, r, p, Ap, dinv, partA, partB, scal, flags, maxit, tol2, nullptr);
 }
 
+// needs[b] = 1 iff some nonzero of CTA b's row block has a halo column (>= n_own)
+__global__ void k_needs_halo(const int* __restrict__ rowptr, const int* __restrict__ colidx, const int* __restrict__ row0,
+                             int n_own, int* __restrict__ needs) {
+  const int b = blockIdx.x;
+  int any = 0;
+  for (int k = rowptr[row0[b]] + threadIdx.x; k < rowptr[row0[b + 1]]; k += blockDim.x) any |= (colidx[k] >= n_own);
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0) needs[b] = any;
+}
+
 // ---- init of a partitioned solve with x0 = 0: r = b, p[own] = Dinv b, local (b.b, r.z) ----
 __global__ void __launch_bounds__(256)
 k_dist_init(int n, const double* __restrict__ b, const double* __restrict__ dinv, double* __restrict__ x,
@@ -505,7 +554,7 @@ struct fs_dist {
   size_t mailbox_bytes = 0;
   void* peer_base[fs::kMaxRanks] = {nullptr};
   bool peer_opened[fs::kMaxRanks] = {false};
-  fs::DBuf<int> send_row, send_peer, send_dst, send_begin;
+  fs::DBuf<int> send_row, send_peer, send_dst, send_begin, needs_halo;
   std::vector<int> nbr;
   unsigned long long red_epoch = 0, halo_epoch = 0;
   bool connected = false;
@@ -595,6 +644,16 @@ int fs_dist_connect(fs_dist* d, const void* all_handles, const int32_t* send_row
   d->send_dst.alloc(std::max<int64_t>(n_send, 1)); d->send_begin.alloc(grid + 1);
   if (n_send) { d->send_row.upload(rows.data(), n_send); d->send_peer.upload(peers.data(), n_send); d->send_dst.upload(dsts.data(), n_send); }
   d->send_begin.upload(begin.data(), grid + 1);
+  {
+    std::vector<int> row0(grid + 1);
+    for (int b = 0; b <= grid; ++b) row0[b] = (b == grid) ? (int)d->n_own : cg_persistent_block_row0(A, b, grid);
+    DBuf<int> drow0(grid + 1);
+    drow0.upload(row0.data(), grid + 1);
+    d->needs_halo.alloc(grid);
+    k_needs_halo<<<grid, 256, 0, stream()>>>(d->mat.rowptr, d->mat.colidx, drow0.p, (int)d->n_own, d->needs_halo.p);
+    FS_LAUNCH_CHECK();
+    fs::sync();
+  }
   fs::sync();
   d->connected = true;
   FS_API_END
@@ -650,7 +709,7 @@ int fs_dist_cg_run(fs_dist* d, double bb_global, double rz_global, double* x_own
       da.haloflag_peer[q] = reinterpret_cast<unsigned long long*>(pb + d->off_haloflag);
       da.p_peer[q] = reinterpret_cast<double*>(pb + fs_dist::off_p);
     }
-    da.send_row = d->send_row.p; da.send_peer = d->send_peer.p; da.send_dst = d->send_dst.p; da.send_begin = d->send_begin.p;
+    da.send_row = d->send_row.p; da.send_peer = d->send_peer.p; da.send_dst = d->send_dst.p; da.send_begin = d->send_begin.p; da.needs_halo = d->needs_halo.p;
     da.red_epoch0 = d->red_epoch; da.halo_epoch0 = d->halo_epoch;
     cg_persistent_launch(A, d->x.p, d->r.p, d->p(), d->Ap.p, dinv, d->mat.partials.p, d->mat.partials.p + 4096,
                          scal, flags, maxit, rtol * rtol, &da);
