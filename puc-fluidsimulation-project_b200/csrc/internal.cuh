@@ -171,6 +171,8 @@ struct CsrView {
 
 }  // namespace fs
 
+namespace fs { struct Amg; void amg_free(Amg*); }
+
 // Opaque handle definitions ----------------------------------------------------
 struct fs_csr {
   int64_t n = 0, nnz = 0;
@@ -187,6 +189,11 @@ struct fs_csr {
   fs::DBuf<double> scal;
   int tile_nnz_max = -1;         // lazily computed by fs::ensure_tiles
   int wtile_nnz_max = 0;
+  fs::Amg* amg = nullptr;        // aggregation-AMG hierarchy (lazy, FS_PRECOND_AMG)
+  fs_csr() = default;
+  fs_csr(const fs_csr&) = delete;
+  fs_csr& operator=(const fs_csr&) = delete;
+  ~fs_csr() { if (amg) fs::amg_free(amg); }
   fs::CsrView view() const {
     return fs::CsrView{(int)n, nnz, rowptr, colidx, vals.p, tile_nnz_max > 0 ? tile_nnz_max : 0, wtile_nnz_max};
   }
@@ -205,7 +212,7 @@ void build_pattern(const int* d_tris, int64_t T, int64_t n, const int* d_dof /*n
 void assemble_on_pattern(const Pattern& pat, const double* d_ke /* (T,9) */, double* d_vals);
 }  // namespace fs
 
-namespace fs { struct Locator; }
+namespace fs { struct Locator; struct Amg; void amg_free(Amg*); }
 
 struct fs_mesh {
   int64_t N = 0, T = 0;
@@ -243,6 +250,9 @@ void grad_update_dev(fs_mesh* m, const double* d_p, const double* d_ui, double* 
                      const unsigned char* d_interior_flag /* null: all nodes */);
 void jacobi_prepare(fs_csr* a);
 void ensure_tiles(fs_csr* a);
+Amg* amg_setup(fs_csr* fine);
+void amg_apply(Amg* amg, const double* r, double* z);
+int amg_levels(const Amg* amg, int* sizes, int cap);
 bool cg_persistent_supported(const CsrView& A, size_t* smem_out);
 void cg_persistent_launch(const CsrView& A, double* x, double* r, double* p, double* Ap, const double* dinv,
                           double* partA, double* partB, double* scal, int* flags, int maxit, double tol2);

@@ -678,9 +678,82 @@ static int cg_impl(fs_csr* a, const double* d_b, double* d_x, double rtol, int m
   return hs.flags[0] ? hs.flags[1] : -hs.flags[1] - 1;   // negative: not converged
 }
 
+__global__ void k_lin3(int64_t n, double a, const double* __restrict__ x, double b, const double* __restrict__ y, double c,
+                       const double* __restrict__ z, double* __restrict__ out);
+
+// ---- CG preconditioned by one AMG V-cycle (amg.cu).  ~50x fewer iterations than Jacobi on
+// the 4M-triangle pressure operator, so the two host reads of scalars per iteration are noise.
+static void dot2(int64_t n, const double* a, const double* b, const double* c, const double* d, double* part, double* out2);
+
+static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, int maxit, int project_mean, double* relres) {
+  const int64_t n = a->n;
+  ensure_ws(a, 5 * (size_t)n);
+  double *r = a->ws.p, *p = r + n, *Ap = p + n, *z = Ap + n, *bproj = z + n;
+  if (!a->amg) a->amg = amg_setup(a);
+  ensure_tiles(a);
+  const CsrView A = a->view();
+  cudaStream_t st = stream();
+  const int g = vec_grid(n);
+  double* part = a->partials.p;
+  double* part0 = a->partials.p + kMaxBlocks * 8;
+  const double* b = d_b;
+  if (project_mean) {
+    k_sum<<<g, kBlock, 0, st>>>(n, d_b, part0); FS_LAUNCH_CHECK();
+    k_sub_mean<<<g, kBlock, 0, st>>>(n, d_b, bproj, part0, g); FS_LAUNCH_CHECK();
+    b = bproj;
+  }
+  auto precond = [&](const double* rin, double* zout) {
+    amg_apply(a->amg, rin, zout);
+    if (project_mean) {
+      k_sum<<<g, kBlock, 0, st>>>(n, zout, part0); FS_LAUNCH_CHECK();
+      k_sub_mean<<<g, kBlock, 0, st>>>(n, zout, zout, part0, g); FS_LAUNCH_CHECK();
+    }
+  };
+  double d2[2];
+  spmv_dev(A, x, Ap);
+  k_lin3<<<g, kBlock, 0, st>>>(n, 1.0, b, -1.0, Ap, 0.0, nullptr, r); FS_LAUNCH_CHECK();
+  dot2(n, b, b, r, r, part, d2);
+  const double bb = d2[0];
+  double rr = d2[1];
+  if (bb == 0.0) { FS_CUDA(cudaMemsetAsync(x, 0, n * sizeof(double), st)); if (relres) *relres = 0.0; return 0; }
+  const double tol2 = rtol * rtol;
+  int it = 0;
+  if (rr > tol2 * bb) {
+    precond(r, z);
+    FS_CUDA(cudaMemcpyAsync(p, z, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    dot2(n, r, z, nullptr, nullptr, part, d2);
+    double rz = d2[0];
+    while (it < maxit) {
+      spmv_dev(A, p, Ap);
+      dot2(n, p, Ap, nullptr, nullptr, part, d2);
+      const double alpha = d2[0] != 0.0 ? rz / d2[0] : 0.0;
+      k_lin3<<<g, kBlock, 0, st>>>(n, 1.0, x, alpha, p, 0.0, nullptr, x); FS_LAUNCH_CHECK();
+      k_lin3<<<g, kBlock, 0, st>>>(n, 1.0, r, -alpha, Ap, 0.0, nullptr, r); FS_LAUNCH_CHECK();
+      ++it;
+      precond(r, z);
+      dot2(n, r, r, r, z, part, d2);
+      rr = d2[0];
+      if (rr <= tol2 * bb) break;
+      const double beta = rz != 0.0 ? d2[1] / rz : 0.0;
+      rz = d2[1];
+      k_lin3<<<g, kBlock, 0, st>>>(n, 1.0, z, beta, p, 0.0, nullptr, p); FS_LAUNCH_CHECK();
+    }
+  }
+  if (project_mean) {
+    k_sum<<<g, kBlock, 0, st>>>(n, x, part0); FS_LAUNCH_CHECK();
+    k_sub_mean<<<g, kBlock, 0, st>>>(n, x, x, part0, g); FS_LAUNCH_CHECK();
+  }
+  if (relres) *relres = std::sqrt(rr / bb);
+  return (rr <= tol2 * bb) ? it : -it - 1;
+}
+
 int cg_dev(fs_csr* a, const double* d_b, double* d_x, int nrhs, double rtol, int maxit, int precond, int project_mean,
            double* relres) {
   FS_REQUIRE(nrhs == 1 || nrhs == 2, "nrhs must be 1 or 2");
+  if (precond == FS_PRECOND_AMG) {
+    FS_REQUIRE(nrhs == 1, "the AMG preconditioner handles one right-hand side");
+    return pcg_amg_impl(a, d_b, d_x, rtol, maxit, project_mean, relres);
+  }
   return nrhs == 1 ? cg_impl<1>(a, d_b, d_x, rtol, maxit, precond, project_mean, relres)
                    : cg_impl<2>(a, d_b, d_x, rtol, maxit, precond, project_mean, relres);
 }

@@ -181,7 +181,9 @@ int fs_stokes_step(fs_stokes* s, double* u, double B1, double B2, const fs_stoke
   std::memset(&sts, 0, sizeof(sts));
   // Step 1: tentative velocity, both components in one 2-RHS CG started from u
   FS_CUDA(cudaMemcpyAsync(s->ustar.p, du, 2 * N * sizeof(double), cudaMemcpyDeviceToDevice, st));
-  int it = cg_dev(&s->a_visc, du, s->ustar.p, 2, o.rtol_visc, o.maxit, o.precond, 0, &sts.relres_visc);
+  // A_visc = I + DT*nu*K has cond ~ 1: Jacobi is all it needs (the AMG option is for the pressure operator)
+  const int pre_visc = (o.precond == FS_PRECOND_AMG) ? FS_PRECOND_JACOBI : o.precond;
+  int it = cg_dev(&s->a_visc, du, s->ustar.p, 2, o.rtol_visc, o.maxit, pre_visc, 0, &sts.relres_visc);
   if (it < 0) throw Error(FS_ERR_NOCONV, "viscous CG did not converge within maxit");
   sts.iters_visc = it;
   per_bcu_dev(m, s->ustar.p);

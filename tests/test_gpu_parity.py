@@ -378,3 +378,52 @@ def test_argument_errors():
         m.divergence(np.zeros((5, 2)))
     with pytest.raises(fb.FluidsimError):
         m.make_dir_bcu(np.zeros((m.N, 2)), 1.0, 0.0)       # fs_bc_set not called
+
+
+# ---- smoothed-aggregation AMG preconditioner (FS_PRECOND_AMG) -------------------------------
+def test_amg_pcg_matches_oracle_and_is_mesh_independent():
+    its = []
+    for nt, nr in ((128, 48), (256, 96), (512, 192)):
+        nodes, markers, tris = fb.square_with_hole(nt, nr)
+        pairs = fb.filter_wall_pairs(nodes, fb.find_boundary_pairs(nodes))
+        ps = R.PressureSystem(nodes, tris, pairs)
+        b = np.random.default_rng(4).standard_normal(len(nodes))
+        rhs = np.bincount(ps.dof, weights=ps.M * b, minlength=ps.nd)
+        A = fb.CsrMatrix.from_arrays(ps.rowptr, ps.colidx, ps.vals)
+        x, it, rr = A.cg(rhs, rtol=1e-12, precond=fb.PRECOND_AMG, project_mean=True)
+        want = ps.solve(b)
+        assert rel(x[ps.dof], want) <= 1e-9
+        xj, itj, _ = A.cg(rhs, rtol=1e-12, precond=fb.PRECOND_JACOBI, project_mean=True)
+        assert it < itj / 4
+        its.append(it)
+    assert its[-1] <= its[0] + 25          # iteration count does not grow like 1/h
+    # SPD (non-singular) system and tiny systems (single level) work too
+    g = load_golden("mesh5_1_ops")
+    K = sp.csr_matrix((g["K"], g["colidx"], g["rowptr"]))
+    S = (K + sp.eye(K.shape[0]) * 1e-2).tocsr()
+    b = np.random.default_rng(5).standard_normal(K.shape[0])
+    import scipy.sparse.linalg as spla
+    x, it, _ = fb.CsrMatrix.from_scipy(S).cg(b, rtol=1e-12, precond=fb.PRECOND_AMG)
+    assert rel(x, spla.spsolve(S.tocsc(), b)) <= 1e-10
+
+
+def test_stokes_color_100_steps_with_amg():
+    g, t, sim = _run_traj(fb.StokesColor, "mesh5_1", "color_pusher", 100, precond=fb.PRECOND_AMG)
+    prog = []
+    for s in range(100):
+        _, pr = sim.step_all()
+        prog.append(pr)
+        if s in t["snap"]:
+            p, _ = sim.pressure()
+            assert rel(sim.u, t[f"res_u_{s}"]) <= 1e-9 and rel(p, t[f"res_p_{s}"]) <= 1e-9
+    assert np.abs(np.array(prog) - t["res_progress"]).max() <= 1e-6
+
+
+def test_stokes_synthetic_amg_vs_jacobi():
+    c, mk, t = fb.square_with_hole(512, 128)
+    a = fb.StokesSolver(c, mk, t, B2=-5.0, rtol_pressure=1e-12, precond=fb.PRECOND_AMG)
+    b = fb.StokesSolver(c, mk, t, B2=-5.0, rtol_pressure=1e-12, precond=fb.PRECOND_JACOBI)
+    for _ in range(3):
+        sa, sb = a.step(), b.step()
+    assert rel(a.u, b.u) <= 1e-9
+    assert sa.iters_p1 * 5 < sb.iters_p1
