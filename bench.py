@@ -65,7 +65,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -170,7 +170,9 @@ def workload_config(args, **extra):
     cfg = {"workload": f"stokes_step square-with-hole n_theta={args.n_theta} n_r={args.n_r} "
                        f"(T={2 * args.n_theta * args.n_r}, N={args.n_theta * (args.n_r + 1)}), pusher B1=-2 B2=-5, "
                        f"nu=0.1, DT=0.05",
-           "solver": f"CG Jacobi, rtol_pressure={RTOL_P:g}, rtol_visc={RTOL_V:g}, warm start from previous step",
+           "solver": f"pressure: CG + smoothed-aggregation AMG V(1,1) [--precond amg] or Jacobi persistent CG "
+                     f"[--precond jacobi], rtol_pressure={RTOL_P:g}; viscous: 2-RHS Jacobi CG rtol={RTOL_V:g}; "
+                     f"warm start from the previous step",
            "l2": "inputs larger than L2 (CSR matrix 185 MB + 4 vectors 67 MB > 126 MB), no flush needed",
            "steps_from": "t=0 (u=0 + squirmer BC); warm-up steps advance the same trajectory"}
     cfg.update(extra)
@@ -178,6 +180,27 @@ def workload_config(args, **extra):
 
 
 # ------------------------------------------------------------------------------ GPU arm
+def timed_steps(sim, u, steps, _lib, barrier):
+    """K steps on the library stream between two CUDA events; returns (seconds, [(iters...)])."""
+    iters = []
+    barrier()
+    _lib.call("fs_timer_start")
+    for _ in range(steps):
+        st = sim.step(u)
+        iters.append((st.iters_visc, st.iters_p1, st.iters_p2))
+    ms = C.c_float(0)
+    _lib.call("fs_timer_stop", C.byref(ms))
+    barrier()
+    return ms.value / 1e3, iters
+
+
+def read_profile(_lib):
+    pms = np.zeros(3)
+    ns, ni = C.c_int64(0), C.c_int64(0)
+    _lib.call("fs_profile_read", _lib.ptr(pms), C.byref(ns), C.byref(ni))
+    return pms, max(int(ns.value), 1)
+
+
 def run_ours(args):
     import torch
     import fluidsim_b200 as fb
@@ -199,48 +222,42 @@ def run_ours(args):
         torch.cuda.synchronize()
         _lib.call("fs_sync")
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     nodes, markers, tris = fb.square_with_hole(args.n_theta, args.n_r)
     B1, B2 = sweep_params(rank, world) if world > 1 else (PARAMS["B1"], PARAMS["B2"])
+    precond = {"amg": fb.PRECOND_AMG, "jacobi": fb.PRECOND_JACOBI}[args.precond]
     sim = fb.StokesSolver(nodes, markers, tris, B1=B1, B2=B2, DT=PARAMS["DT"], v=PARAMS["v"],
-                          rtol_pressure=RTOL_P, rtol_visc=RTOL_V)
+                          rtol_pressure=RTOL_P, rtol_visc=RTOL_V, precond=precond)
     N = sim.N
     _, kp, _ = sim.matrices()
     nd, nnz = kp.n, kp.nnz
     u_dev = torch.from_numpy(sim.u.copy()).cuda()
 
     # ---- device-resident arm: W warm-up steps, then exactly K timed steps
-    iters = []
     for _ in range(args.warmup):
-        st = sim.step(u_dev)
+        sim.step(u_dev)
     barrier()
-    # snapshot the loop state so that the end-to-end arm repeats exactly the same K steps
-    u_snap = u_dev.clone()
+    u_snap = u_dev.clone()                  # loop state, so that the end-to-end arm repeats the same K steps
     warm_snap = sim.get_warm_state()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     launches0 = fb.launch_count()
-    _lib.call("fs_profile", 16)
-    _lib.call("fs_timer_start")
-    for _ in range(args.steps):
-        st = sim.step(u_dev)
-        iters.append((st.iters_visc, st.iters_p1, st.iters_p2))
-    ms = C.c_float(0)
-    _lib.call("fs_timer_stop", C.byref(ms))
-    barrier()
+    _lib.call("fs_profile", 1)
+    t_dev, iters = timed_steps(sim, u_dev, args.steps, _lib, barrier)
     launches = fb.launch_count() - launches0
-    pms = np.zeros(3)
-    ns, ni = C.c_int64(0), C.c_int64(0)
-    _lib.call("fs_profile_read", _lib.ptr(pms), C.byref(ns), C.byref(ni))
+    pms, samples = read_profile(_lib)
     _lib.call("fs_profile", 0)
     clk = clocks.stop() if rank == 0 else None
-    t_ms = torch.tensor([ms.value], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    t_dev = float(t_ms.item()) / 1e3
+    t_dev = max_over_ranks(t_dev)
     value = world * args.steps / t_dev
 
-    # ---- end-to-end arm: same K steps through the host-buffer C-ABI call (pinned numpy view):
+    # ---- end-to-end arm: the same K steps through the host-buffer C-ABI call (pinned numpy view):
     # every step copies u host->device and device->host inside the timed region
     u_pin = torch.empty((N, 2), dtype=torch.float64).pin_memory()
     u_pin.copy_(u_snap.cpu())
@@ -251,10 +268,7 @@ def run_ours(args):
     for _ in range(args.steps):
         sim.step(u_host)
     barrier()
-    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e = world * args.steps / float(t_e2e.item())
+    e2e = world * args.steps / max_over_ranks(time.perf_counter() - t0)
 
     if rank != 0:
         if dist is not None:
@@ -263,53 +277,90 @@ def run_ours(args):
 
     peak, peak_src = measured_peak()
     spmv_bytes = 12.0 * nnz + 20.0 * nd
-    cg_bytes = 12.0 * nnz + 92.0 * nd + 16.0 * nd      # + Jacobi: dinv read in passes B and C
-    samples = max(int(ns.value), 1)
-    t_spmv = pms[0] / samples / 1e3
-    t_iter = pms.sum() / samples / 1e3
-    # the dominant kernel (99.7 % of the step, profiles/r01_launch_list_summary.txt) is the persistent
-    # CG kernel: one launch = one whole solve, so bytes and time are both per launch = iterations x
-    # per-iteration figures.  Phase times come from CTA 0's %globaltimer between the grid barriers.
-    n_launch = 2 * args.steps
-    it_per_launch = samples / n_launch
-    traffic_it = None
-    if os.path.exists(TRAFFIC_FILE):
-        traffic_it = json.load(open(TRAFFIC_FILE)).get("dram_bytes_per_iteration")
-    roof = {"bound": "hbm", "kernel": "k_cg_persistent (pressure PCG: SpMV+dot | x,r update+dots | p update, 3 grid barriers)",
-            "achieved": cg_bytes / t_iter / 1e9, "peak": peak, "unit": "GB/s", "frac": cg_bytes / t_iter / 1e9 / peak,
-            "traffic": None if traffic_it is None else traffic_it * it_per_launch,
-            "peak_source": peak_src, "launches_timed": n_launch, "iterations_per_launch": it_per_launch,
-            "algorithmic_bytes_per_launch": cg_bytes * it_per_launch, "us_per_launch": 1e6 * t_iter * it_per_launch,
-            "algorithmic_bytes_per_iteration": cg_bytes, "us_per_iteration": 1e6 * t_iter,
-            "dram_bytes_per_iteration_ncu": traffic_it, "us_pass_A_B_C": [1e6 * x / samples / 1e3 for x in pms],
-            "frac_of_8TBps_spec": cg_bytes / t_iter / 8e12,
-            "note": "frac can exceed 1: the five CG vectors (84 MB) are kept L2-resident with evict_last hints, so "
-                    "DRAM traffic (ncu, caches left alone) is below the algorithmic bytes"}
-    roof_cg = {"kernel": "k_cg_persistent pass A only: SpMV Ap=A*p fused with p.Ap (the metric's 'pressure-CG SpMV')",
-               "achieved": spmv_bytes / t_spmv / 1e9, "frac": spmv_bytes / t_spmv / 1e9 / peak, "unit": "GB/s",
-               "peak": peak, "algorithmic_bytes_per_pass": spmv_bytes, "us_per_pass": 1e6 * t_spmv,
-               "frac_of_8TBps_spec": spmv_bytes / t_spmv / 8e12}
+    cg_bytes = 12.0 * nnz + 92.0 * nd + 16.0 * nd      # Jacobi PCG iteration: + dinv read in passes B and C
     it_arr = np.array(iters, dtype=np.float64)
-    iters_per_step = float((it_arr[:, 1] + it_arr[:, 2]).mean())
-    os.makedirs(os.path.dirname(ITERS_FILE), exist_ok=True)
+    out_extra = {}
+    if args.precond == "amg":
+        # dominant kernel of this configuration: the fine-level SpMV (CG's A*p and the two smoother
+        # products of the V-cycle are the same kernel on the same matrix); timed with CUDA events
+        # around the CG's A*p launch in every iteration of the timed region
+        t_spmv = pms[0] / samples / 1e3
+        roof = {"bound": "hbm", "kernel": "k_spmv_tile<false> (fine-level CSR SpMV of the AMG-preconditioned pressure CG)",
+                "achieved": spmv_bytes / t_spmv / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": spmv_bytes / t_spmv / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": spmv_bytes, "us_per_launch": 1e6 * t_spmv, "sampled_launches": samples,
+                "frac_of_8TBps_spec": spmv_bytes / t_spmv / 8e12,
+                "us_per_pcg_iteration": {"A*p": 1e6 * t_spmv, "V-cycle": 1e3 * pms[1] / samples,
+                                         "vector ops + dots": 1e3 * pms[2] / samples}}
+        # the Jacobi-preconditioned persistent CG kernel on the same operator: the path's HBM-roofline
+        # kernel and the same algorithm as the CPU baseline (2000 fixed iterations, not part of `value`)
+        b = torch.randn(nd, dtype=torch.float64, device="cuda")
+        x = torch.zeros_like(b)
+        it_c, rr_c = C.c_int(0), C.c_double(0)
+        _lib.call("fs_profile", 1)
+        _lib.lib.fs_cg(kp._h, _lib.ptr(b), _lib.ptr(x), 1, 1e-300, 2000, fb.PRECOND_JACOBI, 1, C.byref(it_c), C.byref(rr_c))
+        pj, sj = read_profile(_lib)
+        _lib.call("fs_profile", 0)
+        t_it = pj.sum() / sj / 1e3
+        traffic_it = json.load(open(TRAFFIC_FILE)).get("dram_bytes_per_iteration") if os.path.exists(TRAFFIC_FILE) else None
+        out_extra["roofline_persistent_cg"] = {
+            "kernel": "k_cg_persistent (Jacobi PCG, one launch per solve: SpMV+dot | x,r update+dots | p update)",
+            "bound": "hbm", "achieved": cg_bytes / t_it / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": cg_bytes / t_it / 1e9 / peak, "traffic": None if traffic_it is None else traffic_it * sj,
+            "iterations_per_launch": sj, "algorithmic_bytes_per_iteration": cg_bytes, "us_per_iteration": 1e6 * t_it,
+            "dram_bytes_per_iteration_ncu": traffic_it, "us_pass_A_B_C": [1e3 * v / sj for v in pj],
+            "spmv_pass_GBs": spmv_bytes / (pj[0] / sj / 1e3) / 1e9,
+            "spmv_pass_frac": spmv_bytes / (pj[0] / sj / 1e3) / 1e9 / peak,
+            "note": "frac can exceed 1: the five CG vectors are kept L2-resident (evict_last), DRAM traffic is below the algorithmic bytes"}
+        # same-algorithm value: the Stokes step with the Jacobi persistent CG (what the CPU baseline runs)
+        simj = fb.StokesSolver(nodes, markers, tris, B1=B1, B2=B2, DT=PARAMS["DT"], v=PARAMS["v"],
+                               rtol_pressure=RTOL_P, rtol_visc=RTOL_V, precond=fb.PRECOND_JACOBI)
+        uj = torch.from_numpy(simj.u.copy()).cuda()
+        for _ in range(args.warmup):          # same point of the trajectory as the timed AMG steps
+            simj.step(uj)
+        tj, itj = timed_steps(simj, uj, 2, _lib, barrier)
+        out_extra["value_jacobi_pcg"] = {"value": 2 / tj, "unit": "steps/s", "cg_iters_per_step": itj,
+                                         "note": "same algorithm as cpu_baseline / the reference arm"}
+        jac_iters = float(np.mean([i[1] + i[2] for i in itj]))
+        visc_iters = float(np.mean([i[0] for i in itj]))
+        del simj, uj
+    else:
+        t_spmv = pms[0] / samples / 1e3
+        t_it = pms.sum() / samples / 1e3
+        n_launch = 2 * args.steps
+        traffic_it = json.load(open(TRAFFIC_FILE)).get("dram_bytes_per_iteration") if os.path.exists(TRAFFIC_FILE) else None
+        roof = {"bound": "hbm", "kernel": "k_cg_persistent (pressure PCG: SpMV+dot | x,r update+dots | p update, 3 grid barriers)",
+                "achieved": cg_bytes / t_it / 1e9, "peak": peak, "unit": "GB/s", "frac": cg_bytes / t_it / 1e9 / peak,
+                "traffic": None if traffic_it is None else traffic_it * samples / n_launch, "peak_source": peak_src,
+                "launches_timed": n_launch, "iterations_per_launch": samples / n_launch,
+                "algorithmic_bytes_per_launch": cg_bytes * samples / n_launch, "us_per_launch": 1e6 * t_it * samples / n_launch,
+                "algorithmic_bytes_per_iteration": cg_bytes, "us_per_iteration": 1e6 * t_it,
+                "dram_bytes_per_iteration_ncu": traffic_it, "us_pass_A_B_C": [1e3 * v / samples for v in pms],
+                "spmv_pass_GBs": spmv_bytes / t_spmv / 1e9, "spmv_pass_frac": spmv_bytes / t_spmv / 1e9 / peak,
+                "frac_of_8TBps_spec": cg_bytes / t_it / 8e12,
+                "note": "frac can exceed 1: the five CG vectors are kept L2-resident (evict_last), DRAM traffic is below the algorithmic bytes"}
+        jac_iters = float((it_arr[:, 1] + it_arr[:, 2]).mean())
+        visc_iters = float(it_arr[:, 0].mean())
     try:
-        json.dump({"iters_per_step": iters_per_step, "iters": iters, "warmup": args.warmup, "steps": args.steps,
-                   "n_theta": args.n_theta, "n_r": args.n_r, "rtol_pressure": RTOL_P},
-                  open(os.path.join(ROOT, "gpurun_out", "bench_iters.json"), "w"))
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        json.dump({"iters_per_step": jac_iters, "algorithm": "Jacobi PCG", "n_theta": args.n_theta, "n_r": args.n_r,
+                   "rtol_pressure": RTOL_P}, open(os.path.join(ROOT, "gpurun_out", "bench_iters.json"), "w"))
     except OSError:
         pass
     cpu = None
     if world == 1 and not args.no_cpu:
         rp, ci, vv = kp.arrays()
-        cpu = cpu_baseline_sample(rp, ci, vv, nodes, tris, iters_per_step + 2 * float(it_arr[:, 0].mean()))
+        cpu = cpu_baseline_sample(rp, ci, vv, nodes, tris, jac_iters + 2 * visc_iters)
     out = {"metric": "stokes_steps_per_sec_4M_tri", "value": value, "unit": "steps/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": workload_config(args, cg_iters_per_step=iters, parallelism=("single GPU" if world == 1 else
-                                     f"{world} independent squirmer (B1,B2) configs, one per GPU, no collective")),
-           "roofline": roof, "roofline_spmv_pass": roof_cg, "cpu_baseline": cpu,
+           "config": workload_config(args, precond=args.precond, cg_iters_per_step=iters,
+                                     parallelism=("single GPU" if world == 1 else
+                                                  f"{world} independent squirmer (B1,B2) configs, one per GPU, no collective")),
+           "roofline": roof, "cpu_baseline": cpu,
            "e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": 16 * N, "d2h_bytes_per_step": 16 * N},
            "gpu_launches": int(launches), "clocks": clk}
+    out.update(out_extra)
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
@@ -318,12 +369,14 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-theta", dest="n_theta", type=int, default=N_THETA)
     ap.add_argument("--n-r", dest="n_r", type=int, default=N_R)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--precond", default="amg", choices=["amg", "jacobi"],
+                    help="pressure-CG preconditioner of the timed steps (default: amg, the fastest)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -32,6 +32,14 @@ struct Amg {
   double omega = 2.0 / 3.0;     // damped-Jacobi smoother
   double omega_p = 2.0 / 3.0;   // prolongator smoothing
   int coarse_sweeps = 40;
+  DBuf<double> coarse_inv;      // dense (pseudo-)inverse of the coarsest operator (n <= 512), row-major
+  int coarse_n = 0;
+  // the V-cycle as a CUDA graph (captured on its second application; one launch per cycle)
+  cudaGraphExec_t graph = nullptr;
+  const double* graph_r = nullptr;
+  double* graph_z = nullptr;
+  int applications = 0;
+  ~Amg() { if (graph) cudaGraphExecDestroy(graph); }
 };
 
 void amg_free(Amg* a) { delete a; }
@@ -290,6 +298,57 @@ static void spgemm(const CsrView& A, const CsrView& B, int n_cols, fs_csr& out) 
   coo_to_csr(keys, v, m, A.n, n_cols, out);
 }
 
+// dense copy of the coarsest operator; a Neumann (singular) operator gets the rank-one term
+// sigma/n * 1 1^T so that its inverse is the pseudo-inverse on mean-free vectors
+__global__ void k_dense_from_csr(CsrView A, double shift, double* __restrict__ M) {
+  const int n = A.n;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += gridDim.x * blockDim.x) M[e] = shift;
+}
+__global__ void k_dense_add_csr(CsrView A, double* __restrict__ M) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n) return;
+  for (int k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) M[(size_t)i * A.n + A.colidx[k]] += A.vals[k];
+}
+__global__ void k_rowsum_max(CsrView A, double* __restrict__ out2) {   // out2 = {max |rowsum|, max diag}
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n) return;
+  double s = 0.0, d = 0.0;
+  for (int k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) { s += A.vals[k]; if (A.colidx[k] == i) d = A.vals[k]; }
+  atomicMax(reinterpret_cast<unsigned long long*>(out2), (unsigned long long)__double_as_longlong(fabs(s)));
+  atomicMax(reinterpret_cast<unsigned long long*>(out2 + 1), (unsigned long long)__double_as_longlong(fabs(d)));
+}
+// in-place Gauss-Jordan inversion of an SPD n x n matrix (no pivoting needed), one CTA
+__global__ void __launch_bounds__(1024) k_dense_invert(int n, double* __restrict__ M) {
+  __shared__ double colk[512];
+  __shared__ double piv;
+  for (int k = 0; k < n; ++k) {
+    if (threadIdx.x == 0) piv = 1.0 / M[(size_t)k * n + k];
+    __syncthreads();
+    const double ip = piv;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) colk[i] = M[(size_t)i * n + k];
+    __syncthreads();
+    // row k: scale; pivot entry becomes 1/pivot
+    for (int j = threadIdx.x; j < n; j += blockDim.x) M[(size_t)k * n + j] = (j == k) ? ip : M[(size_t)k * n + j] * ip;
+    __syncthreads();
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+      const int i = e / n, j = e - i * n;
+      if (i == k) continue;
+      const double f = colk[i];
+      M[e] = (j == k) ? -f * ip : M[e] - f * M[(size_t)k * n + j];
+    }
+    __syncthreads();
+  }
+}
+// x = Minv * b, one warp per row
+__global__ void k_dense_gemv(int n, const double* __restrict__ Minv, const double* __restrict__ b, double* __restrict__ x) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= n) return;
+  double s = 0.0;
+  for (int j = lane; j < n; j += 32) s += Minv[(size_t)row * n + j] * b[j];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) x[row] = s;
+}
+
 static double env_num(const char* name, double dflt) {
   const char* e = std::getenv(name);
   return e ? std::atof(e) : dflt;
@@ -362,6 +421,27 @@ Amg* amg_setup(fs_csr* fine) {
     lv.r.alloc(lv.n);
     if (l > 0) { lv.x.alloc(lv.n); lv.b.alloc(lv.n); }
   }
+  {
+    AmgLevel& last = *amg->L.back();
+    if (amg->L.size() > 1 && last.n <= 512 && env_num("FS_AMG_DENSE_COARSE", 1) != 0) {
+      const CsrView Ac = last.mat().view();
+      const int n = last.n;
+      DBuf<double> stat(2);
+      stat.zero();
+      k_rowsum_max<<<div_up(n, 256), 256, 0, stream()>>>(Ac, stat.p);
+      FS_LAUNCH_CHECK();
+      std::vector<double> hs = stat.to_host();
+      const bool singular = hs[0] <= 1e-9 * hs[1];
+      amg->coarse_inv.alloc((size_t)n * n);
+      k_dense_from_csr<<<div_up(n * n, 256), 256, 0, stream()>>>(Ac, singular ? hs[1] / n : 0.0, amg->coarse_inv.p);
+      FS_LAUNCH_CHECK();
+      k_dense_add_csr<<<div_up(n, 256), 256, 0, stream()>>>(Ac, amg->coarse_inv.p);
+      FS_LAUNCH_CHECK();
+      k_dense_invert<<<1, 1024, 0, stream()>>>(n, amg->coarse_inv.p);
+      FS_LAUNCH_CHECK();
+      amg->coarse_n = n;
+    }
+  }
   FS_CUDA(cudaStreamSynchronize(stream()));
   if (std::getenv("FS_AMG_VERBOSE")) {
     std::fprintf(stderr, "[amg] levels:");
@@ -418,7 +498,10 @@ static void vcycle_level(Amg& amg, size_t l, const double* b, double* x) {
   const int n = lv.n, g = vgrid(n);
   const double w = amg.omega;
   if (l + 1 == amg.L.size()) {
-    if (n <= 1024) {
+    if (amg.coarse_n == n && l > 0) {
+      k_dense_gemv<<<div_up(n * 32, 256), 256, 0, st>>>(n, amg.coarse_inv.p, b, x);
+      FS_LAUNCH_CHECK();
+    } else if (n <= 1024) {
       k_coarse_jacobi<<<1, 1024, 0, st>>>(Av, A.dinv.p, b, x, w, amg.coarse_sweeps);
       FS_LAUNCH_CHECK();
     } else {
@@ -448,7 +531,38 @@ static void vcycle_level(Amg& amg, size_t l, const double* b, double* x) {
   FS_LAUNCH_CHECK();
 }
 
-void amg_apply(Amg* amg, const double* r, double* z) { vcycle_level(*amg, 0, r, z); }
+void amg_apply(Amg* amg, const double* r, double* z) {
+  static const bool use_graph = env_num("FS_AMG_GRAPH", 1) != 0;
+  cudaStream_t st = stream();
+  ++amg->applications;
+  if (use_graph && amg->graph && amg->graph_r == r && amg->graph_z == z) {
+    FS_CUDA(cudaGraphLaunch(amg->graph, st));
+    count_launch();
+    return;
+  }
+  if (use_graph && amg->applications >= 2) {
+    // second application with these buffers: capture the cycle (all kernels go to `st`)
+    if (amg->graph) { cudaGraphExecDestroy(amg->graph); amg->graph = nullptr; }
+    cudaGraph_t g = nullptr;
+    FS_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    bool ok = true;
+    try { vcycle_level(*amg, 0, r, z); } catch (...) { ok = false; }
+    cudaError_t e = cudaStreamEndCapture(st, &g);
+    if (ok && e == cudaSuccess && g) {
+      cudaGraphExec_t ex = nullptr;
+      if (cudaGraphInstantiate(&ex, g, 0) == cudaSuccess) {
+        amg->graph = ex; amg->graph_r = r; amg->graph_z = z;
+        cudaGraphDestroy(g);
+        FS_CUDA(cudaGraphLaunch(amg->graph, st));
+        count_launch();
+        return;
+      }
+    }
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+  }
+  vcycle_level(*amg, 0, r, z);
+}
 
 int amg_levels(const Amg* amg, int* sizes, int cap) {
   int k = 0;

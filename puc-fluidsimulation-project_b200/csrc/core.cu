@@ -20,9 +20,22 @@ static int g_sm_count = 0;
 void set_last_error(const std::string& s) { g_err = s; }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// keep freed stream-ordered staging buffers in the pool: without this every host-buffer call
+// re-maps tens of MB (default release threshold 0 returns the memory at each synchronise)
+static void keep_mempool() {
+  int dev = 0;
+  cudaMemPool_t pool = nullptr;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  cudaGetLastError();
+}
+
 cudaStream_t stream() {
   if (g_use_user_stream) return g_user_stream;
   if (!g_own_stream) {
+    keep_mempool();
     cudaError_t e = cudaStreamCreateWithFlags(&g_own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess)
       throw Error(FS_ERR_CUDA, std::string("no usable CUDA device (cudaStreamCreate: ") +
@@ -108,6 +121,9 @@ int fs_set_device(int device) {
   FS_API_BEGIN
   FS_CUDA(cudaSetDevice(device));
   g_sm_count = 0;
+  if (g_own_stream) { cudaStreamDestroy(g_own_stream); g_own_stream = nullptr; }   // streams belong to a device
+  if (g_ev0) { cudaEventDestroy(g_ev0); cudaEventDestroy(g_ev1); g_ev0 = g_ev1 = nullptr; }
+  keep_mempool();
   FS_API_END
 }
 

@@ -702,12 +702,14 @@ static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, in
     k_sub_mean<<<g, kBlock, 0, st>>>(n, d_b, bproj, part0, g); FS_LAUNCH_CHECK();
     b = bproj;
   }
+  // A constant component of z is harmless for a mean-free r (r.z, A p do not see it) and is
+  // removed from x at the end, so z is not projected every iteration.
+  const bool prof = g_prof.every > 0;
+  if (prof && g_prof.ev.size() < 8) { g_prof.ev.resize(8); for (auto& e : g_prof.ev) cudaEventCreate(&e); }
   auto precond = [&](const double* rin, double* zout) {
+    if (prof) cudaEventRecord(g_prof.ev[2], st);
     amg_apply(a->amg, rin, zout);
-    if (project_mean) {
-      k_sum<<<g, kBlock, 0, st>>>(n, zout, part0); FS_LAUNCH_CHECK();
-      k_sub_mean<<<g, kBlock, 0, st>>>(n, zout, zout, part0, g); FS_LAUNCH_CHECK();
-    }
+    if (prof) cudaEventRecord(g_prof.ev[3], st);
   };
   double d2[2];
   spmv_dev(A, x, Ap);
@@ -724,7 +726,9 @@ static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, in
     dot2(n, r, z, nullptr, nullptr, part, d2);
     double rz = d2[0];
     while (it < maxit) {
+      if (prof) cudaEventRecord(g_prof.ev[0], st);
       spmv_dev(A, p, Ap);
+      if (prof) cudaEventRecord(g_prof.ev[1], st);
       dot2(n, p, Ap, nullptr, nullptr, part, d2);
       const double alpha = d2[0] != 0.0 ? rz / d2[0] : 0.0;
       k_lin3<<<g, kBlock, 0, st>>>(n, 1.0, x, alpha, p, 0.0, nullptr, x); FS_LAUNCH_CHECK();
@@ -732,6 +736,16 @@ static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, in
       ++it;
       precond(r, z);
       dot2(n, r, r, r, z, part, d2);
+      if (prof) {   // dot2 synchronised the stream: the events of this iteration are complete
+        float t_spmv = 0.f, t_v = 0.f, t_it = 0.f;
+        cudaEventElapsedTime(&t_spmv, g_prof.ev[0], g_prof.ev[1]);
+        cudaEventElapsedTime(&t_v, g_prof.ev[2], g_prof.ev[3]);
+        cudaEventRecord(g_prof.ev[4], st);
+        cudaEventSynchronize(g_prof.ev[4]);
+        cudaEventElapsedTime(&t_it, g_prof.ev[0], g_prof.ev[4]);
+        g_prof.ms[0] += t_spmv; g_prof.ms[1] += t_v; g_prof.ms[2] += t_it - t_spmv - t_v;
+        g_prof.samples += 1; g_prof.iters += 1;
+      }
       rr = d2[0];
       if (rr <= tol2 * bb) break;
       const double beta = rz != 0.0 ? d2[1] / rz : 0.0;
