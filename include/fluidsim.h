@@ -40,7 +40,8 @@ typedef struct fs_stokes fs_stokes;   /* operator-split Stokes step state    */
 
 #define FS_PRECOND_NONE 0
 #define FS_PRECOND_JACOBI 1
-#define FS_PRECOND_AMG 2      /* one V(1,1) cycle of plain-aggregation AMG (single RHS) */
+#define FS_PRECOND_AMG 2      /* one V(1,1) cycle of smoothed-aggregation AMG (single RHS) */
+#define FS_PRECOND_AUTO 3     /* AMG for single-RHS systems with more than 20 000 rows, else Jacobi */
 
 int fs_version(void);
 const char* fs_last_error(void);
@@ -153,7 +154,7 @@ typedef struct fs_stokes_opts {
   double rtol_visc;      /* CG tolerance of the viscous solves    (default 1e-12) */
   double rtol_pressure;  /* CG tolerance of the pressure solves   (default 1e-10) */
   int maxit;             /* per solve                              (default 200000) */
-  int precond;           /* FS_PRECOND_* of the pressure solves    (default JACOBI; AMG = fastest) */
+  int precond;           /* FS_PRECOND_* of the pressure solves    (default AUTO) */
   int warm_start;        /* start pressure CG from the previous step's p / p2 (default 1) */
   int final_div;         /* also evaluate final_div (:575) and its max-norm (default 0) */
 } fs_stokes_opts;

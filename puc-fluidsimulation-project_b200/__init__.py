@@ -9,7 +9,7 @@ from .mesh import (readNode, readEle, readPoly, write_node, write_ele, find_boun
                    filter_wall_pairs, index_sets, square_with_hole)
 from .core import (Mesh, CsrMatrix, solve, buildStiffnessMatrix, buildFemSystem, buildLumpedMassMatrix,  # noqa: F401
                    calculate_divergence, calculate_gradiant, PointLocator, mixing_index, mesh_for,
-                   PRECOND_NONE, PRECOND_JACOBI, PRECOND_AMG)
+                   PRECOND_NONE, PRECOND_JACOBI, PRECOND_AMG, PRECOND_AUTO)
 from .stokes import StokesSolver, StokesColor, StokesFood, food_tracer_grid  # noqa: F401
 from .poisson import (PoissonProblem, HeatProblem, apply_periodic_bc, apply_dirichlet_rows,  # noqa: F401
                       add_identity_scaled)

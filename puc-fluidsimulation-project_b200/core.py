@@ -14,7 +14,7 @@ from . import _lib
 from . import mesh as _mesh
 from ._lib import call, ptr, as_f64, as_i32
 
-PRECOND_NONE, PRECOND_JACOBI, PRECOND_AMG = 0, 1, 2
+PRECOND_NONE, PRECOND_JACOBI, PRECOND_AMG, PRECOND_AUTO = 0, 1, 2, 3
 
 
 def _empty_like_buf(ref, n, dtype):

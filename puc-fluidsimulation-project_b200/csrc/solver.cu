@@ -764,6 +764,8 @@ static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, in
 int cg_dev(fs_csr* a, const double* d_b, double* d_x, int nrhs, double rtol, int maxit, int precond, int project_mean,
            double* relres) {
   FS_REQUIRE(nrhs == 1 || nrhs == 2, "nrhs must be 1 or 2");
+  if (precond == FS_PRECOND_AUTO)   // multigrid pays off once the Jacobi iteration count (~1/h) is large
+    precond = (nrhs == 1 && a->n > 20000) ? FS_PRECOND_AMG : FS_PRECOND_JACOBI;
   if (precond == FS_PRECOND_AMG) {
     FS_REQUIRE(nrhs == 1, "the AMG preconditioner handles one right-hand side");
     return pcg_amg_impl(a, d_b, d_x, rtol, maxit, project_mean, relres);

@@ -92,7 +92,7 @@ int fs_stokes_default_opts(fs_stokes_opts* o) {
   o->rtol_visc = 1e-12;
   o->rtol_pressure = 1e-10;
   o->maxit = 200000;
-  o->precond = FS_PRECOND_JACOBI;
+  o->precond = FS_PRECOND_AUTO;
   o->warm_start = 1;
   o->final_div = 0;
   FS_API_END
@@ -182,7 +182,7 @@ int fs_stokes_step(fs_stokes* s, double* u, double B1, double B2, const fs_stoke
   // Step 1: tentative velocity, both components in one 2-RHS CG started from u
   FS_CUDA(cudaMemcpyAsync(s->ustar.p, du, 2 * N * sizeof(double), cudaMemcpyDeviceToDevice, st));
   // A_visc = I + DT*nu*K has cond ~ 1: Jacobi is all it needs (the AMG option is for the pressure operator)
-  const int pre_visc = (o.precond == FS_PRECOND_AMG) ? FS_PRECOND_JACOBI : o.precond;
+  const int pre_visc = (o.precond == FS_PRECOND_AMG || o.precond == FS_PRECOND_AUTO) ? FS_PRECOND_JACOBI : o.precond;
   int it = cg_dev(&s->a_visc, du, s->ustar.p, 2, o.rtol_visc, o.maxit, pre_visc, 0, &sts.relres_visc);
   if (it < 0) throw Error(FS_ERR_NOCONV, "viscous CG did not converge within maxit");
   sts.iters_visc = it;

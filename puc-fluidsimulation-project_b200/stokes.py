@@ -20,7 +20,7 @@ from .core import CsrMatrix, Mesh
 
 class StokesSolver:
     def __init__(self, nodes_coords, nodes_boundary_markers, triangles, B1=-2.0, B2=0.0, DT=0.05, v=0.1,
-                 L=1.0, H=1.0, tol=1e-6, rtol_pressure=1e-10, rtol_visc=1e-12, precond=1, warm_start=True,
+                 L=1.0, H=1.0, tol=1e-6, rtol_pressure=1e-10, rtol_visc=1e-12, precond=3, warm_start=True,
                  maxit=200000, final_div=False):
         self.nodes_coords = np.ascontiguousarray(nodes_coords, dtype=np.float64)
         self.nodes_boundary_markers = np.ascontiguousarray(nodes_boundary_markers, dtype=np.int32)
