@@ -287,11 +287,16 @@ def run_ours(args):
         t_spmv = pms[0] / samples / 1e3
         roof = {"bound": "hbm", "kernel": "k_spmv_tile<false> (fine-level CSR SpMV of the AMG-preconditioned pressure CG)",
                 "achieved": spmv_bytes / t_spmv / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": spmv_bytes / t_spmv / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                "frac": spmv_bytes / t_spmv / 1e9 / peak,
+                "traffic": (json.load(open(TRAFFIC_FILE)).get("spmv_tile_dram_bytes_per_launch")
+                            if os.path.exists(TRAFFIC_FILE) else None), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": spmv_bytes, "us_per_launch": 1e6 * t_spmv, "sampled_launches": samples,
                 "frac_of_8TBps_spec": spmv_bytes / t_spmv / 8e12,
                 "us_per_pcg_iteration": {"A*p": 1e6 * t_spmv, "V-cycle": 1e3 * pms[1] / samples,
                                          "vector ops + dots": 1e3 * pms[2] / samples}}
+        jac_iters = float(json.load(open(ITERS_FILE))["iters_per_step"]) if os.path.exists(ITERS_FILE) else 16000.0
+        visc_iters = float(it_arr[:, 0].mean())
+    if args.precond == "amg" and not args.no_extra:
         # the Jacobi-preconditioned persistent CG kernel on the same operator: the path's HBM-roofline
         # kernel and the same algorithm as the CPU baseline (2000 fixed iterations, not part of `value`)
         b = torch.randn(nd, dtype=torch.float64, device="cuda")
@@ -324,7 +329,7 @@ def run_ours(args):
         jac_iters = float(np.mean([i[1] + i[2] for i in itj]))
         visc_iters = float(np.mean([i[0] for i in itj]))
         del simj, uj
-    else:
+    elif args.precond == "jacobi":
         t_spmv = pms[0] / samples / 1e3
         t_it = pms.sum() / samples / 1e3
         n_launch = 2 * args.steps
@@ -375,6 +380,8 @@ def main():
     ap.add_argument("--n-theta", dest="n_theta", type=int, default=N_THETA)
     ap.add_argument("--n-r", dest="n_r", type=int, default=N_R)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the Jacobi persistent-CG legs (roofline_persistent_cg, value_jacobi_pcg); profiling runs")
     ap.add_argument("--precond", default="amg", choices=["amg", "jacobi"],
                     help="pressure-CG preconditioner of the timed steps (default: amg, the fastest)")
     args = ap.parse_args()

@@ -6,22 +6,35 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 G, P = "gpurun_out", "profiles"
 os.makedirs(P, exist_ok=True)
 
-# 1) launch list -> per-kernel share of the step
+# 1) launch list -> per-kernel share of the step (setup kernels listed separately)
+SETUP = ("cub::", "k_spgemm", "k_pick", "k_match", "k_leftover", "k_is_leader", "k_agg_id", "k_compose", "k_coarse_keys",
+         "k_prolongator", "k_transpose", "k_split_keys", "k_rowptr", "k_make_keys", "k_fill_pattern", "k_head_flags",
+         "k_assemble", "k_element", "k_inc_", "k_check_tris", "k_tile_nnz", "k_diag_inv", "k_dense_", "k_rowsum", "k_flag",
+         "k_visc_vals", "k_inner_trig", "k_elem_thirds", "k_node_sum", "k_iota", "k_ptr_from")
 rows = [r for r in csv.reader(open(f"{G}/{tag}_launches.csv")) if len(r) > 5]
 hdr = rows[0]; ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
 agg = collections.OrderedDict()
 for r in rows[1:]:
     try: v = float(r[vi].replace(",", ""))
     except ValueError: continue
-    a = agg.setdefault(r[ki].split("(")[0], [0, 0.0]); a[0] += 1; a[1] += v
-tot = sum(a[1] for a in agg.values())
+    name = r[ki].split("(")[0]
+    a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += v
+is_setup = lambda k: any(t in k for t in SETUP)
+tot_step = sum(a[1] for k, a in agg.items() if not is_setup(k))
+tot_setup = sum(a[1] for k, a in agg.items() if is_setup(k))
 with open(f"{P}/{tag}_launch_list_summary.txt", "w") as f:
-    f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none -c 400 python bench.py --steps 1 --warmup 1 --no-cpu\n")
-    f.write(f"# per-launch times are cold-cache and serialised: compare SHARES, not absolutes\n")
-    f.write(f"# launches captured: {sum(a[0] for a in agg.values())}, total {tot/1e6:.1f} ms\n")
-    for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        f.write(f"{100*t/tot:7.3f}%  launches={n:4d}  total_us={t/1e3:12.1f}  {k}\n")
-os.system(f"cp {G}/{tag}_launches.csv {P}/{tag}_launches.csv")
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 python bench.py --steps 1 --warmup 1 --no-cpu --no-extra\n")
+    f.write("# (default configuration: AMG-preconditioned pressure CG; the V-cycle's graph nodes appear as kernels)\n")
+    f.write("# per-launch times are cold-cache and serialised: compare SHARES, not absolutes\n")
+    f.write(f"# launches captured: {sum(a[0] for a in agg.values())} (cap 6000 = one-time setup + ~1.5 steps); "
+            f"step kernels {tot_step/1e6:.1f} ms, one-time setup kernels {tot_setup/1e6:.1f} ms\n")
+    f.write("# ---- kernels of the time step (share of step-kernel time)\n")
+    for k, (n, t) in sorted(((k, a) for k, a in agg.items() if not is_setup(k)), key=lambda kv: -kv[1][1]):
+        f.write(f"{100*t/tot_step:7.3f}%  launches={n:5d}  total_us={t/1e3:12.1f}  {k}\n")
+    f.write("# ---- one-time setup (mesh topology, assembly, AMG hierarchy)\n")
+    for k, (n, t) in sorted(((k, a) for k, a in agg.items() if is_setup(k)), key=lambda kv: -kv[1][1]):
+        f.write(f"{100*t/tot_setup:7.3f}%  launches={n:5d}  total_us={t/1e3:12.1f}  {k[:110]}\n")
+os.system(f"gzip -c {G}/{tag}_launches.csv > {P}/{tag}_launches.csv.gz")
 
 # 2) full-set capture of the persistent CG kernel
 raw = subprocess.run(["ncu", "-i", f"{G}/{tag}_cg_persistent.ncu-rep", "--page", "raw", "--csv"],
@@ -43,6 +56,32 @@ with open(f"{P}/{tag}_cg_persistent_ncu_full.txt", "w") as f:
         if k in h: f.write(f"{k:75s} {r[h.index(k)]:>18s} {u[h.index(k)]}\n")
     f.write("# warp stall reasons (warps per issue-active cycle)\n")
     for v, k in stalls[:8]: f.write(f"{k:75s} {v:18.3f}\n")
+def full_summary(rep, outname, header):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(raw.splitlines())); h, u, r = rr[0], rr[1], rr[2]
+    stalls = sorted(((float(r[i].replace(",", "")), h[i]) for i in range(len(h))
+                     if "issue_stalled" in h[i] and h[i].endswith("per_issue_active.ratio")), reverse=True)
+    with open(outname, "w") as f:
+        f.write(header)
+        for k in keep + ["launch__grid_size"]:
+            if k in h: f.write(f"{k:75s} {r[h.index(k)]:>18s} {u[h.index(k)]}\n")
+        f.write("# warp stall reasons (warps per issue-active cycle)\n")
+        for v, k in stalls[:8]: f.write(f"{k:75s} {v:18.3f}\n")
+
+if os.path.exists(f"{G}/{tag}_spmv_tile.ncu-rep"):
+    full_summary(f"{G}/{tag}_spmv_tile.ncu-rep", f"{P}/{tag}_spmv_tile_ncu_full.txt",
+                 "# ncu --set full --clock-control none --import-source on -k regex:k_spmv_tile -s 40 -c 1 python scripts/prof_amg.py 4\n"
+                 "# (one stand-alone SpMV launch of the AMG-preconditioned CG, 4M-triangle pressure operator; cold cache)\n")
+    print(open(f"{P}/{tag}_spmv_tile_ncu_full.txt").read())
+    _raw = subprocess.run(["ncu", "-i", f"{G}/{tag}_spmv_tile.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    _rr = list(csv.reader(_raw.splitlines())); _h, _u, _r = _rr[0], _rr[1], _rr[2]
+    def _bytes(name):
+        v, unit = float(_r[_h.index(name)].replace(",", "")), _u[_h.index(name)]
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+    SPMV_TILE_DRAM = _bytes("dram__bytes_read.sum") + _bytes("dram__bytes_write.sum")
+else:
+    SPMV_TILE_DRAM = None
+
 iters = 200
 d = {}
 for row in csv.reader(open(f"{G}/{tag}_cg_dram_nocachectl.csv")):
@@ -55,6 +94,8 @@ json.dump({"kernel": "k_cg_persistent", "iterations_in_launch": iters,
            "dram_write_per_iteration": d["dram__bytes_write.sum"] / iters,
            "us_per_iteration_under_ncu": d["gpu__time_duration.sum"] / iters / 1e3,
            "lts_hit_rate_pct": d.get("lts__t_sector_hit_rate.pct"),
+           "spmv_tile_dram_bytes_per_launch": SPMV_TILE_DRAM,
+           "spmv_tile_how": "ncu --set full capture of one fine-level k_spmv_tile launch (cold cache)",
            "how": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --cache-control none (single pass, no replay, caches left alone)"},
           open(f"{P}/spmv_traffic.json", "w"), indent=1)
 os.system(f"cp {G}/{tag}_cg_dram_nocachectl.csv {P}/{tag}_cg_dram_nocachectl.csv")
