@@ -23,7 +23,7 @@ struct AmgLevel {
   const fs_csr* Aref = nullptr;
   int n = 0;
   fs_csr P, PT;             // smoothed prolongator (n x n_coarse) and its transpose (restriction)
-  DBuf<double> x, b, r;     // work vectors of this level (level 0 uses caller buffers for b/x)
+  DBuf<double> x, b, r, t;  // work vectors of this level (level 0 uses caller buffers for b/x)
   const fs_csr& mat() const { return Aref ? *Aref : A; }
 };
 
@@ -419,6 +419,7 @@ Amg* amg_setup(fs_csr* fine) {
   for (size_t l = 0; l < amg->L.size(); ++l) {
     AmgLevel& lv = *amg->L[l];
     lv.r.alloc(lv.n);
+    lv.t.alloc(lv.n);
     if (l > 0) { lv.x.alloc(lv.n); lv.b.alloc(lv.n); }
   }
   {
@@ -516,19 +517,30 @@ static void vcycle_level(Amg& amg, size_t l, const double* b, double* x) {
     return;
   }
   AmgLevel& nx = *amg.L[l + 1];
-  k_jac0<<<g, 256, 0, st>>>(n, w, A.dinv.p, b, x);                       // pre-smooth from x = 0
-  FS_LAUNCH_CHECK();
-  spmv_dev(Av, x, lv.r.p);
-  k_resid<<<g, 256, 0, st>>>(n, b, lv.r.p, lv.r.p);
-  FS_LAUNCH_CHECK();
-  spmv_dev(lv.PT.view(), lv.r.p, nx.b.p);                                // restrict
+  double* xt = lv.t.p;                                                   // iterate before the post-smoothing
+  // pre-smooth from a zero guess and residual in one pass: xt = w D^-1 b, r = b - A xt
+  if (!spmv_warp(Av, EPI_PRESM, nullptr, lv.r.p, b, A.dinv.p, w, xt, nullptr)) {
+    k_jac0<<<g, 256, 0, st>>>(n, w, A.dinv.p, b, xt);
+    FS_LAUNCH_CHECK();
+    spmv_dev(Av, xt, lv.r.p);
+    k_resid<<<g, 256, 0, st>>>(n, b, lv.r.p, lv.r.p);
+    FS_LAUNCH_CHECK();
+  }
+  if (!spmv_warp(lv.PT.view(), EPI_AX, lv.r.p, nx.b.p, nullptr, nullptr, 0.0, nullptr, nullptr))   // restrict
+    spmv_dev(lv.PT.view(), lv.r.p, nx.b.p);
   vcycle_level(amg, l + 1, nx.b.p, nx.x.p);
-  spmv_dev(lv.P.view(), nx.x.p, lv.r.p);                                 // prolong
-  k_add<<<g, 256, 0, st>>>(n, lv.r.p, x);
-  FS_LAUNCH_CHECK();
-  spmv_dev(Av, x, lv.r.p);                                              // post-smooth
-  k_jac_update<<<g, 256, 0, st>>>(n, w, A.dinv.p, b, lv.r.p, x);
-  FS_LAUNCH_CHECK();
+  if (!spmv_warp(lv.P.view(), EPI_ADD, nx.x.p, xt, nullptr, nullptr, 0.0, nullptr, nullptr)) {       // xt += P x_c
+    spmv_dev(lv.P.view(), nx.x.p, lv.r.p);
+    k_add<<<g, 256, 0, st>>>(n, lv.r.p, xt);
+    FS_LAUNCH_CHECK();
+  }
+  // post-smooth into the caller's buffer: x = xt + w D^-1 (b - A xt)
+  if (!spmv_warp(Av, EPI_JACOBI, xt, x, b, A.dinv.p, w, nullptr, nullptr)) {
+    spmv_dev(Av, xt, lv.r.p);
+    FS_CUDA(cudaMemcpyAsync(x, xt, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    k_jac_update<<<g, 256, 0, st>>>(n, w, A.dinv.p, b, lv.r.p, x);
+    FS_LAUNCH_CHECK();
+  }
 }
 
 void amg_apply(Amg* amg, const double* r, double* z) {

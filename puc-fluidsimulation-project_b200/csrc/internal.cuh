@@ -250,6 +250,10 @@ void grad_update_dev(fs_mesh* m, const double* d_p, const double* d_ui, double* 
                      const unsigned char* d_interior_flag /* null: all nodes */);
 void jacobi_prepare(fs_csr* a);
 void ensure_tiles(fs_csr* a);
+// warp-granular SpMV with fused epilogues (spmv_warp.cu); returns the grid used or 0 if unsupported
+enum { EPI_AX = 0, EPI_RESID = 1, EPI_JACOBI = 2, EPI_PRESM = 3, EPI_ADD = 4 };
+int spmv_warp(const CsrView& A, int epi, const double* x, double* y, const double* b, const double* dinv, double w,
+              double* xout, double* dot_partials);
 Amg* amg_setup(fs_csr* fine);
 void amg_apply(Amg* amg, const double* r, double* z);
 int amg_levels(const Amg* amg, int* sizes, int cap);

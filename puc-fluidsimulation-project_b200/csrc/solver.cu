@@ -685,6 +685,36 @@ __global__ void k_lin3(int64_t n, double a, const double* __restrict__ x, double
 // the 4M-triangle pressure operator, so the two host reads of scalars per iteration are noise.
 static void dot2(int64_t n, const double* a, const double* b, const double* c, const double* d, double* part, double* out2);
 
+// x += alpha p ; r -= alpha Ap with alpha = rz / (p.Ap) formed on the device from the SpMV's
+// per-CTA partials (rz is known to the host from the previous iteration); partial r.r out.
+__global__ void __launch_bounds__(kBlock)
+k_pcg_xr(int64_t n, const double* __restrict__ p, const double* __restrict__ Ap, double* __restrict__ x, double* __restrict__ r,
+         const double* __restrict__ partA, int nblkA, double rz, double* __restrict__ partB) {
+  __shared__ double red[32];
+  __shared__ double sm[1];
+  double pAp[1];
+  reduce_partials<1>(partA, nblkA, pAp, sm);
+  const double alpha = (pAp[0] != 0.0) ? rz / pAp[0] : 0.0;
+  double acc[1] = {0.0};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double rn = r[i] - alpha * Ap[i];
+    x[i] += alpha * p[i];
+    r[i] = rn;
+    acc[0] += rn * rn;
+  }
+  block_reduce<1>(acc, red);
+  if (threadIdx.x == 0) partB[blockIdx.x] = acc[0];
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_pcg_rz(int64_t n, const double* __restrict__ r, const double* __restrict__ z, double* __restrict__ partC) {
+  __shared__ double red[32];
+  double acc[1] = {0.0};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc[0] += r[i] * z[i];
+  block_reduce<1>(acc, red);
+  if (threadIdx.x == 0) partC[blockIdx.x] = acc[0];
+}
+
 static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, int maxit, int project_mean, double* relres) {
   const int64_t n = a->n;
   ensure_ws(a, 5 * (size_t)n);
@@ -696,6 +726,8 @@ static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, in
   const int g = vec_grid(n);
   double* part = a->partials.p;
   double* part0 = a->partials.p + kMaxBlocks * 8;
+  double* partA = a->partials.p + kMaxBlocks * 10;     // p.Ap partials of the SpMV
+  double* partBC = a->partials.p + kMaxBlocks * 12;    // [0,g): r.r   [g,2g): r.z
   const double* b = d_b;
   if (project_mean) {
     k_sum<<<g, kBlock, 0, st>>>(n, d_b, part0); FS_LAUNCH_CHECK();
@@ -712,8 +744,10 @@ static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, in
     if (prof) cudaEventRecord(g_prof.ev[3], st);
   };
   double d2[2];
-  spmv_dev(A, x, Ap);
-  k_lin3<<<g, kBlock, 0, st>>>(n, 1.0, b, -1.0, Ap, 0.0, nullptr, r); FS_LAUNCH_CHECK();
+  if (!spmv_warp(A, EPI_RESID, x, r, b, nullptr, 0.0, nullptr, nullptr)) {
+    spmv_dev(A, x, Ap);
+    k_lin3<<<g, kBlock, 0, st>>>(n, 1.0, b, -1.0, Ap, 0.0, nullptr, r); FS_LAUNCH_CHECK();
+  }
   dot2(n, b, b, r, r, part, d2);
   const double bb = d2[0];
   double rr = d2[1];
@@ -725,31 +759,34 @@ static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, in
     FS_CUDA(cudaMemcpyAsync(p, z, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     dot2(n, r, z, nullptr, nullptr, part, d2);
     double rz = d2[0];
+    std::vector<double> hp(2 * (size_t)g);
     while (it < maxit) {
+      // one host read per iteration: alpha is formed on the device, beta on the host
       if (prof) cudaEventRecord(g_prof.ev[0], st);
-      spmv_dev(A, p, Ap);
+      int ga = spmv_warp(A, EPI_AX, p, Ap, nullptr, nullptr, 0.0, nullptr, partA);
+      if (!ga) { ga = spmv_launch_grid<1>(A); launch_spmv<1, true>(A, p, Ap, partA, nullptr, ga); }
       if (prof) cudaEventRecord(g_prof.ev[1], st);
-      dot2(n, p, Ap, nullptr, nullptr, part, d2);
-      const double alpha = d2[0] != 0.0 ? rz / d2[0] : 0.0;
-      k_lin3<<<g, kBlock, 0, st>>>(n, 1.0, x, alpha, p, 0.0, nullptr, x); FS_LAUNCH_CHECK();
-      k_lin3<<<g, kBlock, 0, st>>>(n, 1.0, r, -alpha, Ap, 0.0, nullptr, r); FS_LAUNCH_CHECK();
+      k_pcg_xr<<<g, kBlock, 0, st>>>(n, p, Ap, x, r, partA, ga, rz, partBC); FS_LAUNCH_CHECK();
       ++it;
       precond(r, z);
-      dot2(n, r, r, r, z, part, d2);
-      if (prof) {   // dot2 synchronised the stream: the events of this iteration are complete
+      k_pcg_rz<<<g, kBlock, 0, st>>>(n, r, z, partBC + g); FS_LAUNCH_CHECK();
+      FS_CUDA(cudaMemcpyAsync(hp.data(), partBC, sizeof(double) * 2 * g, cudaMemcpyDeviceToHost, st));
+      if (prof) cudaEventRecord(g_prof.ev[4], st);
+      FS_CUDA(cudaStreamSynchronize(st));
+      double s_rr = 0.0, s_rz = 0.0;
+      for (int k = 0; k < g; ++k) { s_rr += hp[k]; s_rz += hp[g + k]; }
+      if (prof) {
         float t_spmv = 0.f, t_v = 0.f, t_it = 0.f;
         cudaEventElapsedTime(&t_spmv, g_prof.ev[0], g_prof.ev[1]);
         cudaEventElapsedTime(&t_v, g_prof.ev[2], g_prof.ev[3]);
-        cudaEventRecord(g_prof.ev[4], st);
-        cudaEventSynchronize(g_prof.ev[4]);
         cudaEventElapsedTime(&t_it, g_prof.ev[0], g_prof.ev[4]);
         g_prof.ms[0] += t_spmv; g_prof.ms[1] += t_v; g_prof.ms[2] += t_it - t_spmv - t_v;
         g_prof.samples += 1; g_prof.iters += 1;
       }
-      rr = d2[0];
+      rr = s_rr;
       if (rr <= tol2 * bb) break;
-      const double beta = rz != 0.0 ? d2[1] / rz : 0.0;
-      rz = d2[1];
+      const double beta = rz != 0.0 ? s_rz / rz : 0.0;
+      rz = s_rz;
       k_lin3<<<g, kBlock, 0, st>>>(n, 1.0, z, beta, p, 0.0, nullptr, p); FS_LAUNCH_CHECK();
     }
   }

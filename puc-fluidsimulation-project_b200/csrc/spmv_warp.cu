@@ -1,0 +1,178 @@
+// spmv_warp.cu -- the warp-granular CSR-stream SpMV of the persistent CG kernel (pass A of
+// cg_persistent.cu) as a stand-alone kernel with fused epilogues, used by the AMG V-cycle
+// and the AMG-preconditioned CG:
+//   EPI_AX      y  = A x
+//   EPI_RESID   y  = b - A x
+//   EPI_JACOBI  y  = x + w D^-1 (b - A x)                      (y must not alias x)
+//   EPI_PRESM   x0 = w D^-1 b (stored to xout),  y = b - A x0   (pre-smoothing from a zero guess
+//               and the residual in one pass: the gather reads dinv[col]*b[col])
+//   EPI_ADD     y += A x
+// plus an optional fused dot product x.(A x) (per-CTA partials) for the CG.
+// A warp owns 32-row mini-tiles; values/columns of the next mini-tile are in flight in registers
+// while the current one is multiplied and reduced through the warp's shared-memory slice.
+#include "internal.cuh"
+
+namespace fs {
+
+constexpr int kWT = 512;        // threads per CTA
+constexpr int kWW = kWT / 32;   // warps per CTA
+constexpr int kWU = 8;          // prefetched nonzeros per lane (window of 256 per mini-tile)
+
+__device__ __forceinline__ uint64_t w_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ double w_ld_stream_f64(const double* a, uint64_t pol) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(a), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ int w_ld_stream_s32(const int* a, uint64_t pol) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
+  return v;
+}
+
+struct SpmvWarpArgs {
+  CsrView A;
+  const double* x;
+  double* y;
+  const double* b;
+  const double* dinv;
+  double w;
+  double* xout;
+  double* part;   // per-CTA partial of x.(A x) when DOT
+  int wcap;
+  int ntiles;     // 512-row tiles
+};
+
+template <int EPI, bool DOT>
+__global__ void __launch_bounds__(kWT, 2) k_spmv_warp(SpmvWarpArgs a) {
+  extern __shared__ double prod[];
+  __shared__ double red[kWW];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nb = gridDim.x, bi = blockIdx.x;
+  const uint64_t pf = w_evict_first();
+  const int tile0 = (int)(((long long)a.ntiles * bi) / nb);
+  const int tile1 = (int)(((long long)a.ntiles * (bi + 1)) / nb);
+  const int R0 = tile0 * kWT, R1 = min(a.A.n, tile1 * kWT);
+  const int* __restrict__ rowptr = a.A.rowptr;
+  const double* __restrict__ vals = a.A.vals;
+  const int* __restrict__ colidx = a.A.colidx;
+  const unsigned full = 0xffffffffu;
+  double* pw = prod + (size_t)warp * a.wcap;
+  const int nmt = (R1 - R0 + 31) >> 5;
+  double acc = 0.0;
+  double va[kWU];
+  int ca[kWU];
+  auto xval = [&](int j) -> double {
+    if (EPI == EPI_PRESM) return a.w * __ldg(a.dinv + j) * __ldg(a.b + j);
+    return __ldg(a.x + j);
+  };
+  auto load_rp = [&](int mt, int& rp, int& rend) {
+    if (mt < nmt) {
+      const int r0 = R0 + (mt << 5);
+      const int nr = min(32, R1 - r0);
+      rp = __ldg(rowptr + r0 + min(lane, nr));
+      rend = __ldg(rowptr + r0 + nr);
+    } else { rp = 0; rend = 0; }
+  };
+  auto stream = [&](int base, int cnt) {
+#pragma unroll
+    for (int j = 0; j < kWU; ++j) {
+      const int k = (j << 5) + lane;
+      const bool ok = k < cnt;
+      va[j] = ok ? w_ld_stream_f64(vals + base + k, pf) : 0.0;
+      ca[j] = ok ? w_ld_stream_s32(colidx + base + k, pf) : -1;
+    }
+  };
+  int rpA, endA, rpB, endB;
+  load_rp(warp, rpA, endA);
+  load_rp(warp + kWW, rpB, endB);
+  int baseA = __shfl_sync(full, rpA, 0);
+  int cntA = endA - baseA;
+  stream(baseA, cntA);
+  for (int mt = warp; mt < nmt; mt += kWW) {
+#pragma unroll
+    for (int j = 0; j < kWU; ++j)
+      if (ca[j] >= 0) pw[(j << 5) + lane] = va[j] * xval(ca[j]);
+    for (int k = (kWU << 5) + lane; k < cntA; k += 32)
+      pw[k] = w_ld_stream_f64(vals + baseA + k, pf) * xval(w_ld_stream_s32(colidx + baseA + k, pf));
+    __syncwarp();
+    int rpC, endC;
+    load_rp(mt + 2 * kWW, rpC, endC);
+    const int baseB = __shfl_sync(full, rpB, 0);
+    const int cntB = endB - baseB;
+    stream(baseB, cntB);
+    int nxt = __shfl_down_sync(full, rpA, 1);
+    if (lane == 31) nxt = endA;
+    const int row = R0 + (mt << 5) + lane;
+    if (row < R1) {
+      double s = 0.0;
+      for (int k = rpA - baseA; k < nxt - baseA; ++k) s += pw[k];
+      if (DOT) acc += __ldg(a.x + row) * s;
+      if (EPI == EPI_AX) a.y[row] = s;
+      else if (EPI == EPI_RESID) a.y[row] = a.b[row] - s;
+      else if (EPI == EPI_JACOBI) a.y[row] = a.x[row] + a.w * a.dinv[row] * (a.b[row] - s);
+      else if (EPI == EPI_PRESM) { const double bv = a.b[row]; a.xout[row] = a.w * a.dinv[row] * bv; a.y[row] = bv - s; }
+      else if (EPI == EPI_ADD) a.y[row] += s;
+    }
+    __syncwarp();
+    rpA = rpB; endA = endB; baseA = baseB; cntA = cntB;
+    rpB = rpC; endB = endC;
+  }
+  if (DOT) {
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(full, acc, o);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (t == 0) {
+      double s = 0.0;
+      for (int k = 0; k < kWW; ++k) s += red[k];
+      a.part[bi] = s;
+    }
+  }
+}
+
+static bool g_warp_attr = false;
+
+template <int EPI, bool DOT>
+static void launch_one(const SpmvWarpArgs& args, int grid, size_t smem) {
+  k_spmv_warp<EPI, DOT><<<grid, kWT, smem, stream()>>>(args);
+}
+
+// Returns the grid size used (>0), or 0 when the matrix does not fit this kernel (the caller
+// falls back to the tile / vector kernels).
+int spmv_warp(const CsrView& A, int epi, const double* x, double* y, const double* b, const double* dinv, double w,
+              double* xout, double* dot_partials) {
+  if (A.wtile_nnz_max <= 0) return 0;
+  const int wcap = (A.wtile_nnz_max + 31) / 32 * 32;
+  const size_t smem = (size_t)kWW * wcap * sizeof(double);
+  if (smem > 100 * 1024) return 0;
+  if (!g_warp_attr) {
+    const int big = 100 * 1024;
+    FS_CUDA(cudaFuncSetAttribute(k_spmv_warp<EPI_AX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    FS_CUDA(cudaFuncSetAttribute(k_spmv_warp<EPI_AX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    FS_CUDA(cudaFuncSetAttribute(k_spmv_warp<EPI_RESID, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    FS_CUDA(cudaFuncSetAttribute(k_spmv_warp<EPI_JACOBI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    FS_CUDA(cudaFuncSetAttribute(k_spmv_warp<EPI_PRESM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    FS_CUDA(cudaFuncSetAttribute(k_spmv_warp<EPI_ADD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    g_warp_attr = true;
+  }
+  const int ntiles = div_up(A.n, kWT);
+  const int per_sm = smem > 48 * 1024 ? (smem > 100 * 1024 / 1 ? 1 : 2) : 2;
+  const int grid = std::max(1, std::min(sm_count() * per_sm, ntiles));
+  SpmvWarpArgs args{A, x, y, b, dinv, w, xout, dot_partials, wcap, ntiles};
+  const bool dot = dot_partials != nullptr;
+  switch (epi) {
+    case EPI_AX: if (dot) launch_one<EPI_AX, true>(args, grid, smem); else launch_one<EPI_AX, false>(args, grid, smem); break;
+    case EPI_RESID: launch_one<EPI_RESID, false>(args, grid, smem); break;
+    case EPI_JACOBI: launch_one<EPI_JACOBI, false>(args, grid, smem); break;
+    case EPI_PRESM: launch_one<EPI_PRESM, false>(args, grid, smem); break;
+    case EPI_ADD: launch_one<EPI_ADD, false>(args, grid, smem); break;
+    default: throw Error(FS_ERR_INTERNAL, "spmv_warp: bad epilogue");
+  }
+  FS_LAUNCH_CHECK();
+  return grid;
+}
+
+}  // namespace fs
