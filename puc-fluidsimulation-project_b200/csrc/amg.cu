@@ -361,6 +361,8 @@ Amg* amg_setup(fs_csr* fine) {
   amg->coarse_sweeps = (int)env_num("FS_AMG_COARSE_SWEEPS", amg->coarse_sweeps);
   const int min_rows = (int)env_num("FS_AMG_MIN_ROWS", 400);
   const size_t max_levels = (size_t)env_num("FS_AMG_MAX_LEVELS", 16);
+  const int passes0 = std::max(1, (int)env_num("FS_AMG_PASSES0", 2));       // pairwise passes on the finest level
+  const int passes_rest = std::max(1, (int)env_num("FS_AMG_PASSES", 2));    // ... and on the coarser ones
   ensure_tiles(fine);
   jacobi_prepare(fine);
   {
@@ -374,18 +376,29 @@ Amg* amg_setup(fs_csr* fine) {
     const fs_csr& A = cur.mat();
     const CsrView Av = A.view();
     cudaStream_t st = stream();
-    // aggregates of ~4: two pairwise passes along the strongest couplings
-    DBuf<int> agg1, agg2, agg(cur.n);
-    const int n1 = pairwise(Av, agg1);
-    int nc;
+    // aggregates from repeated pairwise passes along the strongest couplings (each pass roughly
+    // halves the row count; the plain Galerkin product of a pass is the next pass's graph)
+    const int passes = (amg->L.size() == 1) ? passes0 : passes_rest;
+    DBuf<int> agg(cur.n);
+    int nc = 0;
     {
-      fs_csr A1;
-      galerkin(Av, agg1.p, n1, A1);
-      nc = pairwise(A1.view(), agg2);
+      DBuf<int> a1;
+      nc = pairwise(Av, a1);
+      FS_CUDA(cudaMemcpyAsync(agg.p, a1.p, cur.n * sizeof(int), cudaMemcpyDeviceToDevice, st));
+      std::unique_ptr<fs_csr> Ak;
+      for (int ps = 1; ps < passes; ++ps) {
+        std::unique_ptr<fs_csr> An(new fs_csr());
+        galerkin(Ak ? Ak->view() : Av, Ak ? a1.p : agg.p, nc, *An);   // operator on the current aggregates
+        DBuf<int> a2;
+        const int n2 = pairwise(An->view(), a2);
+        k_compose<<<div_up(cur.n, 256), 256, 0, st>>>(cur.n, agg.p, a2.p, agg.p);
+        FS_LAUNCH_CHECK();
+        a1 = std::move(a2);
+        Ak = std::move(An);
+        nc = n2;
+      }
     }
     if (nc >= cur.n * 0.8) break;                      // coarsening stalled
-    k_compose<<<div_up(cur.n, 256), 256, 0, st>>>(cur.n, agg1.p, agg2.p, agg.p);
-    FS_LAUNCH_CHECK();
     // smoothed prolongator, its transpose, and the Galerkin operator P^T (A P)
     {
       const size_t m = (size_t)Av.nnz + cur.n;

@@ -23,6 +23,7 @@ struct Locator {
   DBuf<double> cen;           // (T,2) centroids
   DBuf<int> cell_start;       // (G*G+1)
   DBuf<int> cell_tri;         // (T) triangle ids sorted by cell (ascending id inside a cell)
+  DBuf<double> cen_sorted;    // (T,2) centroids in cell_tri order: a row of cells is one contiguous run
   DBuf<int> nbr;              // (T,3) neighbour across the edge opposite corner i, -1 on the boundary
 };
 
@@ -35,6 +36,7 @@ struct LocView {
   const double2* cen;
   const int* cell_start;
   const int* cell_tri;
+  const double2* cen_s;
   const int* nbr;
   const double2* coords;
   const int* tris;
@@ -66,6 +68,12 @@ __global__ void k_cell_keys(const double2* __restrict__ cen, int64_t T, double x
   int cx = cell_coord(cen[e].x, x0, inv_h, G), cy = cell_coord(cen[e].y, y0, inv_h, G);
   keys[e] = (unsigned)(cy * G + cx);
   ids[e] = (int)e;
+}
+
+__global__ void k_gather_cen(const double2* __restrict__ cen, const int* __restrict__ order, int64_t T,
+                             double2* __restrict__ out) {
+  int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k < T) out[k] = cen[order[k]];
 }
 
 __global__ void k_cell_start(const unsigned* __restrict__ skeys, int64_t T, int64_t ncell, int* __restrict__ start) {
@@ -148,6 +156,9 @@ static Locator* build_locator(fs_mesh* m) {
     k_cell_start<<<div_up(T + 1, 256), 256, 0, st>>>(kb.Current(), T, ncell, L->cell_start.p);
     FS_LAUNCH_CHECK();
     FS_CUDA(cudaMemcpyAsync(L->cell_tri.p, vb.Current(), T * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    L->cen_sorted.alloc(2 * T);
+    k_gather_cen<<<div_up(T, 256), 256, 0, st>>>((const double2*)L->cen.p, L->cell_tri.p, T, (double2*)L->cen_sorted.p);
+    FS_LAUNCH_CHECK();
     FS_CUDA(cudaStreamSynchronize(st));
   }
   {
@@ -175,7 +186,7 @@ static LocView loc_view(fs_mesh* m) {
   if (!m->loc) m->loc = build_locator(m);
   Locator* L = m->loc;
   return LocView{L->G, L->x0, L->y0, L->h, 1.0 / L->h, L->R_max, (const double2*)L->cen.p, L->cell_start.p,
-                 L->cell_tri.p, L->nbr.p, (const double2*)m->coords.p, m->tris.p, (int)m->T};
+                 L->cell_tri.p, (const double2*)L->cen_sorted.p, L->nbr.p, (const double2*)m->coords.p, m->tris.p, (int)m->T};
 }
 
 // barycentric weights of code/StokesColor.py:334-340; returns false for |det|<1e-14
@@ -204,18 +215,24 @@ __device__ int locate_knn(const LocView& V, double x, double y) {
   for (int r = 0; r < V.G; ++r) {
     const int xl = cx - r, xh = cx + r, yl = cy - r, yh = cy + r;
     for (int yy = max(yl, 0); yy <= min(yh, V.G - 1); ++yy) {
+      // the new cells of this ring in row yy: the whole span on the two edge rows, else the two
+      // end cells.  Cells of a row are consecutive in the sorted arrays, so a span is ONE run.
       const bool edge_row = (yy == yl || yy == yh);
-      const int step = edge_row ? 1 : max(2 * r, 1);
-      for (int xx = xl; xx <= xh; xx += step) {
-        if (xx < 0 || xx >= V.G) continue;
-        const int c = yy * V.G + xx;
-        for (int k = __ldg(&V.cell_start[c]); k < __ldg(&V.cell_start[c + 1]); ++k) {
-          const int t = __ldg(&V.cell_tri[k]);
-          const double2 cc = __ldg(&V.cen[t]);
+      const int nspan = (edge_row || r == 0) ? 1 : 2;
+      for (int sp = 0; sp < nspan; ++sp) {
+        int xa, xb;
+        if (nspan == 1) { xa = max(xl, 0); xb = min(xh, V.G - 1); }
+        else { xa = xb = (sp == 0) ? xl : xh; if (xa < 0 || xa >= V.G) continue; }
+        if (xa > xb) continue;
+        const int k0 = __ldg(&V.cell_start[yy * V.G + xa]);
+        const int k1 = __ldg(&V.cell_start[yy * V.G + xb + 1]);
+        for (int k = k0; k < k1; ++k) {
+          const double2 cc = __ldg(&V.cen_s[k]);
           const double dx = cc.x - x, dy = cc.y - y;
           double d = dx * dx + dy * dy;
-          int id = t;
-          if (d < bd[KNN - 1] || (d == bd[KNN - 1] && id < bi[KNN - 1])) {
+          if (d > bd[KNN - 1]) continue;
+          int id = __ldg(&V.cell_tri[k]);
+          if (d < bd[KNN - 1] || id < bi[KNN - 1]) {
             // insertion keeping (d, id) ascending; fully unrolled so the arrays stay in registers
 #pragma unroll
             for (int q = 0; q < KNN; ++q) {
