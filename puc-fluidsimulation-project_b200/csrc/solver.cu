@@ -852,8 +852,125 @@ static void dot2(int64_t n, const double* a, const double* b, const double* c, c
   for (int i = 0; i < g; ++i) { out2[0] += h[2 * i]; out2[1] += h[2 * i + 1]; }
 }
 
+// ---- small systems: the whole (Jacobi right-preconditioned) BiCGStab in ONE CTA --------------
+// The Poisson / heat systems of the shipped meshes have a few hundred rows: with one launch per
+// vector operation every iteration is pure launch latency.  Here one CTA of 1024 threads runs
+// the complete solve (rows strided over the threads, block-level reductions, no host reads).
+constexpr int kSmallN = 16384;
+
+__device__ __forceinline__ double cta_sum(double v, double* red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();                      // red may still be read from the previous reduction
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+  return s;
+}
+
+__global__ void __launch_bounds__(1024)
+k_bicgstab_small(CsrView A, const double* __restrict__ dinv, const double* __restrict__ b, double* __restrict__ x,
+                 double* __restrict__ ws, double tol2, int maxit, double* __restrict__ out /* {rr, bb} */,
+                 int* __restrict__ flags /* {converged, iterations} */) {
+  __shared__ double red[32];
+  const int n = A.n, t = threadIdx.x, nt = blockDim.x;
+  double *r = ws, *r0 = r + n, *p = r0 + n, *v = p + n, *s = v + n, *tt = s + n, *ph = tt + n, *sh = ph + n;
+  auto spmv = [&](const double* in, double* outv) {
+    for (int i = t; i < n; i += nt) {
+      double acc = 0.0;
+      for (int k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) acc += A.vals[k] * in[A.colidx[k]];
+      outv[i] = acc;
+    }
+    __syncthreads();
+  };
+  spmv(x, v);
+  double lb = 0.0, lr = 0.0;
+  for (int i = t; i < n; i += nt) {
+    const double ri = b[i] - v[i];
+    r[i] = ri; r0[i] = ri; p[i] = 0.0; v[i] = 0.0;
+    lb += b[i] * b[i]; lr += ri * ri;
+  }
+  const double bb = cta_sum(lb, red);
+  double rr = cta_sum(lr, red);
+  double rho = 1.0, alpha = 1.0, omega = 1.0;
+  int it = 0;
+  bool broke = false;
+  if (bb > 0.0) {
+    while (rr > tol2 * bb && it < maxit) {
+      double l = 0.0;
+      for (int i = t; i < n; i += nt) l += r0[i] * r[i];
+      const double rho_new = cta_sum(l, red);
+      if (rho_new == 0.0) { broke = true; break; }
+      const double beta = (rho_new / rho) * (alpha / omega);
+      for (int i = t; i < n; i += nt) {
+        const double pi = r[i] + beta * (p[i] - omega * v[i]);
+        p[i] = pi;
+        ph[i] = dinv ? dinv[i] * pi : pi;
+      }
+      __syncthreads();
+      spmv(ph, v);
+      l = 0.0;
+      for (int i = t; i < n; i += nt) l += r0[i] * v[i];
+      const double r0v = cta_sum(l, red);
+      if (r0v == 0.0) { broke = true; break; }
+      alpha = rho_new / r0v;
+      for (int i = t; i < n; i += nt) {
+        const double si = r[i] - alpha * v[i];
+        s[i] = si;
+        sh[i] = dinv ? dinv[i] * si : si;
+      }
+      __syncthreads();
+      spmv(sh, tt);
+      double l1 = 0.0, l2 = 0.0;
+      for (int i = t; i < n; i += nt) { l1 += tt[i] * s[i]; l2 += tt[i] * tt[i]; }
+      const double ts = cta_sum(l1, red), t2 = cta_sum(l2, red);
+      omega = (t2 != 0.0) ? ts / t2 : 0.0;
+      l = 0.0;
+      for (int i = t; i < n; i += nt) {
+        x[i] += alpha * ph[i] + omega * sh[i];
+        const double ri = s[i] - omega * tt[i];
+        r[i] = ri;
+        l += ri * ri;
+      }
+      rr = cta_sum(l, red);
+      rho = rho_new;
+      ++it;
+      if (omega == 0.0) { broke = true; break; }
+    }
+  } else {
+    for (int i = t; i < n; i += nt) x[i] = 0.0;
+    rr = 0.0;
+  }
+  if (t == 0) {
+    out[0] = rr; out[1] = bb;
+    flags[0] = (bb == 0.0 || rr <= tol2 * bb) ? 1 : 0;
+    flags[1] = it;
+    (void)broke;
+  }
+}
+
+static int bicgstab_small(fs_csr* a, const double* d_b, double* x, double rtol, int maxit, int precond, double* relres) {
+  const int64_t n = a->n;
+  ensure_ws(a, 8 * (size_t)n);
+  const double* dinv = nullptr;
+  if (precond == FS_PRECOND_JACOBI) { jacobi_prepare(a); dinv = a->dinv.p; }
+  cudaStream_t st = stream();
+  double* out = a->scal.p;
+  int* flags = reinterpret_cast<int*>(a->scal.p + 32);
+  k_bicgstab_small<<<1, 1024, 0, st>>>(a->view(), dinv, d_b, x, a->ws.p, rtol * rtol, maxit, out, flags);
+  FS_LAUNCH_CHECK();
+  double ho[2];
+  int hf[2];
+  FS_CUDA(cudaMemcpyAsync(ho, out, sizeof(ho), cudaMemcpyDeviceToHost, st));
+  FS_CUDA(cudaMemcpyAsync(hf, flags, sizeof(hf), cudaMemcpyDeviceToHost, st));
+  FS_CUDA(cudaStreamSynchronize(st));
+  if (relres) *relres = ho[1] > 0.0 ? std::sqrt(ho[0] / ho[1]) : 0.0;
+  return hf[0] ? hf[1] : -hf[1] - 1;
+}
+
 static int bicgstab_impl(fs_csr* a, const double* d_b, double* x, double rtol, int maxit, int precond, double* relres) {
   const int64_t n = a->n;
+  if (n <= kSmallN) return bicgstab_small(a, d_b, x, rtol, maxit, precond, relres);
   ensure_ws(a, 8 * (size_t)n);
   double *r = a->ws.p, *r0 = r + n, *p = r0 + n, *v = p + n, *s = v + n, *t = s + n, *ph = t + n, *sh = ph + n;
   const double* dinv = nullptr;

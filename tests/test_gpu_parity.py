@@ -362,6 +362,12 @@ def test_large_mesh_properties():
     b = rng.standard_normal(m.N)
     xs, it, rr = Sd.cg(b, rtol=1e-10)
     assert np.linalg.norm(b - (Sd @ xs)) <= 1e-9 * np.linalg.norm(b)
+    # the multi-kernel BiCGStab path (n above the single-CTA limit) on a non-symmetric variant
+    import scipy.sparse as sp
+    N1 = sp.csr_matrix((vals, colidx, rowptr), shape=(m.N, m.N)) + sp.diags(np.full(m.N - 1, 1e-4), 1)
+    Nd = fb.CsrMatrix.from_scipy(N1.tocsr())
+    xb, itb, _ = Nd.bicgstab(b, rtol=1e-9)
+    assert np.linalg.norm(b - N1 @ xb) <= 1e-8 * np.linalg.norm(b) and itb > 0
     ids = m.locate(rng.random((200000, 2)))
     inside = ids >= 0
     assert 0.75 < inside.mean() < 0.85                             # 1 - pi/16 of the square is mesh
