@@ -563,6 +563,165 @@ double max_abs_dev(const double* d_x, int64_t n) {
   return m;
 }
 
+// ---- small systems: the whole (Jacobi-)PCG solve in ONE CTA (shipped meshes: a few hundred rows).
+// Same recurrence and stopping rule as the large paths; R interleaved right-hand sides;
+// project_mean handled inside.  No grid barrier, no host read until the end.
+constexpr int kSmallCgN = 8192;
+
+template <int R>
+__global__ void __launch_bounds__(1024)
+k_cg_small(CsrView A, const double* __restrict__ dinv, const double* __restrict__ b_in, double* __restrict__ x,
+           double* __restrict__ ws, double tol2, int maxit, int project_mean, double* __restrict__ out /* rr[R], bb[R] */,
+           int* __restrict__ flags) {
+  __shared__ double red[32];
+  const int n = A.n, t = threadIdx.x, nt = blockDim.x;
+  double *r = ws, *p = r + (size_t)n * R, *Ap = p + (size_t)n * R, *b = Ap + (size_t)n * R;
+  auto csum = [&](double v) -> double {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((t & 31) == 0) red[t >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int w = 0; w < (nt >> 5); ++w) s += red[w];
+    return s;
+  };
+  // b (mean-free if requested)
+  double mean = 0.0;
+  if (project_mean) {
+    double l = 0.0;
+    for (int i = t; i < n; i += nt) l += b_in[i];
+    mean = csum(l) / (double)n;
+  }
+  for (int i = t; i < n * R; i += nt) b[i] = b_in[i] - mean;
+  __syncthreads();
+  auto spmv = [&](const double* in, double* outv) {
+    for (int i = t; i < n; i += nt) {
+      double acc[R];
+#pragma unroll
+      for (int c = 0; c < R; ++c) acc[c] = 0.0;
+      for (int k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) {
+        const double av = A.vals[k];
+        const int j = A.colidx[k];
+#pragma unroll
+        for (int c = 0; c < R; ++c) acc[c] += av * in[(size_t)j * R + c];
+      }
+#pragma unroll
+      for (int c = 0; c < R; ++c) outv[(size_t)i * R + c] = acc[c];
+    }
+    __syncthreads();
+  };
+  spmv(x, Ap);
+  double rr[R], rz[R], bb[R];
+  {
+    double l[3 * R];
+#pragma unroll
+    for (int k = 0; k < 3 * R; ++k) l[k] = 0.0;
+    for (int i = t; i < n; i += nt) {
+      const double di = dinv ? dinv[i] : 1.0;
+#pragma unroll
+      for (int c = 0; c < R; ++c) {
+        const double bv = b[(size_t)i * R + c], rv = bv - Ap[(size_t)i * R + c], zv = di * rv;
+        r[(size_t)i * R + c] = rv;
+        p[(size_t)i * R + c] = zv;
+        l[c] += rv * rv; l[R + c] += rv * zv; l[2 * R + c] += bv * bv;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < R; ++c) { rr[c] = csum(l[c]); rz[c] = csum(l[R + c]); bb[c] = csum(l[2 * R + c]); }
+  }
+  auto all_done = [&]() { bool d = true;
+#pragma unroll
+    for (int c = 0; c < R; ++c) d = d && (rr[c] <= tol2 * bb[c]);
+    return d; };
+  bool zero_rhs = true;
+#pragma unroll
+  for (int c = 0; c < R; ++c) zero_rhs = zero_rhs && (bb[c] == 0.0);
+  int it = 0;
+  if (zero_rhs) {
+    for (int i = t; i < n * R; i += nt) x[i] = 0.0;
+#pragma unroll
+    for (int c = 0; c < R; ++c) rr[c] = 0.0;
+  } else {
+    while (!all_done() && it < maxit) {
+      spmv(p, Ap);
+      double l[R];
+#pragma unroll
+      for (int c = 0; c < R; ++c) l[c] = 0.0;
+      for (int i = t; i < n; i += nt)
+#pragma unroll
+        for (int c = 0; c < R; ++c) l[c] += p[(size_t)i * R + c] * Ap[(size_t)i * R + c];
+      double alpha[R];
+#pragma unroll
+      for (int c = 0; c < R; ++c) { const double pAp = csum(l[c]); alpha[c] = pAp != 0.0 ? rz[c] / pAp : 0.0; }
+      double l2[2 * R];
+#pragma unroll
+      for (int k = 0; k < 2 * R; ++k) l2[k] = 0.0;
+      for (int i = t; i < n; i += nt) {
+        const double di = dinv ? dinv[i] : 1.0;
+#pragma unroll
+        for (int c = 0; c < R; ++c) {
+          const size_t q = (size_t)i * R + c;
+          x[q] += alpha[c] * p[q];
+          const double rn = r[q] - alpha[c] * Ap[q];
+          r[q] = rn;
+          l2[c] += rn * rn; l2[R + c] += rn * (di * rn);
+        }
+      }
+      double beta[R];
+#pragma unroll
+      for (int c = 0; c < R; ++c) {
+        rr[c] = csum(l2[c]);
+        const double rzn = csum(l2[R + c]);
+        beta[c] = rz[c] != 0.0 ? rzn / rz[c] : 0.0;
+        rz[c] = rzn;
+      }
+      ++it;
+      if (all_done()) break;
+      for (int i = t; i < n; i += nt) {
+        const double di = dinv ? dinv[i] : 1.0;
+#pragma unroll
+        for (int c = 0; c < R; ++c) { const size_t q = (size_t)i * R + c; p[q] = di * r[q] + beta[c] * p[q]; }
+      }
+      __syncthreads();
+    }
+  }
+  if (project_mean) {
+    double l = 0.0;
+    for (int i = t; i < n; i += nt) l += x[i];
+    const double mx = csum(l) / (double)n;
+    for (int i = t; i < n; i += nt) x[i] -= mx;
+  }
+  if (t == 0) {
+#pragma unroll
+    for (int c = 0; c < R; ++c) { out[c] = rr[c]; out[R + c] = bb[c]; }
+    flags[0] = (zero_rhs || all_done()) ? 1 : 0;
+    flags[1] = it;
+  }
+}
+
+template <int R>
+static int cg_small(fs_csr* a, const double* d_b, double* d_x, double rtol, int maxit, int precond, int project_mean,
+                    double* relres) {
+  const int64_t n = a->n;
+  ensure_ws(a, 4 * (size_t)n * R);
+  const double* dinv = nullptr;
+  if (precond == FS_PRECOND_JACOBI) { jacobi_prepare(a); dinv = a->dinv.p; }
+  cudaStream_t st = stream();
+  double* out = a->scal.p;
+  int* flags = reinterpret_cast<int*>(a->scal.p + 32);
+  k_cg_small<R><<<1, 1024, 0, st>>>(a->view(), dinv, d_b, d_x, a->ws.p, rtol * rtol, maxit, project_mean, out, flags);
+  FS_LAUNCH_CHECK();
+  double ho[2 * R];
+  int hf[2];
+  FS_CUDA(cudaMemcpyAsync(ho, out, sizeof(ho), cudaMemcpyDeviceToHost, st));
+  FS_CUDA(cudaMemcpyAsync(hf, flags, sizeof(hf), cudaMemcpyDeviceToHost, st));
+  FS_CUDA(cudaStreamSynchronize(st));
+  double worst = 0.0;
+  for (int c = 0; c < R; ++c) if (ho[R + c] > 0.0) worst = std::max(worst, std::sqrt(ho[c] / ho[R + c]));
+  if (relres) *relres = worst;
+  return hf[0] ? hf[1] : -hf[1] - 1;
+}
+
 // FS_CG_MODE=multi forces the 3-kernels-per-iteration path (A/B testing); default persistent
 static int cg_mode() {
   static int mode = -1;
@@ -577,6 +736,9 @@ template <int R>
 static int cg_impl(fs_csr* a, const double* d_b, double* d_x, double rtol, int maxit, int precond, int project_mean,
                    double* relres) {
   const int64_t n = a->n;
+  if (n <= kSmallCgN && (precond == FS_PRECOND_JACOBI || precond == FS_PRECOND_NONE) && (!project_mean || R == 1) &&
+      cg_mode() == 1)
+    return cg_small<R>(a, d_b, d_x, rtol, maxit, precond, project_mean, relres);
   const size_t len = (size_t)n * R;
   ensure_ws(a, 4 * len);
   double* r = a->ws.p;
