@@ -285,10 +285,10 @@ def run_ours(args):
         # products of the V-cycle are the same kernel on the same matrix); timed with CUDA events
         # around the CG's A*p launch in every iteration of the timed region
         t_spmv = pms[0] / samples / 1e3
-        roof = {"bound": "hbm", "kernel": "k_spmv_tile<false> (fine-level CSR SpMV of the AMG-preconditioned pressure CG)",
+        roof = {"bound": "hbm", "kernel": "k_spmv_warp<EPI_AX,DOT> (fine-level CSR SpMV A*p of the AMG-preconditioned pressure CG, fused p.Ap)",
                 "achieved": spmv_bytes / t_spmv / 1e9, "peak": peak, "unit": "GB/s",
                 "frac": spmv_bytes / t_spmv / 1e9 / peak,
-                "traffic": (json.load(open(TRAFFIC_FILE)).get("spmv_tile_dram_bytes_per_launch")
+                "traffic": (json.load(open(TRAFFIC_FILE)).get("spmv_warp_dram_bytes_per_launch")
                             if os.path.exists(TRAFFIC_FILE) else None), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": spmv_bytes, "us_per_launch": 1e6 * t_spmv, "sampled_launches": samples,
                 "frac_of_8TBps_spec": spmv_bytes / t_spmv / 8e12,

@@ -68,19 +68,19 @@ def full_summary(rep, outname, header):
         f.write("# warp stall reasons (warps per issue-active cycle)\n")
         for v, k in stalls[:8]: f.write(f"{k:75s} {v:18.3f}\n")
 
-if os.path.exists(f"{G}/{tag}_spmv_tile.ncu-rep"):
-    full_summary(f"{G}/{tag}_spmv_tile.ncu-rep", f"{P}/{tag}_spmv_tile_ncu_full.txt",
-                 "# ncu --set full --clock-control none --import-source on -k regex:k_spmv_tile -s 40 -c 1 python scripts/prof_amg.py 4\n"
+if os.path.exists(f"{G}/{tag}_spmv_warp.ncu-rep"):
+    full_summary(f"{G}/{tag}_spmv_warp.ncu-rep", f"{P}/{tag}_spmv_warp_ncu_full.txt",
+                 "# ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"k_spmv_warp<0, true>" -s 3 -c 1 python scripts/prof_amg.py 4\n"
                  "# (one stand-alone SpMV launch of the AMG-preconditioned CG, 4M-triangle pressure operator; cold cache)\n")
-    print(open(f"{P}/{tag}_spmv_tile_ncu_full.txt").read())
-    _raw = subprocess.run(["ncu", "-i", f"{G}/{tag}_spmv_tile.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    print(open(f"{P}/{tag}_spmv_warp_ncu_full.txt").read())
+    _raw = subprocess.run(["ncu", "-i", f"{G}/{tag}_spmv_warp.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     _rr = list(csv.reader(_raw.splitlines())); _h, _u, _r = _rr[0], _rr[1], _rr[2]
     def _bytes(name):
         v, unit = float(_r[_h.index(name)].replace(",", "")), _u[_h.index(name)]
         return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
-    SPMV_TILE_DRAM = _bytes("dram__bytes_read.sum") + _bytes("dram__bytes_write.sum")
+    SPMV_WARP_DRAM = _bytes("dram__bytes_read.sum") + _bytes("dram__bytes_write.sum")
 else:
-    SPMV_TILE_DRAM = None
+    SPMV_WARP_DRAM = None
 
 iters = 200
 d = {}
@@ -94,8 +94,8 @@ json.dump({"kernel": "k_cg_persistent", "iterations_in_launch": iters,
            "dram_write_per_iteration": d["dram__bytes_write.sum"] / iters,
            "us_per_iteration_under_ncu": d["gpu__time_duration.sum"] / iters / 1e3,
            "lts_hit_rate_pct": d.get("lts__t_sector_hit_rate.pct"),
-           "spmv_tile_dram_bytes_per_launch": SPMV_TILE_DRAM,
-           "spmv_tile_how": "ncu --set full capture of one fine-level k_spmv_tile launch (cold cache)",
+           "spmv_warp_dram_bytes_per_launch": SPMV_WARP_DRAM,
+           "spmv_warp_how": "ncu --set full capture of one fine-level k_spmv_warp launch (cold cache)",
            "how": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --cache-control none (single pass, no replay, caches left alone)"},
           open(f"{P}/spmv_traffic.json", "w"), indent=1)
 os.system(f"cp {G}/{tag}_cg_dram_nocachectl.csv {P}/{tag}_cg_dram_nocachectl.csv")
