@@ -349,6 +349,11 @@ __global__ void k_dense_gemv(int n, const double* __restrict__ Minv, const doubl
   if (lane == 0) x[row] = s;
 }
 
+__global__ void k_to_f32(const double* __restrict__ in, int64_t n, float* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
+}
+
 static double env_num(const char* name, double dflt) {
   const char* e = std::getenv(name);
   return e ? std::atof(e) : dflt;
@@ -428,6 +433,20 @@ Amg* amg_setup(fs_csr* fine) {
     ensure_tiles(&nxt->A);
     jacobi_prepare(&nxt->A);
     amg->L.push_back(std::move(nxt));
+  }
+  if (env_num("FS_AMG_FP32", 1) != 0) {
+    // mixed precision: the cycle streams fp32 copies of all its matrices (vectors stay fp64)
+    auto to32 = [&](const fs_csr& M) {
+      fs_csr& W = const_cast<fs_csr&>(M);
+      if (W.vals32.n == (size_t)W.nnz || W.nnz == 0) return;
+      W.vals32.alloc(W.nnz);
+      k_to_f32<<<div_up(W.nnz, 256), 256, 0, stream()>>>(W.vals.p, W.nnz, W.vals32.p);
+      FS_LAUNCH_CHECK();
+    };
+    for (auto& l : amg->L) {
+      to32(l->mat());
+      if (l->P.nnz) { to32(l->P); to32(l->PT); }
+    }
   }
   for (size_t l = 0; l < amg->L.size(); ++l) {
     AmgLevel& lv = *amg->L[l];
@@ -532,23 +551,24 @@ static void vcycle_level(Amg& amg, size_t l, const double* b, double* x) {
   AmgLevel& nx = *amg.L[l + 1];
   double* xt = lv.t.p;                                                   // iterate before the post-smoothing
   // pre-smooth from a zero guess and residual in one pass: xt = w D^-1 b, r = b - A xt
-  if (!spmv_warp(Av, EPI_PRESM, nullptr, lv.r.p, b, A.dinv.p, w, xt, nullptr)) {
+  const CsrView Av32 = A.view32();
+  if (!spmv_warp(Av32, EPI_PRESM, nullptr, lv.r.p, b, A.dinv.p, w, xt, nullptr)) {
     k_jac0<<<g, 256, 0, st>>>(n, w, A.dinv.p, b, xt);
     FS_LAUNCH_CHECK();
     spmv_dev(Av, xt, lv.r.p);
     k_resid<<<g, 256, 0, st>>>(n, b, lv.r.p, lv.r.p);
     FS_LAUNCH_CHECK();
   }
-  if (!spmv_warp(lv.PT.view(), EPI_AX, lv.r.p, nx.b.p, nullptr, nullptr, 0.0, nullptr, nullptr))   // restrict
+  if (!spmv_warp(lv.PT.view32(), EPI_AX, lv.r.p, nx.b.p, nullptr, nullptr, 0.0, nullptr, nullptr))   // restrict
     spmv_dev(lv.PT.view(), lv.r.p, nx.b.p);
   vcycle_level(amg, l + 1, nx.b.p, nx.x.p);
-  if (!spmv_warp(lv.P.view(), EPI_ADD, nx.x.p, xt, nullptr, nullptr, 0.0, nullptr, nullptr)) {       // xt += P x_c
+  if (!spmv_warp(lv.P.view32(), EPI_ADD, nx.x.p, xt, nullptr, nullptr, 0.0, nullptr, nullptr)) {       // xt += P x_c
     spmv_dev(lv.P.view(), nx.x.p, lv.r.p);
     k_add<<<g, 256, 0, st>>>(n, lv.r.p, xt);
     FS_LAUNCH_CHECK();
   }
   // post-smooth into the caller's buffer: x = xt + w D^-1 (b - A xt)
-  if (!spmv_warp(Av, EPI_JACOBI, xt, x, b, A.dinv.p, w, nullptr, nullptr)) {
+  if (!spmv_warp(Av32, EPI_JACOBI, xt, x, b, A.dinv.p, w, nullptr, nullptr)) {
     spmv_dev(Av, xt, lv.r.p);
     FS_CUDA(cudaMemcpyAsync(x, xt, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     k_jac_update<<<g, 256, 0, st>>>(n, w, A.dinv.p, b, lv.r.p, x);

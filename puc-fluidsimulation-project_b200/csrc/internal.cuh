@@ -167,6 +167,7 @@ struct CsrView {
   const double* vals;
   int tile_nnz_max = 0;   // max nonzeros in a 256-row tile (0: not computed -> vector SpMV)
   int wtile_nnz_max = 0;  // max nonzeros in a 32-row (one warp) tile
+  const float* vals32 = nullptr;   // optional fp32 copy of the values (AMG V-cycle only)
 };
 
 }  // namespace fs
@@ -194,8 +195,14 @@ struct fs_csr {
   fs_csr(const fs_csr&) = delete;
   fs_csr& operator=(const fs_csr&) = delete;
   ~fs_csr() { if (amg) fs::amg_free(amg); }
+  fs::DBuf<float> vals32;        // fp32 copy of the values for the mixed-precision V-cycle (lazy)
   fs::CsrView view() const {
-    return fs::CsrView{(int)n, nnz, rowptr, colidx, vals.p, tile_nnz_max > 0 ? tile_nnz_max : 0, wtile_nnz_max};
+    return fs::CsrView{(int)n, nnz, rowptr, colidx, vals.p, tile_nnz_max > 0 ? tile_nnz_max : 0, wtile_nnz_max, nullptr};
+  }
+  fs::CsrView view32() const {   // same matrix, values streamed as fp32 where the kernel supports it
+    fs::CsrView v = view();
+    v.vals32 = vals32.n ? vals32.p : nullptr;
+    return v;
   }
 };
 

@@ -47,7 +47,15 @@ struct SpmvWarpArgs {
   int ntiles;     // 512-row tiles
 };
 
-template <int EPI, bool DOT>
+__device__ __forceinline__ float w_ld_stream_f32(const float* a, uint64_t pol) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(a), "l"(pol));
+  return v;
+}
+
+// F32: the matrix values are streamed from the fp32 copy (8 instead of 12 bytes per nonzero);
+// vectors and accumulation stay fp64.  Used for the AMG V-cycle, which is only a preconditioner.
+template <int EPI, bool DOT, bool F32>
 __global__ void __launch_bounds__(kWT, 2) k_spmv_warp(SpmvWarpArgs a) {
   extern __shared__ double prod[];
   __shared__ double red[kWW];
@@ -58,6 +66,7 @@ __global__ void __launch_bounds__(kWT, 2) k_spmv_warp(SpmvWarpArgs a) {
   const int R0 = tile0 * kWT, R1 = min(a.A.n, tile1 * kWT);
   const int* __restrict__ rowptr = a.A.rowptr;
   const double* __restrict__ vals = a.A.vals;
+  const float* __restrict__ vals32 = a.A.vals32;
   const int* __restrict__ colidx = a.A.colidx;
   const unsigned full = 0xffffffffu;
   double* pw = prod + (size_t)warp * a.wcap;
@@ -82,7 +91,7 @@ __global__ void __launch_bounds__(kWT, 2) k_spmv_warp(SpmvWarpArgs a) {
     for (int j = 0; j < kWU; ++j) {
       const int k = (j << 5) + lane;
       const bool ok = k < cnt;
-      va[j] = ok ? w_ld_stream_f64(vals + base + k, pf) : 0.0;
+      va[j] = ok ? (F32 ? (double)w_ld_stream_f32(vals32 + base + k, pf) : w_ld_stream_f64(vals + base + k, pf)) : 0.0;
       ca[j] = ok ? w_ld_stream_s32(colidx + base + k, pf) : -1;
     }
   };
@@ -93,17 +102,24 @@ __global__ void __launch_bounds__(kWT, 2) k_spmv_warp(SpmvWarpArgs a) {
   int cntA = endA - baseA;
   stream(baseA, cntA);
   for (int mt = warp; mt < nmt; mt += kWW) {
-#pragma unroll
-    for (int j = 0; j < kWU; ++j)
-      if (ca[j] >= 0) pw[(j << 5) + lane] = va[j] * xval(ca[j]);
-    for (int k = (kWU << 5) + lane; k < cntA; k += 32)
-      pw[k] = w_ld_stream_f64(vals + baseA + k, pf) * xval(w_ld_stream_s32(colidx + baseA + k, pf));
-    __syncwarp();
+    // the mini-tile's nonzeros in chunks of 256 (kWU per lane); the registers always hold the chunk
+    // that is multiplied next, the following one (of this mini-tile or the first of the next) is
+    // requested before the current one is consumed any further
     int rpC, endC;
     load_rp(mt + 2 * kWW, rpC, endC);
     const int baseB = __shfl_sync(full, rpB, 0);
     const int cntB = endB - baseB;
-    stream(baseB, cntB);
+    constexpr int kChunk = kWU << 5;
+    for (int c0 = 0;; c0 += kChunk) {
+#pragma unroll
+      for (int j = 0; j < kWU; ++j)
+        if (ca[j] >= 0) pw[c0 + (j << 5) + lane] = va[j] * xval(ca[j]);
+      const bool last = c0 + kChunk >= cntA;
+      if (last) stream(baseB, cntB);                         // first chunk of the next mini-tile
+      else stream(baseA + c0 + kChunk, cntA - c0 - kChunk);  // next chunk of this one
+      if (last) break;
+    }
+    __syncwarp();
     int nxt = __shfl_down_sync(full, rpA, 1);
     if (lane == 31) nxt = endA;
     const int row = R0 + (mt << 5) + lane;
@@ -137,7 +153,14 @@ static bool g_warp_attr = false;
 
 template <int EPI, bool DOT>
 static void launch_one(const SpmvWarpArgs& args, int grid, size_t smem) {
-  k_spmv_warp<EPI, DOT><<<grid, kWT, smem, stream()>>>(args);
+  if (args.A.vals32) k_spmv_warp<EPI, DOT, true><<<grid, kWT, smem, stream()>>>(args);
+  else k_spmv_warp<EPI, DOT, false><<<grid, kWT, smem, stream()>>>(args);
+}
+
+template <int EPI, bool DOT>
+static void set_smem_attr(int bytes) {
+  FS_CUDA(cudaFuncSetAttribute(k_spmv_warp<EPI, DOT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  FS_CUDA(cudaFuncSetAttribute(k_spmv_warp<EPI, DOT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
 }
 
 // Returns the grid size used (>0), or 0 when the matrix does not fit this kernel (the caller
@@ -150,12 +173,12 @@ int spmv_warp(const CsrView& A, int epi, const double* x, double* y, const doubl
   if (smem > 100 * 1024) return 0;
   if (!g_warp_attr) {
     const int big = 100 * 1024;
-    FS_CUDA(cudaFuncSetAttribute(k_spmv_warp<EPI_AX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    FS_CUDA(cudaFuncSetAttribute(k_spmv_warp<EPI_AX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    FS_CUDA(cudaFuncSetAttribute(k_spmv_warp<EPI_RESID, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    FS_CUDA(cudaFuncSetAttribute(k_spmv_warp<EPI_JACOBI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    FS_CUDA(cudaFuncSetAttribute(k_spmv_warp<EPI_PRESM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    FS_CUDA(cudaFuncSetAttribute(k_spmv_warp<EPI_ADD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    set_smem_attr<EPI_AX, false>(big);
+    set_smem_attr<EPI_AX, true>(big);
+    set_smem_attr<EPI_RESID, false>(big);
+    set_smem_attr<EPI_JACOBI, false>(big);
+    set_smem_attr<EPI_PRESM, false>(big);
+    set_smem_attr<EPI_ADD, false>(big);
     g_warp_attr = true;
   }
   const int ntiles = div_up(A.n, kWT);
