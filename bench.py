@@ -163,7 +163,7 @@ def run_reference(args):
            "config": workload_config(args, iters_note=src), "cpu_baseline": best,
            "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    emit(out)
 
 
 def workload_config(args, **extra):
@@ -270,10 +270,16 @@ def run_ours(args):
     barrier()
     e2e = world * args.steps / max_over_ranks(time.perf_counter() - t0)
 
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()       # everything below is rank-0 only and must not touch the group
+        dist = None
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
         return
+
+    def barrier():                          # local from here on
+        torch.cuda.synchronize()
+        _lib.call("fs_sync")
 
     peak, peak_src = measured_peak()
     spmv_bytes = 12.0 * nnz + 20.0 * nd
@@ -296,7 +302,7 @@ def run_ours(args):
                                          "vector ops + dots": 1e3 * pms[2] / samples}}
         jac_iters = float(json.load(open(ITERS_FILE))["iters_per_step"]) if os.path.exists(ITERS_FILE) else 16000.0
         visc_iters = float(it_arr[:, 0].mean())
-    if args.precond == "amg" and not args.no_extra:
+    if args.precond == "amg" and not args.no_extra and world == 1:
         # the Jacobi-preconditioned persistent CG kernel on the same operator: the path's HBM-roofline
         # kernel and the same algorithm as the CPU baseline (2000 fixed iterations, not part of `value`)
         b = torch.randn(nd, dtype=torch.float64, device="cuda")
@@ -366,12 +372,30 @@ def run_ours(args):
            "e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": 16 * N, "d2h_bytes_per_step": 16 * N},
            "gpu_launches": int(launches), "clocks": clk}
     out.update(out_extra)
-    print(json.dumps(out))
-    if dist is not None:
-        dist.destroy_process_group()
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Send fd 1 to stderr while the benchmark runs: NCCL / the driver write banners such as
+    'NCCL version ...' straight to fd 1, and stdout must carry exactly one JSON line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(obj), flush=True)
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
