@@ -134,3 +134,20 @@ def test_poisson_heat_golden(mesh):
         u = np.linalg.solve(Ah, u)
         u = R.heat_reapply(u, nodes32, markers, pa)
         assert np.allclose(u, g[f"heat_u_{n}"], rtol=0, atol=1e-12)
+
+
+def test_c_port_matches_scipy():
+    """oracle/cg_port.c (the OpenMP CPU baseline of bench.py) against the numpy/scipy restatement."""
+    from oracle import cgport
+    o = load_golden("mesh_fine_1_ops")
+    ps = R.PressureSystem(o["nodes"], o["tris"], [tuple(p) for p in o["pairs"]])
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal(ps.nd)
+    y = cgport.spmv(ps.rowptr.astype(np.int32), ps.colidx.astype(np.int32), ps.vals, x)
+    assert np.abs(y - ps.K @ x).max() <= 1e-12 * np.abs(y).max()
+    b = rng.standard_normal(len(o["nodes"]))
+    q, it, rr = cgport.cg(ps.rowptr, ps.colidx, ps.vals, ps.reduce_rhs(b), rtol=1e-12, project_mean=True)
+    want = ps.solve(b)
+    assert it > 10 and rr <= 1e-12
+    assert np.linalg.norm(q[ps.dof] - want) <= 1e-9 * np.linalg.norm(want)
+    assert cgport.threads() >= 1
