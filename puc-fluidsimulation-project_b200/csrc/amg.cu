@@ -8,10 +8,11 @@
 //   prolongator P = (I - w D^-1 A) P_tent with piecewise-constant P_tent (the constants
 //   stay in the range of P, so every level keeps the null space of the Neumann operator);
 //   coarse operator P^T (A P).  All sparse products are expand / radix-sort / reduce-by-key
-//   on the GPU.  Levels are added until <= 400 rows.
+//   on the GPU.  Levels are added until <= 2048 rows; that last operator is inverted densely.
 // Application (one symmetric V(1,1) cycle, damped Jacobi, fixed => a valid CG
 //   preconditioner): x = w D^-1 b; r = b - A x; b_c = P^T r; recurse; x += P x_c;
-//   x += w D^-1 (b - A x).  Coarsest level: 40 Jacobi sweeps inside one CTA.
+//   x += w D^-1 (b - A x), with the smoother / residual fused into the SpMV epilogues and the
+//   matrices streamed as fp32 copies (vectors fp64).  Coarsest level: dense (pseudo-)inverse GEMV.
 #include <cub/cub.cuh>
 
 #include "internal.cuh"
@@ -32,7 +33,7 @@ struct Amg {
   double omega = 2.0 / 3.0;     // damped-Jacobi smoother
   double omega_p = 2.0 / 3.0;   // prolongator smoothing
   int coarse_sweeps = 40;
-  DBuf<double> coarse_inv;      // dense (pseudo-)inverse of the coarsest operator (n <= 512), row-major
+  DBuf<double> coarse_inv;      // dense (pseudo-)inverse of the coarsest operator (n <= 2048), row-major
   int coarse_n = 0;
   // the V-cycle as a CUDA graph (captured on its second application; one launch per cycle)
   cudaGraphExec_t graph = nullptr;
@@ -319,7 +320,7 @@ __global__ void k_rowsum_max(CsrView A, double* __restrict__ out2) {   // out2 =
 }
 // in-place Gauss-Jordan inversion of an SPD n x n matrix (no pivoting needed), one CTA
 __global__ void __launch_bounds__(1024) k_dense_invert(int n, double* __restrict__ M) {
-  __shared__ double colk[512];
+  __shared__ double colk[2048];
   __shared__ double piv;
   for (int k = 0; k < n; ++k) {
     if (threadIdx.x == 0) piv = 1.0 / M[(size_t)k * n + k];
@@ -364,7 +365,7 @@ Amg* amg_setup(fs_csr* fine) {
   amg->omega = env_num("FS_AMG_OMEGA", amg->omega);
   amg->omega_p = env_num("FS_AMG_OMEGA_P", amg->omega_p);
   amg->coarse_sweeps = (int)env_num("FS_AMG_COARSE_SWEEPS", amg->coarse_sweeps);
-  const int min_rows = (int)env_num("FS_AMG_MIN_ROWS", 400);
+  const int min_rows = (int)env_num("FS_AMG_MIN_ROWS", 2048);   // coarsest level: dense inverse
   const size_t max_levels = (size_t)env_num("FS_AMG_MAX_LEVELS", 16);
   const int passes0 = std::max(1, (int)env_num("FS_AMG_PASSES0", 2));       // pairwise passes on the finest level
   const int passes_rest = std::max(1, (int)env_num("FS_AMG_PASSES", 2));    // ... and on the coarser ones
@@ -456,7 +457,7 @@ Amg* amg_setup(fs_csr* fine) {
   }
   {
     AmgLevel& last = *amg->L.back();
-    if (amg->L.size() > 1 && last.n <= 512 && env_num("FS_AMG_DENSE_COARSE", 1) != 0) {
+    if (amg->L.size() > 1 && last.n <= 2048 && env_num("FS_AMG_DENSE_COARSE", 1) != 0) {
       const CsrView Ac = last.mat().view();
       const int n = last.n;
       DBuf<double> stat(2);
