@@ -14,7 +14,7 @@ python bench.py --steps 1 --warmup 1 --no-cpu --no-extra > $out/${tag}_plain_ben
 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 1 --warmup 1 --no-cpu --no-extra > $out/${tag}_ncu_launches.log 2>&1
 python scripts/prof_amg.py 4 > $out/${tag}_plain_amg.log 2>&1 || { echo "plain amg failed"; exit 1; }
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"k_spmv_warp<0, true>" -s 3 -c 1 -o $out/${tag}_spmv_warp \
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"k_spmv_warp<.int.0, .bool.1" -s 3 -c 1 -o $out/${tag}_spmv_warp \
     python scripts/prof_amg.py 4 > $out/${tag}_ncu_spmv.log 2>&1
 python scripts/prof_cg.py 200 > $out/${tag}_plain_cg.log 2>&1 || { echo "plain cg failed"; exit 1; }
 ncu --set full --clock-control none --import-source on -k regex:k_cg_persistent -c 1 -o $out/${tag}_cg_persistent \

@@ -70,7 +70,7 @@ def full_summary(rep, outname, header):
 
 if os.path.exists(f"{G}/{tag}_spmv_warp.ncu-rep"):
     full_summary(f"{G}/{tag}_spmv_warp.ncu-rep", f"{P}/{tag}_spmv_warp_ncu_full.txt",
-                 "# ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"k_spmv_warp<0, true>" -s 3 -c 1 python scripts/prof_amg.py 4\n"
+                 "# ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'k_spmv_warp<.int.0, .bool.1' -s 3 -c 1 python scripts/prof_amg.py 4\n"
                  "# (one stand-alone SpMV launch of the AMG-preconditioned CG, 4M-triangle pressure operator; cold cache)\n")
     print(open(f"{P}/{tag}_spmv_warp_ncu_full.txt").read())
     _raw = subprocess.run(["ncu", "-i", f"{G}/{tag}_spmv_warp.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
