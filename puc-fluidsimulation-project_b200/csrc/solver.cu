@@ -2,13 +2,16 @@
 // dense np.linalg.solve (code/StokesColor.py:544-545,555,569; code/heatEq.py:323;
 // code/poisson.py:285).
 //
-// CG schedule (3 passes per iteration, dots fused into the passes):
-//   A: Ap = A p            + partial p.Ap          (matrix stream + p gather)
-//   B: x += a p; r -= a Ap + partial r.r, r.z      (z = Dinv r never stored)
-//   C: p = z + b p
-// Scalars never visit the host inside a chunk of iterations: each pass
-// re-reduces the previous pass's per-block partials in a fixed order
-// (deterministic, no atomics); the host polls a "done" flag every chunk.
+// Paths, chosen by size and preconditioner (cg_dev / fs_bicgstab):
+//   * n <= 8192: the whole CG (1 or 2 RHS) or BiCGStab solve in one CTA (k_cg_small, k_bicgstab_small)
+//   * Jacobi, 1 RHS: the persistent cooperative kernel of cg_persistent.cu
+//   * AMG: pcg_amg_impl below (V-cycle of amg.cu, SpMV of spmv_warp.cu)
+//   * 2 RHS / fallback (FS_CG_MODE=multi): 3 kernels per iteration with device-side scalars:
+//       A: Ap = A p            + partial p.Ap          (matrix stream + p gather)
+//       B: x += a p; r -= a Ap + partial r.r, r.z      (z = Dinv r never stored)
+//       C: p = z + b p
+//     each pass re-reduces the previous pass's per-block partials in a fixed order
+//     (deterministic, no atomics); the host polls a "done" flag every chunk.
 #include <algorithm>
 
 #include "internal.cuh"
@@ -17,21 +20,6 @@ namespace fs {
 
 constexpr int kBlock = 256;
 constexpr int kMaxBlocks = 1024;   // partial arrays are sized for this
-
-template <int R>
-struct VecT;
-template <>
-struct VecT<1> {
-  using type = double;
-};
-template <>
-struct VecT<2> {
-  using type = double2;
-};
-
-template <int R> struct Acc { double v[R]; };
-
-__device__ __forceinline__ double ld_c(const double* p, int64_t i, int) { return p[i]; }
 
 template <int R>
 __device__ __forceinline__ void load_vec(const double* __restrict__ p, int64_t i, double (&o)[R]) {
