@@ -5,7 +5,8 @@
 // Setup (device only, once per matrix):
 //   aggregates of ~4 rows from two passes of pairwise "handshake" matching along the
 //   strongest negative coupling (deterministic: ties go to the smaller index);
-//   prolongator P = (I - w D^-1 A) P_tent with piecewise-constant P_tent (the constants
+//   prolongator P = (I - w D_F^-1 A_F) P_tent with piecewise-constant P_tent and A_F = A with the
+//   couplings weaker than 0.25 x the row's strongest lumped onto the diagonal (the constants
 //   stay in the range of P, so every level keeps the null space of the Neumann operator);
 //   coarse operator P^T (A P).  All sparse products are expand / radix-sort / reduce-by-key
 //   on the GPU.  Levels are added until <= 2048 rows; that last operator is inverted densely.
@@ -32,6 +33,7 @@ struct Amg {
   std::vector<std::unique_ptr<AmgLevel>> L;
   double omega = 2.0 / 3.0;     // damped-Jacobi smoother
   double omega_p = 2.0 / 3.0;   // prolongator smoothing
+  double theta = 0.25;          // strength threshold of the filtered prolongator smoothing (0 = unfiltered)
   int coarse_sweeps = 40;
   DBuf<double> coarse_inv;      // dense (pseudo-)inverse of the coarsest operator (n <= 2048), row-major
   int coarse_n = 0;
@@ -230,18 +232,37 @@ static void galerkin(const CsrView& A, const int* agg, int nc, fs_csr& out) {
 }
 
 // smoothed prolongator P = (I - w D^-1 A) P_tent,  P_tent(i, agg[i]) = 1
+// Filtered smoothing (theta > 0): couplings weaker than theta x the row's strongest one are
+// lumped onto the diagonal before P is smoothed, so P only spreads along strong couplings and
+// the Galerkin operator stays sparse on anisotropic meshes.  theta = 0: plain smoothing.
 __global__ void k_prolongator_coo(CsrView A, const int* __restrict__ agg, const double* __restrict__ dinv, double w,
-                                  unsigned long long* __restrict__ keys, double* __restrict__ v) {
+                                  double theta, unsigned long long* __restrict__ keys, double* __restrict__ v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.n) return;
   const unsigned long long ri = (unsigned long long)(unsigned)i << 32;
-  const double s = -w * dinv[i];
+  double wmax = 0.0, diag = 0.0;
   for (int k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) {
-    keys[k + i] = ri | (unsigned)agg[A.colidx[k]];
-    v[k + i] = s * A.vals[k];
+    if (A.colidx[k] == i) diag = A.vals[k];
+    else wmax = fmax(wmax, -A.vals[k]);
+  }
+  const double thr = theta * wmax;
+  double dF = diag;
+  if (theta > 0.0)
+    for (int k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k)
+      if (A.colidx[k] != i && -A.vals[k] < thr) dF += A.vals[k];
+  const double s = (theta > 0.0) ? ((dF != 0.0) ? -w / dF : 0.0) : -w * dinv[i];
+  const unsigned self = (unsigned)agg[i];
+  for (int k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) {
+    const int j = A.colidx[k];
+    double val;
+    if (j == i) val = s * ((theta > 0.0) ? dF : A.vals[k]);
+    else val = (theta > 0.0 && -A.vals[k] < thr) ? 0.0 : s * A.vals[k];
+    // dropped (weak) entries are parked on the row's own aggregate with value 0: they vanish in the reduce
+    keys[k + i] = ri | ((val == 0.0 && j != i) ? self : (unsigned)agg[j]);
+    v[k + i] = val;
   }
   const int e = A.rowptr[i + 1] + i;          // one extra slot per row for the tentative entry
-  keys[e] = ri | (unsigned)agg[i];
+  keys[e] = ri | self;
   v[e] = 1.0;
 }
 
@@ -364,6 +385,7 @@ Amg* amg_setup(fs_csr* fine) {
   std::unique_ptr<Amg> amg(new Amg());
   amg->omega = env_num("FS_AMG_OMEGA", amg->omega);
   amg->omega_p = env_num("FS_AMG_OMEGA_P", amg->omega_p);
+  amg->theta = env_num("FS_AMG_THETA", amg->theta);
   amg->coarse_sweeps = (int)env_num("FS_AMG_COARSE_SWEEPS", amg->coarse_sweeps);
   const int min_rows = (int)env_num("FS_AMG_MIN_ROWS", 2048);   // coarsest level: dense inverse
   const size_t max_levels = (size_t)env_num("FS_AMG_MAX_LEVELS", 16);
@@ -410,7 +432,7 @@ Amg* amg_setup(fs_csr* fine) {
       const size_t m = (size_t)Av.nnz + cur.n;
       DBuf<unsigned long long> keys(m);
       DBuf<double> v(m);
-      k_prolongator_coo<<<div_up(cur.n, 256), 256, 0, st>>>(Av, agg.p, A.dinv.p, amg->omega_p, keys.p, v.p);
+      k_prolongator_coo<<<div_up(cur.n, 256), 256, 0, st>>>(Av, agg.p, A.dinv.p, amg->omega_p, amg->theta, keys.p, v.p);
       FS_LAUNCH_CHECK();
       coo_to_csr(keys, v, m, cur.n, nc, cur.P);
     }

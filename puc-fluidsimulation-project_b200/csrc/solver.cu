@@ -263,8 +263,10 @@ static int tile_grid(const CsrView& A) {
 template <bool DOT>
 static void launch_spmv_tile(const CsrView& A, const double* x, double* y, double* part, const int* done, int grid) {
   const size_t smem = (size_t)A.tile_nnz_max * 8;
+  // raise the limit on first use whatever the size: the kernel's static shared memory (row
+  // pointers, reduction scratch) counts against the default 48 KB too
   static bool attr_set[2] = {false, false};
-  if (smem > 48 * 1024 && !attr_set[DOT]) {
+  if (!attr_set[DOT]) {
     FS_CUDA(cudaFuncSetAttribute(k_spmv_tile<DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemMax));
     attr_set[DOT] = true;
   }
