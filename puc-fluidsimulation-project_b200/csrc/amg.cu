@@ -41,6 +41,7 @@ struct Amg {
   cudaGraphExec_t graph = nullptr;
   const double* graph_r = nullptr;
   double* graph_z = nullptr;
+  bool graph_x0 = false;
   int applications = 0;
   ~Amg() { if (graph) cudaGraphExecDestroy(graph); }
 };
@@ -546,7 +547,9 @@ k_coarse_jacobi(CsrView A, const double* __restrict__ dinv, const double* __rest
 
 static int vgrid(int n) { return std::max(1, std::min(div_up(n, 256), sm_count() * 8)); }
 
-static void vcycle_level(Amg& amg, size_t l, const double* b, double* x) {
+// x0_ready: lv.t already holds the pre-smoothed iterate w D^-1 b (written by the producer of b:
+// the CG update kernel on level 0, the restriction's epilogue below it)
+static void vcycle_level(Amg& amg, size_t l, const double* b, double* x, bool x0_ready) {
   cudaStream_t st = stream();
   AmgLevel& lv = *amg.L[l];
   const fs_csr& A = lv.mat();
@@ -573,18 +576,24 @@ static void vcycle_level(Amg& amg, size_t l, const double* b, double* x) {
   }
   AmgLevel& nx = *amg.L[l + 1];
   double* xt = lv.t.p;                                                   // iterate before the post-smoothing
-  // pre-smooth from a zero guess and residual in one pass: xt = w D^-1 b, r = b - A xt
+  // pre-smooth from a zero guess and residual: xt = w D^-1 b, r = b - A xt
   const CsrView Av32 = A.view32();
-  if (!spmv_warp(Av32, EPI_PRESM, nullptr, lv.r.p, b, A.dinv.p, w, xt, nullptr)) {
+  if (x0_ready && spmv_warp(Av32, EPI_RESID, xt, lv.r.p, b, nullptr, 0.0, nullptr, nullptr)) {
+    // xt came with b: one gather per nonzero instead of two
+  } else if (!spmv_warp(Av32, EPI_PRESM, nullptr, lv.r.p, b, A.dinv.p, w, xt, nullptr)) {
     k_jac0<<<g, 256, 0, st>>>(n, w, A.dinv.p, b, xt);
     FS_LAUNCH_CHECK();
     spmv_dev(Av, xt, lv.r.p);
     k_resid<<<g, 256, 0, st>>>(n, b, lv.r.p, lv.r.p);
     FS_LAUNCH_CHECK();
   }
-  if (!spmv_warp(lv.PT.view32(), EPI_AX, lv.r.p, nx.b.p, nullptr, nullptr, 0.0, nullptr, nullptr))   // restrict
+  // restrict; unless the next level is the dense one, the epilogue also emits its pre-smoothed iterate
+  const bool nx_last = (l + 2 == amg.L.size());
+  bool nx_ready = false;
+  if (!nx_last && spmv_warp(lv.PT.view32(), EPI_AX2, lv.r.p, nx.b.p, nullptr, nx.mat().dinv.p, w, nx.t.p, nullptr)) nx_ready = true;
+  else if (!spmv_warp(lv.PT.view32(), EPI_AX, lv.r.p, nx.b.p, nullptr, nullptr, 0.0, nullptr, nullptr))
     spmv_dev(lv.PT.view(), lv.r.p, nx.b.p);
-  vcycle_level(amg, l + 1, nx.b.p, nx.x.p);
+  vcycle_level(amg, l + 1, nx.b.p, nx.x.p, nx_ready);
   if (!spmv_warp(lv.P.view32(), EPI_ADD, nx.x.p, xt, nullptr, nullptr, 0.0, nullptr, nullptr)) {       // xt += P x_c
     spmv_dev(lv.P.view(), nx.x.p, lv.r.p);
     k_add<<<g, 256, 0, st>>>(n, lv.r.p, xt);
@@ -599,11 +608,18 @@ static void vcycle_level(Amg& amg, size_t l, const double* b, double* x) {
   }
 }
 
-void amg_apply(Amg* amg, const double* r, double* z) {
+void amg_presmooth_target(Amg* amg, double** x0, const double** dinv, double* omega) {
+  AmgLevel& l0 = *amg->L[0];
+  *x0 = (amg->L.size() > 1) ? l0.t.p : nullptr;
+  *dinv = l0.mat().dinv.p;
+  *omega = amg->omega;
+}
+
+void amg_apply(Amg* amg, const double* r, double* z, bool x0_ready) {
   static const bool use_graph = env_num("FS_AMG_GRAPH", 1) != 0;
   cudaStream_t st = stream();
   ++amg->applications;
-  if (use_graph && amg->graph && amg->graph_r == r && amg->graph_z == z) {
+  if (use_graph && amg->graph && amg->graph_r == r && amg->graph_z == z && amg->graph_x0 == x0_ready) {
     FS_CUDA(cudaGraphLaunch(amg->graph, st));
     count_launch();
     return;
@@ -614,12 +630,12 @@ void amg_apply(Amg* amg, const double* r, double* z) {
     cudaGraph_t g = nullptr;
     FS_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     bool ok = true;
-    try { vcycle_level(*amg, 0, r, z); } catch (...) { ok = false; }
+    try { vcycle_level(*amg, 0, r, z, x0_ready); } catch (...) { ok = false; }
     cudaError_t e = cudaStreamEndCapture(st, &g);
     if (ok && e == cudaSuccess && g) {
       cudaGraphExec_t ex = nullptr;
       if (cudaGraphInstantiate(&ex, g, 0) == cudaSuccess) {
-        amg->graph = ex; amg->graph_r = r; amg->graph_z = z;
+        amg->graph = ex; amg->graph_r = r; amg->graph_z = z; amg->graph_x0 = x0_ready;
         cudaGraphDestroy(g);
         FS_CUDA(cudaGraphLaunch(amg->graph, st));
         count_launch();
@@ -629,7 +645,7 @@ void amg_apply(Amg* amg, const double* r, double* z) {
     if (g) cudaGraphDestroy(g);
     cudaGetLastError();
   }
-  vcycle_level(*amg, 0, r, z);
+  vcycle_level(*amg, 0, r, z, x0_ready);
 }
 
 int amg_levels(const Amg* amg, int* sizes, int cap) {

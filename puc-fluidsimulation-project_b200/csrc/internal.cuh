@@ -258,11 +258,13 @@ void grad_update_dev(fs_mesh* m, const double* d_p, const double* d_ui, double* 
 void jacobi_prepare(fs_csr* a);
 void ensure_tiles(fs_csr* a);
 // warp-granular SpMV with fused epilogues (spmv_warp.cu); returns the grid used or 0 if unsupported
-enum { EPI_AX = 0, EPI_RESID = 1, EPI_JACOBI = 2, EPI_PRESM = 3, EPI_ADD = 4 };
+enum { EPI_AX = 0, EPI_RESID = 1, EPI_JACOBI = 2, EPI_PRESM = 3, EPI_ADD = 4, EPI_AX2 = 5 };
 int spmv_warp(const CsrView& A, int epi, const double* x, double* y, const double* b, const double* dinv, double w,
               double* xout, double* dot_partials);
 Amg* amg_setup(fs_csr* fine);
-void amg_apply(Amg* amg, const double* r, double* z);
+// x0_ready: the caller has written w D^-1 r into the buffer given by amg_presmooth_target
+void amg_apply(Amg* amg, const double* r, double* z, bool x0_ready = false);
+void amg_presmooth_target(Amg* amg, double** x0, const double** dinv, double* omega);
 int amg_levels(const Amg* amg, int* sizes, int cap);
 bool cg_persistent_supported(const CsrView& A, size_t* smem_out);
 void cg_persistent_launch(const CsrView& A, double* x, double* r, double* p, double* Ap, const double* dinv,

@@ -841,7 +841,8 @@ static void dot2(int64_t n, const double* a, const double* b, const double* c, c
 // per-CTA partials (rz is known to the host from the previous iteration); partial r.r out.
 __global__ void __launch_bounds__(kBlock)
 k_pcg_xr(int64_t n, const double* __restrict__ p, const double* __restrict__ Ap, double* __restrict__ x, double* __restrict__ r,
-         const double* __restrict__ partA, int nblkA, double rz, double* __restrict__ partB) {
+         const double* __restrict__ partA, int nblkA, double rz, double* __restrict__ partB,
+         double* __restrict__ x0out, const double* __restrict__ dinv, double w) {
   __shared__ double red[32];
   __shared__ double sm[1];
   double pAp[1];
@@ -852,6 +853,7 @@ k_pcg_xr(int64_t n, const double* __restrict__ p, const double* __restrict__ Ap,
     const double rn = r[i] - alpha * Ap[i];
     x[i] += alpha * p[i];
     r[i] = rn;
+    if (x0out) x0out[i] = w * dinv[i] * rn;     // the V-cycle's pre-smoothed iterate, for free
     acc[0] += rn * rn;
   }
   block_reduce<1>(acc, red);
@@ -890,9 +892,13 @@ static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, in
   // removed from x at the end, so z is not projected every iteration.
   const bool prof = g_prof.every > 0;
   if (prof && g_prof.ev.size() < 8) { g_prof.ev.resize(8); for (auto& e : g_prof.ev) cudaEventCreate(&e); }
-  auto precond = [&](const double* rin, double* zout) {
+  double* x0 = nullptr;
+  const double* dinv0 = nullptr;
+  double w0 = 0.0;
+  amg_presmooth_target(a->amg, &x0, &dinv0, &w0);
+  auto precond = [&](const double* rin, double* zout, bool x0_ready) {
     if (prof) cudaEventRecord(g_prof.ev[2], st);
-    amg_apply(a->amg, rin, zout);
+    amg_apply(a->amg, rin, zout, x0_ready);
     if (prof) cudaEventRecord(g_prof.ev[3], st);
   };
   double d2[2];
@@ -907,7 +913,7 @@ static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, in
   const double tol2 = rtol * rtol;
   int it = 0;
   if (rr > tol2 * bb) {
-    precond(r, z);
+    precond(r, z, false);
     FS_CUDA(cudaMemcpyAsync(p, z, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     dot2(n, r, z, nullptr, nullptr, part, d2);
     double rz = d2[0];
@@ -918,9 +924,9 @@ static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, in
       int ga = spmv_warp(A, EPI_AX, p, Ap, nullptr, nullptr, 0.0, nullptr, partA);
       if (!ga) { ga = spmv_launch_grid<1>(A); launch_spmv<1, true>(A, p, Ap, partA, nullptr, ga); }
       if (prof) cudaEventRecord(g_prof.ev[1], st);
-      k_pcg_xr<<<g, kBlock, 0, st>>>(n, p, Ap, x, r, partA, ga, rz, partBC); FS_LAUNCH_CHECK();
+      k_pcg_xr<<<g, kBlock, 0, st>>>(n, p, Ap, x, r, partA, ga, rz, partBC, x0, dinv0, w0); FS_LAUNCH_CHECK();
       ++it;
-      precond(r, z);
+      precond(r, z, x0 != nullptr);
       k_pcg_rz<<<g, kBlock, 0, st>>>(n, r, z, partBC + g); FS_LAUNCH_CHECK();
       FS_CUDA(cudaMemcpyAsync(hp.data(), partBC, sizeof(double) * 2 * g, cudaMemcpyDeviceToHost, st));
       if (prof) cudaEventRecord(g_prof.ev[4], st);

@@ -7,6 +7,7 @@
 //   EPI_PRESM   x0 = w D^-1 b (stored to xout),  y = b - A x0   (pre-smoothing from a zero guess
 //               and the residual in one pass: the gather reads dinv[col]*b[col])
 //   EPI_ADD     y += A x
+//   EPI_AX2     y  = A x,  xout = w D^-1 y                       (restriction that also pre-smooths)
 // plus an optional fused dot product x.(A x) (per-CTA partials) for the CG.
 // A warp owns 32-row mini-tiles; values/columns of the next mini-tile are in flight in registers
 // while the current one is multiplied and reduced through the warp's shared-memory slice.
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(kWT, 2) k_spmv_warp(SpmvWarpArgs a) {
       else if (EPI == EPI_JACOBI) a.y[row] = a.x[row] + a.w * a.dinv[row] * (a.b[row] - s);
       else if (EPI == EPI_PRESM) { const double bv = a.b[row]; a.xout[row] = a.w * a.dinv[row] * bv; a.y[row] = bv - s; }
       else if (EPI == EPI_ADD) a.y[row] += s;
+      else if (EPI == EPI_AX2) { a.y[row] = s; a.xout[row] = a.w * a.dinv[row] * s; }
     }
     __syncwarp();
     rpA = rpB; endA = endB; baseA = baseB; cntA = cntB;
@@ -179,6 +181,7 @@ int spmv_warp(const CsrView& A, int epi, const double* x, double* y, const doubl
     set_smem_attr<EPI_JACOBI, false>(big);
     set_smem_attr<EPI_PRESM, false>(big);
     set_smem_attr<EPI_ADD, false>(big);
+    set_smem_attr<EPI_AX2, false>(big);
     g_warp_attr = true;
   }
   const int ntiles = div_up(A.n, kWT);
@@ -192,6 +195,7 @@ int spmv_warp(const CsrView& A, int epi, const double* x, double* y, const doubl
     case EPI_JACOBI: launch_one<EPI_JACOBI, false>(args, grid, smem); break;
     case EPI_PRESM: launch_one<EPI_PRESM, false>(args, grid, smem); break;
     case EPI_ADD: launch_one<EPI_ADD, false>(args, grid, smem); break;
+    case EPI_AX2: launch_one<EPI_AX2, false>(args, grid, smem); break;
     default: throw Error(FS_ERR_INTERNAL, "spmv_warp: bad epilogue");
   }
   FS_LAUNCH_CHECK();
