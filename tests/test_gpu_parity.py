@@ -433,3 +433,31 @@ def test_stokes_synthetic_amg_vs_jacobi():
         sa, sb = a.step(), b.step()
     assert rel(a.u, b.u) <= 1e-9
     assert sa.iters_p1 * 5 < sb.iters_p1
+
+
+def test_full_size_4m_triangles():
+    """BASELINE's bench size (T = 4 194 304): size-independent properties and solver self-consistency."""
+    import torch
+    c, mk, t = fb.square_with_hole(2048, 1024)
+    a = fb.StokesSolver(c, mk, t, B1=-2.0, B2=-5.0, precond=fb.PRECOND_AMG)
+    m = a.mesh
+    assert (m.N, m.T) == (2048 * 1025, 4194304) and m.nnz == 3 * m.N + 2 * m.T     # nnz = N + 2E, E = N + T (annulus)
+    assert len(a.pairs) == 2048 // 4 - 1
+    av, kp, dof = a.matrices()
+    assert kp.n == m.N - len(a.pairs) and dof.max() == kp.n - 1
+    ones = torch.ones(kp.n, dtype=torch.float64, device="cuda")
+    assert float((kp @ ones).abs().max()) < 1e-8                                     # constants in the null space
+    x = torch.randn(kp.n, dtype=torch.float64, device="cuda")
+    y = torch.randn(kp.n, dtype=torch.float64, device="cuda")
+    assert abs(float(x @ (kp @ y)) - float(y @ (kp @ x))) <= 1e-9 * abs(float(x @ (kp @ y)))   # symmetry
+    assert np.isclose(a.M_lumped_diag.sum(), 1.0 - np.pi * 0.0625, rtol=2e-5)
+    # one step with either preconditioner: same fields; the pressure solve's true residual is small
+    b = fb.StokesSolver(c, mk, t, B1=-2.0, B2=-5.0, precond=fb.PRECOND_JACOBI)
+    sa, sb = a.step(), b.step()
+    assert sa.iters_p1 < 80 and sb.iters_p1 > 5000
+    assert rel(a.u, b.u) <= 1e-8
+    pa, _ = a.pressure()
+    pb, _ = b.pressure()
+    assert rel(pa, pb) <= 1e-8
+    div = m.divergence(a.u)
+    assert np.isfinite(div).all()
