@@ -6,7 +6,7 @@ Import name: ``fluidsim_b200`` (this directory's name has hyphens; the top-level
 """
 from ._lib import FluidsimError, device_count, lib as _clib  # noqa: F401  (loads / builds the .so, fails loudly)
 from .mesh import (readNode, readEle, readPoly, write_node, write_ele, find_boundary_pairs,  # noqa: F401
-                   filter_wall_pairs, index_sets, square_with_hole)
+                   filter_wall_pairs, index_sets, square_with_hole, refine_mesh)
 from .core import (Mesh, CsrMatrix, solve, buildStiffnessMatrix, buildFemSystem, buildLumpedMassMatrix,  # noqa: F401
                    calculate_divergence, calculate_gradiant, PointLocator, mixing_index, mesh_for,
                    PRECOND_NONE, PRECOND_JACOBI, PRECOND_AMG, PRECOND_AUTO)

@@ -169,3 +169,39 @@ def square_with_hole(n_theta, n_r, radius=0.25, center=(0.5, 0.5), half=0.5):
     t2 = np.stack([a, d, c], axis=-1)
     tris = np.stack([t1, t2], axis=2).reshape(-1, 3).astype(np.int32)
     return np.ascontiguousarray(coords), markers.ravel(), tris
+
+
+# --------------------------------------------------------------------------- refinement
+def refine_mesh(nodes_coords, markers, triangles, levels=1, circle=((0.5, 0.5), 0.25), inner_marker=2):
+    """Uniform red refinement (every triangle -> 4) of a Triangle mesh, `levels` times.
+
+    New mid-edge nodes on a boundary edge (an edge owned by a single triangle) inherit the marker its
+    two end nodes share; nodes created on the inner boundary (marker ``inner_marker``) are projected
+    onto the circle so that the refined squirmer boundary stays round.  Orientation is preserved.
+    Gives refined UNSTRUCTURED meshes from the shipped ones without the external `triangle` binary
+    (SURVEY section 8 f3)."""
+    nodes = np.asarray(nodes_coords, dtype=np.float64)
+    mk = np.asarray(markers, dtype=np.int32)
+    tris = np.asarray(triangles, dtype=np.int64)
+    (cx, cy), rad = circle
+    for _ in range(levels):
+        n = nodes.shape[0]
+        e = np.concatenate([tris[:, [0, 1]], tris[:, [1, 2]], tris[:, [2, 0]]])      # (3T,2): edges 01, 12, 20
+        lo, hi = e.min(axis=1), e.max(axis=1)
+        key = lo * n + hi
+        uniq, inv, cnt = np.unique(key, return_inverse=True, return_counts=True)
+        ua, ub = uniq // n, uniq % n
+        mid = 0.5 * (nodes[ua] + nodes[ub])
+        mm = np.where((cnt == 1) & (mk[ua] == mk[ub]) & (mk[ua] != 0), mk[ua], 0).astype(np.int32)
+        on_circle = mm == inner_marker
+        if on_circle.any():
+            d = mid[on_circle] - np.array([cx, cy])
+            mid[on_circle] = np.array([cx, cy]) + rad * d / np.linalg.norm(d, axis=1, keepdims=True)
+        t = len(tris)
+        m01, m12, m20 = n + inv[:t], n + inv[t:2 * t], n + inv[2 * t:]
+        a, b, c = tris[:, 0], tris[:, 1], tris[:, 2]
+        tris = np.concatenate([np.stack([a, m01, m20], 1), np.stack([m01, b, m12], 1),
+                               np.stack([m20, m12, c], 1), np.stack([m01, m12, m20], 1)])
+        nodes = np.concatenate([nodes, mid])
+        mk = np.concatenate([mk, mm])
+    return np.ascontiguousarray(nodes), mk, np.ascontiguousarray(tris.astype(np.int32))

@@ -136,3 +136,21 @@ def test_row_editor_matches_dense_surgery():
     rp, ci, v = ed.finish()
     assert np.array_equal(sp.csr_matrix((v, ci, rp), shape=(n, n)).toarray(), D)
     assert np.all(np.diff(rp) >= 0) and all(np.all(np.diff(ci[rp[i]:rp[i + 1]]) > 0) for i in range(n))
+
+
+def test_refine_mesh():
+    g = load_golden("mesh5_1_ops")
+    n, m, t = fb.refine_mesh(g["nodes"], g["markers"], g["tris"], 2)
+    assert t.shape == (16 * len(g["tris"]), 3) and len(n) == len(m)
+    x = n[t]
+    det = (x[:, 1, 0] - x[:, 0, 0]) * (x[:, 2, 1] - x[:, 0, 1]) - (x[:, 2, 0] - x[:, 0, 0]) * (x[:, 1, 1] - x[:, 0, 1])
+    assert det.min() > 0                                                   # orientation preserved
+    assert abs(0.5 * det.sum() - (1 - np.pi * 0.0625)) < 2e-4              # circle nodes projected: area converges
+    assert np.allclose(np.hypot(n[m == 2, 0] - 0.5, n[m == 2, 1] - 0.5), 0.25, atol=1e-9)
+    assert (m == 2).sum() == 4 * (g["markers"] == 2).sum() and (m == 1).sum() == 4 * (g["markers"] == 1).sum()
+    pairs = fb.filter_wall_pairs(n, fb.find_boundary_pairs(n))
+    assert len(pairs) == 4 * (len(g["pairs"]) + 1) - 1 and max(abs(n[a, 1] - n[b, 1]) for a, b in pairs) == 0.0
+    # Euler characteristic of the annulus: V - E + T = 0
+    e = np.concatenate([t[:, [0, 1]], t[:, [1, 2]], t[:, [2, 0]]])
+    E = len(np.unique(np.sort(e, axis=1), axis=0))
+    assert len(n) - E + len(t) == 0
