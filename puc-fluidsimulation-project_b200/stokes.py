@@ -93,6 +93,22 @@ class StokesSolver:
     def set_warm_state(self, q):
         call("fs_stokes_warm_state", self._h, ptr(np.ascontiguousarray(q, dtype=np.float64)), 1)
 
+    # -- checkpoint / resume (the reference keeps its state in module globals)
+    def _state_arrays(self):
+        return {"u": self.u}
+
+    def save_state(self, path):
+        """Write the complete loop state (velocity, CG warm-start vectors, and the dye / tracer
+        arrays of the subclasses) to an .npz file."""
+        np.savez(path, warm=self.get_warm_state(), **self._state_arrays())
+
+    def load_state(self, path):
+        """Restore a state written by save_state; the run continues bit for bit."""
+        z = np.load(path)
+        for k, arr in self._state_arrays().items():
+            arr[...] = z[k]
+        self.set_warm_state(z["warm"])
+
     def pressure(self):
         p = np.empty(self.N)
         p2 = np.empty(self.N)
@@ -111,6 +127,9 @@ class StokesColor(StokesSolver):
         self.inner = np.where(self.nodes_boundary_markers == 0)[0].astype(np.int32)
         self.I0, self.mu0, self.var0 = self.mesh.mixing_index(self.c, self.M_lumped_diag, self.inner)
         self.progress = 0.0
+
+    def _state_arrays(self):
+        return {"u": self.u, "c": self.c}
 
     def advect_semilagrange(self, c, u, DT):
         """code/StokesColor.py:347-389 (in place on c)."""
@@ -151,6 +170,10 @@ class StokesFood(StokesSolver):
         self.tracer_status = np.zeros(self.num_tracers, dtype=np.int32)
         self._hint = np.full(self.num_tracers, -1, dtype=np.int32)
         self.num_eaten = 0
+
+    def _state_arrays(self):
+        return {"u": self.u, "tracer_points": self.tracer_points, "tracer_status": self.tracer_status,
+                "_hint": self._hint}
 
     def tracer_step(self):
         """code/StokesFood.py:482-503."""

@@ -491,3 +491,25 @@ def test_refined_unstructured_mesh_vs_oracle():
     assert sts[0].iters_p1 < 60 and sts[0].iters_p1 * 5 < sts[1].iters_p1
     pts = np.random.default_rng(9).random((50000, 2))
     assert np.array_equal(m.locate(pts), loc.find(pts))
+
+
+def test_checkpoint_resume_is_bit_exact(tmp_path):
+    g = load_golden("mesh5_1_ops")
+    for cls in (fb.StokesColor, fb.StokesFood):
+        a = cls(g["nodes"], g["markers"], g["tris"], B2=-5.0)
+        for _ in range(3):
+            a.step_all()
+        ck = str(tmp_path / (cls.__name__ + ".npz"))
+        a.save_state(ck)
+        for _ in range(3):
+            a.step_all()
+        b = cls(g["nodes"], g["markers"], g["tris"], B2=-5.0)
+        b.load_state(ck)
+        for _ in range(3):
+            b.step_all()
+        assert np.array_equal(a.u, b.u)
+        if cls is fb.StokesColor:
+            assert np.array_equal(a.c, b.c)
+        else:
+            assert np.array_equal(a.tracer_points, b.tracer_points, equal_nan=True)
+            assert np.array_equal(a.tracer_status, b.tracer_status)
