@@ -12,8 +12,14 @@
 //   on the GPU.  Levels are added until <= 2048 rows; that last operator is inverted densely.
 // Application (one symmetric V(1,1) cycle, damped Jacobi, fixed => a valid CG
 //   preconditioner): x = w D^-1 b; r = b - A x; b_c = P^T r; recurse; x += P x_c;
-//   x += w D^-1 (b - A x), with the smoother / residual fused into the SpMV epilogues and the
-//   matrices streamed as fp32 copies (vectors fp64).  Coarsest level: dense (pseudo-)inverse GEMV.
+//   x += w D^-1 (b - A x).  Coarsest level: dense (pseudo-)inverse GEMV.
+//   Folded form (default): with S = I - w D^-1 A the same cycle is
+//       b_c = R~ b,            R~ = P^T S^T = (S P)^T          (one SpMV down)
+//       x   = G b + P~ x_c,    P~ = S P,  G = w D^-1 (2I - w A D^-1)   (one SpMV up, on [G | P~])
+//   i.e. two dependent kernels per level instead of four and no intermediate vectors; P~ comes
+//   for free from the A P product of the Galerkin step.  The unfolded form (FS_AMG_FOLD=0) fuses
+//   smoother / residual into SpMV epilogues instead.  Matrices are streamed as fp32 copies
+//   (vectors and sums fp64).
 #include <cub/cub.cuh>
 
 #include "internal.cuh"
@@ -25,6 +31,8 @@ struct AmgLevel {
   const fs_csr* Aref = nullptr;
   int n = 0;
   fs_csr P, PT;             // smoothed prolongator (n x n_coarse) and its transpose (restriction)
+  fs_csr U, Rt;             // folded cycle: U = [G | S P] (n x (n + n_coarse)),  Rt = (S P)^T
+  fs_sell Us, Rts;          // ... and their SELL-32 copies (what the cycle streams; CSR kept on small levels)
   DBuf<double> x, b, r, t;  // work vectors of this level (level 0 uses caller buffers for b/x)
   const fs_csr& mat() const { return Aref ? *Aref : A; }
 };
@@ -42,7 +50,14 @@ struct Amg {
   const double* graph_r = nullptr;
   double* graph_z = nullptr;
   bool graph_x0 = false;
+  bool graph_failed = false;
+  double* graph_part = nullptr;
+  int graph_nparts = 0;
+  bool folded = true;           // two-kernel-per-level form of the cycle
+  bool sell = true;             // folded operators in SELL-32 layout
+  int sub_rows = 0;             // matrices with at most this many rows use the lanes-per-row CSR kernel
   int applications = 0;
+  int tail_start = -1;          // first level handled by the one-kernel coarse tail (amg_tail.cu); -1: none
   ~Amg() { if (graph) cudaGraphExecDestroy(graph); }
 };
 
@@ -276,6 +291,43 @@ __global__ void k_transpose_coo(CsrView P, unsigned long long* __restrict__ keys
   }
 }
 
+// Folded cycle operators from A, Q = A P and P (all n rows):
+//   U  = [G | P~]  with G_ij = 2 w d_i delta_ij - w^2 (d_i d_j) A_ij,  P~ = P - w D^-1 Q  (columns shifted by n)
+//   R~ = P~^T
+// as COO lists (duplicates are summed by coo_to_csr).
+__global__ void k_fold_coo(CsrView A, CsrView Q, CsrView P, const double* __restrict__ dinv, double w,
+                           unsigned long long* __restrict__ ukeys, double* __restrict__ uv,
+                           unsigned long long* __restrict__ rkeys, double* __restrict__ rv) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n) return;
+  const double di = dinv[i];
+  const unsigned long long ri = (unsigned long long)(unsigned)i << 32;
+  for (int k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k) {
+    const int j = A.colidx[k];
+    double g = -(w * w) * ((di * dinv[j]) * A.vals[k]);
+    if (j == i) g += 2.0 * w * di;
+    ukeys[k] = ri | (unsigned)j;
+    uv[k] = g;
+  }
+  const size_t oq = (size_t)A.nnz, op = (size_t)A.nnz + (size_t)Q.nnz;
+  for (int q = Q.rowptr[i]; q < Q.rowptr[i + 1]; ++q) {
+    const int c = Q.colidx[q];
+    const double val = -w * di * Q.vals[q];
+    ukeys[oq + q] = ri | (unsigned)(A.n + c);
+    uv[oq + q] = val;
+    rkeys[q] = ((unsigned long long)(unsigned)c << 32) | (unsigned)i;
+    rv[q] = val;
+  }
+  for (int q = P.rowptr[i]; q < P.rowptr[i + 1]; ++q) {
+    const int c = P.colidx[q];
+    const double val = P.vals[q];
+    ukeys[op + q] = ri | (unsigned)(A.n + c);
+    uv[op + q] = val;
+    rkeys[(size_t)Q.nnz + q] = ((unsigned long long)(unsigned)c << 32) | (unsigned)i;
+    rv[(size_t)Q.nnz + q] = val;
+  }
+}
+
 // C = A * B : per nonzero (i,k) of A the whole row k of B
 __global__ void k_spgemm_count(CsrView A, const int* __restrict__ Browptr, int* __restrict__ cnt) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -392,6 +444,10 @@ Amg* amg_setup(fs_csr* fine) {
   const size_t max_levels = (size_t)env_num("FS_AMG_MAX_LEVELS", 16);
   const int passes0 = std::max(1, (int)env_num("FS_AMG_PASSES0", 2));       // pairwise passes on the finest level
   const int passes_rest = std::max(1, (int)env_num("FS_AMG_PASSES", 2));    // ... and on the coarser ones
+  amg->folded = env_num("FS_AMG_FOLD", 1) != 0;
+  amg->sell = env_num("FS_AMG_SELL", 1) != 0;
+  amg->sub_rows = (int)env_num("FS_AMG_SUB_ROWS", 100000);
+  const bool fp32 = env_num("FS_AMG_FP32", 1) != 0;
   ensure_tiles(fine);
   jacobi_prepare(fine);
   {
@@ -450,32 +506,58 @@ Amg* amg_setup(fs_csr* fine) {
       fs_csr Q;
       spgemm(Av, cur.P.view(), nc, Q);
       spgemm(cur.PT.view(), Q.view(), nc, nxt->A);
+      if (amg->folded) {
+        const size_t mu = (size_t)Av.nnz + (size_t)Q.nnz + (size_t)cur.P.nnz, mr = (size_t)Q.nnz + (size_t)cur.P.nnz;
+        DBuf<unsigned long long> ukeys(mu), rkeys(mr);
+        DBuf<double> uv(mu), rv(mr);
+        k_fold_coo<<<div_up(cur.n, 256), 256, 0, st>>>(Av, Q.view(), cur.P.view(), A.dinv.p, amg->omega, ukeys.p, uv.p, rkeys.p, rv.p);
+        FS_LAUNCH_CHECK();
+        coo_to_csr(ukeys, uv, mu, cur.n, cur.n + nc, cur.U);
+        coo_to_csr(rkeys, rv, mr, nc, cur.n, cur.Rt);
+        if (amg->sell) {
+          sell_build(cur.U, fp32, cur.Us);
+          sell_build(cur.Rt, fp32, cur.Rts);
+        }
+        auto drop = [](fs_csr& M) { M.vals.release(); M.colidx_own.release(); M.rowptr_own.release(); M.rowptr = M.colidx = nullptr; };
+        if (amg->sell && cur.n > amg->sub_rows) drop(cur.U); else ensure_tiles(&cur.U);
+        if (amg->sell && nc > amg->sub_rows) drop(cur.Rt); else ensure_tiles(&cur.Rt);
+      }
     }
-    ensure_tiles(&cur.P);
-    ensure_tiles(&cur.PT);
+    if (amg->folded) {   // the folded cycle does not touch P / P^T again
+      cur.P.vals.release(); cur.P.colidx_own.release(); cur.P.rowptr_own.release(); cur.P.nnz = 0;
+      cur.PT.vals.release(); cur.PT.colidx_own.release(); cur.PT.rowptr_own.release(); cur.PT.nnz = 0;
+    } else {
+      ensure_tiles(&cur.P);
+      ensure_tiles(&cur.PT);
+    }
     nxt->n = nc;
     ensure_tiles(&nxt->A);
     jacobi_prepare(&nxt->A);
     amg->L.push_back(std::move(nxt));
   }
-  if (env_num("FS_AMG_FP32", 1) != 0) {
+  if (fp32) {
     // mixed precision: the cycle streams fp32 copies of all its matrices (vectors stay fp64)
     auto to32 = [&](const fs_csr& M) {
       fs_csr& W = const_cast<fs_csr&>(M);
-      if (W.vals32.n == (size_t)W.nnz || W.nnz == 0) return;
+      if (W.vals32.n == (size_t)W.nnz || W.nnz == 0 || !W.vals.p) return;
       W.vals32.alloc(W.nnz);
       k_to_f32<<<div_up(W.nnz, 256), 256, 0, stream()>>>(W.vals.p, W.nnz, W.vals32.p);
       FS_LAUNCH_CHECK();
     };
     for (auto& l : amg->L) {
-      to32(l->mat());
+      if (!amg->folded) to32(l->mat());
       if (l->P.nnz) { to32(l->P); to32(l->PT); }
+      if (l->U.nnz) {   // only the fp32 copies of the folded operators are ever read
+        to32(l->U); to32(l->Rt);
+        FS_CUDA(cudaStreamSynchronize(stream()));
+        if (l->U.vals32.n) l->U.vals.release();
+        if (l->Rt.vals32.n) l->Rt.vals.release();
+      }
     }
   }
   for (size_t l = 0; l < amg->L.size(); ++l) {
     AmgLevel& lv = *amg->L[l];
-    lv.r.alloc(lv.n);
-    lv.t.alloc(lv.n);
+    if (!amg->folded || l + 1 == amg->L.size()) { lv.r.alloc(lv.n); lv.t.alloc(lv.n); }
     if (l > 0) { lv.x.alloc(lv.n); lv.b.alloc(lv.n); }
   }
   {
@@ -499,11 +581,23 @@ Amg* amg_setup(fs_csr* fine) {
       amg->coarse_n = n;
     }
   }
+  // levels at or below FS_AMG_TAIL_ROWS rows (down to the dense coarsest one) run as one kernel
+  {
+    const int tail_rows = (int)env_num("FS_AMG_TAIL_ROWS", 0);
+    const int nl = (int)amg->L.size();
+    if (!amg->folded && tail_rows > 0 && amg->coarse_n > 0 && nl >= 2 && amg_tail_supported()) {
+      int t = nl - 1;
+      while (t > 0 && amg->L[t - 1]->n <= tail_rows && nl - (t - 1) <= kTailMaxLevels) --t;
+      if (t <= nl - 2) amg->tail_start = t;
+    }
+  }
   FS_CUDA(cudaStreamSynchronize(stream()));
   if (std::getenv("FS_AMG_VERBOSE")) {
     std::fprintf(stderr, "[amg] levels:");
-    for (auto& l : amg->L) std::fprintf(stderr, " %d(nnz %lld)", l->n, (long long)l->mat().nnz);
-    std::fprintf(stderr, "\n");
+    for (auto& l : amg->L)
+      std::fprintf(stderr, " %d(nnz %lld, U %lld [sell %lld], Rt %lld [sell %lld])", l->n, (long long)l->mat().nnz, (long long)l->U.nnz,
+                   l->Us.padded, (long long)l->Rt.nnz, l->Rts.padded);
+    std::fprintf(stderr, "  folded %d  tail from level %d\n", (int)amg->folded, amg->tail_start);
   }
   return amg.release();
 }
@@ -547,6 +641,121 @@ k_coarse_jacobi(CsrView A, const double* __restrict__ dinv, const double* __rest
 
 static int vgrid(int n) { return std::max(1, std::min(div_up(n, 256), sm_count() * 8)); }
 
+static TailMat tail_mat(const fs_csr& M) {
+  TailMat t;
+  t.rowptr = M.rowptr; t.colidx = M.colidx; t.vals = M.vals.p;
+  t.vals32 = M.vals32.n ? M.vals32.p : nullptr;
+  t.n = (int)M.n;
+  return t;
+}
+
+// levels l .. last in one cooperative kernel; lv.t must hold w D^-1 b
+static void vcycle_tail(Amg& amg, size_t l, const double* b, double* x) {
+  TailArgs args;
+  const size_t nl = amg.L.size();
+  for (size_t k = l; k < nl; ++k) {
+    AmgLevel& lv = *amg.L[k];
+    TailLevel& t = args.lv[k - l];
+    t.A = tail_mat(lv.mat());
+    if (k + 1 < nl) { t.P = tail_mat(lv.P); t.PT = tail_mat(lv.PT); }
+    t.dinv = lv.mat().dinv.p;
+    t.b = (k == l) ? b : lv.b.p;
+    t.bw = (k == l) ? nullptr : lv.b.p;
+    t.x = (k == l) ? x : lv.x.p;
+    t.r = lv.r.p;
+    t.t = lv.t.p;
+    t.n = lv.n;
+  }
+  args.nlev = (int)(nl - l);
+  args.Minv = amg.coarse_inv.p;
+  args.w = amg.omega;
+  static const bool timing = std::getenv("FS_AMG_TAIL_TIME") != nullptr;
+  if (timing) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream(), &cs);
+    if (cs == cudaStreamCaptureStatusNone) {
+      cudaEvent_t e0, e1;
+      cudaEventCreate(&e0); cudaEventCreate(&e1);
+      static DBuf<long long> dbg;
+      if (!dbg.n) dbg.alloc(64);
+      dbg.zero();
+      args.dbg = dbg.p;
+      cudaStreamSynchronize(stream());
+      cudaEventRecord(e0, stream());
+      amg_tail_launch(args);
+      cudaEventRecord(e1, stream());
+      cudaEventSynchronize(e1);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      std::fprintf(stderr, "[amg] tail kernel (%d levels from %d rows): %.1f us; CTA0 phase cycles:", args.nlev, args.lv[0].n, ms * 1e3);
+      std::vector<long long> h = dbg.to_host();
+      for (int k = 1; k < 64 && h[k]; ++k) std::fprintf(stderr, " %lld", h[k] - h[k - 1]);
+      std::fprintf(stderr, "\n");
+      cudaEventDestroy(e0); cudaEventDestroy(e1);
+      return;
+    }
+  }
+  amg_tail_launch(args);
+}
+
+static void coarse_solve(Amg& amg, size_t l, const double* b, double* x) {
+  cudaStream_t st = stream();
+  AmgLevel& lv = *amg.L[l];
+  const fs_csr& A = lv.mat();
+  const CsrView Av = A.view();
+  const int n = lv.n, g = vgrid(n);
+  const double w = amg.omega;
+  if (amg.coarse_n == n && l > 0) {
+    k_dense_gemv<<<div_up(n * 32, 256), 256, 0, st>>>(n, amg.coarse_inv.p, b, x);
+    FS_LAUNCH_CHECK();
+  } else if (n <= 1024) {
+    k_coarse_jacobi<<<1, 1024, 0, st>>>(Av, A.dinv.p, b, x, w, amg.coarse_sweeps);
+    FS_LAUNCH_CHECK();
+  } else {
+    k_jac0<<<g, 256, 0, st>>>(n, w, A.dinv.p, b, x);
+    FS_LAUNCH_CHECK();
+    for (int s = 1; s < amg.coarse_sweeps; ++s) {
+      spmv_dev(Av, x, lv.r.p);
+      k_jac_update<<<g, 256, 0, st>>>(n, w, A.dinv.p, b, lv.r.p, x);
+      FS_LAUNCH_CHECK();
+    }
+  }
+}
+
+// The folded cycle: b_c = R~ b ; recurse ; x = [G | P~] [b; x_c].  With dot_part the up-sweep of
+// this level also leaves the per-CTA partials of b.x (the CG's r.z); returns their count.
+static int vcycle_folded(Amg& amg, size_t l, const double* b, double* x, double* dot_part) {
+  static const bool use_win = env_num("FS_AMG_WIN", 1) != 0;        // windowed fp32 CSR kernel when there is no SELL copy
+  if (l + 1 == amg.L.size()) {
+    coarse_solve(amg, l, b, x);
+    return 0;
+  }
+  AmgLevel& lv = *amg.L[l];
+  AmgLevel& nx = *amg.L[l + 1];
+  const int sub_rows = amg.sub_rows;
+  // down: b_c = R~ b
+  if (nx.n <= sub_rows && lv.Rt.rowptr) spmv_sub(lv.Rt.view32(), b, nx.b.p, nullptr, 0);
+  else if (lv.Rts.nslices) spmv_sell(lv.Rts, b, nx.b.p, nullptr, 0, nullptr);
+  else {
+    const CsrView Rt = lv.Rt.view32();
+    if (!((use_win && spmv_win(Rt, b, nx.b.p, nullptr, 0, nullptr)) ||
+          spmv_warp(Rt, EPI_AX, b, nx.b.p, nullptr, nullptr, 0.0, nullptr, nullptr)))
+      spmv_sub(Rt, b, nx.b.p, nullptr, 0);
+  }
+  vcycle_folded(amg, l + 1, nx.b.p, nx.x.p, nullptr);
+  // up: x = [G | P~] [b; x_c]
+  int g = 0;
+  if (lv.n <= sub_rows && lv.U.rowptr) spmv_sub(lv.U.view32(), b, x, nx.x.p, lv.n);
+  else if (lv.Us.nslices) g = spmv_sell(lv.Us, b, x, nx.x.p, lv.n, dot_part);
+  else {
+    const CsrView U = lv.U.view32();
+    if (use_win) g = spmv_win(U, b, x, nx.x.p, lv.n, dot_part);
+    if (!g) g = spmv_warp(U, EPI_AXS, b, x, nullptr, nullptr, 0.0, nullptr, dot_part, nx.x.p, lv.n);
+    if (!g) spmv_sub(U, b, x, nx.x.p, lv.n);
+  }
+  return dot_part ? g : 0;
+}
+
 // x0_ready: lv.t already holds the pre-smoothed iterate w D^-1 b (written by the producer of b:
 // the CG update kernel on level 0, the restriction's epilogue below it)
 static void vcycle_level(Amg& amg, size_t l, const double* b, double* x, bool x0_ready) {
@@ -556,22 +765,16 @@ static void vcycle_level(Amg& amg, size_t l, const double* b, double* x, bool x0
   const CsrView Av = A.view();
   const int n = lv.n, g = vgrid(n);
   const double w = amg.omega;
-  if (l + 1 == amg.L.size()) {
-    if (amg.coarse_n == n && l > 0) {
-      k_dense_gemv<<<div_up(n * 32, 256), 256, 0, st>>>(n, amg.coarse_inv.p, b, x);
+  if ((int)l == amg.tail_start) {
+    if (!x0_ready) {
+      k_jac0<<<g, 256, 0, st>>>(n, w, A.dinv.p, b, lv.t.p);
       FS_LAUNCH_CHECK();
-    } else if (n <= 1024) {
-      k_coarse_jacobi<<<1, 1024, 0, st>>>(Av, A.dinv.p, b, x, w, amg.coarse_sweeps);
-      FS_LAUNCH_CHECK();
-    } else {
-      k_jac0<<<g, 256, 0, st>>>(n, w, A.dinv.p, b, x);
-      FS_LAUNCH_CHECK();
-      for (int s = 1; s < amg.coarse_sweeps; ++s) {
-        spmv_dev(Av, x, lv.r.p);
-        k_jac_update<<<g, 256, 0, st>>>(n, w, A.dinv.p, b, lv.r.p, x);
-        FS_LAUNCH_CHECK();
-      }
     }
+    vcycle_tail(amg, l, b, x);
+    return;
+  }
+  if (l + 1 == amg.L.size()) {
+    coarse_solve(amg, l, b, x);
     return;
   }
   AmgLevel& nx = *amg.L[l + 1];
@@ -610,42 +813,54 @@ static void vcycle_level(Amg& amg, size_t l, const double* b, double* x, bool x0
 
 void amg_presmooth_target(Amg* amg, double** x0, const double** dinv, double* omega) {
   AmgLevel& l0 = *amg->L[0];
-  *x0 = (amg->L.size() > 1) ? l0.t.p : nullptr;
+  *x0 = (amg->L.size() > 1 && !amg->folded) ? l0.t.p : nullptr;
   *dinv = l0.mat().dinv.p;
   *omega = amg->omega;
 }
 
-void amg_apply(Amg* amg, const double* r, double* z, bool x0_ready) {
+int amg_apply(Amg* amg, const double* r, double* z, bool x0_ready, double* rz_part) {
   static const bool use_graph = env_num("FS_AMG_GRAPH", 1) != 0;
   cudaStream_t st = stream();
   ++amg->applications;
-  if (use_graph && amg->graph && amg->graph_r == r && amg->graph_z == z && amg->graph_x0 == x0_ready) {
+  const bool fold = amg->folded && amg->L.size() > 1;
+  auto cycle = [&]() -> int {
+    if (fold) return vcycle_folded(*amg, 0, r, z, rz_part);
+    vcycle_level(*amg, 0, r, z, x0_ready);
+    return 0;
+  };
+  if (use_graph && amg->graph && amg->graph_r == r && amg->graph_z == z && amg->graph_x0 == x0_ready &&
+      amg->graph_part == rz_part) {
     FS_CUDA(cudaGraphLaunch(amg->graph, st));
     count_launch();
-    return;
+    return amg->graph_nparts;
   }
-  if (use_graph && amg->applications >= 2) {
+  if (use_graph && amg->applications >= 2 && !amg->graph_failed) {
     // second application with these buffers: capture the cycle (all kernels go to `st`)
     if (amg->graph) { cudaGraphExecDestroy(amg->graph); amg->graph = nullptr; }
     cudaGraph_t g = nullptr;
     FS_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     bool ok = true;
-    try { vcycle_level(*amg, 0, r, z, x0_ready); } catch (...) { ok = false; }
+    int nparts = 0;
+    try { nparts = cycle(); } catch (...) { ok = false; }
     cudaError_t e = cudaStreamEndCapture(st, &g);
     if (ok && e == cudaSuccess && g) {
       cudaGraphExec_t ex = nullptr;
       if (cudaGraphInstantiate(&ex, g, 0) == cudaSuccess) {
         amg->graph = ex; amg->graph_r = r; amg->graph_z = z; amg->graph_x0 = x0_ready;
+        amg->graph_part = rz_part; amg->graph_nparts = nparts;
+        if (std::getenv("FS_AMG_VERBOSE")) std::fprintf(stderr, "[amg] V-cycle captured as a graph\n");
         cudaGraphDestroy(g);
         FS_CUDA(cudaGraphLaunch(amg->graph, st));
         count_launch();
-        return;
+        return nparts;
       }
     }
     if (g) cudaGraphDestroy(g);
     cudaGetLastError();
+    if (std::getenv("FS_AMG_VERBOSE")) std::fprintf(stderr, "[amg] graph capture failed (%s)\n", cudaGetErrorString(e));
+    amg->graph_failed = true;   // e.g. a driver that cannot capture the cooperative launch: run the cycle eagerly
   }
-  vcycle_level(*amg, 0, r, z, x0_ready);
+  return cycle();
 }
 
 int amg_levels(const Amg* amg, int* sizes, int cap) {

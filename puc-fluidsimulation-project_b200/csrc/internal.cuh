@@ -258,14 +258,57 @@ void grad_update_dev(fs_mesh* m, const double* d_p, const double* d_ui, double* 
 void jacobi_prepare(fs_csr* a);
 void ensure_tiles(fs_csr* a);
 // warp-granular SpMV with fused epilogues (spmv_warp.cu); returns the grid used or 0 if unsupported
-enum { EPI_AX = 0, EPI_RESID = 1, EPI_JACOBI = 2, EPI_PRESM = 3, EPI_ADD = 4, EPI_AX2 = 5 };
+enum { EPI_AX = 0, EPI_RESID = 1, EPI_JACOBI = 2, EPI_PRESM = 3, EPI_ADD = 4, EPI_AX2 = 5, EPI_AXS = 6 };
 int spmv_warp(const CsrView& A, int epi, const double* x, double* y, const double* b, const double* dinv, double w,
-              double* xout, double* dot_partials);
+              double* xout, double* dot_partials, const double* x2 = nullptr, int nsplit = 0);
+// SELL-32 copy of a CSR matrix (spmv_sell.cu): slices of 32 rows, column-major, padded per slice
+struct fs_sell {
+  int n = 0, nslices = 0;
+  long long padded = 0, nnz = 0;
+  DBuf<long long> sptr;   // nslices + 1 element offsets (multiples of 32)
+  DBuf<int> cols;
+  DBuf<float> v32;        // exactly one of v32 / v64 is filled
+  DBuf<double> v64;
+};
+void sell_build(const fs_csr& A, bool f32, fs_sell& out);
+int spmv_sell(const fs_sell& S, const double* x, double* y, const double* x2, int nsplit, double* dot_partials);
+// windowed fp32-matrix kernel of the folded V-cycle: y = A [x; x2], optional partials of x.y; 0 if A has no fp32 copy
+int spmv_win(const CsrView& A, const double* x, double* y, const double* x2, int nsplit, double* dot_partials);
+// any-matrix fallback: y = A [x; x2] (columns >= nsplit gather from x2; x2 null: y = A x)
+void spmv_sub(const CsrView& A, const double* x, double* y, const double* x2, int nsplit);
 Amg* amg_setup(fs_csr* fine);
-// x0_ready: the caller has written w D^-1 r into the buffer given by amg_presmooth_target
-void amg_apply(Amg* amg, const double* r, double* z, bool x0_ready = false);
+// x0_ready: the caller has written w D^-1 r into the buffer given by amg_presmooth_target (unfolded
+// cycle only).  rz_part (optional): room for per-CTA partial sums of r.z; the return value is how
+// many were written by the cycle's last kernel (0: the caller computes r.z itself).
+int amg_apply(Amg* amg, const double* r, double* z, bool x0_ready = false, double* rz_part = nullptr);
 void amg_presmooth_target(Amg* amg, double** x0, const double** dinv, double* omega);
 int amg_levels(const Amg* amg, int* sizes, int cap);
+// the coarse levels of the V-cycle as one cooperative kernel (amg_tail.cu)
+constexpr int kTailMaxLevels = 8;
+struct TailMat {
+  const int* rowptr = nullptr;
+  const int* colidx = nullptr;
+  const double* vals = nullptr;
+  const float* vals32 = nullptr;
+  int n = 0;
+};
+struct TailLevel {
+  TailMat A, P, PT;
+  const double* dinv = nullptr;
+  const double* b = nullptr;   // right-hand side of the level (written by the level above inside the kernel)
+  double* bw = nullptr;        // same buffer, writable (null on the first level of the tail)
+  double *x = nullptr, *r = nullptr, *t = nullptr;
+  int n = 0;
+};
+struct TailArgs {
+  TailLevel lv[kTailMaxLevels];
+  int nlev = 0;
+  const double* Minv = nullptr;   // dense inverse of the last level's operator
+  double w = 0.0;
+  long long* dbg = nullptr;       // optional: clock64 of CTA 0 at every phase boundary (FS_AMG_TAIL_TIME)
+};
+bool amg_tail_supported();
+void amg_tail_launch(const TailArgs& args);
 bool cg_persistent_supported(const CsrView& A, size_t* smem_out);
 void cg_persistent_launch(const CsrView& A, double* x, double* r, double* p, double* Ap, const double* dinv,
                           double* partA, double* partB, double* scal, int* flags, int maxit, double tol2);

@@ -896,10 +896,18 @@ static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, in
   const double* dinv0 = nullptr;
   double w0 = 0.0;
   amg_presmooth_target(a->amg, &x0, &dinv0, &w0);
-  auto precond = [&](const double* rin, double* zout, bool x0_ready) {
+  // r.r partials at partBC[0, g); r.z partials at partRZ[0, nrz): written by the cycle's last kernel when
+  // it can (folded cycle), else by k_pcg_rz
+  double* partRZ = partBC + kMaxBlocks;
+  auto precond = [&](const double* rin, double* zout, bool x0_ready) -> int {
     if (prof) cudaEventRecord(g_prof.ev[2], st);
-    amg_apply(a->amg, rin, zout, x0_ready);
+    int nrz = amg_apply(a->amg, rin, zout, x0_ready, partRZ);
     if (prof) cudaEventRecord(g_prof.ev[3], st);
+    if (!nrz) {
+      k_pcg_rz<<<g, kBlock, 0, st>>>(n, rin, zout, partRZ); FS_LAUNCH_CHECK();
+      nrz = g;
+    }
+    return nrz;
   };
   double d2[2];
   if (!spmv_warp(A, EPI_RESID, x, r, b, nullptr, 0.0, nullptr, nullptr)) {
@@ -913,11 +921,18 @@ static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, in
   const double tol2 = rtol * rtol;
   int it = 0;
   if (rr > tol2 * bb) {
-    precond(r, z, false);
+    std::vector<double> hp(2 * (size_t)kMaxBlocks);
+    auto read_sums = [&](int nrz, double& s_rr, double& s_rz) {
+      FS_CUDA(cudaMemcpyAsync(hp.data(), partBC, sizeof(double) * (kMaxBlocks + nrz), cudaMemcpyDeviceToHost, st));
+      FS_CUDA(cudaStreamSynchronize(st));
+      s_rr = 0.0; s_rz = 0.0;
+      for (int k = 0; k < g; ++k) s_rr += hp[k];
+      for (int k = 0; k < nrz; ++k) s_rz += hp[kMaxBlocks + k];
+    };
+    int nrz = precond(r, z, false);
     FS_CUDA(cudaMemcpyAsync(p, z, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    dot2(n, r, z, nullptr, nullptr, part, d2);
-    double rz = d2[0];
-    std::vector<double> hp(2 * (size_t)g);
+    double rz = 0.0, dummy = 0.0;
+    read_sums(nrz, dummy, rz);
     while (it < maxit) {
       // one host read per iteration: alpha is formed on the device, beta on the host
       if (prof) cudaEventRecord(g_prof.ev[0], st);
@@ -926,13 +941,10 @@ static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, in
       if (prof) cudaEventRecord(g_prof.ev[1], st);
       k_pcg_xr<<<g, kBlock, 0, st>>>(n, p, Ap, x, r, partA, ga, rz, partBC, x0, dinv0, w0); FS_LAUNCH_CHECK();
       ++it;
-      precond(r, z, x0 != nullptr);
-      k_pcg_rz<<<g, kBlock, 0, st>>>(n, r, z, partBC + g); FS_LAUNCH_CHECK();
-      FS_CUDA(cudaMemcpyAsync(hp.data(), partBC, sizeof(double) * 2 * g, cudaMemcpyDeviceToHost, st));
+      nrz = precond(r, z, x0 != nullptr);
       if (prof) cudaEventRecord(g_prof.ev[4], st);
-      FS_CUDA(cudaStreamSynchronize(st));
       double s_rr = 0.0, s_rz = 0.0;
-      for (int k = 0; k < g; ++k) { s_rr += hp[k]; s_rz += hp[g + k]; }
+      read_sums(nrz, s_rr, s_rz);
       if (prof) {
         float t_spmv = 0.f, t_v = 0.f, t_it = 0.f;
         cudaEventElapsedTime(&t_spmv, g_prof.ev[0], g_prof.ev[1]);

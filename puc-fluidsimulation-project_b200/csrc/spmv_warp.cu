@@ -8,7 +8,11 @@
 //               and the residual in one pass: the gather reads dinv[col]*b[col])
 //   EPI_ADD     y += A x
 //   EPI_AX2     y  = A x,  xout = w D^-1 y                       (restriction that also pre-smooths)
+//   EPI_AXS     y  = A [x; x2]: columns >= nsplit gather from x2 (the folded V-cycle's
+//               up-sweep operator [G | P~] applied to [b; x_coarse] without concatenating them)
 // plus an optional fused dot product x.(A x) (per-CTA partials) for the CG.
+// k_spmv_sub is the fallback for matrices whose 32-row mini-tiles do not fit shared memory
+// (very long rows): LPR lanes per row, same gather options.
 // A warp owns 32-row mini-tiles; values/columns of the next mini-tile are in flight in registers
 // while the current one is multiplied and reduced through the warp's shared-memory slice.
 #include "internal.cuh"
@@ -46,6 +50,8 @@ struct SpmvWarpArgs {
   double* part;   // per-CTA partial of x.(A x) when DOT
   int wcap;
   int ntiles;     // 512-row tiles
+  const double* x2 = nullptr;   // EPI_AXS: second gather source
+  int nsplit = 0;               // EPI_AXS: first column served by x2
 };
 
 __device__ __forceinline__ float w_ld_stream_f32(const float* a, uint64_t pol) {
@@ -77,6 +83,7 @@ __global__ void __launch_bounds__(kWT, 2) k_spmv_warp(SpmvWarpArgs a) {
   int ca[kWU];
   auto xval = [&](int j) -> double {
     if (EPI == EPI_PRESM) return a.w * __ldg(a.dinv + j) * __ldg(a.b + j);
+    if (EPI == EPI_AXS) return j < a.nsplit ? __ldg(a.x + j) : __ldg(a.x2 + (j - a.nsplit));
     return __ldg(a.x + j);
   };
   auto load_rp = [&](int mt, int& rp, int& rend) {
@@ -128,7 +135,7 @@ __global__ void __launch_bounds__(kWT, 2) k_spmv_warp(SpmvWarpArgs a) {
       double s = 0.0;
       for (int k = rpA - baseA; k < nxt - baseA; ++k) s += pw[k];
       if (DOT) acc += __ldg(a.x + row) * s;
-      if (EPI == EPI_AX) a.y[row] = s;
+      if (EPI == EPI_AX || EPI == EPI_AXS) a.y[row] = s;
       else if (EPI == EPI_RESID) a.y[row] = a.b[row] - s;
       else if (EPI == EPI_JACOBI) a.y[row] = a.x[row] + a.w * a.dinv[row] * (a.b[row] - s);
       else if (EPI == EPI_PRESM) { const double bv = a.b[row]; a.xout[row] = a.w * a.dinv[row] * bv; a.y[row] = bv - s; }
@@ -151,6 +158,184 @@ __global__ void __launch_bounds__(kWT, 2) k_spmv_warp(SpmvWarpArgs a) {
   }
 }
 
+// ---- windowed fp32-matrix variant for the folded V-cycle (y = A x or A [x; x2], optional x.y partials)
+// Same warp / mini-tile ownership as k_spmv_warp, but (a) 16 nonzeros per lane are in flight (the
+// fp32 values and the columns take the registers of 8 fp64 ones: the loop is latency-bound, so
+// bytes in flight per warp are what sets the rate) and (b) the products of one 512-nonzero
+// chunk are summed into the per-lane row sums before the next chunk overwrites the window, so
+// shared memory is 4 KB per warp whatever the row length and two CTAs always fit an SM.
+constexpr int kVU = 16;
+constexpr int kVC = kVU * 32;
+
+template <bool SPLIT, bool DOT>
+__global__ void __launch_bounds__(kWT, 2) k_spmv_win(SpmvWarpArgs a) {
+  extern __shared__ double win[];
+  __shared__ double red[kWW];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nb = gridDim.x, bi = blockIdx.x;
+  const uint64_t pf = w_evict_first();
+  const int tile0 = (int)(((long long)a.ntiles * bi) / nb);
+  const int tile1 = (int)(((long long)a.ntiles * (bi + 1)) / nb);
+  const int R0 = tile0 * kWT, R1 = min(a.A.n, tile1 * kWT);
+  const int* __restrict__ rowptr = a.A.rowptr;
+  const float* __restrict__ vals32 = a.A.vals32;
+  const int* __restrict__ colidx = a.A.colidx;
+  const unsigned full = 0xffffffffu;
+  double* pw = win + warp * kVC;
+  const int nmt = (R1 - R0 + 31) >> 5;
+  double acc = 0.0;
+  float va[kVU];
+  int ca[kVU];
+  auto xval = [&](int j) -> double {
+    if (SPLIT) return j < a.nsplit ? __ldg(a.x + j) : __ldg(a.x2 + (j - a.nsplit));
+    return __ldg(a.x + j);
+  };
+  auto load_rp = [&](int mt, int& rp, int& rend) {
+    if (mt < nmt) {
+      const int r0 = R0 + (mt << 5);
+      const int nr = min(32, R1 - r0);
+      rp = __ldg(rowptr + r0 + min(lane, nr));
+      rend = __ldg(rowptr + r0 + nr);
+    } else { rp = 0; rend = 0; }
+  };
+  auto stream = [&](int base, int cnt) {
+#pragma unroll
+    for (int j = 0; j < kVU; ++j) {
+      const int k = (j << 5) + lane;
+      const bool ok = k < cnt;
+      va[j] = ok ? w_ld_stream_f32(vals32 + base + k, pf) : 0.f;
+      ca[j] = ok ? w_ld_stream_s32(colidx + base + k, pf) : -1;
+    }
+  };
+  int rpA, endA, rpB, endB;
+  load_rp(warp, rpA, endA);
+  load_rp(warp + kWW, rpB, endB);
+  int baseA = __shfl_sync(full, rpA, 0);
+  int cntA = endA - baseA;
+  stream(baseA, cntA);
+  for (int mt = warp; mt < nmt; mt += kWW) {
+    int rpC, endC;
+    load_rp(mt + 2 * kWW, rpC, endC);
+    const int baseB = __shfl_sync(full, rpB, 0);
+    const int cntB = endB - baseB;
+    int nxt = __shfl_down_sync(full, rpA, 1);
+    if (lane == 31) nxt = endA;
+    const int lo0 = rpA - baseA, hi0 = nxt - baseA;   // this lane's row inside the mini-tile's nonzeros
+    double s = 0.0;
+    for (int c0 = 0;; c0 += kVC) {
+#pragma unroll
+      for (int j = 0; j < kVU; ++j)
+        if (ca[j] >= 0) pw[(j << 5) + lane] = (double)va[j] * xval(ca[j]);
+      const bool last = c0 + kVC >= cntA;
+      if (last) stream(baseB, cntB);
+      else stream(baseA + c0 + kVC, cntA - c0 - kVC);
+      __syncwarp();
+      const int lo = max(lo0, c0) - c0, hi = min(hi0, c0 + kVC) - c0;
+      for (int k = lo; k < hi; ++k) s += pw[k];
+      __syncwarp();
+      if (last) break;
+    }
+    const int row = R0 + (mt << 5) + lane;
+    if (row < R1) {
+      if (DOT) acc += __ldg(a.x + row) * s;
+      a.y[row] = s;
+    }
+    rpA = rpB; endA = endB; baseA = baseB; cntA = cntB;
+    rpB = rpC; endB = endC;
+  }
+  if (DOT) {
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(full, acc, o);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (t == 0) {
+      double sum = 0.0;
+      for (int k = 0; k < kWW; ++k) sum += red[k];
+      a.part[bi] = sum;
+    }
+  }
+}
+
+// y = A [x; x2] (x2 null: y = A x) with the fp32 copy of A; returns the grid (= number of dot partials)
+int spmv_win(const CsrView& A, const double* x, double* y, const double* x2, int nsplit, double* dot_partials) {
+  if (!A.vals32) return 0;
+  static bool attr = false;
+  const int smem = (int)(kWW * kVC * sizeof(double));   // 64 KB: above the default limit
+  if (!attr) {
+    FS_CUDA(cudaFuncSetAttribute(k_spmv_win<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    FS_CUDA(cudaFuncSetAttribute(k_spmv_win<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    FS_CUDA(cudaFuncSetAttribute(k_spmv_win<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  const int ntiles = div_up(A.n, kWT);
+  const int grid = std::max(1, std::min(sm_count() * 2, ntiles));
+  SpmvWarpArgs args{A, x, y, nullptr, nullptr, 0.0, nullptr, dot_partials, 0, ntiles};
+  args.x2 = x2;
+  args.nsplit = nsplit;
+  if (x2) {
+    if (dot_partials) k_spmv_win<true, true><<<grid, kWT, smem, stream()>>>(args);
+    else k_spmv_win<true, false><<<grid, kWT, smem, stream()>>>(args);
+  } else {
+    FS_REQUIRE(!dot_partials, "spmv_win: dot needs the split form");
+    k_spmv_win<false, false><<<grid, kWT, smem, stream()>>>(args);
+  }
+  FS_LAUNCH_CHECK();
+  return grid;
+}
+
+// LPR lanes per row (4..32), lane-strided partial sums combined by an xor tree: deterministic, any
+// row length; y = A x or A [x; x2]
+template <int LPR, bool F32>
+__global__ void __launch_bounds__(256) k_spmv_sub(SpmvWarpArgs a) {
+  const int row = (int)((blockIdx.x * 256ll + threadIdx.x) / LPR), sub = threadIdx.x % LPR;
+  double s = 0.0;
+  if (row < a.A.n) {
+    const int rs = __ldg(a.A.rowptr + row), re = __ldg(a.A.rowptr + row + 1);
+    // four strided entries per lane in flight: loads first, then the gathers, then the sums
+    for (int k0 = rs + sub; k0 < re; k0 += 4 * LPR) {
+      double v[4];
+      int c[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = k0 + j * LPR;
+        const bool ok = k < re;
+        v[j] = ok ? (F32 ? (double)__ldg(a.A.vals32 + k) : __ldg(a.A.vals + k)) : 0.0;
+        c[j] = ok ? __ldg(a.A.colidx + k) : 0;
+      }
+      double xx[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) xx[j] = c[j] < a.nsplit ? __ldg(a.x + c[j]) : __ldg(a.x2 + (c[j] - a.nsplit));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s += v[j] * xx[j];
+    }
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (row < a.A.n && sub == 0) a.y[row] = s;
+}
+
+template <int LPR>
+static void launch_sub(const SpmvWarpArgs& args) {
+  const int grid = (int)div_up((int64_t)args.A.n * LPR, 256);
+  if (args.A.vals32) k_spmv_sub<LPR, true><<<grid, 256, 0, stream()>>>(args);
+  else k_spmv_sub<LPR, false><<<grid, 256, 0, stream()>>>(args);
+  FS_LAUNCH_CHECK();
+}
+
+// y = A [x; x2] (x2 may be null: plain y = A x) for any CSR matrix.  Lanes per row: about a quarter of
+// the mean row length (each lane keeps four entries in flight), so that small matrices still
+// spread over the whole machine in one wave.
+void spmv_sub(const CsrView& A, const double* x, double* y, const double* x2, int nsplit) {
+  SpmvWarpArgs args{A, x, y, nullptr, nullptr, 0.0, nullptr, nullptr, 0, 0};
+  args.x2 = x2;
+  args.nsplit = x2 ? nsplit : 0x7fffffff;
+  static const double per_lane = [] { const char* e = std::getenv("FS_SUB_PER_LANE"); return e ? std::atof(e) : 4.0; }();
+  const double avg = A.n > 0 ? (double)A.nnz / A.n : 0.0;
+  const double lanes = avg / per_lane;
+  if (lanes <= 4.0) launch_sub<4>(args);
+  else if (lanes <= 8.0) launch_sub<8>(args);
+  else if (lanes <= 16.0) launch_sub<16>(args);
+  else launch_sub<32>(args);
+}
+
 static bool g_warp_attr = false;
 
 template <int EPI, bool DOT>
@@ -160,21 +345,21 @@ static void launch_one(const SpmvWarpArgs& args, int grid, size_t smem) {
 }
 
 template <int EPI, bool DOT>
-static void set_smem_attr(int bytes) {
-  FS_CUDA(cudaFuncSetAttribute(k_spmv_warp<EPI, DOT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  FS_CUDA(cudaFuncSetAttribute(k_spmv_warp<EPI, DOT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+static void set_smem_attr(size_t bytes) {
+  FS_CUDA(cudaFuncSetAttribute(k_spmv_warp<EPI, DOT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  FS_CUDA(cudaFuncSetAttribute(k_spmv_warp<EPI, DOT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
 }
 
 // Returns the grid size used (>0), or 0 when the matrix does not fit this kernel (the caller
 // falls back to the tile / vector kernels).
 int spmv_warp(const CsrView& A, int epi, const double* x, double* y, const double* b, const double* dinv, double w,
-              double* xout, double* dot_partials) {
+              double* xout, double* dot_partials, const double* x2, int nsplit) {
   if (A.wtile_nnz_max <= 0) return 0;
   const int wcap = (A.wtile_nnz_max + 31) / 32 * 32;
   const size_t smem = (size_t)kWW * wcap * sizeof(double);
-  if (smem > 100 * 1024) return 0;
+  const size_t big = 200 * 1024;   // above 100 KB one CTA per SM
+  if (smem > big) return 0;
   if (!g_warp_attr) {
-    const int big = 100 * 1024;
     set_smem_attr<EPI_AX, false>(big);
     set_smem_attr<EPI_AX, true>(big);
     set_smem_attr<EPI_RESID, false>(big);
@@ -182,12 +367,16 @@ int spmv_warp(const CsrView& A, int epi, const double* x, double* y, const doubl
     set_smem_attr<EPI_PRESM, false>(big);
     set_smem_attr<EPI_ADD, false>(big);
     set_smem_attr<EPI_AX2, false>(big);
+    set_smem_attr<EPI_AXS, false>(big);
+    set_smem_attr<EPI_AXS, true>(big);
     g_warp_attr = true;
   }
   const int ntiles = div_up(A.n, kWT);
-  const int per_sm = smem > 48 * 1024 ? (smem > 100 * 1024 / 1 ? 1 : 2) : 2;
+  const int per_sm = smem > 100 * 1024 ? 1 : 2;
   const int grid = std::max(1, std::min(sm_count() * per_sm, ntiles));
   SpmvWarpArgs args{A, x, y, b, dinv, w, xout, dot_partials, wcap, ntiles};
+  args.x2 = x2;
+  args.nsplit = nsplit;
   const bool dot = dot_partials != nullptr;
   switch (epi) {
     case EPI_AX: if (dot) launch_one<EPI_AX, true>(args, grid, smem); else launch_one<EPI_AX, false>(args, grid, smem); break;
@@ -196,6 +385,7 @@ int spmv_warp(const CsrView& A, int epi, const double* x, double* y, const doubl
     case EPI_PRESM: launch_one<EPI_PRESM, false>(args, grid, smem); break;
     case EPI_ADD: launch_one<EPI_ADD, false>(args, grid, smem); break;
     case EPI_AX2: launch_one<EPI_AX2, false>(args, grid, smem); break;
+    case EPI_AXS: if (dot) launch_one<EPI_AXS, true>(args, grid, smem); else launch_one<EPI_AXS, false>(args, grid, smem); break;
     default: throw Error(FS_ERR_INTERNAL, "spmv_warp: bad epilogue");
   }
   FS_LAUNCH_CHECK();
