@@ -252,6 +252,8 @@ def run_ours(args):
     t_dev, iters = timed_steps(sim, u_dev, args.steps, _lib, barrier)
     launches = fb.launch_count() - launches0
     pms, samples = read_profile(_lib)
+    top_ms, top_n, top_bytes = C.c_double(0), C.c_int64(0), C.c_double(0)
+    _lib.call("fs_profile_read_top", C.byref(top_ms), C.byref(top_n), C.byref(top_bytes))
     _lib.call("fs_profile", 0)
     clk = clocks.stop() if rank == 0 else None
     t_dev = max_over_ranks(t_dev)
@@ -287,19 +289,32 @@ def run_ours(args):
     it_arr = np.array(iters, dtype=np.float64)
     out_extra = {}
     if args.precond == "amg":
-        # dominant kernel of this configuration: the fine-level SpMV (CG's A*p and the two smoother
-        # products of the V-cycle are the same kernel on the same matrix); timed with CUDA events
-        # around the CG's A*p launch in every iteration of the timed region
+        # dominant kernel of this configuration: k_spmv_sell, the SELL-32 SpMV that runs the CG's A*p (fp64
+        # values) and every large operator of the folded V-cycle (fp32 values).  Its longest launch is the
+        # finest level's up-sweep z = [G | SP] [r; x_c] (+ fused r.z): timed with its own CUDA event pair on
+        # every 8th PCG iteration of the timed region (that cycle runs outside its CUDA graph); the A*p
+        # launch is bracketed by events in every iteration.
         t_spmv = pms[0] / samples / 1e3
-        roof = {"bound": "hbm", "kernel": "k_spmv_warp<EPI_AX,DOT> (fine-level CSR SpMV A*p of the AMG-preconditioned pressure CG, fused p.Ap)",
-                "achieved": spmv_bytes / t_spmv / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": spmv_bytes / t_spmv / 1e9 / peak,
-                "traffic": (json.load(open(TRAFFIC_FILE)).get("spmv_warp_dram_bytes_per_launch")
-                            if os.path.exists(TRAFFIC_FILE) else None), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": spmv_bytes, "us_per_launch": 1e6 * t_spmv, "sampled_launches": samples,
-                "frac_of_8TBps_spec": spmv_bytes / t_spmv / 8e12,
-                "us_per_pcg_iteration": {"A*p": 1e6 * t_spmv, "V-cycle": 1e3 * pms[1] / samples,
-                                         "vector ops + dots": 1e3 * pms[2] / samples}}
+        ap_bytes = 12.0 * nnz + 16.25 * nd      # values + columns, slice pointers (8 B / 32 rows), p gathered, A*p written
+        traffic = json.load(open(TRAFFIC_FILE)) if os.path.exists(TRAFFIC_FILE) else {}
+        ap_line = {"kernel": "k_spmv_sell<plain,DOT,f64> (A*p of the pressure CG, fused p.Ap)",
+                   "achieved": ap_bytes / t_spmv / 1e9, "frac": ap_bytes / t_spmv / 1e9 / peak,
+                   "algorithmic_bytes_per_launch": ap_bytes, "us_per_launch": 1e6 * t_spmv, "sampled_launches": samples,
+                   "traffic": traffic.get("sell_ap_dram_bytes_per_launch")}
+        if top_n.value > 0:
+            t_top = top_ms.value / top_n.value / 1e3
+            roof = {"bound": "hbm", "kernel": "k_spmv_sell<split,DOT,f32> (finest up-sweep of the folded AMG V-cycle: "
+                                              "z = [G | SP] [r; x_c], fused r.z)",
+                    "achieved": top_bytes.value / t_top / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": top_bytes.value / t_top / 1e9 / peak, "traffic": traffic.get("sell_up0_dram_bytes_per_launch"),
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": top_bytes.value, "us_per_launch": 1e6 * t_top,
+                    "sampled_launches": int(top_n.value), "frac_of_8TBps_spec": top_bytes.value / t_top / 8e12,
+                    "same_kernel_A*p": ap_line}
+        else:   # unfolded cycle (FS_AMG_FOLD=0): the CG's A*p is the largest launch
+            roof = dict(ap_line, bound="hbm", peak=peak, unit="GB/s", peak_source=peak_src,
+                        frac_of_8TBps_spec=ap_bytes / t_spmv / 8e12)
+        roof["us_per_pcg_iteration"] = {"A*p": 1e6 * t_spmv, "V-cycle": 1e3 * pms[1] / samples,
+                                        "vector ops + dots": 1e3 * pms[2] / samples}
         jac_iters = float(json.load(open(ITERS_FILE))["iters_per_step"]) if os.path.exists(ITERS_FILE) else 16000.0
         visc_iters = float(it_arr[:, 0].mean())
     if args.precond == "amg" and not args.no_extra and world == 1:

@@ -65,6 +65,10 @@ int fs_timer_stop(float* ms);
  * the CG iterations launched since fs_profile(every).  every=0 switches it off. */
 int fs_profile(int every);
 int fs_profile_read(double* ms3, int64_t* samples, int64_t* iters);
+/* AMG-preconditioned CG only: the V-cycle's largest kernel (the finest level's up-sweep SpMV) is
+ * timed with its own event pair on every 8th iteration (that cycle runs outside its CUDA graph).
+ * Summed milliseconds, number of timed launches, algorithmic bytes of one launch. */
+int fs_profile_read_top(double* ms, int64_t* samples, double* bytes_per_launch);
 
 /* ---- ingest: readNode / readEle, code/StokesColor.py:54-95 (fp32 variant
  * code/poisson.py:27-74 = same parse, caller casts).  Two-step: count, then fill. */

@@ -52,6 +52,7 @@ SIGNATURES = {
     "fs_timer_stop": (C.c_int, [P(C.c_float)]),
     "fs_profile": (C.c_int, [C.c_int]),
     "fs_profile_read": (C.c_int, [c_vp, P(c_i64), P(c_i64)]),
+    "fs_profile_read_top": (C.c_int, [P(C.c_double), P(c_i64), P(C.c_double)]),
     "fs_node_file_count": (C.c_int, [C.c_char_p, P(c_i64)]),
     "fs_read_node": (C.c_int, [C.c_char_p, c_vp, c_vp, c_i64]),
     "fs_ele_file_count": (C.c_int, [C.c_char_p, P(c_i64), P(c_i32)]),

@@ -55,6 +55,7 @@ struct Amg {
   int graph_nparts = 0;
   bool folded = true;           // two-kernel-per-level form of the cycle
   bool sell = true;             // folded operators in SELL-32 layout
+  cudaEvent_t* top_ev = nullptr; // transient: events around the finest up-sweep (amg_apply's top_ev)
   int sub_rows = 0;             // matrices with at most this many rows use the lanes-per-row CSR kernel
   int applications = 0;
   int tail_start = -1;          // first level handled by the one-kernel coarse tail (amg_tail.cu); -1: none
@@ -746,7 +747,11 @@ static int vcycle_folded(Amg& amg, size_t l, const double* b, double* x, double*
   // up: x = [G | P~] [b; x_c]
   int g = 0;
   if (lv.n <= sub_rows && lv.U.rowptr) spmv_sub(lv.U.view32(), b, x, nx.x.p, lv.n);
-  else if (lv.Us.nslices) g = spmv_sell(lv.Us, b, x, nx.x.p, lv.n, dot_part);
+  else if (lv.Us.nslices) {
+    if (l == 0 && amg.top_ev) cudaEventRecord(amg.top_ev[0], stream());
+    g = spmv_sell(lv.Us, b, x, nx.x.p, lv.n, dot_part);
+    if (l == 0 && amg.top_ev) cudaEventRecord(amg.top_ev[1], stream());
+  }
   else {
     const CsrView U = lv.U.view32();
     if (use_win) g = spmv_win(U, b, x, nx.x.p, lv.n, dot_part);
@@ -818,7 +823,15 @@ void amg_presmooth_target(Amg* amg, double** x0, const double** dinv, double* om
   *omega = amg->omega;
 }
 
-int amg_apply(Amg* amg, const double* r, double* z, bool x0_ready, double* rz_part) {
+double amg_top_bytes(const Amg* amg) {
+  if (!amg->folded || amg->L.size() < 2 || !amg->L[0]->Us.nslices) return 0.0;
+  const AmgLevel& l0 = *amg->L[0];
+  const double val_bytes = l0.Us.v32.n ? 4.0 : 8.0;
+  // true nonzeros (value + column), slice pointers, b gathered + re-read for the dot, x_c gathered, y written
+  return (double)l0.Us.nnz * (val_bytes + 4.0) + 8.0 * (l0.Us.nslices + 1) + 8.0 * l0.n + 8.0 * amg->L[1]->n + 8.0 * l0.n;
+}
+
+int amg_apply(Amg* amg, const double* r, double* z, bool x0_ready, double* rz_part, cudaEvent_t* top_ev) {
   static const bool use_graph = env_num("FS_AMG_GRAPH", 1) != 0;
   cudaStream_t st = stream();
   ++amg->applications;
@@ -828,6 +841,12 @@ int amg_apply(Amg* amg, const double* r, double* z, bool x0_ready, double* rz_pa
     vcycle_level(*amg, 0, r, z, x0_ready);
     return 0;
   };
+  if (top_ev && fold) {   // sampled timing: eager, with the event pair around the finest up-sweep
+    amg->top_ev = top_ev;
+    const int np = vcycle_folded(*amg, 0, r, z, rz_part);
+    amg->top_ev = nullptr;
+    return np;
+  }
   if (use_graph && amg->graph && amg->graph_r == r && amg->graph_z == z && amg->graph_x0 == x0_ready &&
       amg->graph_part == rz_part) {
     FS_CUDA(cudaGraphLaunch(amg->graph, st));

@@ -172,7 +172,7 @@ struct CsrView {
 
 }  // namespace fs
 
-namespace fs { struct Amg; void amg_free(Amg*); }
+namespace fs { struct Amg; void amg_free(Amg*); struct fs_sell; void sell_free(fs_sell*); }
 
 // Opaque handle definitions ----------------------------------------------------
 struct fs_csr {
@@ -194,7 +194,8 @@ struct fs_csr {
   fs_csr() = default;
   fs_csr(const fs_csr&) = delete;
   fs_csr& operator=(const fs_csr&) = delete;
-  ~fs_csr() { if (amg) fs::amg_free(amg); }
+  fs::fs_sell* sell64 = nullptr; // SELL-32 fp64 copy for the AMG-preconditioned CG's A*p (lazy)
+  ~fs_csr() { if (amg) fs::amg_free(amg); if (sell64) fs::sell_free(sell64); }
   fs::DBuf<float> vals32;        // fp32 copy of the values for the mixed-precision V-cycle (lazy)
   fs::CsrView view() const {
     return fs::CsrView{(int)n, nnz, rowptr, colidx, vals.p, tile_nnz_max > 0 ? tile_nnz_max : 0, wtile_nnz_max, nullptr};
@@ -280,7 +281,11 @@ Amg* amg_setup(fs_csr* fine);
 // x0_ready: the caller has written w D^-1 r into the buffer given by amg_presmooth_target (unfolded
 // cycle only).  rz_part (optional): room for per-CTA partial sums of r.z; the return value is how
 // many were written by the cycle's last kernel (0: the caller computes r.z itself).
-int amg_apply(Amg* amg, const double* r, double* z, bool x0_ready = false, double* rz_part = nullptr);
+// top_ev (optional, two events): run the cycle eagerly and bracket its largest kernel (the finest
+// level's up-sweep) with them -- the sampled roofline timing of bench.py.
+int amg_apply(Amg* amg, const double* r, double* z, bool x0_ready = false, double* rz_part = nullptr,
+              cudaEvent_t* top_ev = nullptr);
+double amg_top_bytes(const Amg* amg);   // algorithmic bytes of one launch of that kernel (0: unfolded cycle)
 void amg_presmooth_target(Amg* amg, double** x0, const double** dinv, double* omega);
 int amg_levels(const Amg* amg, int* sizes, int cap);
 // the coarse levels of the V-cycle as one cooperative kernel (amg_tail.cu)

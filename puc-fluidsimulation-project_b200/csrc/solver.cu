@@ -516,6 +516,9 @@ struct PassProf {
   double ms[3] = {0, 0, 0};
   long long samples = 0;
   long long iters = 0;   // CG iterations launched while enabled
+  // AMG-PCG: the V-cycle's largest kernel (finest up-sweep), timed on every 8th iteration
+  double top_ms = 0.0, top_bytes = 0.0;
+  long long top_samples = 0;
 };
 static PassProf g_prof;
 
@@ -875,6 +878,11 @@ static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, in
   double *r = a->ws.p, *p = r + n, *Ap = p + n, *z = Ap + n, *bproj = z + n;
   if (!a->amg) a->amg = amg_setup(a);
   ensure_tiles(a);
+  static const bool sell_ap = [] { const char* e = std::getenv("FS_PCG_SELL"); return !e || std::atoi(e) != 0; }();
+  if (sell_ap && !a->sell64 && n > 100000) {   // the CG's own A*p in the same SELL-32 layout (fp64 values)
+    a->sell64 = new fs_sell();
+    sell_build(*a, false, *a->sell64);
+  }
   const CsrView A = a->view();
   cudaStream_t st = stream();
   const int g = vec_grid(n);
@@ -899,9 +907,13 @@ static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, in
   // r.r partials at partBC[0, g); r.z partials at partRZ[0, nrz): written by the cycle's last kernel when
   // it can (folded cycle), else by k_pcg_rz
   double* partRZ = partBC + kMaxBlocks;
+  bool top_pending = false;
+  int napply = 0;
   auto precond = [&](const double* rin, double* zout, bool x0_ready) -> int {
     if (prof) cudaEventRecord(g_prof.ev[2], st);
-    int nrz = amg_apply(a->amg, rin, zout, x0_ready, partRZ);
+    const bool samp_top = prof && (napply++ % 8 == 4);
+    int nrz = amg_apply(a->amg, rin, zout, x0_ready, partRZ, samp_top ? &g_prof.ev[5] : nullptr);
+    top_pending = samp_top;
     if (prof) cudaEventRecord(g_prof.ev[3], st);
     if (!nrz) {
       k_pcg_rz<<<g, kBlock, 0, st>>>(n, rin, zout, partRZ); FS_LAUNCH_CHECK();
@@ -936,7 +948,8 @@ static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, in
     while (it < maxit) {
       // one host read per iteration: alpha is formed on the device, beta on the host
       if (prof) cudaEventRecord(g_prof.ev[0], st);
-      int ga = spmv_warp(A, EPI_AX, p, Ap, nullptr, nullptr, 0.0, nullptr, partA);
+      int ga = a->sell64 ? spmv_sell(*a->sell64, p, Ap, nullptr, 0, partA) : 0;
+      if (!ga) ga = spmv_warp(A, EPI_AX, p, Ap, nullptr, nullptr, 0.0, nullptr, partA);
       if (!ga) { ga = spmv_launch_grid<1>(A); launch_spmv<1, true>(A, p, Ap, partA, nullptr, ga); }
       if (prof) cudaEventRecord(g_prof.ev[1], st);
       k_pcg_xr<<<g, kBlock, 0, st>>>(n, p, Ap, x, r, partA, ga, rz, partBC, x0, dinv0, w0); FS_LAUNCH_CHECK();
@@ -952,6 +965,12 @@ static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, in
         cudaEventElapsedTime(&t_it, g_prof.ev[0], g_prof.ev[4]);
         g_prof.ms[0] += t_spmv; g_prof.ms[1] += t_v; g_prof.ms[2] += t_it - t_spmv - t_v;
         g_prof.samples += 1; g_prof.iters += 1;
+        if (top_pending) {
+          float t_top = 0.f;
+          if (cudaEventElapsedTime(&t_top, g_prof.ev[5], g_prof.ev[6]) == cudaSuccess && t_top > 0.f) {
+            g_prof.top_ms += t_top; g_prof.top_samples += 1; g_prof.top_bytes = amg_top_bytes(a->amg);
+          }
+        }
       }
       rr = s_rr;
       if (rr <= tol2 * bb) break;
@@ -1207,6 +1226,8 @@ int fs_profile(int every) {
   g_prof.ms[0] = g_prof.ms[1] = g_prof.ms[2] = 0.0;
   g_prof.samples = 0;
   g_prof.iters = 0;
+  g_prof.top_ms = 0.0;
+  g_prof.top_samples = 0;
   if (every > 0 && g_prof.ev.empty()) {
     g_prof.ev.resize(4 * 64);
     for (auto& e : g_prof.ev) FS_CUDA(cudaEventCreate(&e));
@@ -1219,6 +1240,14 @@ int fs_profile_read(double* ms3, int64_t* samples, int64_t* iters) {
   if (ms3) for (int j = 0; j < 3; ++j) ms3[j] = g_prof.ms[j];
   if (samples) *samples = g_prof.samples;
   if (iters) *iters = g_prof.iters;
+  FS_API_END
+}
+
+int fs_profile_read_top(double* ms, int64_t* samples, double* bytes_per_launch) {
+  FS_API_BEGIN
+  if (ms) *ms = g_prof.top_ms;
+  if (samples) *samples = g_prof.top_samples;
+  if (bytes_per_launch) *bytes_per_launch = g_prof.top_bytes;
   FS_API_END
 }
 

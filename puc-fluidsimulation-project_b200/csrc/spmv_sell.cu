@@ -136,6 +136,8 @@ __global__ void k_sell_fill(CsrView A, int nslices, const long long* __restrict_
   }
 }
 
+void sell_free(fs_sell* s) { delete s; }
+
 void sell_build(const fs_csr& A, bool f32, fs_sell& out) {
   cudaStream_t st = stream();
   const int n = (int)A.n;
