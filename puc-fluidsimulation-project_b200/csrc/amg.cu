@@ -516,7 +516,7 @@ Amg* amg_setup(fs_csr* fine) {
         coo_to_csr(ukeys, uv, mu, cur.n, cur.n + nc, cur.U);
         coo_to_csr(rkeys, rv, mr, nc, cur.n, cur.Rt);
         if (amg->sell) {
-          sell_build(cur.U, fp32, cur.Us);
+          sell_build(cur.U, fp32, cur.Us, cur.n);
           sell_build(cur.Rt, fp32, cur.Rts);
         }
         auto drop = [](fs_csr& M) { M.vals.release(); M.colidx_own.release(); M.rowptr_own.release(); M.rowptr = M.colidx = nullptr; };
@@ -736,7 +736,7 @@ static int vcycle_folded(Amg& amg, size_t l, const double* b, double* x, double*
   const int sub_rows = amg.sub_rows;
   // down: b_c = R~ b
   if (nx.n <= sub_rows && lv.Rt.rowptr) spmv_sub(lv.Rt.view32(), b, nx.b.p, nullptr, 0);
-  else if (lv.Rts.nslices) spmv_sell(lv.Rts, b, nx.b.p, nullptr, 0, nullptr);
+  else if (lv.Rts.nslices) spmv_sell(lv.Rts, b, nx.b.p, nullptr, nullptr);
   else {
     const CsrView Rt = lv.Rt.view32();
     if (!((use_win && spmv_win(Rt, b, nx.b.p, nullptr, 0, nullptr)) ||
@@ -749,7 +749,7 @@ static int vcycle_folded(Amg& amg, size_t l, const double* b, double* x, double*
   if (lv.n <= sub_rows && lv.U.rowptr) spmv_sub(lv.U.view32(), b, x, nx.x.p, lv.n);
   else if (lv.Us.nslices) {
     if (l == 0 && amg.top_ev) cudaEventRecord(amg.top_ev[0], stream());
-    g = spmv_sell(lv.Us, b, x, nx.x.p, lv.n, dot_part);
+    g = spmv_sell(lv.Us, b, x, nx.x.p, dot_part);
     if (l == 0 && amg.top_ev) cudaEventRecord(amg.top_ev[1], stream());
   }
   else {

@@ -194,6 +194,7 @@ struct fs_csr {
   fs_csr() = default;
   fs_csr(const fs_csr&) = delete;
   fs_csr& operator=(const fs_csr&) = delete;
+  int pcg_hint = 0, pcg_hint_prev = 0;   // iterations of the last two converged AMG-PCG solves (lagged convergence polling)
   fs::fs_sell* sell64 = nullptr; // SELL-32 fp64 copy for the AMG-preconditioned CG's A*p (lazy)
   ~fs_csr() { if (amg) fs::amg_free(amg); if (sell64) fs::sell_free(sell64); }
   fs::DBuf<float> vals32;        // fp32 copy of the values for the mixed-precision V-cycle (lazy)
@@ -266,13 +267,15 @@ int spmv_warp(const CsrView& A, int epi, const double* x, double* y, const doubl
 struct fs_sell {
   int n = 0, nslices = 0;
   long long padded = 0, nnz = 0;
+  int nsplit = -1;        // >= 0: split form (see spmv_sell.cu)
   DBuf<long long> sptr;   // nslices + 1 element offsets (multiples of 32)
+  DBuf<int> wg;           // split form: per-slice width of the first part
   DBuf<int> cols;
   DBuf<float> v32;        // exactly one of v32 / v64 is filled
   DBuf<double> v64;
 };
-void sell_build(const fs_csr& A, bool f32, fs_sell& out);
-int spmv_sell(const fs_sell& S, const double* x, double* y, const double* x2, int nsplit, double* dot_partials);
+void sell_build(const fs_csr& A, bool f32, fs_sell& out, int nsplit = -1);
+int spmv_sell(const fs_sell& S, const double* x, double* y, const double* x2, double* dot_partials);
 // windowed fp32-matrix kernel of the folded V-cycle: y = A [x; x2], optional partials of x.y; 0 if A has no fp32 copy
 int spmv_win(const CsrView& A, const double* x, double* y, const double* x2, int nsplit, double* dot_partials);
 // any-matrix fallback: y = A [x; x2] (columns >= nsplit gather from x2; x2 null: y = A x)

@@ -61,21 +61,41 @@ __device__ __forceinline__ void block_reduce(double (&v)[K], double* smem /* K*3
   __syncthreads();
 }
 
-// every block re-reduces the partial array (nblk x K) in the same fixed order;
+// every block re-reduces the partial array (nblk x K) in the same fixed order (thread-strided
+// sums with the loads issued together, warp xor trees, then the warps in ascending order);
 // result broadcast to all threads through shared memory.
 template <int K>
 __device__ __forceinline__ void reduce_partials(const double* __restrict__ part, int nblk, double (&out)[K],
                                                 double* smem /* K */) {
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
+  __shared__ double scr[32 * K];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5, nw = blockDim.x >> 5;
+  double acc[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      double t = 0.0;
-      for (int b = lane; b < nblk; b += 32) t += part[(size_t)b * K + k];
+  for (int k = 0; k < K; ++k) acc[k] = 0.0;
+  for (int b0 = t; b0 < nblk; b0 += 4 * blockDim.x) {
+    double v[4][K];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if (lane == 0) smem[k] = t;
+    for (int j = 0; j < 4; ++j) {
+      const int b = b0 + j * blockDim.x;
+#pragma unroll
+      for (int k = 0; k < K; ++k) v[j][k] = (b < nblk) ? part[(size_t)b * K + k] : 0.0;
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc[k] += v[j][k];
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    if (lane == 0) scr[w * K + k] = acc[k];
+  }
+  __syncthreads();
+  if (t < K) {
+    double s = 0.0;
+    for (int q = 0; q < nw; ++q) s += scr[q * K + t];
+    smem[t] = s;
   }
   __syncthreads();
 #pragma unroll
@@ -837,26 +857,45 @@ __global__ void k_lin3(int64_t n, double a, const double* __restrict__ x, double
                        const double* __restrict__ z, double* __restrict__ out);
 
 // ---- CG preconditioned by one AMG V-cycle (amg.cu).  ~50x fewer iterations than Jacobi on
-// the 4M-triangle pressure operator, so the two host reads of scalars per iteration are noise.
+// the 4M-triangle pressure operator.  All scalars live on the device:
+//   sc[0], sc[1]  r.z of the previous / current iteration (slot = iteration parity)
+//   sc[2] b.b   sc[3] latest r.r   sc[4] tol^2      flags[0] converged   flags[1] iterations done
+// alpha is formed in k_pcg_xr from the SpMV's partials, beta and the convergence test in k_pcg_p
+// from the partials of r.r (k_pcg_xr) and r.z (the V-cycle's last kernel); both kernels return at
+// once when flags[0] is set, so x stays the converged iterate however many more iterations are
+// queued.  The host therefore queues iterations without reading anything back for as long as the
+// previous solve on this matrix needed (minus 3), and only then polls the flag once per iteration.
 static void dot2(int64_t n, const double* a, const double* b, const double* c, const double* d, double* part, double* out2);
 
-// x += alpha p ; r -= alpha Ap with alpha = rz / (p.Ap) formed on the device from the SpMV's
-// per-CTA partials (rz is known to the host from the previous iteration); partial r.r out.
+__global__ void k_pcg_init(const double* __restrict__ partRZ, int nrz, double bb, double rr, double tol2,
+                           double* __restrict__ sc, int* __restrict__ flags) {
+  __shared__ double sm[1];
+  double rz[1];
+  reduce_partials<1>(partRZ, nrz, rz, sm);
+  if (threadIdx.x == 0) {
+    sc[0] = rz[0]; sc[1] = 0.0; sc[2] = bb; sc[3] = rr; sc[4] = tol2;
+    flags[0] = 0; flags[1] = 0;
+  }
+}
+
+// x += alpha p ; r -= alpha Ap with alpha = rz / (p.Ap); partial r.r out.
 __global__ void __launch_bounds__(kBlock)
 k_pcg_xr(int64_t n, const double* __restrict__ p, const double* __restrict__ Ap, double* __restrict__ x, double* __restrict__ r,
-         const double* __restrict__ partA, int nblkA, double rz, double* __restrict__ partB,
-         double* __restrict__ x0out, const double* __restrict__ dinv, double w) {
+         const double* __restrict__ partA, int nblkA, const double* __restrict__ sc, int slot, const int* __restrict__ flags,
+         double* __restrict__ partB, double* __restrict__ x0out, const double* __restrict__ dinv, double w) {
   __shared__ double red[32];
   __shared__ double sm[1];
+  if (flags[0]) return;
   double pAp[1];
   reduce_partials<1>(partA, nblkA, pAp, sm);
+  const double rz = sc[slot];
   const double alpha = (pAp[0] != 0.0) ? rz / pAp[0] : 0.0;
   double acc[1] = {0.0};
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const double rn = r[i] - alpha * Ap[i];
     x[i] += alpha * p[i];
     r[i] = rn;
-    if (x0out) x0out[i] = w * dinv[i] * rn;     // the V-cycle's pre-smoothed iterate, for free
+    if (x0out) x0out[i] = w * dinv[i] * rn;     // the unfolded V-cycle's pre-smoothed iterate, for free
     acc[0] += rn * rn;
   }
   block_reduce<1>(acc, red);
@@ -872,6 +911,30 @@ k_pcg_rz(int64_t n, const double* __restrict__ r, const double* __restrict__ z, 
   if (threadIdx.x == 0) partC[blockIdx.x] = acc[0];
 }
 
+// convergence test, beta = r.z / (r.z)_old, p = z + beta p; block 0 publishes the scalars
+__global__ void __launch_bounds__(kBlock)
+k_pcg_p(int64_t n, const double* __restrict__ z, double* __restrict__ p, const double* __restrict__ partB, int nB,
+        const double* __restrict__ partRZ, int nRZ, double* __restrict__ sc, int slot, int* __restrict__ flags) {
+  __shared__ double sm[1];
+  if (flags[0]) return;
+  double rr[1], rzn[1];
+  reduce_partials<1>(partB, nB, rr, sm);
+  reduce_partials<1>(partRZ, nRZ, rzn, sm);
+  const double rz_old = sc[slot];
+  const bool conv = rr[0] <= sc[4] * sc[2];
+  if (!conv) {
+    const double beta = rz_old != 0.0 ? rzn[0] / rz_old : 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+      p[i] = z[i] + beta * p[i];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    sc[slot ^ 1] = rzn[0];
+    sc[3] = rr[0];
+    flags[1] += 1;
+    if (conv) flags[0] = 1;
+  }
+}
+
 static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, int maxit, int project_mean, double* relres) {
   const int64_t n = a->n;
   ensure_ws(a, 5 * (size_t)n);
@@ -879,6 +942,7 @@ static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, in
   if (!a->amg) a->amg = amg_setup(a);
   ensure_tiles(a);
   static const bool sell_ap = [] { const char* e = std::getenv("FS_PCG_SELL"); return !e || std::atoi(e) != 0; }();
+  static const bool lagged = [] { const char* e = std::getenv("FS_PCG_LAGGED"); return !e || std::atoi(e) != 0; }();
   if (sell_ap && !a->sell64 && n > 100000) {   // the CG's own A*p in the same SELL-32 layout (fp64 values)
     a->sell64 = new fs_sell();
     sell_build(*a, false, *a->sell64);
@@ -889,7 +953,10 @@ static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, in
   double* part = a->partials.p;
   double* part0 = a->partials.p + kMaxBlocks * 8;
   double* partA = a->partials.p + kMaxBlocks * 10;     // p.Ap partials of the SpMV
-  double* partBC = a->partials.p + kMaxBlocks * 12;    // [0,g): r.r   [g,2g): r.z
+  double* partB = a->partials.p + kMaxBlocks * 12;     // r.r partials of k_pcg_xr
+  double* partRZ = partB + kMaxBlocks;                 // r.z partials: the cycle's last kernel (folded cycle) or k_pcg_rz
+  double* sc = a->scal.p;
+  int* flags = reinterpret_cast<int*>(a->scal.p + 32);
   const double* b = d_b;
   if (project_mean) {
     k_sum<<<g, kBlock, 0, st>>>(n, d_b, part0); FS_LAUNCH_CHECK();
@@ -898,23 +965,28 @@ static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, in
   }
   // A constant component of z is harmless for a mean-free r (r.z, A p do not see it) and is
   // removed from x at the end, so z is not projected every iteration.
+  // Profiling (bench.py): 7 events per iteration from the pool -- A*p [0,1], V-cycle [2,3], end [4], and on every
+  // 8th iteration the cycle runs eagerly with [5,6] around its largest kernel; read back after the solve.
   const bool prof = g_prof.every > 0;
-  if (prof && g_prof.ev.size() < 8) { g_prof.ev.resize(8); for (auto& e : g_prof.ev) cudaEventCreate(&e); }
+  constexpr int kEvPer = 7;
+  if (prof && g_prof.ev.size() < 640) {
+    const size_t old = g_prof.ev.size();
+    g_prof.ev.resize(640);
+    for (size_t k = old; k < g_prof.ev.size(); ++k) cudaEventCreate(&g_prof.ev[k]);
+  }
+  const int ev_iters = prof ? (int)(g_prof.ev.size() / kEvPer) : 0;
+  std::vector<char> top_sampled;
   double* x0 = nullptr;
   const double* dinv0 = nullptr;
   double w0 = 0.0;
   amg_presmooth_target(a->amg, &x0, &dinv0, &w0);
-  // r.r partials at partBC[0, g); r.z partials at partRZ[0, nrz): written by the cycle's last kernel when
-  // it can (folded cycle), else by k_pcg_rz
-  double* partRZ = partBC + kMaxBlocks;
-  bool top_pending = false;
   int napply = 0;
-  auto precond = [&](const double* rin, double* zout, bool x0_ready) -> int {
-    if (prof) cudaEventRecord(g_prof.ev[2], st);
-    const bool samp_top = prof && (napply++ % 8 == 4);
-    int nrz = amg_apply(a->amg, rin, zout, x0_ready, partRZ, samp_top ? &g_prof.ev[5] : nullptr);
-    top_pending = samp_top;
-    if (prof) cudaEventRecord(g_prof.ev[3], st);
+  auto precond = [&](const double* rin, double* zout, bool x0_ready, cudaEvent_t* ev /* 7 events or null */) -> int {
+    if (ev) cudaEventRecord(ev[2], st);
+    const bool samp_top = ev && (napply % 8 == 4);
+    ++napply;
+    int nrz = amg_apply(a->amg, rin, zout, x0_ready, partRZ, samp_top ? ev + 5 : nullptr);
+    if (ev) { cudaEventRecord(ev[3], st); top_sampled.push_back(samp_top ? 1 : 0); }
     if (!nrz) {
       k_pcg_rz<<<g, kBlock, 0, st>>>(n, rin, zout, partRZ); FS_LAUNCH_CHECK();
       nrz = g;
@@ -932,51 +1004,55 @@ static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, in
   if (bb == 0.0) { FS_CUDA(cudaMemsetAsync(x, 0, n * sizeof(double), st)); if (relres) *relres = 0.0; return 0; }
   const double tol2 = rtol * rtol;
   int it = 0;
-  if (rr > tol2 * bb) {
-    std::vector<double> hp(2 * (size_t)kMaxBlocks);
-    auto read_sums = [&](int nrz, double& s_rr, double& s_rz) {
-      FS_CUDA(cudaMemcpyAsync(hp.data(), partBC, sizeof(double) * (kMaxBlocks + nrz), cudaMemcpyDeviceToHost, st));
-      FS_CUDA(cudaStreamSynchronize(st));
-      s_rr = 0.0; s_rz = 0.0;
-      for (int k = 0; k < g; ++k) s_rr += hp[k];
-      for (int k = 0; k < nrz; ++k) s_rz += hp[kMaxBlocks + k];
-    };
-    int nrz = precond(r, z, false);
+  bool done = rr <= tol2 * bb;
+  if (!done) {
+    int nrz = precond(r, z, false, nullptr);
     FS_CUDA(cudaMemcpyAsync(p, z, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    double rz = 0.0, dummy = 0.0;
-    read_sums(nrz, dummy, rz);
-    while (it < maxit) {
-      // one host read per iteration: alpha is formed on the device, beta on the host
-      if (prof) cudaEventRecord(g_prof.ev[0], st);
-      int ga = a->sell64 ? spmv_sell(*a->sell64, p, Ap, nullptr, 0, partA) : 0;
+    k_pcg_init<<<1, kBlock, 0, st>>>(partRZ, nrz, bb, rr, tol2, sc, flags); FS_LAUNCH_CHECK();
+    const int unchecked = lagged ? std::max(0, std::min(std::min(a->pcg_hint, a->pcg_hint_prev) - 3, maxit)) : 0;
+    int queued = 0, hflags[2] = {0, 0};
+    while (queued < maxit) {
+      cudaEvent_t* ev = (prof && queued < ev_iters) ? &g_prof.ev[(size_t)queued * kEvPer] : nullptr;
+      const int slot = queued & 1;
+      if (ev) cudaEventRecord(ev[0], st);
+      int ga = a->sell64 ? spmv_sell(*a->sell64, p, Ap, nullptr, partA) : 0;
       if (!ga) ga = spmv_warp(A, EPI_AX, p, Ap, nullptr, nullptr, 0.0, nullptr, partA);
       if (!ga) { ga = spmv_launch_grid<1>(A); launch_spmv<1, true>(A, p, Ap, partA, nullptr, ga); }
-      if (prof) cudaEventRecord(g_prof.ev[1], st);
-      k_pcg_xr<<<g, kBlock, 0, st>>>(n, p, Ap, x, r, partA, ga, rz, partBC, x0, dinv0, w0); FS_LAUNCH_CHECK();
-      ++it;
-      nrz = precond(r, z, x0 != nullptr);
-      if (prof) cudaEventRecord(g_prof.ev[4], st);
-      double s_rr = 0.0, s_rz = 0.0;
-      read_sums(nrz, s_rr, s_rz);
-      if (prof) {
-        float t_spmv = 0.f, t_v = 0.f, t_it = 0.f;
-        cudaEventElapsedTime(&t_spmv, g_prof.ev[0], g_prof.ev[1]);
-        cudaEventElapsedTime(&t_v, g_prof.ev[2], g_prof.ev[3]);
-        cudaEventElapsedTime(&t_it, g_prof.ev[0], g_prof.ev[4]);
+      if (ev) cudaEventRecord(ev[1], st);
+      k_pcg_xr<<<g, kBlock, 0, st>>>(n, p, Ap, x, r, partA, ga, sc, slot, flags, partB, x0, dinv0, w0); FS_LAUNCH_CHECK();
+      nrz = precond(r, z, x0 != nullptr, ev);
+      k_pcg_p<<<g, kBlock, 0, st>>>(n, z, p, partB, g, partRZ, nrz, sc, slot, flags); FS_LAUNCH_CHECK();
+      if (ev) cudaEventRecord(ev[4], st);
+      ++queued;
+      if (queued > unchecked) {
+        FS_CUDA(cudaMemcpyAsync(hflags, flags, sizeof(hflags), cudaMemcpyDeviceToHost, st));
+        FS_CUDA(cudaStreamSynchronize(st));
+        if (hflags[0]) break;
+      }
+    }
+    double hsc[5];
+    FS_CUDA(cudaMemcpyAsync(hflags, flags, sizeof(hflags), cudaMemcpyDeviceToHost, st));
+    FS_CUDA(cudaMemcpyAsync(hsc, sc, sizeof(hsc), cudaMemcpyDeviceToHost, st));
+    FS_CUDA(cudaStreamSynchronize(st));
+    done = hflags[0] != 0;
+    it = hflags[1];
+    rr = hsc[3];
+    if (done) { a->pcg_hint_prev = a->pcg_hint; a->pcg_hint = it; }
+    if (prof) {
+      const int nk = std::min(std::min(it, queued), ev_iters);
+      for (int k = 0; k < nk; ++k) {
+        cudaEvent_t* ev = &g_prof.ev[(size_t)k * kEvPer];
+        float t_spmv = 0.f, t_v = 0.f, t_it = 0.f, t_top = 0.f;
+        if (cudaEventElapsedTime(&t_spmv, ev[0], ev[1]) != cudaSuccess || cudaEventElapsedTime(&t_v, ev[2], ev[3]) != cudaSuccess ||
+            cudaEventElapsedTime(&t_it, ev[0], ev[4]) != cudaSuccess) { cudaGetLastError(); continue; }
         g_prof.ms[0] += t_spmv; g_prof.ms[1] += t_v; g_prof.ms[2] += t_it - t_spmv - t_v;
-        g_prof.samples += 1; g_prof.iters += 1;
-        if (top_pending) {
-          float t_top = 0.f;
-          if (cudaEventElapsedTime(&t_top, g_prof.ev[5], g_prof.ev[6]) == cudaSuccess && t_top > 0.f) {
-            g_prof.top_ms += t_top; g_prof.top_samples += 1; g_prof.top_bytes = amg_top_bytes(a->amg);
-          }
+        g_prof.samples += 1;
+        if (k < (int)top_sampled.size() && top_sampled[k] && cudaEventElapsedTime(&t_top, ev[5], ev[6]) == cudaSuccess && t_top > 0.f) {
+          g_prof.top_ms += t_top; g_prof.top_samples += 1; g_prof.top_bytes = amg_top_bytes(a->amg);
         }
       }
-      rr = s_rr;
-      if (rr <= tol2 * bb) break;
-      const double beta = rz != 0.0 ? s_rz / rz : 0.0;
-      rz = s_rz;
-      k_lin3<<<g, kBlock, 0, st>>>(n, 1.0, z, beta, p, 0.0, nullptr, p); FS_LAUNCH_CHECK();
+      cudaGetLastError();
+      g_prof.iters += it;
     }
   }
   if (project_mean) {
@@ -984,7 +1060,7 @@ static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, in
     k_sub_mean<<<g, kBlock, 0, st>>>(n, x, x, part0, g); FS_LAUNCH_CHECK();
   }
   if (relres) *relres = std::sqrt(rr / bb);
-  return (rr <= tol2 * bb) ? it : -it - 1;
+  return done ? it : -it - 1;
 }
 
 int cg_dev(fs_csr* a, const double* d_b, double* d_x, int nrhs, double rtol, int maxit, int precond, int project_mean,
@@ -1229,7 +1305,7 @@ int fs_profile(int every) {
   g_prof.top_ms = 0.0;
   g_prof.top_samples = 0;
   if (every > 0 && g_prof.ev.empty()) {
-    g_prof.ev.resize(4 * 64);
+    g_prof.ev.resize(640);
     for (auto& e : g_prof.ev) FS_CUDA(cudaEventCreate(&e));
   }
   FS_API_END

@@ -8,6 +8,9 @@
 //   * for a fixed k the 32 lanes gather the k-th neighbours of 32 consecutive rows, which on a mesh
 //     numbering are close together: far fewer L1 sectors per gather than the CSR-stream layout, where
 //     a warp's lanes walk along single rows.
+// Split form for y = A [x; x2]: the entries with column < nsplit come first, padded to the slice's
+// longest first part, then the rest with columns relative to nsplit -- the gather source is then
+// uniform per step and there is no per-entry select.
 // The CSR-stream kernels measured ~1.0-1.3 nonzeros / cycle / SM whatever the value width (L1TEX
 // bound: scattered gathers + shared-memory staging), so fp32 values bought nothing there.
 // y = A x or A [x; x2] (columns >= nsplit read x2), optional per-CTA partials of x.y.
@@ -24,35 +27,64 @@ constexpr int kSU = 8;          // entries per lane per batch
 struct SellArgs {
   int n, nslices;
   const long long* sptr;
+  const int* wg;        // split form: width of the first part of every slice
   const int* cols;
   const float* v32;
   const double* v64;
   const double* x;
   const double* x2;
-  int nsplit;
   double* y;
   double* part;
 };
 
-__device__ __forceinline__ uint64_t s_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
+// One part of a slice: W entries per lane at stride 32, all gathered from x.  Unguarded batches of 8
+// and 4 (loads first, then the gathers, then the sums), then a guarded batch for the last 1-3.
+// The fp32 (preconditioner) form uses fused multiply-adds; the fp64 form keeps multiply-then-add so
+// that its sums have the same bits as the CSR kernels' (the library is built with -fmad=false).
+template <class VT>
+__device__ __forceinline__ double sell_mac(VT v, double xv, double acc) {
+  if (sizeof(VT) == 4) return fma((double)v, xv, acc);
+  return acc + (double)v * xv;
 }
-__device__ __forceinline__ float s_ld_f32(const float* a, uint64_t pol) {
-  float v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(a), "l"(pol));
-  return v;
+
+template <int U, class VT>
+__device__ __forceinline__ double sell_batch(const VT* __restrict__ vp, const int* __restrict__ cp, const double* __restrict__ x,
+                                             double acc) {
+  VT vv[U];
+  int cc[U];
+#pragma unroll
+  for (int j = 0; j < U; ++j) { vv[j] = __ldcs(vp + (j << 5)); cc[j] = __ldcs(cp + (j << 5)); }
+  double xx[U];
+#pragma unroll
+  for (int j = 0; j < U; ++j) xx[j] = __ldg(x + cc[j]);
+#pragma unroll
+  for (int j = 0; j < U; ++j) acc = sell_mac<VT>(vv[j], xx[j], acc);
+  return acc;
 }
-__device__ __forceinline__ double s_ld_f64(const double* a, uint64_t pol) {
-  double v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(a), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ int s_ld_s32(const int* a, uint64_t pol) {
-  int v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
-  return v;
+
+template <class VT>
+__device__ __forceinline__ double sell_part(const VT* __restrict__ vp, const int* __restrict__ cp, int W,
+                                            const double* __restrict__ x, double acc) {
+  int k = 0;
+  for (; k + 8 <= W; k += 8, vp += 256, cp += 256) acc = sell_batch<8, VT>(vp, cp, x, acc);
+  if (k + 4 <= W) { acc = sell_batch<4, VT>(vp, cp, x, acc); k += 4; vp += 128; cp += 128; }
+  if (k < W) {
+    const int rem = W - k;
+    VT vv[3];
+    int cc[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const bool ok = j < rem;
+      vv[j] = ok ? __ldcs(vp + (j << 5)) : VT(0);
+      cc[j] = ok ? __ldcs(cp + (j << 5)) : 0;
+    }
+    double xx[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) xx[j] = __ldg(x + cc[j]);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) acc = sell_mac<VT>(vv[j], xx[j], acc);
+  }
+  return acc;
 }
 
 template <bool SPLIT, bool DOT, bool F32>
@@ -60,33 +92,21 @@ __global__ void __launch_bounds__(kST, 6) k_spmv_sell(SellArgs a) {
   __shared__ double red[kSW];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nwarps = gridDim.x * kSW;
-  const uint64_t pf = s_evict_first();
   double dacc = 0.0;
   for (int s = blockIdx.x * kSW + warp; s < a.nslices; s += nwarps) {
     const long long off = __ldg(a.sptr + s);
     const int W = (int)((__ldg(a.sptr + s + 1) - off) >> 5);
-    const int* __restrict__ c = a.cols + off + lane;
-    const float* __restrict__ v32 = a.v32 + off + lane;
-    const double* __restrict__ v64 = a.v64 + off + lane;
+    const int Wg = SPLIT ? __ldg(a.wg + s) : W;
+    const int* __restrict__ cp = a.cols + off + lane;
     double acc = 0.0;
-    for (int k0 = 0; k0 < W; k0 += kSU) {
-      double vv[kSU];
-      int cc[kSU];
-#pragma unroll
-      for (int j = 0; j < kSU; ++j) {
-        const bool ok = k0 + j < W;
-        const int o = (k0 + j) << 5;
-        vv[j] = ok ? (F32 ? (double)s_ld_f32(v32 + o, pf) : s_ld_f64(v64 + o, pf)) : 0.0;
-        cc[j] = ok ? s_ld_s32(c + o, pf) : 0;
-      }
-      double xx[kSU];
-#pragma unroll
-      for (int j = 0; j < kSU; ++j) {
-        if (SPLIT) xx[j] = cc[j] < a.nsplit ? __ldg(a.x + cc[j]) : __ldg(a.x2 + (cc[j] - a.nsplit));
-        else xx[j] = __ldg(a.x + cc[j]);
-      }
-#pragma unroll
-      for (int j = 0; j < kSU; ++j) acc += vv[j] * xx[j];
+    if (F32) {
+      const float* __restrict__ vp = a.v32 + off + lane;
+      acc = sell_part<float>(vp, cp, Wg, a.x, acc);
+      if (SPLIT) acc = sell_part<float>(vp + ((long long)Wg << 5), cp + ((long long)Wg << 5), W - Wg, a.x2, acc);
+    } else {
+      const double* __restrict__ vp = a.v64 + off + lane;
+      acc = sell_part<double>(vp, cp, Wg, a.x, acc);
+      if (SPLIT) acc = sell_part<double>(vp + ((long long)Wg << 5), cp + ((long long)Wg << 5), W - Wg, a.x2, acc);
     }
     const int row = (s << 5) + lane;
     if (row < a.n) {
@@ -107,45 +127,72 @@ __global__ void __launch_bounds__(kST, 6) k_spmv_sell(SellArgs a) {
 }
 
 // ---- build -------------------------------------------------------------------------------
-__global__ void k_sell_width(CsrView A, int nslices, long long* __restrict__ w32) {
+// number of leading entries of a (column-sorted) row with column < nsplit
+__device__ __forceinline__ int row_split(const CsrView& A, int rs, int len, int nsplit) {
+  int g = 0;
+  while (g < len && A.colidx[rs + g] < nsplit) ++g;
+  return g;
+}
+
+// per slice: 32 * (max first-part length + max second-part length); nsplit = INT_MAX: one part
+__global__ void k_sell_width(CsrView A, int nslices, int nsplit, long long* __restrict__ w32, int* __restrict__ wg) {
   const int s = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (s > nslices) return;
-  int len = 0;
+  int lg = 0, lp = 0;
   const int row = (s << 5) + lane;
-  if (s < nslices && row < A.n) len = A.rowptr[row + 1] - A.rowptr[row];
-  for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
-  if (lane == 0) w32[s] = (long long)len << 5;   // entry nslices = 0: the scan's total lands there
+  if (s < nslices && row < A.n) {
+    const int rs = A.rowptr[row], len = A.rowptr[row + 1] - rs;
+    lg = row_split(A, rs, len, nsplit);
+    lp = len - lg;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lg = max(lg, __shfl_xor_sync(0xffffffffu, lg, o));
+    lp = max(lp, __shfl_xor_sync(0xffffffffu, lp, o));
+  }
+  if (lane == 0) {
+    w32[s] = (long long)(lg + lp) << 5;   // entry nslices = 0: the scan's total lands there
+    if (wg && s < nslices) wg[s] = lg;
+  }
 }
 
 template <bool F32>
-__global__ void k_sell_fill(CsrView A, int nslices, const long long* __restrict__ sptr, int* __restrict__ cols,
-                            float* __restrict__ v32, double* __restrict__ v64) {
+__global__ void k_sell_fill(CsrView A, int nslices, int nsplit, const long long* __restrict__ sptr, const int* __restrict__ wg,
+                            int* __restrict__ cols, float* __restrict__ v32, double* __restrict__ v64) {
   const int s = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (s >= nslices) return;
   const long long off = sptr[s];
   const int W = (int)((sptr[s + 1] - off) >> 5);
+  const int Wg = wg ? wg[s] : W;
   const int row = (s << 5) + lane;
-  int rs = 0, len = 0;
-  if (row < A.n) { rs = A.rowptr[row]; len = A.rowptr[row + 1] - rs; }
+  int rs = 0, len = 0, lg = 0;
+  if (row < A.n) { rs = A.rowptr[row]; len = A.rowptr[row + 1] - rs; lg = row_split(A, rs, len, nsplit); }
   for (int k = 0; k < W; ++k) {
     const long long idx = off + ((long long)k << 5) + lane;
-    const bool ok = k < len;
-    cols[idx] = ok ? A.colidx[rs + k] : 0;      // padding: value 0 times x[0]
-    const double v = ok ? A.vals[rs + k] : 0.0;
+    // source entry: first part k < lg, second part (k - Wg) < len - lg; padding: value 0 times x[0]
+    int src = -1;
+    if (k < Wg) { if (k < lg) src = rs + k; }
+    else if (k - Wg < len - lg) src = rs + lg + (k - Wg);
+    const int col = src >= 0 ? A.colidx[src] : 0;
+    cols[idx] = (src >= 0 && k >= Wg) ? col - nsplit : col;
+    const double v = src >= 0 ? A.vals[src] : 0.0;
     if (F32) v32[idx] = (float)v; else v64[idx] = v;
   }
 }
 
 void sell_free(fs_sell* s) { delete s; }
 
-void sell_build(const fs_csr& A, bool f32, fs_sell& out) {
+// nsplit >= 0: two-part slices (columns < nsplit first, padded per slice; the second part's columns
+// are stored relative to nsplit), for y = A [x; x2] without a per-entry select.
+void sell_build(const fs_csr& A, bool f32, fs_sell& out, int nsplit) {
   cudaStream_t st = stream();
   const int n = (int)A.n;
   const int nslices = div_up(n, 32);
+  const bool split = nsplit >= 0;
   DBuf<long long> w32((size_t)nslices + 1);
   out.sptr.alloc((size_t)nslices + 1);
+  if (split) out.wg.alloc((size_t)nslices);
   const int g = (int)div_up(((int64_t)nslices + 1) * 32, 256);
-  k_sell_width<<<g, 256, 0, st>>>(A.view(), nslices, w32.p);
+  k_sell_width<<<g, 256, 0, st>>>(A.view(), nslices, split ? nsplit : 0x7fffffff, w32.p, split ? out.wg.p : nullptr);
   FS_LAUNCH_CHECK();
   size_t bytes = 0;
   FS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, w32.p, out.sptr.p, nslices + 1, st));
@@ -159,10 +206,12 @@ void sell_build(const fs_csr& A, bool f32, fs_sell& out) {
   out.nslices = nslices;
   out.padded = total;
   out.nnz = A.nnz;
+  out.nsplit = nsplit;
   out.cols.alloc((size_t)total);
   if (f32) out.v32.alloc((size_t)total); else out.v64.alloc((size_t)total);
-  if (f32) k_sell_fill<true><<<g, 256, 0, st>>>(A.view(), nslices, out.sptr.p, out.cols.p, out.v32.p, nullptr);
-  else k_sell_fill<false><<<g, 256, 0, st>>>(A.view(), nslices, out.sptr.p, out.cols.p, nullptr, out.v64.p);
+  const int ns = split ? nsplit : 0x7fffffff;
+  if (f32) k_sell_fill<true><<<g, 256, 0, st>>>(A.view(), nslices, ns, out.sptr.p, out.wg.p, out.cols.p, out.v32.p, nullptr);
+  else k_sell_fill<false><<<g, 256, 0, st>>>(A.view(), nslices, ns, out.sptr.p, out.wg.p, out.cols.p, nullptr, out.v64.p);
   FS_LAUNCH_CHECK();
   FS_CUDA(cudaStreamSynchronize(st));
 }
@@ -173,11 +222,13 @@ static void launch_sell(const SellArgs& args, int grid) {
   else k_spmv_sell<SPLIT, DOT, false><<<grid, kST, 0, stream()>>>(args);
 }
 
-// Returns the grid (= number of dot partials when asked for), 0 if S is empty.
-int spmv_sell(const fs_sell& S, const double* x, double* y, const double* x2, int nsplit, double* dot_partials) {
+// y = S x, or S [x; x2] for a matrix built in split form.  Returns the grid (= number of dot
+// partials when asked for), 0 if S is empty.
+int spmv_sell(const fs_sell& S, const double* x, double* y, const double* x2, double* dot_partials) {
   if (!S.nslices) return 0;
+  FS_REQUIRE((S.nsplit >= 0) == (x2 != nullptr), "spmv_sell: split form and second vector must come together");
   const int grid = std::max(1, std::min(div_up(S.nslices, kSW), sm_count() * 6));
-  SellArgs args{S.n, S.nslices, S.sptr.p, S.cols.p, S.v32.p, S.v64.p, x, x2, x2 ? nsplit : 0x7fffffff, y, dot_partials};
+  SellArgs args{S.n, S.nslices, S.sptr.p, S.wg.p, S.cols.p, S.v32.p, S.v64.p, x, x2, y, dot_partials};
   if (x2) {
     if (dot_partials) launch_sell<true, true>(args, grid);
     else launch_sell<true, false>(args, grid);

@@ -14,6 +14,8 @@
 // equations are multiplied by the lumped mass and the SPD system
 //     (Z^T K Z) q = Z^T (M * b) - mean,   p = Z (q - mean q)
 // is solved by CG.
+#include <chrono>
+
 #include "internal.cuh"
 
 struct fs_stokes {
@@ -179,6 +181,16 @@ int fs_stokes_step(fs_stokes* s, double* u, double B1, double B2, const fs_stoke
   double* du = ou.d;
   fs_stokes_stats sts;
   std::memset(&sts, 0, sizeof(sts));
+  // FS_STEP_TIMING=1 (diagnostic): synchronise and print the wall time of each phase
+  static const bool timing = std::getenv("FS_STEP_TIMING") != nullptr;
+  double tmark[8];
+  int nmark = 0;
+  auto mark = [&]() {
+    if (!timing) return;
+    cudaStreamSynchronize(st);
+    tmark[nmark++] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  };
+  mark();
   // Step 1: tentative velocity, both components in one 2-RHS CG started from u
   FS_CUDA(cudaMemcpyAsync(s->ustar.p, du, 2 * N * sizeof(double), cudaMemcpyDeviceToDevice, st));
   // A_visc = I + DT*nu*K has cond ~ 1: Jacobi is all it needs (the AMG option is for the pressure operator)
@@ -188,14 +200,18 @@ int fs_stokes_step(fs_stokes* s, double* u, double B1, double B2, const fs_stoke
   sts.iters_visc = it;
   per_bcu_dev(m, s->ustar.p);
   dir_bcu_dev(m, s->ustar.p, B1, B2);
+  mark();
   // Step 2+3: pressure correction and velocity update
   pressure_solve(s, s->ustar.p, s->p_red.p, s->p_full.p, o, &sts.iters_p1, &sts.relres_p1,
                  o.final_div ? &sts.max_div_ustar : nullptr);
+  mark();
   grad_update_dev(m, s->p_full.p, s->ustar.p, du, s->DT, nullptr);
   per_bcu_dev(m, du);
   dir_bcu_dev(m, du, B1, B2);
+  mark();
   // second projection, interior nodes only, no BC re-imposition (:566-573)
   pressure_solve(s, du, s->p2_red.p, s->p2_full.p, o, &sts.iters_p2, &sts.relres_p2, nullptr);
+  mark();
   grad_update_dev(m, s->p2_full.p, du, du, s->DT, s->is_interior.p);
   s->have_p = true;
   if (o.final_div) {
@@ -204,6 +220,11 @@ int fs_stokes_step(fs_stokes* s, double* u, double B1, double B2, const fs_stoke
   }
   ou.commit();
   fs::sync();
+  mark();
+  if (timing && nmark == 6)
+    std::fprintf(stderr, "[step] viscous %.0f us | pressure-1 %.0f us (%d it) | grad+bc %.0f us | pressure-2 %.0f us (%d it) | tail %.0f us\n",
+                 tmark[1] - tmark[0], tmark[2] - tmark[1], sts.iters_p1, tmark[3] - tmark[2], tmark[4] - tmark[3], sts.iters_p2,
+                 tmark[5] - tmark[4]);
   if (stats) *stats = sts;
   FS_API_END
 }
