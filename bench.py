@@ -170,10 +170,11 @@ def workload_config(args, **extra):
     cfg = {"workload": f"stokes_step square-with-hole n_theta={args.n_theta} n_r={args.n_r} "
                        f"(T={2 * args.n_theta * args.n_r}, N={args.n_theta * (args.n_r + 1)}), pusher B1=-2 B2=-5, "
                        f"nu=0.1, DT=0.05",
-           "solver": f"pressure: CG + smoothed-aggregation AMG V(1,1) [--precond amg] or Jacobi persistent CG "
-                     f"[--precond jacobi], rtol_pressure={RTOL_P:g}; viscous: 2-RHS Jacobi CG rtol={RTOL_V:g}; "
-                     f"warm start from the previous step",
-           "l2": "inputs larger than L2 (CSR matrix 185 MB + 4 vectors 67 MB > 126 MB), no flush needed",
+           "solver": f"pressure: CG + smoothed-aggregation AMG V(1,1), cycle folded to two SELL-32 SpMVs per level "
+                     f"[--precond amg] or Jacobi persistent CG [--precond jacobi], rtol_pressure={RTOL_P:g}; "
+                     f"viscous: 2-RHS Jacobi CG rtol={RTOL_V:g}; warm start from the previous step",
+           "l2": "inputs larger than L2 (per PCG iteration: A 190 MB fp64 SELL + V-cycle operators ~440 MB fp32 SELL "
+                 "+ 5 vectors 84 MB > 126 MB), no flush needed",
            "steps_from": "t=0 (u=0 + squirmer BC); warm-up steps advance the same trajectory"}
     cfg.update(extra)
     return cfg

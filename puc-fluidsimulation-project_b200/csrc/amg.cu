@@ -58,7 +58,6 @@ struct Amg {
   cudaEvent_t* top_ev = nullptr; // transient: events around the finest up-sweep (amg_apply's top_ev)
   int sub_rows = 0;             // matrices with at most this many rows use the lanes-per-row CSR kernel
   int applications = 0;
-  int tail_start = -1;          // first level handled by the one-kernel coarse tail (amg_tail.cu); -1: none
   ~Amg() { if (graph) cudaGraphExecDestroy(graph); }
 };
 
@@ -415,12 +414,20 @@ __global__ void __launch_bounds__(1024) k_dense_invert(int n, double* __restrict
     __syncthreads();
   }
 }
-// x = Minv * b, one warp per row
+// x = Minv * b, one warp per row, four independent partial sums per lane (the row is a dependent
+// chain of ~n/32 loads otherwise: this kernel is pure latency)
 __global__ void k_dense_gemv(int n, const double* __restrict__ Minv, const double* __restrict__ b, double* __restrict__ x) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= n) return;
-  double s = 0.0;
-  for (int j = lane; j < n; j += 32) s += Minv[(size_t)row * n + j] * b[j];
+  const double* __restrict__ m = Minv + (size_t)row * n;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int j = lane;
+  for (; j + 96 < n; j += 128) {
+    const double m0 = __ldg(m + j), m1 = __ldg(m + j + 32), m2 = __ldg(m + j + 64), m3 = __ldg(m + j + 96);
+    s0 += m0 * __ldg(b + j); s1 += m1 * __ldg(b + j + 32); s2 += m2 * __ldg(b + j + 64); s3 += m3 * __ldg(b + j + 96);
+  }
+  for (; j < n; j += 32) s0 += __ldg(m + j) * __ldg(b + j);
+  double s = (s0 + s1) + (s2 + s3);
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (lane == 0) x[row] = s;
 }
@@ -582,23 +589,13 @@ Amg* amg_setup(fs_csr* fine) {
       amg->coarse_n = n;
     }
   }
-  // levels at or below FS_AMG_TAIL_ROWS rows (down to the dense coarsest one) run as one kernel
-  {
-    const int tail_rows = (int)env_num("FS_AMG_TAIL_ROWS", 0);
-    const int nl = (int)amg->L.size();
-    if (!amg->folded && tail_rows > 0 && amg->coarse_n > 0 && nl >= 2 && amg_tail_supported()) {
-      int t = nl - 1;
-      while (t > 0 && amg->L[t - 1]->n <= tail_rows && nl - (t - 1) <= kTailMaxLevels) --t;
-      if (t <= nl - 2) amg->tail_start = t;
-    }
-  }
   FS_CUDA(cudaStreamSynchronize(stream()));
   if (std::getenv("FS_AMG_VERBOSE")) {
     std::fprintf(stderr, "[amg] levels:");
     for (auto& l : amg->L)
       std::fprintf(stderr, " %d(nnz %lld, U %lld [sell %lld], Rt %lld [sell %lld])", l->n, (long long)l->mat().nnz, (long long)l->U.nnz,
                    l->Us.padded, (long long)l->Rt.nnz, l->Rts.padded);
-    std::fprintf(stderr, "  folded %d  tail from level %d\n", (int)amg->folded, amg->tail_start);
+    std::fprintf(stderr, "  folded %d\n", (int)amg->folded);
   }
   return amg.release();
 }
@@ -642,63 +639,6 @@ k_coarse_jacobi(CsrView A, const double* __restrict__ dinv, const double* __rest
 
 static int vgrid(int n) { return std::max(1, std::min(div_up(n, 256), sm_count() * 8)); }
 
-static TailMat tail_mat(const fs_csr& M) {
-  TailMat t;
-  t.rowptr = M.rowptr; t.colidx = M.colidx; t.vals = M.vals.p;
-  t.vals32 = M.vals32.n ? M.vals32.p : nullptr;
-  t.n = (int)M.n;
-  return t;
-}
-
-// levels l .. last in one cooperative kernel; lv.t must hold w D^-1 b
-static void vcycle_tail(Amg& amg, size_t l, const double* b, double* x) {
-  TailArgs args;
-  const size_t nl = amg.L.size();
-  for (size_t k = l; k < nl; ++k) {
-    AmgLevel& lv = *amg.L[k];
-    TailLevel& t = args.lv[k - l];
-    t.A = tail_mat(lv.mat());
-    if (k + 1 < nl) { t.P = tail_mat(lv.P); t.PT = tail_mat(lv.PT); }
-    t.dinv = lv.mat().dinv.p;
-    t.b = (k == l) ? b : lv.b.p;
-    t.bw = (k == l) ? nullptr : lv.b.p;
-    t.x = (k == l) ? x : lv.x.p;
-    t.r = lv.r.p;
-    t.t = lv.t.p;
-    t.n = lv.n;
-  }
-  args.nlev = (int)(nl - l);
-  args.Minv = amg.coarse_inv.p;
-  args.w = amg.omega;
-  static const bool timing = std::getenv("FS_AMG_TAIL_TIME") != nullptr;
-  if (timing) {
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    cudaStreamIsCapturing(stream(), &cs);
-    if (cs == cudaStreamCaptureStatusNone) {
-      cudaEvent_t e0, e1;
-      cudaEventCreate(&e0); cudaEventCreate(&e1);
-      static DBuf<long long> dbg;
-      if (!dbg.n) dbg.alloc(64);
-      dbg.zero();
-      args.dbg = dbg.p;
-      cudaStreamSynchronize(stream());
-      cudaEventRecord(e0, stream());
-      amg_tail_launch(args);
-      cudaEventRecord(e1, stream());
-      cudaEventSynchronize(e1);
-      float ms = 0.f;
-      cudaEventElapsedTime(&ms, e0, e1);
-      std::fprintf(stderr, "[amg] tail kernel (%d levels from %d rows): %.1f us; CTA0 phase cycles:", args.nlev, args.lv[0].n, ms * 1e3);
-      std::vector<long long> h = dbg.to_host();
-      for (int k = 1; k < 64 && h[k]; ++k) std::fprintf(stderr, " %lld", h[k] - h[k - 1]);
-      std::fprintf(stderr, "\n");
-      cudaEventDestroy(e0); cudaEventDestroy(e1);
-      return;
-    }
-  }
-  amg_tail_launch(args);
-}
-
 static void coarse_solve(Amg& amg, size_t l, const double* b, double* x) {
   cudaStream_t st = stream();
   AmgLevel& lv = *amg.L[l];
@@ -707,7 +647,7 @@ static void coarse_solve(Amg& amg, size_t l, const double* b, double* x) {
   const int n = lv.n, g = vgrid(n);
   const double w = amg.omega;
   if (amg.coarse_n == n && l > 0) {
-    k_dense_gemv<<<div_up(n * 32, 256), 256, 0, st>>>(n, amg.coarse_inv.p, b, x);
+    k_dense_gemv<<<div_up(n * 32, 128), 128, 0, st>>>(n, amg.coarse_inv.p, b, x);
     FS_LAUNCH_CHECK();
   } else if (n <= 1024) {
     k_coarse_jacobi<<<1, 1024, 0, st>>>(Av, A.dinv.p, b, x, w, amg.coarse_sweeps);
@@ -726,7 +666,6 @@ static void coarse_solve(Amg& amg, size_t l, const double* b, double* x) {
 // The folded cycle: b_c = R~ b ; recurse ; x = [G | P~] [b; x_c].  With dot_part the up-sweep of
 // this level also leaves the per-CTA partials of b.x (the CG's r.z); returns their count.
 static int vcycle_folded(Amg& amg, size_t l, const double* b, double* x, double* dot_part) {
-  static const bool use_win = env_num("FS_AMG_WIN", 1) != 0;        // windowed fp32 CSR kernel when there is no SELL copy
   if (l + 1 == amg.L.size()) {
     coarse_solve(amg, l, b, x);
     return 0;
@@ -739,9 +678,7 @@ static int vcycle_folded(Amg& amg, size_t l, const double* b, double* x, double*
   else if (lv.Rts.nslices) spmv_sell(lv.Rts, b, nx.b.p, nullptr, nullptr);
   else {
     const CsrView Rt = lv.Rt.view32();
-    if (!((use_win && spmv_win(Rt, b, nx.b.p, nullptr, 0, nullptr)) ||
-          spmv_warp(Rt, EPI_AX, b, nx.b.p, nullptr, nullptr, 0.0, nullptr, nullptr)))
-      spmv_sub(Rt, b, nx.b.p, nullptr, 0);
+    if (!spmv_warp(Rt, EPI_AX, b, nx.b.p, nullptr, nullptr, 0.0, nullptr, nullptr)) spmv_sub(Rt, b, nx.b.p, nullptr, 0);
   }
   vcycle_folded(amg, l + 1, nx.b.p, nx.x.p, nullptr);
   // up: x = [G | P~] [b; x_c]
@@ -754,8 +691,7 @@ static int vcycle_folded(Amg& amg, size_t l, const double* b, double* x, double*
   }
   else {
     const CsrView U = lv.U.view32();
-    if (use_win) g = spmv_win(U, b, x, nx.x.p, lv.n, dot_part);
-    if (!g) g = spmv_warp(U, EPI_AXS, b, x, nullptr, nullptr, 0.0, nullptr, dot_part, nx.x.p, lv.n);
+    g = spmv_warp(U, EPI_AXS, b, x, nullptr, nullptr, 0.0, nullptr, dot_part, nx.x.p, lv.n);
     if (!g) spmv_sub(U, b, x, nx.x.p, lv.n);
   }
   return dot_part ? g : 0;
@@ -770,14 +706,6 @@ static void vcycle_level(Amg& amg, size_t l, const double* b, double* x, bool x0
   const CsrView Av = A.view();
   const int n = lv.n, g = vgrid(n);
   const double w = amg.omega;
-  if ((int)l == amg.tail_start) {
-    if (!x0_ready) {
-      k_jac0<<<g, 256, 0, st>>>(n, w, A.dinv.p, b, lv.t.p);
-      FS_LAUNCH_CHECK();
-    }
-    vcycle_tail(amg, l, b, x);
-    return;
-  }
   if (l + 1 == amg.L.size()) {
     coarse_solve(amg, l, b, x);
     return;
@@ -877,7 +805,7 @@ int amg_apply(Amg* amg, const double* r, double* z, bool x0_ready, double* rz_pa
     if (g) cudaGraphDestroy(g);
     cudaGetLastError();
     if (std::getenv("FS_AMG_VERBOSE")) std::fprintf(stderr, "[amg] graph capture failed (%s)\n", cudaGetErrorString(e));
-    amg->graph_failed = true;   // e.g. a driver that cannot capture the cooperative launch: run the cycle eagerly
+    amg->graph_failed = true;   // run the cycle eagerly from now on
   }
   return cycle();
 }

@@ -276,8 +276,8 @@ struct fs_sell {
 };
 void sell_build(const fs_csr& A, bool f32, fs_sell& out, int nsplit = -1);
 int spmv_sell(const fs_sell& S, const double* x, double* y, const double* x2, double* dot_partials);
-// windowed fp32-matrix kernel of the folded V-cycle: y = A [x; x2], optional partials of x.y; 0 if A has no fp32 copy
-int spmv_win(const CsrView& A, const double* x, double* y, const double* x2, int nsplit, double* dot_partials);
+int spmv_sell_grid(const fs_sell& S);   // grid (= dot partials per column) of spmv_sell2
+void spmv_sell2(const fs_sell& S, const double* x, double* y, double* dot_partials, const int* done);
 // any-matrix fallback: y = A [x; x2] (columns >= nsplit gather from x2; x2 null: y = A x)
 void spmv_sub(const CsrView& A, const double* x, double* y, const double* x2, int nsplit);
 Amg* amg_setup(fs_csr* fine);
@@ -291,32 +291,6 @@ int amg_apply(Amg* amg, const double* r, double* z, bool x0_ready = false, doubl
 double amg_top_bytes(const Amg* amg);   // algorithmic bytes of one launch of that kernel (0: unfolded cycle)
 void amg_presmooth_target(Amg* amg, double** x0, const double** dinv, double* omega);
 int amg_levels(const Amg* amg, int* sizes, int cap);
-// the coarse levels of the V-cycle as one cooperative kernel (amg_tail.cu)
-constexpr int kTailMaxLevels = 8;
-struct TailMat {
-  const int* rowptr = nullptr;
-  const int* colidx = nullptr;
-  const double* vals = nullptr;
-  const float* vals32 = nullptr;
-  int n = 0;
-};
-struct TailLevel {
-  TailMat A, P, PT;
-  const double* dinv = nullptr;
-  const double* b = nullptr;   // right-hand side of the level (written by the level above inside the kernel)
-  double* bw = nullptr;        // same buffer, writable (null on the first level of the tail)
-  double *x = nullptr, *r = nullptr, *t = nullptr;
-  int n = 0;
-};
-struct TailArgs {
-  TailLevel lv[kTailMaxLevels];
-  int nlev = 0;
-  const double* Minv = nullptr;   // dense inverse of the last level's operator
-  double w = 0.0;
-  long long* dbg = nullptr;       // optional: clock64 of CTA 0 at every phase boundary (FS_AMG_TAIL_TIME)
-};
-bool amg_tail_supported();
-void amg_tail_launch(const TailArgs& args);
 bool cg_persistent_supported(const CsrView& A, size_t* smem_out);
 void cg_persistent_launch(const CsrView& A, double* x, double* r, double* p, double* Ap, const double* dinv,
                           double* partA, double* partB, double* scal, int* flags, int maxit, double tol2);

@@ -779,7 +779,15 @@ static int cg_impl(fs_csr* a, const double* d_b, double* d_x, double rtol, int m
     FS_LAUNCH_CHECK();
     b_use = bproj;
   }
-  launch_spmv<R, false>(A, d_x, Ap, nullptr, nullptr);
+  // two right-hand sides on a large matrix (the viscous solve): SELL-32 copy, A streamed once for both
+  static const bool sell2 = [] { const char* e = std::getenv("FS_CG_SELL2"); return !e || std::atoi(e) != 0; }();
+  const bool use_sell2 = R == 2 && sell2 && n > 100000;
+  if (use_sell2 && !a->sell64) {
+    a->sell64 = new fs_sell();
+    sell_build(*a, false, *a->sell64);
+  }
+  if (use_sell2) spmv_sell2(*a->sell64, d_x, Ap, nullptr, nullptr);
+  else launch_spmv<R, false>(A, d_x, Ap, nullptr, nullptr);
   k_cg_init<R><<<gv, kBlock, 0, st>>>(n, b_use, Ap, dinv, r, p, part0);
   FS_LAUNCH_CHECK();
   k_cg_init_fin<R><<<1, 32, 0, st>>>(part0, gv, sc, tol2);
@@ -812,7 +820,7 @@ static int cg_impl(fs_csr* a, const double* d_b, double* d_x, double rtol, int m
     }
     maxit = 0;   // skip the multi-kernel loop below
   }
-  const int ga = spmv_launch_grid<R>(A);
+  const int ga = use_sell2 ? spmv_sell_grid(*a->sell64) : spmv_launch_grid<R>(A);
   int launched = 0, chunk = 8, slot = 0;
   while (!hs.flags[0] && launched < maxit) {
     int todo = std::min(chunk, maxit - launched);
@@ -820,7 +828,8 @@ static int cg_impl(fs_csr* a, const double* d_b, double* d_x, double rtol, int m
       const bool samp = R == 1 && g_prof.every > 0 && ((launched + k) % g_prof.every == 0) &&
                         g_prof.used + 4 <= (int)g_prof.ev.size();
       if (samp) cudaEventRecord(g_prof.ev[g_prof.used++], st);
-      launch_spmv<R, true>(A, p, Ap, partA, sc.flags, ga);
+      if (use_sell2) spmv_sell2(*a->sell64, p, Ap, partA, sc.flags);
+      else launch_spmv<R, true>(A, p, Ap, partA, sc.flags, ga);
       if (samp) cudaEventRecord(g_prof.ev[g_prof.used++], st);
       k_cg_update_xr<R><<<gv, kBlock, 0, st>>>(n, p, Ap, dinv, d_x, r, partA, ga, sc, slot, partB);
       FS_LAUNCH_CHECK();

@@ -126,6 +126,54 @@ __global__ void __launch_bounds__(kST, 6) k_spmv_sell(SellArgs a) {
   }
 }
 
+// two interleaved right-hand sides (x, y are (n,2) row-major), fp64 values: the viscous 2-RHS CG
+template <bool DOT>
+__global__ void __launch_bounds__(kST, 4) k_spmv_sell2(SellArgs a, const int* __restrict__ done) {
+  __shared__ double red[2 * kSW];
+  if (done && *done) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = gridDim.x * kSW;
+  const double2* __restrict__ x2v = reinterpret_cast<const double2*>(a.x);
+  double d0 = 0.0, d1 = 0.0;
+  for (int s = blockIdx.x * kSW + warp; s < a.nslices; s += nwarps) {
+    const long long off = __ldg(a.sptr + s);
+    const int W = (int)((__ldg(a.sptr + s + 1) - off) >> 5);
+    const int* __restrict__ cp = a.cols + off + lane;
+    const double* __restrict__ vp = a.v64 + off + lane;
+    double a0 = 0.0, a1 = 0.0;
+    for (int k0 = 0; k0 < W; k0 += 4, vp += 128, cp += 128) {
+      double vv[4];
+      int cc[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool ok = k0 + j < W;
+        vv[j] = ok ? __ldcs(vp + (j << 5)) : 0.0;
+        cc[j] = ok ? __ldcs(cp + (j << 5)) : 0;
+      }
+      double2 xx[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) xx[j] = __ldg(x2v + cc[j]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { a0 += vv[j] * xx[j].x; a1 += vv[j] * xx[j].y; }
+    }
+    const int row = (s << 5) + lane;
+    if (row < a.n) {
+      reinterpret_cast<double2*>(a.y)[row] = make_double2(a0, a1);
+      if (DOT) { const double2 xr = __ldg(x2v + row); d0 += xr.x * a0; d1 += xr.y * a1; }
+    }
+  }
+  if (DOT) {
+    for (int o = 16; o > 0; o >>= 1) { d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o); }
+    if (lane == 0) { red[2 * warp] = d0; red[2 * warp + 1] = d1; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      double sum = 0.0;
+      for (int k = 0; k < kSW; ++k) sum += red[2 * k + threadIdx.x];
+      a.part[2 * blockIdx.x + threadIdx.x] = sum;
+    }
+  }
+}
+
 // ---- build -------------------------------------------------------------------------------
 // number of leading entries of a (column-sorted) row with column < nsplit
 __device__ __forceinline__ int row_split(const CsrView& A, int rs, int len, int nsplit) {
@@ -238,6 +286,18 @@ int spmv_sell(const fs_sell& S, const double* x, double* y, const double* x2, do
   }
   FS_LAUNCH_CHECK();
   return grid;
+}
+
+int spmv_sell_grid(const fs_sell& S) { return std::max(1, std::min(div_up(S.nslices, kSW), sm_count() * 4)); }
+
+// (n,2) interleaved x, y; fp64 one-part matrix; optional partials of x.y per column (2 per CTA) and early-exit flag
+void spmv_sell2(const fs_sell& S, const double* x, double* y, double* dot_partials, const int* done) {
+  FS_REQUIRE(S.nslices && S.v64.p && S.nsplit < 0, "spmv_sell2: needs a one-part fp64 SELL matrix");
+  const int grid = spmv_sell_grid(S);
+  SellArgs args{S.n, S.nslices, S.sptr.p, nullptr, S.cols.p, nullptr, S.v64.p, x, nullptr, y, dot_partials};
+  if (dot_partials) k_spmv_sell2<true><<<grid, kST, 0, stream()>>>(args, done);
+  else k_spmv_sell2<false><<<grid, kST, 0, stream()>>>(args, done);
+  FS_LAUNCH_CHECK();
 }
 
 }  // namespace fs

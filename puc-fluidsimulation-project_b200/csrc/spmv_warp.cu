@@ -158,129 +158,6 @@ __global__ void __launch_bounds__(kWT, 2) k_spmv_warp(SpmvWarpArgs a) {
   }
 }
 
-// ---- windowed fp32-matrix variant for the folded V-cycle (y = A x or A [x; x2], optional x.y partials)
-// Same warp / mini-tile ownership as k_spmv_warp, but (a) 16 nonzeros per lane are in flight (the
-// fp32 values and the columns take the registers of 8 fp64 ones: the loop is latency-bound, so
-// bytes in flight per warp are what sets the rate) and (b) the products of one 512-nonzero
-// chunk are summed into the per-lane row sums before the next chunk overwrites the window, so
-// shared memory is 4 KB per warp whatever the row length and two CTAs always fit an SM.
-constexpr int kVU = 16;
-constexpr int kVC = kVU * 32;
-
-template <bool SPLIT, bool DOT>
-__global__ void __launch_bounds__(kWT, 2) k_spmv_win(SpmvWarpArgs a) {
-  extern __shared__ double win[];
-  __shared__ double red[kWW];
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nb = gridDim.x, bi = blockIdx.x;
-  const uint64_t pf = w_evict_first();
-  const int tile0 = (int)(((long long)a.ntiles * bi) / nb);
-  const int tile1 = (int)(((long long)a.ntiles * (bi + 1)) / nb);
-  const int R0 = tile0 * kWT, R1 = min(a.A.n, tile1 * kWT);
-  const int* __restrict__ rowptr = a.A.rowptr;
-  const float* __restrict__ vals32 = a.A.vals32;
-  const int* __restrict__ colidx = a.A.colidx;
-  const unsigned full = 0xffffffffu;
-  double* pw = win + warp * kVC;
-  const int nmt = (R1 - R0 + 31) >> 5;
-  double acc = 0.0;
-  float va[kVU];
-  int ca[kVU];
-  auto xval = [&](int j) -> double {
-    if (SPLIT) return j < a.nsplit ? __ldg(a.x + j) : __ldg(a.x2 + (j - a.nsplit));
-    return __ldg(a.x + j);
-  };
-  auto load_rp = [&](int mt, int& rp, int& rend) {
-    if (mt < nmt) {
-      const int r0 = R0 + (mt << 5);
-      const int nr = min(32, R1 - r0);
-      rp = __ldg(rowptr + r0 + min(lane, nr));
-      rend = __ldg(rowptr + r0 + nr);
-    } else { rp = 0; rend = 0; }
-  };
-  auto stream = [&](int base, int cnt) {
-#pragma unroll
-    for (int j = 0; j < kVU; ++j) {
-      const int k = (j << 5) + lane;
-      const bool ok = k < cnt;
-      va[j] = ok ? w_ld_stream_f32(vals32 + base + k, pf) : 0.f;
-      ca[j] = ok ? w_ld_stream_s32(colidx + base + k, pf) : -1;
-    }
-  };
-  int rpA, endA, rpB, endB;
-  load_rp(warp, rpA, endA);
-  load_rp(warp + kWW, rpB, endB);
-  int baseA = __shfl_sync(full, rpA, 0);
-  int cntA = endA - baseA;
-  stream(baseA, cntA);
-  for (int mt = warp; mt < nmt; mt += kWW) {
-    int rpC, endC;
-    load_rp(mt + 2 * kWW, rpC, endC);
-    const int baseB = __shfl_sync(full, rpB, 0);
-    const int cntB = endB - baseB;
-    int nxt = __shfl_down_sync(full, rpA, 1);
-    if (lane == 31) nxt = endA;
-    const int lo0 = rpA - baseA, hi0 = nxt - baseA;   // this lane's row inside the mini-tile's nonzeros
-    double s = 0.0;
-    for (int c0 = 0;; c0 += kVC) {
-#pragma unroll
-      for (int j = 0; j < kVU; ++j)
-        if (ca[j] >= 0) pw[(j << 5) + lane] = (double)va[j] * xval(ca[j]);
-      const bool last = c0 + kVC >= cntA;
-      if (last) stream(baseB, cntB);
-      else stream(baseA + c0 + kVC, cntA - c0 - kVC);
-      __syncwarp();
-      const int lo = max(lo0, c0) - c0, hi = min(hi0, c0 + kVC) - c0;
-      for (int k = lo; k < hi; ++k) s += pw[k];
-      __syncwarp();
-      if (last) break;
-    }
-    const int row = R0 + (mt << 5) + lane;
-    if (row < R1) {
-      if (DOT) acc += __ldg(a.x + row) * s;
-      a.y[row] = s;
-    }
-    rpA = rpB; endA = endB; baseA = baseB; cntA = cntB;
-    rpB = rpC; endB = endC;
-  }
-  if (DOT) {
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(full, acc, o);
-    if (lane == 0) red[warp] = acc;
-    __syncthreads();
-    if (t == 0) {
-      double sum = 0.0;
-      for (int k = 0; k < kWW; ++k) sum += red[k];
-      a.part[bi] = sum;
-    }
-  }
-}
-
-// y = A [x; x2] (x2 null: y = A x) with the fp32 copy of A; returns the grid (= number of dot partials)
-int spmv_win(const CsrView& A, const double* x, double* y, const double* x2, int nsplit, double* dot_partials) {
-  if (!A.vals32) return 0;
-  static bool attr = false;
-  const int smem = (int)(kWW * kVC * sizeof(double));   // 64 KB: above the default limit
-  if (!attr) {
-    FS_CUDA(cudaFuncSetAttribute(k_spmv_win<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    FS_CUDA(cudaFuncSetAttribute(k_spmv_win<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    FS_CUDA(cudaFuncSetAttribute(k_spmv_win<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
-  const int ntiles = div_up(A.n, kWT);
-  const int grid = std::max(1, std::min(sm_count() * 2, ntiles));
-  SpmvWarpArgs args{A, x, y, nullptr, nullptr, 0.0, nullptr, dot_partials, 0, ntiles};
-  args.x2 = x2;
-  args.nsplit = nsplit;
-  if (x2) {
-    if (dot_partials) k_spmv_win<true, true><<<grid, kWT, smem, stream()>>>(args);
-    else k_spmv_win<true, false><<<grid, kWT, smem, stream()>>>(args);
-  } else {
-    FS_REQUIRE(!dot_partials, "spmv_win: dot needs the split form");
-    k_spmv_win<false, false><<<grid, kWT, smem, stream()>>>(args);
-  }
-  FS_LAUNCH_CHECK();
-  return grid;
-}
-
 // LPR lanes per row (4..32), lane-strided partial sums combined by an xor tree: deterministic, any
 // row length; y = A x or A [x; x2]
 template <int LPR, bool F32>

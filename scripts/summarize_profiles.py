@@ -1,104 +1,123 @@
 """Turn the raw ncu outputs in gpurun_out/ into the committed summaries under profiles/.
     python scripts/summarize_profiles.py r01
+Every part runs only if its raw input is present (scripts/profile.sh can run a subset of its steps);
+profiles/spmv_traffic.json is updated key by key.
 """
 import collections, csv, json, os, subprocess, sys
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 G, P = "gpurun_out", "profiles"
 os.makedirs(P, exist_ok=True)
+TRAFFIC = f"{P}/spmv_traffic.json"
+traffic = json.load(open(TRAFFIC)) if os.path.exists(TRAFFIC) else {}
 
-# 1) launch list -> per-kernel share of the step (setup kernels listed separately)
-SETUP = ("cub::", "k_spgemm", "k_pick", "k_match", "k_leftover", "k_is_leader", "k_agg_id", "k_compose", "k_coarse_keys",
-         "k_prolongator", "k_transpose", "k_split_keys", "k_rowptr", "k_make_keys", "k_fill_pattern", "k_head_flags",
-         "k_assemble", "k_element", "k_inc_", "k_check_tris", "k_tile_nnz", "k_diag_inv", "k_dense_", "k_rowsum", "k_flag",
-         "k_visc_vals", "k_inner_trig", "k_elem_thirds", "k_node_sum", "k_iota", "k_ptr_from")
-rows = [r for r in csv.reader(open(f"{G}/{tag}_launches.csv")) if len(r) > 5]
-hdr = rows[0]; ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
-agg = collections.OrderedDict()
-for r in rows[1:]:
-    try: v = float(r[vi].replace(",", ""))
-    except ValueError: continue
-    name = r[ki].split("(")[0]
-    a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += v
-is_setup = lambda k: any(t in k for t in SETUP)
-tot_step = sum(a[1] for k, a in agg.items() if not is_setup(k))
-tot_setup = sum(a[1] for k, a in agg.items() if is_setup(k))
-with open(f"{P}/{tag}_launch_list_summary.txt", "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 python bench.py --steps 1 --warmup 1 --no-cpu --no-extra\n")
-    f.write("# (default configuration: AMG-preconditioned pressure CG; the V-cycle's graph nodes appear as kernels)\n")
-    f.write("# per-launch times are cold-cache and serialised: compare SHARES, not absolutes\n")
-    f.write(f"# launches captured: {sum(a[0] for a in agg.values())} (cap 6000 = one-time setup + ~1.5 steps); "
-            f"step kernels {tot_step/1e6:.1f} ms, one-time setup kernels {tot_setup/1e6:.1f} ms\n")
-    f.write("# ---- kernels of the time step (share of step-kernel time)\n")
-    for k, (n, t) in sorted(((k, a) for k, a in agg.items() if not is_setup(k)), key=lambda kv: -kv[1][1]):
-        f.write(f"{100*t/tot_step:7.3f}%  launches={n:5d}  total_us={t/1e3:12.1f}  {k}\n")
-    f.write("# ---- one-time setup (mesh topology, assembly, AMG hierarchy)\n")
-    for k, (n, t) in sorted(((k, a) for k, a in agg.items() if is_setup(k)), key=lambda kv: -kv[1][1]):
-        f.write(f"{100*t/tot_setup:7.3f}%  launches={n:5d}  total_us={t/1e3:12.1f}  {k[:110]}\n")
-os.system(f"gzip -c {G}/{tag}_launches.csv > {P}/{tag}_launches.csv.gz")
-
-# 2) full-set capture of the persistent CG kernel
-raw = subprocess.run(["ncu", "-i", f"{G}/{tag}_cg_persistent.ncu-rep", "--page", "raw", "--csv"],
-                     capture_output=True, text=True).stdout
-rr = list(csv.reader(raw.splitlines())); h, u, r = rr[0], rr[1], rr[2]
-keep = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__cycles_active.avg",
         "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
         "launch__block_size", "launch__shared_mem_per_block_dynamic", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
-stalls = sorted(((float(r[i].replace(",", "")), h[i]) for i in range(len(h))
-                 if "issue_stalled" in h[i] and h[i].endswith("per_issue_active.ratio")), reverse=True)
-with open(f"{P}/{tag}_cg_persistent_ncu_full.txt", "w") as f:
-    f.write("# ncu --set full --clock-control none --import-source on -k regex:k_cg_persistent -c 1 python scripts/prof_cg.py 200\n")
-    f.write("# (200 CG iterations of the 4M-triangle pressure operator in ONE launch; ncu flushes caches before the launch only)\n")
-    for k in keep:
+UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+
+def raw_page(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(raw.splitlines()))
+    return rr[0], rr[1], rr[2:]
+
+
+def write_full(h, u, r, f):
+    f.write(f"kernel: {r[h.index('Kernel Name')]}\n")
+    for k in KEEP:
         if k in h: f.write(f"{k:75s} {r[h.index(k)]:>18s} {u[h.index(k)]}\n")
+    stalls = sorted(((float(r[i].replace(",", "") or 0), h[i]) for i in range(len(h))
+                     if "issue_stalled" in h[i] and h[i].endswith("per_issue_active.ratio")), reverse=True)
     f.write("# warp stall reasons (warps per issue-active cycle)\n")
     for v, k in stalls[:8]: f.write(f"{k:75s} {v:18.3f}\n")
-def full_summary(rep, outname, header):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rr = list(csv.reader(raw.splitlines())); h, u, r = rr[0], rr[1], rr[2]
-    stalls = sorted(((float(r[i].replace(",", "")), h[i]) for i in range(len(h))
-                     if "issue_stalled" in h[i] and h[i].endswith("per_issue_active.ratio")), reverse=True)
-    with open(outname, "w") as f:
-        f.write(header)
-        for k in keep + ["launch__grid_size"]:
-            if k in h: f.write(f"{k:75s} {r[h.index(k)]:>18s} {u[h.index(k)]}\n")
-        f.write("# warp stall reasons (warps per issue-active cycle)\n")
-        for v, k in stalls[:8]: f.write(f"{k:75s} {v:18.3f}\n")
 
-if os.path.exists(f"{G}/{tag}_spmv_warp.ncu-rep"):
-    full_summary(f"{G}/{tag}_spmv_warp.ncu-rep", f"{P}/{tag}_spmv_warp_ncu_full.txt",
-                 "# ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'k_spmv_warp<.int.0, .bool.1' -s 3 -c 1 python scripts/prof_amg.py 4\n"
-                 "# (one stand-alone SpMV launch of the AMG-preconditioned CG, 4M-triangle pressure operator; cold cache)\n")
-    print(open(f"{P}/{tag}_spmv_warp_ncu_full.txt").read())
-    _raw = subprocess.run(["ncu", "-i", f"{G}/{tag}_spmv_warp.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    _rr = list(csv.reader(_raw.splitlines())); _h, _u, _r = _rr[0], _rr[1], _rr[2]
-    def _bytes(name):
-        v, unit = float(_r[_h.index(name)].replace(",", "")), _u[_h.index(name)]
-        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
-    SPMV_WARP_DRAM = _bytes("dram__bytes_read.sum") + _bytes("dram__bytes_write.sum")
-else:
-    SPMV_WARP_DRAM = None
 
-iters = 200
-d = {}
-for row in csv.reader(open(f"{G}/{tag}_cg_dram_nocachectl.csv")):
-    if len(row) > 14 and row[12] in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum", "lts__t_sector_hit_rate.pct"):
-        d[row[12]] = float(row[14].replace(",", ""))
-per = (d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"]) / iters
-json.dump({"kernel": "k_cg_persistent", "iterations_in_launch": iters,
-           "dram_bytes_per_launch": d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"],
-           "dram_bytes_per_iteration": per, "dram_read_per_iteration": d["dram__bytes_read.sum"] / iters,
-           "dram_write_per_iteration": d["dram__bytes_write.sum"] / iters,
-           "us_per_iteration_under_ncu": d["gpu__time_duration.sum"] / iters / 1e3,
-           "lts_hit_rate_pct": d.get("lts__t_sector_hit_rate.pct"),
-           "spmv_warp_dram_bytes_per_launch": SPMV_WARP_DRAM,
-           "spmv_warp_how": "ncu --set full capture of one fine-level k_spmv_warp launch (cold cache)",
-           "how": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --cache-control none (single pass, no replay, caches left alone)"},
-          open(f"{P}/spmv_traffic.json", "w"), indent=1)
-os.system(f"cp {G}/{tag}_cg_dram_nocachectl.csv {P}/{tag}_cg_dram_nocachectl.csv")
-print(open(f"{P}/{tag}_launch_list_summary.txt").read()[:1500])
-print(open(f"{P}/{tag}_cg_persistent_ncu_full.txt").read())
-print(open(f"{P}/spmv_traffic.json").read())
+def dram_bytes(h, u, r):
+    tot = 0.0
+    for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        tot += float(r[h.index(name)].replace(",", "")) * UNIT[u[h.index(name)]]
+    return tot
+
+
+# 1) launch list -> per-kernel share of the step (setup kernels listed separately)
+SETUP = ("cub::", "k_spgemm", "k_pick", "k_match", "k_leftover", "k_is_leader", "k_agg_id", "k_compose", "k_coarse_keys",
+         "k_prolongator", "k_transpose", "k_split_keys", "k_rowptr", "k_make_keys", "k_fill_pattern", "k_head_flags",
+         "k_assemble", "k_element", "k_inc_", "k_check_tris", "k_tile_nnz", "k_diag_inv", "k_dense_from", "k_dense_add",
+         "k_dense_invert", "k_rowsum", "k_flag", "k_visc_vals", "k_inner_trig", "k_elem_thirds", "k_node_sum", "k_iota",
+         "k_ptr_from", "k_fold_coo", "k_sell_", "k_to_f32")
+if os.path.exists(f"{G}/{tag}_launches.csv"):
+    rows = [r for r in csv.reader(open(f"{G}/{tag}_launches.csv")) if len(r) > 5]
+    hdr = rows[0]; ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    agg = collections.OrderedDict()
+    for r in rows[1:]:
+        try: v = float(r[vi].replace(",", ""))
+        except ValueError: continue
+        a = agg.setdefault(r[ki].split("(")[0], [0, 0.0]); a[0] += 1; a[1] += v
+    is_setup = lambda k: any(t in k for t in SETUP)
+    tot_step = sum(a[1] for k, a in agg.items() if not is_setup(k))
+    tot_setup = sum(a[1] for k, a in agg.items() if is_setup(k))
+    with open(f"{P}/{tag}_launch_list_summary.txt", "w") as f:
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 python bench.py --steps 1 --warmup 1 --no-cpu --no-extra\n")
+        f.write("# (default configuration: AMG-preconditioned pressure CG; the V-cycle's graph nodes appear as kernels)\n")
+        f.write("# per-launch times are cold-cache and serialised: compare SHARES, not absolutes\n")
+        f.write(f"# launches captured: {sum(a[0] for a in agg.values())} (one-time setup + the warm-up and the timed step); "
+                f"step kernels {tot_step/1e6:.1f} ms, one-time setup kernels {tot_setup/1e6:.1f} ms\n")
+        f.write("# ---- kernels of the time step (share of step-kernel time)\n")
+        for k, (n, t) in sorted(((k, a) for k, a in agg.items() if not is_setup(k)), key=lambda kv: -kv[1][1]):
+            f.write(f"{100*t/tot_step:7.3f}%  launches={n:5d}  total_us={t/1e3:12.1f}  {k}\n")
+        f.write("# ---- one-time setup (mesh topology, assembly, AMG hierarchy)\n")
+        for k, (n, t) in sorted(((k, a) for k, a in agg.items() if is_setup(k)), key=lambda kv: -kv[1][1]):
+            f.write(f"{100*t/tot_setup:7.3f}%  launches={n:5d}  total_us={t/1e3:12.1f}  {k[:110]}\n")
+    os.system(f"gzip -c {G}/{tag}_launches.csv > {P}/{tag}_launches.csv.gz")
+    print(open(f"{P}/{tag}_launch_list_summary.txt").read()[:2200])
+
+# 2) full-set capture of the two big k_spmv_sell instances
+if os.path.exists(f"{G}/{tag}_spmv_sell.ncu-rep"):
+    h, u, rs = raw_page(f"{G}/{tag}_spmv_sell.ncu-rep")
+    with open(f"{P}/{tag}_spmv_sell_ncu_full.txt", "w") as f:
+        f.write("# ncu --set full --clock-control none --import-source on --kernel-name-base demangled "
+                "-k regex:'k_spmv_sell<.bool.(0|1), .bool.1' --launch-skip 6 -c 2 python scripts/prof_amg.py 6\n"
+                "# (4M-triangle pressure operator, AMG-preconditioned CG; template arguments <SPLIT, DOT, F32>: <1,1,1> = finest\n"
+                "#  up-sweep of the folded V-cycle, <0,1,0> = the CG's A*p; cold cache, one launch each)\n")
+        for r in rs:
+            write_full(h, u, r, f)
+            name = r[h.index("Kernel Name")]
+            key = "sell_up0_dram_bytes_per_launch" if "<1, 1, 1>" in name or "(bool)1, (bool)1, (bool)1" in name else "sell_ap_dram_bytes_per_launch"
+            traffic[key] = dram_bytes(h, u, r)
+            f.write("\n")
+    traffic["sell_how"] = "ncu --set full capture of one launch of each k_spmv_sell instance (cold cache)"
+    print(open(f"{P}/{tag}_spmv_sell_ncu_full.txt").read())
+
+# 3) full-set capture of the persistent CG kernel
+if os.path.exists(f"{G}/{tag}_cg_persistent.ncu-rep"):
+    h, u, rs = raw_page(f"{G}/{tag}_cg_persistent.ncu-rep")
+    with open(f"{P}/{tag}_cg_persistent_ncu_full.txt", "w") as f:
+        f.write("# ncu --set full --clock-control none --import-source on -k regex:k_cg_persistent -c 1 python scripts/prof_cg.py 200\n")
+        f.write("# (200 CG iterations of the 4M-triangle pressure operator in ONE launch; ncu flushes caches before the launch only)\n")
+        write_full(h, u, rs[0], f)
+    print(open(f"{P}/{tag}_cg_persistent_ncu_full.txt").read())
+
+# 4) DRAM traffic of the persistent kernel with caches left alone
+if os.path.exists(f"{G}/{tag}_cg_dram_nocachectl.csv"):
+    iters = 200
+    d = {}
+    for row in csv.reader(open(f"{G}/{tag}_cg_dram_nocachectl.csv")):
+        if len(row) > 14 and row[12] in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum", "lts__t_sector_hit_rate.pct"):
+            d[row[12]] = float(row[14].replace(",", ""))
+    traffic.update({"kernel": "k_cg_persistent", "iterations_in_launch": iters,
+                    "dram_bytes_per_launch": d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"],
+                    "dram_bytes_per_iteration": (d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"]) / iters,
+                    "dram_read_per_iteration": d["dram__bytes_read.sum"] / iters,
+                    "dram_write_per_iteration": d["dram__bytes_write.sum"] / iters,
+                    "us_per_iteration_under_ncu": d["gpu__time_duration.sum"] / iters / 1e3,
+                    "lts_hit_rate_pct": d.get("lts__t_sector_hit_rate.pct"),
+                    "how": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --cache-control none (single pass, no replay, caches left alone)"})
+    os.system(f"cp {G}/{tag}_cg_dram_nocachectl.csv {P}/{tag}_cg_dram_nocachectl.csv")
+
+json.dump(traffic, open(TRAFFIC, "w"), indent=1)
+print(open(TRAFFIC).read())

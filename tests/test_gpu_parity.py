@@ -426,6 +426,54 @@ def test_amg_pcg_matches_oracle_and_is_mesh_independent():
     assert np.linalg.norm(b - (Sd @ xa)) <= 1e-10 * np.linalg.norm(b) and ita * 3 < itj and rel(xa, xj) <= 1e-8
 
 
+def test_amg_cycle_forms_agree(monkeypatch):
+    """The folded two-SpMV-per-level V-cycle (SELL-32 on the large levels, lanes-per-row CSR kernel on the
+    small ones) is the same operator as the unfolded smoother/residual/transfer sequence: same iteration
+    counts (+-1), same solution; 131k rows so that the SELL kernels, the fp64 SELL A*p and the split-form
+    up-sweep all run."""
+    nodes, markers, tris = fb.square_with_hole(512, 256)
+    mm = fb.Mesh(nodes, tris, markers)
+    rowptr, colidx = mm.csr_pattern()
+    vals = mm.stiffness_values()
+    b = np.random.default_rng(8).standard_normal(mm.N)
+    b -= b.mean()
+    out = {}
+    for name, env in (("folded_sell", {}), ("folded_csr", {"FS_AMG_SELL": "0"}), ("folded_all_sell", {"FS_AMG_SUB_ROWS": "0"}),
+                      ("unfolded", {"FS_AMG_FOLD": "0"}), ("folded_fp64", {"FS_AMG_FP32": "0"})):
+        for k in ("FS_AMG_SELL", "FS_AMG_FOLD", "FS_AMG_SUB_ROWS", "FS_AMG_FP32"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        A = mm.matrix(vals)                       # a fresh handle: the hierarchy reads the knobs at set-up
+        x, it, rr = A.cg(b, rtol=1e-11, precond=fb.PRECOND_AMG, project_mean=True)
+        assert np.linalg.norm(b - (A @ x)) <= 1e-10 * np.linalg.norm(b), name
+        out[name] = (x, it)
+    xj, itj, _ = mm.matrix(vals).cg(b, rtol=1e-11, precond=fb.PRECOND_JACOBI, project_mean=True)
+    ref, it_ref = out["unfolded"]
+    for name, (x, it) in out.items():
+        assert abs(it - it_ref) <= 1, (name, it, it_ref)
+        assert rel(x, ref) <= 1e-9, name
+        assert rel(x, xj) <= 1e-8 and it * 4 < itj, name
+
+
+def test_two_rhs_cg_large_matches_single_rhs():
+    """n > 100 000: the 2-RHS CG streams the SELL-32 copy of the matrix once for both columns."""
+    nodes, markers, tris = fb.square_with_hole(512, 256)
+    mm = fb.Mesh(nodes, tris, markers)
+    rowptr, colidx = mm.csr_pattern()
+    vals = mm.stiffness_values() * 0.005
+    rows = np.repeat(np.arange(mm.N), np.diff(rowptr))
+    vals[rows == colidx] += 1.0                   # I + DT*nu*K, the viscous operator's shape
+    A = mm.matrix(vals)
+    B = np.random.default_rng(9).standard_normal((mm.N, 2))
+    X, it, rr = A.cg(B, rtol=1e-12, precond=fb.PRECOND_JACOBI)
+    assert rr <= 1e-12 and it < 60
+    for c in range(2):
+        xc, _, _ = A.cg(np.ascontiguousarray(B[:, c]), rtol=1e-12, precond=fb.PRECOND_JACOBI)
+        assert rel(X[:, c], xc) <= 1e-10
+        assert np.linalg.norm(B[:, c] - (A @ np.ascontiguousarray(X[:, c]))) <= 1e-11 * np.linalg.norm(B[:, c])
+
+
 def test_stokes_color_100_steps_with_amg():
     g, t, sim = _run_traj(fb.StokesColor, "mesh5_1", "color_pusher", 100, precond=fb.PRECOND_AMG)
     prog = []
