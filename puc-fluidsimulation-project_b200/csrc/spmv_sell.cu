@@ -22,7 +22,6 @@ namespace fs {
 
 constexpr int kST = 256;        // threads per CTA
 constexpr int kSW = kST / 32;   // warps (slices in flight) per CTA
-constexpr int kSU = 8;          // entries per lane per batch
 
 struct SellArgs {
   int n, nslices;
@@ -37,8 +36,25 @@ struct SellArgs {
   double* part;
 };
 
+// streamed once per launch: read-only path, no L1 allocation (the L1 is for the gathered vectors)
+__device__ __forceinline__ float ld_stream(const float* a) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(a));
+  return v;
+}
+__device__ __forceinline__ double ld_stream(const double* a) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(a));
+  return v;
+}
+__device__ __forceinline__ int ld_stream(const int* a) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(a));
+  return v;
+}
+
 // One part of a slice: W entries per lane at stride 32, all gathered from x.  Unguarded batches of 8
-// and 4 (loads first, then the gathers, then the sums), then a guarded batch for the last 1-3.
+// (loads first, then the gathers, then the sums), then a guarded tail.
 // The fp32 (preconditioner) form uses fused multiply-adds; the fp64 form keeps multiply-then-add so
 // that its sums have the same bits as the CSR kernels' (the library is built with -fmad=false).
 template <class VT>
@@ -53,7 +69,27 @@ __device__ __forceinline__ double sell_batch(const VT* __restrict__ vp, const in
   VT vv[U];
   int cc[U];
 #pragma unroll
-  for (int j = 0; j < U; ++j) { vv[j] = __ldcs(vp + (j << 5)); cc[j] = __ldcs(cp + (j << 5)); }
+  for (int j = 0; j < U; ++j) { vv[j] = ld_stream(vp + (j << 5)); cc[j] = ld_stream(cp + (j << 5)); }
+  double xx[U];
+#pragma unroll
+  for (int j = 0; j < U; ++j) xx[j] = __ldg(x + cc[j]);
+#pragma unroll
+  for (int j = 0; j < U; ++j) acc = sell_mac<VT>(vv[j], xx[j], acc);
+  return acc;
+}
+
+// guarded batch for the last rem < U entries
+template <int U, class VT>
+__device__ __forceinline__ double sell_tail(const VT* __restrict__ vp, const int* __restrict__ cp, int rem,
+                                            const double* __restrict__ x, double acc) {
+  VT vv[U];
+  int cc[U];
+#pragma unroll
+  for (int j = 0; j < U; ++j) {
+    const bool ok = j < rem;
+    vv[j] = ok ? ld_stream(vp + (j << 5)) : VT(0);
+    cc[j] = ok ? ld_stream(cp + (j << 5)) : 0;
+  }
   double xx[U];
 #pragma unroll
   for (int j = 0; j < U; ++j) xx[j] = __ldg(x + cc[j]);
@@ -67,22 +103,14 @@ __device__ __forceinline__ double sell_part(const VT* __restrict__ vp, const int
                                             const double* __restrict__ x, double acc) {
   int k = 0;
   for (; k + 8 <= W; k += 8, vp += 256, cp += 256) acc = sell_batch<8, VT>(vp, cp, x, acc);
-  if (k + 4 <= W) { acc = sell_batch<4, VT>(vp, cp, x, acc); k += 4; vp += 128; cp += 128; }
-  if (k < W) {
-    const int rem = W - k;
-    VT vv[3];
-    int cc[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const bool ok = j < rem;
-      vv[j] = ok ? __ldcs(vp + (j << 5)) : VT(0);
-      cc[j] = ok ? __ldcs(cp + (j << 5)) : 0;
-    }
-    double xx[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) xx[j] = __ldg(x + cc[j]);
-#pragma unroll
-    for (int j = 0; j < 3; ++j) acc = sell_mac<VT>(vv[j], xx[j], acc);
+  if (sizeof(VT) == 8) {
+    // fp64 (the CG's A*p, rows of ~7): the last 1..7 entries as ONE guarded batch -- a second dependent
+    // load / gather round costs more than the guards
+    if (k < W) acc = sell_tail<7, VT>(vp, cp, W - k, x, acc);
+  } else {
+    // fp32 two-part operators: 4 unguarded + up to 3 guarded keeps the kernel inside 40 registers
+    if (k + 4 <= W) { acc = sell_batch<4, VT>(vp, cp, x, acc); k += 4; vp += 128; cp += 128; }
+    if (k < W) acc = sell_tail<3, VT>(vp, cp, W - k, x, acc);
   }
   return acc;
 }
@@ -147,8 +175,8 @@ __global__ void __launch_bounds__(kST, 4) k_spmv_sell2(SellArgs a, const int* __
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const bool ok = k0 + j < W;
-        vv[j] = ok ? __ldcs(vp + (j << 5)) : 0.0;
-        cc[j] = ok ? __ldcs(cp + (j << 5)) : 0;
+        vv[j] = ok ? ld_stream(vp + (j << 5)) : 0.0;
+        cc[j] = ok ? ld_stream(cp + (j << 5)) : 0;
       }
       double2 xx[4];
 #pragma unroll
