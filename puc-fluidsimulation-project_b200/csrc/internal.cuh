@@ -298,6 +298,8 @@ void cg_persistent_launch(const CsrView& A, double* x, double* r, double* p, dou
 int cg_dev(fs_csr* a, const double* d_b, double* d_x, int nrhs, double rtol, int maxit, int precond,
            int project_mean, double* relres);
 void spmv_dev(const CsrView& A, const double* d_x, double* d_y);
+double resid_norm2_dev(fs_csr* a, const double* b, const double* x, double* work);   // |b - A x|^2
+void lin3_dev(int64_t n, double a, const double* x, double b, const double* y, double* out);   // out = a x + b y
 double max_abs_dev(const double* d_x, int64_t n);
 void free_locator(Locator* l);
 }  // namespace fs

@@ -1126,6 +1126,26 @@ static void dot2(int64_t n, const double* a, const double* b, const double* c, c
   for (int i = 0; i < g; ++i) { out2[0] += h[2 * i]; out2[1] += h[2 * i + 1]; }
 }
 
+void lin3_dev(int64_t n, double a, const double* x, double b, const double* y, double* out) {
+  k_lin3<<<vec_grid(n), kBlock, 0, stream()>>>(n, a, x, b, y, 0.0, nullptr, out);
+  FS_LAUNCH_CHECK();
+}
+
+// |b - A x|^2 (host value; `work` holds n doubles).  Used to choose between warm-start candidates.
+double resid_norm2_dev(fs_csr* a, const double* b, const double* x, double* work) {
+  ensure_ws(a, 4 * (size_t)a->n);
+  ensure_tiles(a);
+  const int64_t n = a->n;
+  const CsrView A = a->view();
+  if (!spmv_warp(A, EPI_RESID, x, work, b, nullptr, 0.0, nullptr, nullptr)) {
+    spmv_dev(A, x, work);
+    k_lin3<<<vec_grid(n), kBlock, 0, stream()>>>(n, 1.0, b, -1.0, work, 0.0, nullptr, work); FS_LAUNCH_CHECK();
+  }
+  double d2[2];
+  dot2(n, work, work, nullptr, nullptr, a->partials.p, d2);
+  return d2[0];
+}
+
 // ---- small systems: the whole (Jacobi right-preconditioned) BiCGStab in ONE CTA --------------
 // The Poisson / heat systems of the shipped meshes have a few hundred rows: with one launch per
 // vector operation every iteration is pure launch latency.  Here one CTA of 1024 threads runs

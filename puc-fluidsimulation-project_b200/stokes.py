@@ -84,14 +84,19 @@ class StokesSolver:
         return self.stats
 
     def get_warm_state(self):
-        """CG warm-start vectors of the two pressure solves (with ``u`` the full loop state)."""
+        """CG warm-start state of the two pressure solves: last two solutions of each + validity flags
+        (with ``u`` the full loop state)."""
         _, kp, _ = self.matrices()
-        q = np.empty(2 * kp.n)
+        q = np.empty(4 * kp.n + 2)
         call("fs_stokes_warm_state", self._h, ptr(q), 0)
         return q
 
     def set_warm_state(self, q):
-        call("fs_stokes_warm_state", self._h, ptr(np.ascontiguousarray(q, dtype=np.float64)), 1)
+        _, kp, _ = self.matrices()
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        if q.size != 4 * kp.n + 2:
+            raise ValueError(f"warm state has {q.size} entries, expected {4 * kp.n + 2}")
+        call("fs_stokes_warm_state", self._h, ptr(q), 1)
 
     # -- checkpoint / resume (SURVEY 5.4: the reference keeps its state in module globals)
     def _state_arrays(self):
