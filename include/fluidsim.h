@@ -176,12 +176,12 @@ int fs_stokes_step(fs_stokes* s, double* u /* (n,2) in/out */, double B1, double
 int fs_stokes_pressure(fs_stokes* s, double* p /* n or NULL */, double* p2 /* n or NULL */);
 /* the two operators, for inspection / parity (borrowed handles, do not destroy) */
 int fs_stokes_matrices(fs_stokes* s, fs_csr** a_visc, fs_csr** k_pressure, int32_t* dof /* n or NULL */);
-/* the CG warm-start state: the merged-dof pressures of the two solves of the last step and of the
- * step before (the initial guess is extrapolated in time when that lowers the residual), then two
- * flags saying whether the older pair is valid: 4*n_dof + 2 doubles, n_dof = fs_csr_sizes(k_pressure).
+/* the CG warm-start state: the merged-dof pressures of the two solves of the last three steps (the
+ * initial guess is extrapolated in time when that lowers the residual), then how many of the older
+ * pairs are valid (2 values): 6*n_dof + 2 doubles, n_dof = fs_csr_sizes(k_pressure).
  * Read (set=0) or restore (set=1).  With u this is the complete state of the time loop
  * (checkpoint / resume, repeatable benchmarks). */
-int fs_stokes_warm_state(fs_stokes* s, double* q /* 4*n_dof + 2 */, int set);
+int fs_stokes_warm_state(fs_stokes* s, double* q /* 6*n_dof + 2 */, int set);
 
 /* ---- partitioned pressure CG, one rank (process) per GPU, peer memory over NVLink.
  * Replaces the same np.linalg.solve(A_pressure, .) for meshes that are split across GPUs

@@ -30,8 +30,8 @@ struct fs_stokes {
   fs::DBuf<double> ustar, div, rhs_red, p_red, p2_red, p_full, p2_full;
   bool have_p = false;
   // previous solutions of the two pressure solves: the warm start may be extrapolated in time
-  fs::DBuf<double> p_prev, p2_prev, q_try;
-  int hist_p = 0, hist_p2 = 0;
+  fs::DBuf<double> p_prev, p2_prev, p_prev2, p2_prev2, q_try, q_try2;   // one and two steps back; candidates
+  int hist_p = 0, hist_p2 = 0;                                  // how many of them are valid
 };
 
 namespace fs {
@@ -68,12 +68,13 @@ __global__ void k_expand(int64_t N, const int* __restrict__ dof, const double* _
   if (n < N) p[n] = q[dof[n]];
 }
 
-// Warm start: the previous step's solution q, or the linear extrapolation 2 q - q_prev from the last two
-// steps when its residual |b - K q|^2 is the smaller one (both are evaluated: two SpMVs buy several PCG
-// iterations while the flow evolves smoothly, and nothing is lost when it does not).
-static void pressure_solve(fs_stokes* s, const double* d_vel, double* q, double* q_prev, int* hist, double* p_full,
+// Warm start: the previous step's solution q, or its extrapolation in time from the last two / three
+// steps (2 q - q1, 3 q - 3 q1 + q2), whichever has the smallest residual |b - K q|^2.  The candidates
+// are all evaluated: an SpMV each buys several PCG iterations while the flow evolves smoothly, and
+// nothing is lost when it does not.
+static void pressure_solve(fs_stokes* s, const double* d_vel, double* q, double* q1, double* q2, int* hist, double* p_full,
                            const fs_stokes_opts& o, int* iters, double* relres, double* max_div) {
-  static const bool extrap = [] { const char* e = std::getenv("FS_STOKES_EXTRAP"); return !e || std::atoi(e) != 0; }();
+  static const int extrap = [] { const char* e = std::getenv("FS_STOKES_EXTRAP"); return e ? std::atoi(e) : 2; }();
   fs_mesh* m = s->mesh;
   cudaStream_t st = stream();
   divergence_dev(m, d_vel, s->div.p, nullptr);
@@ -84,18 +85,26 @@ static void pressure_solve(fs_stokes* s, const double* d_vel, double* q, double*
   if (!o.warm_start || !s->have_p) {
     FS_CUDA(cudaMemsetAsync(q, 0, s->nd * sizeof(double), st));
     *hist = 0;
-  } else if (extrap) {
+  } else if (extrap > 0) {
     const size_t bytes = s->nd * sizeof(double);
-    bool use_ext = false;
+    int best = 0;   // 0: q, 1: linear, 2: quadratic (left in q_try)
     if (*hist >= 1) {
-      lin3_dev(s->nd, 2.0, q, -1.0, q_prev, s->q_try.p);
-      const double r_plain = resid_norm2_dev(&s->k_red, s->rhs_red.p, q, s->div.p);
-      const double r_ext = resid_norm2_dev(&s->k_red, s->rhs_red.p, s->q_try.p, s->div.p);
-      use_ext = r_ext < r_plain;
+      double r_best = resid_norm2_dev(&s->k_red, s->rhs_red.p, q, s->div.p);
+      lin3_dev(s->nd, 2.0, q, -1.0, q1, s->q_try.p);
+      const double r_lin = resid_norm2_dev(&s->k_red, s->rhs_red.p, s->q_try.p, s->div.p);
+      if (r_lin < r_best) { best = 1; r_best = r_lin; }
+      if (*hist >= 2 && extrap >= 2) {
+        lin3_dev(s->nd, 3.0, q, -3.0, q1, s->q_try2.p);
+        lin3_dev(s->nd, 1.0, s->q_try2.p, 1.0, q2, s->q_try2.p);
+        const double r_quad = resid_norm2_dev(&s->k_red, s->rhs_red.p, s->q_try2.p, s->div.p);
+        if (r_quad < r_best) { best = 2; r_best = r_quad; }
+      }
     }
-    FS_CUDA(cudaMemcpyAsync(q_prev, q, bytes, cudaMemcpyDeviceToDevice, st));
-    if (use_ext) FS_CUDA(cudaMemcpyAsync(q, s->q_try.p, bytes, cudaMemcpyDeviceToDevice, st));
-    *hist = 1;
+    FS_CUDA(cudaMemcpyAsync(q2, q1, bytes, cudaMemcpyDeviceToDevice, st));
+    FS_CUDA(cudaMemcpyAsync(q1, q, bytes, cudaMemcpyDeviceToDevice, st));
+    if (best == 1) FS_CUDA(cudaMemcpyAsync(q, s->q_try.p, bytes, cudaMemcpyDeviceToDevice, st));
+    if (best == 2) FS_CUDA(cudaMemcpyAsync(q, s->q_try2.p, bytes, cudaMemcpyDeviceToDevice, st));
+    *hist = std::min(*hist + 1, 2);
   }
   int it = cg_dev(&s->k_red, s->rhs_red.p, q, 1, o.rtol_pressure, o.maxit, o.precond, 1, relres);
   if (it < 0) throw Error(FS_ERR_NOCONV, "pressure CG did not converge within maxit");
@@ -178,8 +187,9 @@ int fs_stokes_create(fs_mesh* m, double DT, double nu, fs_stokes** out) {
   s->pat_red.contrib.release(); s->pat_red.seg_start.release(); s->pat_red.scatter.release();
   s->ustar.alloc(2 * N); s->div.alloc(N); s->rhs_red.alloc(nd);
   s->p_red.alloc(nd); s->p2_red.alloc(nd); s->p_full.alloc(N); s->p2_full.alloc(N);
-  s->p_prev.alloc(nd); s->p2_prev.alloc(nd); s->q_try.alloc(nd);
-  s->p_prev.zero(); s->p2_prev.zero();
+  s->p_prev.alloc(nd); s->p2_prev.alloc(nd); s->p_prev2.alloc(nd); s->p2_prev2.alloc(nd);
+  s->q_try.alloc(nd); s->q_try2.alloc(nd);
+  s->p_prev.zero(); s->p2_prev.zero(); s->p_prev2.zero(); s->p2_prev2.zero();
   s->p_red.zero(); s->p2_red.zero(); s->p_full.zero(); s->p2_full.zero();
   fs::sync();
   *out = s.release();
@@ -226,7 +236,7 @@ int fs_stokes_step(fs_stokes* s, double* u, double B1, double B2, const fs_stoke
   dir_bcu_dev(m, s->ustar.p, B1, B2);
   mark();
   // Step 2+3: pressure correction and velocity update
-  pressure_solve(s, s->ustar.p, s->p_red.p, s->p_prev.p, &s->hist_p, s->p_full.p, o, &sts.iters_p1, &sts.relres_p1,
+  pressure_solve(s, s->ustar.p, s->p_red.p, s->p_prev.p, s->p_prev2.p, &s->hist_p, s->p_full.p, o, &sts.iters_p1, &sts.relres_p1,
                  o.final_div ? &sts.max_div_ustar : nullptr);
   mark();
   grad_update_dev(m, s->p_full.p, s->ustar.p, du, s->DT, nullptr);
@@ -234,7 +244,7 @@ int fs_stokes_step(fs_stokes* s, double* u, double B1, double B2, const fs_stoke
   dir_bcu_dev(m, du, B1, B2);
   mark();
   // second projection, interior nodes only, no BC re-imposition (:566-573)
-  pressure_solve(s, du, s->p2_red.p, s->p2_prev.p, &s->hist_p2, s->p2_full.p, o, &sts.iters_p2, &sts.relres_p2, nullptr);
+  pressure_solve(s, du, s->p2_red.p, s->p2_prev.p, s->p2_prev2.p, &s->hist_p2, s->p2_full.p, o, &sts.iters_p2, &sts.relres_p2, nullptr);
   mark();
   grad_update_dev(m, s->p2_full.p, du, du, s->DT, s->is_interior.p);
   s->have_p = true;
@@ -280,18 +290,18 @@ int fs_stokes_warm_state(fs_stokes* s, double* q, int set) {
   FS_REQUIRE(s && q, "NULL argument");
   const size_t nd = (size_t)s->nd;
   cudaStream_t st = stream();
-  double* bufs[4] = {s->p_red.p, s->p2_red.p, s->p_prev.p, s->p2_prev.p};
+  double* bufs[6] = {s->p_red.p, s->p2_red.p, s->p_prev.p, s->p2_prev.p, s->p_prev2.p, s->p2_prev2.p};
   double hist[2] = {(double)s->hist_p, (double)s->hist_p2};
   if (set) {
-    for (int k = 0; k < 4; ++k) FS_CUDA(cudaMemcpyAsync(bufs[k], q + k * nd, nd * sizeof(double), cudaMemcpyDefault, st));
-    FS_CUDA(cudaMemcpyAsync(hist, q + 4 * nd, sizeof(hist), cudaMemcpyDefault, st));
+    for (int k = 0; k < 6; ++k) FS_CUDA(cudaMemcpyAsync(bufs[k], q + k * nd, nd * sizeof(double), cudaMemcpyDefault, st));
+    FS_CUDA(cudaMemcpyAsync(hist, q + 6 * nd, sizeof(hist), cudaMemcpyDefault, st));
     fs::sync();
-    s->hist_p = hist[0] != 0.0;
-    s->hist_p2 = hist[1] != 0.0;
+    s->hist_p = std::max(0, std::min(2, (int)hist[0]));
+    s->hist_p2 = std::max(0, std::min(2, (int)hist[1]));
     s->have_p = true;
   } else {
-    for (int k = 0; k < 4; ++k) FS_CUDA(cudaMemcpyAsync(q + k * nd, bufs[k], nd * sizeof(double), cudaMemcpyDefault, st));
-    FS_CUDA(cudaMemcpyAsync(q + 4 * nd, hist, sizeof(hist), cudaMemcpyDefault, st));
+    for (int k = 0; k < 6; ++k) FS_CUDA(cudaMemcpyAsync(q + k * nd, bufs[k], nd * sizeof(double), cudaMemcpyDefault, st));
+    FS_CUDA(cudaMemcpyAsync(q + 6 * nd, hist, sizeof(hist), cudaMemcpyDefault, st));
   }
   fs::sync();
   FS_API_END

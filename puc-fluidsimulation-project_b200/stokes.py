@@ -84,18 +84,18 @@ class StokesSolver:
         return self.stats
 
     def get_warm_state(self):
-        """CG warm-start state of the two pressure solves: last two solutions of each + validity flags
+        """CG warm-start state of the two pressure solves: last three solutions of each + history depth
         (with ``u`` the full loop state)."""
         _, kp, _ = self.matrices()
-        q = np.empty(4 * kp.n + 2)
+        q = np.empty(6 * kp.n + 2)
         call("fs_stokes_warm_state", self._h, ptr(q), 0)
         return q
 
     def set_warm_state(self, q):
         _, kp, _ = self.matrices()
         q = np.ascontiguousarray(q, dtype=np.float64)
-        if q.size != 4 * kp.n + 2:
-            raise ValueError(f"warm state has {q.size} entries, expected {4 * kp.n + 2}")
+        if q.size != 6 * kp.n + 2:
+            raise ValueError(f"warm state has {q.size} entries, expected {6 * kp.n + 2}")
         call("fs_stokes_warm_state", self._h, ptr(q), 1)
 
     # -- checkpoint / resume (SURVEY 5.4: the reference keeps its state in module globals)
