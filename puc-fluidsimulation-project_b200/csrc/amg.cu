@@ -134,7 +134,7 @@ __global__ void k_agg_id(int n, const int* __restrict__ leader, const int* __res
   if (i < n) agg[i] = scan_excl[leader[i]];
 }
 
-__global__ void k_compose(int n, const int* __restrict__ a1, const int* __restrict__ a2, int* __restrict__ out) {
+__global__ void k_compose(int n, const int* a1, const int* __restrict__ a2, int* out /* may be a1 */) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = a2[a1[i]];
 }
@@ -606,7 +606,7 @@ __global__ void k_jac0(int n, double w, const double* __restrict__ dinv, const d
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] = w * dinv[i] * b[i];
 }
 // r = b - Ax (Ax given)
-__global__ void k_resid(int n, const double* __restrict__ b, const double* __restrict__ Ax, double* __restrict__ r) {
+__global__ void k_resid(int n, const double* __restrict__ b, const double* Ax, double* r /* may be Ax */) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) r[i] = b[i] - Ax[i];
 }
 // x += w * dinv * (b - Ax)

@@ -504,7 +504,7 @@ k_sum(int64_t n, const double* __restrict__ v, double* __restrict__ part) {
 }
 
 __global__ void __launch_bounds__(kBlock)
-k_sub_mean(int64_t n, const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ part, int nblk) {
+k_sub_mean(int64_t n, const double* in, double* out /* may be `in` */, const double* __restrict__ part, int nblk) {
   __shared__ double sm[1];
   double s[1];
   reduce_partials<1>(part, nblk, s, sm);
@@ -862,8 +862,7 @@ static int cg_impl(fs_csr* a, const double* d_b, double* d_x, double rtol, int m
   return hs.flags[0] ? hs.flags[1] : -hs.flags[1] - 1;   // negative: not converged
 }
 
-__global__ void k_lin3(int64_t n, double a, const double* __restrict__ x, double b, const double* __restrict__ y, double c,
-                       const double* __restrict__ z, double* __restrict__ out);
+__global__ void k_lin3(int64_t n, double a, const double* x, double b, const double* y, double c, const double* z, double* out);
 
 // ---- CG preconditioned by one AMG V-cycle (amg.cu).  ~50x fewer iterations than Jacobi on
 // the 4M-triangle pressure operator.  All scalars live on the device:
@@ -1100,8 +1099,8 @@ k_dot2(int64_t n, const double* __restrict__ a, const double* __restrict__ b, co
 }
 
 // out = a*x + b*y + c*z (any of y,z may be null)
-__global__ void k_lin3(int64_t n, double a, const double* __restrict__ x, double b, const double* __restrict__ y, double c,
-                       const double* __restrict__ z, double* __restrict__ out) {
+// out = a x + b y + c z, element by element; out may be any of the inputs (no __restrict__)
+__global__ void k_lin3(int64_t n, double a, const double* x, double b, const double* y, double c, const double* z, double* out) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     double v = a * x[i];
     if (y) v += b * y[i];
