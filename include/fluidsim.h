@@ -229,6 +229,24 @@ int fs_tracer_step(fs_mesh* m, double* pts /* (P,2) in/out */, int32_t* status /
                    int32_t* hint_ids /* P in/out */, int64_t n_pts, const double* u /* (n,2) */,
                    double DT, double L, double cx, double cy, double rcap, int64_t* eaten);
 
+/* ---- output sink: the picture the reference draws every step with
+ * ax.tripcolor(triang, c, shading="gouraud", cmap=..., vmin, vmax) + ax.scatter(tracers) + plt.pause
+ * (code/StokesColor.py:508-511,593-598; code/StokesFood.py:511-526), rendered on the device.
+ * fs_raster_field: sample the nodal (P1) field at the centres of a W x H pixel grid over
+ *   [x0,x1] x [y0,y1] (row 0 is the top row) by barycentric interpolation in the containing
+ *   triangle; pixels outside the mesh (the hole) are NaN.  img: H*W floats, row-major.
+ * fs_raster_colormap: NaN -> background_rgba (4 bytes, host), else lut[round(255*clamp((v-vmin)/(vmax-vmin)))]
+ *   (lut: 256x3 bytes), alpha 255.  rgba: H*W*4 bytes.
+ * fs_raster_points: discs of radius_px pixels at the tracer positions, colour colors[status[i]]
+ *   (status NULL: colors[0]); where discs overlap, the tracer with the largest index is on top. */
+int fs_raster_field(fs_mesh* m, const double* field /* n */, int32_t W, int32_t H, double x0, double x1, double y0,
+                    double y1, float* img /* H*W */);
+int fs_raster_colormap(const float* img, int32_t W, int32_t H, double vmin, double vmax, const uint8_t* lut256x3,
+                       const uint8_t* background_rgba /* host */, uint8_t* rgba /* H*W*4 */);
+int fs_raster_points(uint8_t* rgba /* H*W*4 in/out */, int32_t W, int32_t H, double x0, double x1, double y0, double y1,
+                     const double* pts /* (P,2) */, const int32_t* status /* P or NULL */, int64_t P,
+                     const uint8_t* colors_kx3, int32_t n_colors, double radius_px);
+
 #ifdef __cplusplus
 }
 #endif

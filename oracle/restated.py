@@ -596,3 +596,77 @@ def heat_reapply(u, nodes32, markers, pairs_all, wall_value=1.0, inner_value=0.0
     u[is_wall & ~is_inner] = wall_value
     u[is_inner] = inner_value
     return u
+
+
+# ---- output sink (test infrastructure for fs_raster_field / fs_raster_colormap / fs_raster_points) -------
+def raster_field(nodes, tris, field, width, height, extent=(0.0, 1.0, 0.0, 1.0)):
+    """Restatement of what ``ax.tripcolor(triang, c, shading="gouraud")`` shows
+    (code/StokesColor.py:508-511): the P1 field sampled at the pixel centres (row 0 = top), NaN
+    outside the mesh.  Barycentric weights exactly as PointLocator.find computes them
+    (code/StokesColor.py:334-340); a pixel centre on a shared edge takes the lower triangle id (the
+    value is the same on both sides).  Plain loops over triangles: small meshes only."""
+    x0, x1, y0, y1 = extent
+    dx, dy = (x1 - x0) / width, (y1 - y0) / height
+    xs = x0 + (np.arange(width) + 0.5) * dx
+    ys = y1 - (np.arange(height) + 0.5) * dy
+    img = np.full((height, width), np.nan, dtype=np.float64)
+    owner = np.full((height, width), -1, dtype=np.int64)
+    for t in range(len(tris) - 1, -1, -1):          # descending, so that the lowest id is written last
+        a, b, c = tris[t]
+        p1, p2, p3 = nodes[a], nodes[b], nodes[c]
+        det = (p2[0] - p1[0]) * (p3[1] - p1[1]) - (p3[0] - p1[0]) * (p2[1] - p1[1])
+        if abs(det) < 1e-14:
+            continue
+        lo_x, hi_x = min(p1[0], p2[0], p3[0]), max(p1[0], p2[0], p3[0])
+        lo_y, hi_y = min(p1[1], p2[1], p3[1]), max(p1[1], p2[1], p3[1])
+        ix = np.nonzero((xs >= lo_x - dx) & (xs <= hi_x + dx))[0]
+        iy = np.nonzero((ys >= lo_y - dy) & (ys <= hi_y + dy))[0]
+        if len(ix) == 0 or len(iy) == 0:
+            continue
+        X, Y = np.meshgrid(xs[ix], ys[iy])
+        w1 = ((p2[0] - X) * (p3[1] - Y) - (p3[0] - X) * (p2[1] - Y)) / det
+        w2 = ((p3[0] - X) * (p1[1] - Y) - (p1[0] - X) * (p3[1] - Y)) / det
+        w3 = 1.0 - w1 - w2
+        inside = (w1 >= 0) & (w2 >= 0) & (w3 >= 0)
+        val = w1 * field[a] + w2 * field[b] + w3 * field[c]
+        sub = np.ix_(iy, ix)
+        img_sub, own_sub = img[sub], owner[sub]
+        img_sub[inside] = val[inside]
+        own_sub[inside] = t
+        img[sub], owner[sub] = img_sub, own_sub
+    return img, owner
+
+
+def colorize(img, vmin, vmax, lut, background=(0, 0, 0, 255)):
+    """NaN -> background, else lut[round(255 * clamp((v - vmin) / (vmax - vmin)))] in float32 like the kernel."""
+    v = img.astype(np.float32)
+    s = (v - np.float32(vmin)) / np.float32(np.float32(vmax) - np.float32(vmin))
+    s = np.clip(s, np.float32(0), np.float32(1))
+    k = np.where(np.isnan(v), 0, (s * np.float32(255) + np.float32(0.5))).astype(np.int64)
+    rgba = np.empty(img.shape + (4,), dtype=np.uint8)
+    rgba[..., :3] = np.asarray(lut, dtype=np.uint8)[k]
+    rgba[..., 3] = 255
+    rgba[np.isnan(v)] = np.asarray(background, dtype=np.uint8)
+    return rgba
+
+
+def splat_points(rgba, points, status, colors, radius_px, extent=(0.0, 1.0, 0.0, 1.0)):
+    """Discs of radius_px pixels; overlapping discs: the largest point index is on top."""
+    h, w = rgba.shape[:2]
+    x0, x1, y0, y1 = extent
+    r = np.float32(radius_px)
+    for i, (px, py) in enumerate(points):
+        if np.isnan(px) or np.isnan(py):
+            continue
+        cx = np.float32((px - x0) * (w / (x1 - x0)))
+        cy = np.float32((y1 - py) * (h / (y1 - y0)))
+        for yy in range(max(int(np.floor(cy - r)), 0), min(int(np.ceil(cy + r)), h - 1) + 1):
+            for xx in range(max(int(np.floor(cx - r)), 0), min(int(np.ceil(cx + r)), w - 1) + 1):
+                ddx = np.float32(xx + 0.5) - cx
+                ddy = np.float32(yy + 0.5) - cy
+                if ddx * ddx + ddy * ddy <= r * r:
+                    k = 0 if status is None else int(status[i])
+                    k = min(max(k, 0), len(colors) - 1)
+                    rgba[yy, xx, :3] = colors[k]
+                    rgba[yy, xx, 3] = 255
+    return rgba

@@ -98,6 +98,9 @@ SIGNATURES = {
     "fs_mixing_index": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "fs_locate_exact": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),
     "fs_tracer_step": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, P(c_i64)]),
+    "fs_raster_field": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_dbl, c_dbl, c_dbl, c_dbl, c_vp]),
+    "fs_raster_colormap": (C.c_int, [c_vp, c_i32, c_i32, c_dbl, c_dbl, c_vp, c_vp, c_vp]),
+    "fs_raster_points": (C.c_int, [c_vp, c_i32, c_i32, c_dbl, c_dbl, c_dbl, c_dbl, c_vp, c_vp, c_i64, c_vp, c_i32, c_dbl]),
 }
 
 _NO_CHECK = {"fs_version", "fs_last_error", "fs_launch_count"}

@@ -433,6 +433,76 @@ k_mix_pass(const double* __restrict__ c, const double* __restrict__ mass, const 
   }
 }
 
+// ---- output sink: what ax.tripcolor(triang, c, shading="gouraud") +
+// ax.scatter(tracers) + plt.pause draw (code/StokesColor.py:508-511,593-598, code/StokesFood.py:511-526),
+// as a device raster: the nodal field is sampled at the pixel centres by barycentric interpolation in
+// the containing triangle (NaN outside the mesh, i.e. in the hole), colour-mapped through a 256-entry
+// table, and tracers are drawn as discs on top.
+constexpr int kRasterRun = 8;   // consecutive pixels of a row per thread: the previous triangle seeds the walk
+
+__global__ void __launch_bounds__(128)
+k_raster_field(LocView V, const double* __restrict__ field, int W, int H, double x0, double dx, double ytop, double dy,
+               float* __restrict__ img) {
+  const int runs_per_row = (W + kRasterRun - 1) / kRasterRun;
+  const long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (id >= (long long)runs_per_row * H) return;
+  const int iy = (int)(id / runs_per_row), ix0 = (int)(id % runs_per_row) * kRasterRun;
+  const double y = ytop - (iy + 0.5) * dy;
+  int t = -1;
+  for (int ix = ix0; ix < min(ix0 + kRasterRun, W); ++ix) {
+    const double x = x0 + (ix + 0.5) * dx;
+    t = locate_exact(V, x, y, t);
+    float v = __int_as_float(0x7fc00000);
+    if (t >= 0) {
+      double w1, w2, w3;
+      bary(V, t, x, y, w1, w2, w3);
+      v = (float)(w1 * __ldg(field + V.tris[3 * t]) + w2 * __ldg(field + V.tris[3 * t + 1]) + w3 * __ldg(field + V.tris[3 * t + 2]));
+    }
+    img[(size_t)iy * W + ix] = v;
+  }
+}
+
+__global__ void k_raster_colormap(const float* __restrict__ img, long long n, float vmin, float vmax,
+                                  const unsigned char* __restrict__ lut, uchar4 bg, uchar4* __restrict__ rgba) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = img[i];
+  if (!(v == v)) { rgba[i] = bg; return; }
+  float s = (vmax > vmin) ? (v - vmin) / (vmax - vmin) : 0.f;
+  s = fminf(fmaxf(s, 0.f), 1.f);
+  const int k = (int)(s * 255.f + 0.5f);
+  rgba[i] = make_uchar4(lut[3 * k], lut[3 * k + 1], lut[3 * k + 2], 255);
+}
+
+// discs of radius r pixels; where discs overlap the point with the largest index wins (two passes:
+// owner by atomicMax, then colour), so the picture does not depend on the thread schedule
+__global__ void k_raster_owner(const double2* __restrict__ pts, long long P, int W, int H, double x0, double inv_dx, double ytop,
+                               double inv_dy, float r, int* __restrict__ owner) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const double2 p = pts[i];
+  if (!(p.x == p.x) || !(p.y == p.y)) return;
+  const float cx = (float)((p.x - x0) * inv_dx), cy = (float)((ytop - p.y) * inv_dy);   // pixel coordinates (centres at +0.5)
+  const int xl = max((int)floorf(cx - r), 0), xh = min((int)ceilf(cx + r), W - 1);
+  const int yl = max((int)floorf(cy - r), 0), yh = min((int)ceilf(cy + r), H - 1);
+  for (int yy = yl; yy <= yh; ++yy)
+    for (int xx = xl; xx <= xh; ++xx) {
+      const float ddx = xx + 0.5f - cx, ddy = yy + 0.5f - cy;
+      if (ddx * ddx + ddy * ddy <= r * r) atomicMax(&owner[(size_t)yy * W + xx], (int)i);
+    }
+}
+
+__global__ void k_raster_paint(const int* __restrict__ owner, long long n, const int* __restrict__ status,
+                               const unsigned char* __restrict__ colors, int n_colors, uchar4* __restrict__ rgba) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int o = owner[i];
+  if (o < 0) return;
+  int k = status ? status[o] : 0;
+  k = min(max(k, 0), n_colors - 1);
+  rgba[i] = make_uchar4(colors[3 * k], colors[3 * k + 1], colors[3 * k + 2], 255);
+}
+
 }  // namespace fs
 
 using namespace fs;
@@ -532,6 +602,63 @@ int fs_tracer_step(fs_mesh* m, double* pts, int32_t* status, int32_t* hint_ids, 
   op.commit(); os.commit(); oh.commit();
   unsigned long long h = cnt.to_host()[0];
   if (eaten) *eaten = (int64_t)h;
+  FS_API_END
+}
+
+int fs_raster_field(fs_mesh* m, const double* field, int32_t W, int32_t H, double x0, double x1, double y0, double y1,
+                    float* img) {
+  FS_API_BEGIN
+  FS_REQUIRE(m && field && img, "NULL argument");
+  FS_REQUIRE(W > 0 && H > 0 && x1 > x0 && y1 > y0, "empty raster");
+  LocView V = loc_view(m);
+  In<double> ifld(field, m->N);
+  Out<float> oi(img, (size_t)W * H, false);
+  const long long runs = (long long)((W + kRasterRun - 1) / kRasterRun) * H;
+  k_raster_field<<<(unsigned)div_up(runs, 128), 128, 0, stream()>>>(V, ifld.d, W, H, x0, (x1 - x0) / W, y1, (y1 - y0) / H, oi.d);
+  FS_LAUNCH_CHECK();
+  oi.commit();
+  fs::sync();
+  FS_API_END
+}
+
+int fs_raster_colormap(const float* img, int32_t W, int32_t H, double vmin, double vmax, const uint8_t* lut256x3,
+                       const uint8_t* background_rgba, uint8_t* rgba) {
+  FS_API_BEGIN
+  FS_REQUIRE(img && lut256x3 && background_rgba && rgba, "NULL argument");
+  FS_REQUIRE(W > 0 && H > 0, "empty raster");
+  const long long n = (long long)W * H;
+  In<float> ii(img, n);
+  In<unsigned char> il(lut256x3, 768);
+  Out<unsigned char> oo(rgba, 4 * n, false);
+  const uchar4 bg = make_uchar4(background_rgba[0], background_rgba[1], background_rgba[2], background_rgba[3]);
+  k_raster_colormap<<<(unsigned)div_up(n, 256), 256, 0, stream()>>>(ii.d, n, (float)vmin, (float)vmax, il.d, bg, (uchar4*)oo.d);
+  FS_LAUNCH_CHECK();
+  oo.commit();
+  fs::sync();
+  FS_API_END
+}
+
+int fs_raster_points(uint8_t* rgba, int32_t W, int32_t H, double x0, double x1, double y0, double y1, const double* pts,
+                     const int32_t* status, int64_t P, const uint8_t* colors_kx3, int32_t n_colors, double radius_px) {
+  FS_API_BEGIN
+  FS_REQUIRE(rgba && colors_kx3 && (P == 0 || pts), "NULL argument");
+  FS_REQUIRE(W > 0 && H > 0 && x1 > x0 && y1 > y0 && n_colors > 0 && radius_px >= 0, "bad raster arguments");
+  FS_REQUIRE(P < ((int64_t)1 << 31), "too many points");
+  if (P == 0) return FS_OK;
+  const long long n = (long long)W * H;
+  In<double> ip(pts, 2 * P);
+  In<int> is(status, status ? P : 0);
+  In<unsigned char> ic(colors_kx3, 3 * (size_t)n_colors);
+  Out<unsigned char> oo(rgba, 4 * n, true);
+  DBuf<int> owner((size_t)n);
+  FS_CUDA(cudaMemsetAsync(owner.p, 0xff, n * sizeof(int), stream()));
+  k_raster_owner<<<(unsigned)div_up(P, 128), 128, 0, stream()>>>((const double2*)ip.d, P, W, H, x0, W / (x1 - x0), y1, H / (y1 - y0),
+                                                                 (float)radius_px, owner.p);
+  FS_LAUNCH_CHECK();
+  k_raster_paint<<<(unsigned)div_up(n, 256), 256, 0, stream()>>>(owner.p, n, status ? is.d : nullptr, ic.d, n_colors, (uchar4*)oo.d);
+  FS_LAUNCH_CHECK();
+  oo.commit();
+  fs::sync();
   FS_API_END
 }
 

@@ -574,3 +574,54 @@ def test_checkpoint_resume_is_bit_exact(tmp_path):
         else:
             assert np.array_equal(a.tracer_points, b.tracer_points, equal_nan=True)
             assert np.array_equal(a.tracer_status, b.tracer_status)
+
+
+# ---- output sink: device raster of the dye / velocity field + tracers -----------
+def test_raster_field_colormap_and_points_match_oracle(tmp_path):
+    g = load_golden("mesh5_1_ops")
+    nodes, tris = g["nodes"], g["tris"]
+    m = fb.Mesh(nodes, tris, g["markers"])
+    rng = np.random.default_rng(11)
+    field = rng.standard_normal(m.N)
+    W, H, extent = 160, 96, (-0.05, 1.1, 0.0, 1.0)          # non-square pixels, a margin outside the box
+    img = fb.raster_field(m, field, W, H, extent)
+    want, owner = R.raster_field(nodes, tris, field, W, H, extent)
+    assert img.shape == (H, W) and img.dtype == np.float32
+    both = ~np.isnan(img) & ~np.isnan(want)
+    assert (np.isnan(img) != np.isnan(want)).mean() <= 2e-3    # pixel centres within rounding of a boundary edge
+    assert both.mean() > 0.6 and np.abs(img[both] - want[both]).max() <= 1e-6
+    assert np.isnan(img[:, 0]).all()                           # x < 0: outside the mesh
+    # colour mapping of the SAME float raster: exact
+    lut = fb.colormap_lut("plasma")
+    rgba = fb.colorize(img, -1.5, 2.0, lut, background=(1, 2, 3, 4))
+    assert np.array_equal(rgba, R.colorize(img, -1.5, 2.0, lut, background=(1, 2, 3, 4)))
+    # tracers: overlapping discs, NaN (lost) tracers, statuses outside the colour table are clamped
+    pts = rng.uniform(0.0, 1.0, size=(300, 2))
+    pts[5] = np.nan
+    pts[100:110] = pts[99] + 1e-3 * rng.standard_normal((10, 2))
+    status = rng.integers(0, 2, size=300).astype(np.int32)
+    status[7] = 9
+    colors = ((0, 0, 255), (255, 0, 0))
+    got = fb.splat_points(rgba.copy(), pts, status, colors, 3.5, extent)
+    assert np.array_equal(got, R.splat_points(rgba.copy(), pts, status, colors, 3.5, extent))
+    assert not np.array_equal(got, rgba)
+    # the frame sink writes what render() returns
+    sink = fb.FrameSink(str(tmp_path / "frames"), m, W, H, extent)
+    path = sink.field(field, -1.5, 2.0, cmap="plasma", tracers=pts, status=status, radius_px=3.5, background=(1, 2, 3, 4))
+    assert path.endswith("frame_000000.png") and np.array_equal(fb.read_png(path), got)
+
+
+def test_raster_large_mesh_is_exact_for_linear_fields():
+    nodes, markers, tris = fb.square_with_hole(1024, 512)      # 1M triangles
+    m = fb.Mesh(nodes, tris, markers)
+    f = 0.5 * nodes[:, 0] - 2.0 * nodes[:, 1] + 0.25
+    W = H = 768
+    img = fb.raster_field(m, f, W, H)
+    xs = (np.arange(W) + 0.5) / W
+    ys = 1.0 - (np.arange(H) + 0.5) / H
+    X, Y = np.meshgrid(xs, ys)
+    inside = ~np.isnan(img)
+    assert np.abs(img[inside] - (0.5 * X - 2.0 * Y + 0.25)[inside]).max() <= 1e-6
+    rad = np.hypot(X - 0.5, Y - 0.5)
+    assert not inside[rad < 0.249].any() and inside[rad > 0.251].all()
+    assert abs((~inside).mean() - np.pi * 0.25 ** 2) < 2e-3

@@ -151,3 +151,43 @@ def test_c_port_matches_scipy():
     assert it > 10 and rr <= 1e-12
     assert np.linalg.norm(q[ps.dof] - want) <= 1e-9 * np.linalg.norm(want)
     assert cgport.threads() >= 1
+
+
+# ---- output sink: oracle restatement and the host-side PNG codec -------------
+def test_raster_oracle_reproduces_linear_fields_and_the_hole():
+    from oracle import restated as R
+    g = load_golden("mesh5_1_ops")
+    nodes, tris = g["nodes"], g["tris"]
+    f = 2.0 * nodes[:, 0] + 3.0 * nodes[:, 1] - 1.0
+    W, H = 96, 64
+    img, owner = R.raster_field(nodes, tris, f, W, H)
+    xs = (np.arange(W) + 0.5) / W
+    ys = 1.0 - (np.arange(H) + 0.5) / H
+    X, Y = np.meshgrid(xs, ys)
+    inside = ~np.isnan(img)
+    assert np.abs(img[inside] - (2.0 * X + 3.0 * Y - 1.0)[inside]).max() <= 1e-13      # P1 interpolation is exact for linear fields
+    rad = np.hypot(X - 0.5, Y - 0.5)
+    assert not inside[rad < 0.24].any() and inside[rad > 0.26].all()                    # the squirmer hole, radius 0.25
+    assert (owner[inside] >= 0).all() and (owner[~inside] == -1).all()
+    # colour mapping: NaN -> background, ends of the table at vmin / vmax
+    lut = np.stack([np.arange(256)] * 3, axis=1).astype(np.uint8)
+    rgba = R.colorize(np.array([[0.0, 1.0, np.nan, 0.5, -3.0, 7.0]]), 0.0, 1.0, lut, background=(9, 8, 7, 6))
+    assert rgba[0, :, 0].tolist() == [0, 255, 9, 128, 0, 255] and rgba[0, 2].tolist() == [9, 8, 7, 6]
+
+
+def test_png_codec_roundtrip_and_colormaps(tmp_path):
+    import fluidsim_b200 as fb
+    rng = np.random.default_rng(3)
+    rgba = rng.integers(0, 256, size=(37, 53, 4), dtype=np.uint8)
+    path = str(tmp_path / "frame.png")
+    fb.write_png(path, rgba)
+    head = open(path, "rb").read(24)
+    assert head[:8] == b"\x89PNG\r\n\x1a\n" and head[12:16] == b"IHDR"
+    assert int.from_bytes(head[16:20], "big") == 53 and int.from_bytes(head[20:24], "big") == 37
+    assert np.array_equal(fb.read_png(path), rgba)
+    for name, first, last in (("viridis", (68, 1, 84), (253, 231, 37)), ("plasma", (13, 8, 135), (240, 249, 33))):
+        lut = fb.colormap_lut(name)
+        assert lut.shape == (256, 3) and lut.dtype == np.uint8
+        assert tuple(lut[0]) == first and tuple(lut[255]) == last
+    with pytest.raises(ValueError):
+        fb.colormap_lut("no-such-map")
