@@ -625,3 +625,27 @@ def test_raster_large_mesh_is_exact_for_linear_fields():
     rad = np.hypot(X - 0.5, Y - 0.5)
     assert not inside[rad < 0.249].any() and inside[rad > 0.251].all()
     assert abs((~inside).mean() - np.pi * 0.25 ** 2) < 2e-3
+
+
+def test_amg_pcg_lagged_polling_with_a_much_easier_second_solve():
+    """The host queues PCG iterations without reading the convergence flag for as long as the previous solves
+    on the matrix needed; a following solve that converges much earlier must still return the iterate at
+    which it converged (the update kernels freeze once the flag is set) and the true iteration count."""
+    nodes, markers, tris = fb.square_with_hole(512, 256)
+    mm = fb.Mesh(nodes, tris, markers)
+    A = mm.matrix(mm.stiffness_values())
+    rng = np.random.default_rng(12)
+    b = rng.standard_normal(mm.N)
+    b -= b.mean()
+    x1, it1, _ = A.cg(b, rtol=1e-10, precond=fb.PRECOND_AMG, project_mean=True)
+    x1b, it1b, _ = A.cg(b, rtol=1e-10, precond=fb.PRECOND_AMG, project_mean=True)       # second solve: hint = it1
+    assert it1b == it1 and np.array_equal(x1, x1b)
+    b2 = b + 1e-7 * rng.standard_normal(mm.N)
+    b2 -= b2.mean()
+    x2, it2, rr2 = A.cg(b2, x0=x1, rtol=1e-10, precond=fb.PRECOND_AMG, project_mean=True)
+    assert 0 < it2 < it1 - 10 and rr2 <= 1e-10
+    assert np.linalg.norm(b2 - (A @ x2)) <= 2e-10 * np.linalg.norm(b2)
+    # the same solve on a fresh handle (no history, polled every iteration) gives the same bits
+    A2 = mm.matrix(mm.stiffness_values())
+    x2f, it2f, _ = A2.cg(b2, x0=x1, rtol=1e-10, precond=fb.PRECOND_AMG, project_mean=True)
+    assert it2f == it2 and np.array_equal(x2, x2f)
