@@ -172,7 +172,8 @@ def workload_config(args, **extra):
                        f"nu=0.1, DT=0.05",
            "solver": f"pressure: CG + smoothed-aggregation AMG V(1,1), cycle folded to two SELL-32 SpMVs per level "
                      f"[--precond amg] or Jacobi persistent CG [--precond jacobi], rtol_pressure={RTOL_P:g}; "
-                     f"viscous: 2-RHS Jacobi CG rtol={RTOL_V:g}; warm start from the previous step",
+                     f"viscous: 2-RHS Jacobi CG rtol={RTOL_V:g}; pressure warm start = best of the previous solution and its "
+                     f"linear / quadratic extrapolation in time (every solve still runs to rtol)",
            "l2": "inputs larger than L2 (per PCG iteration: A 190 MB fp64 SELL + V-cycle operators ~440 MB fp32 SELL "
                  "+ 5 vectors 84 MB > 126 MB), no flush needed",
            "steps_from": "t=0 (u=0 + squirmer BC); warm-up steps advance the same trajectory"}
