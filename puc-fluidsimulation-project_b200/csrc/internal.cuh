@@ -299,6 +299,9 @@ int cg_dev(fs_csr* a, const double* d_b, double* d_x, int nrhs, double rtol, int
            int project_mean, double* relres);
 void spmv_dev(const CsrView& A, const double* d_x, double* d_y);
 double resid_norm2_dev(fs_csr* a, const double* b, const double* x, double* work);   // |b - A x|^2
+void spmv_best_dev(fs_csr* a, const double* x, double* y);                          // y = A x, fastest layout at hand
+void cand_norms3_dev(fs_csr* a, const double* b, const double* y0, const double* y1, const double* y2 /* nullable */,
+                     double* out3);   // |b - y0|^2, |b - (2 y0 - y1)|^2, |b - (3 y0 - 3 y1 + y2)|^2
 void lin3_dev(int64_t n, double a, const double* x, double b, const double* y, double* out);   // out = a x + b y
 double max_abs_dev(const double* d_x, int64_t n);
 void free_locator(Locator* l);

@@ -1125,6 +1125,45 @@ static void dot2(int64_t n, const double* a, const double* b, const double* c, c
   for (int i = 0; i < g; ++i) { out2[0] += h[2 * i]; out2[1] += h[2 * i + 1]; }
 }
 
+// y = A x through the fastest layout the handle has (SELL-32 copy, else CSR-stream, else CSR-vector)
+void spmv_best_dev(fs_csr* a, const double* x, double* y) {
+  if (a->sell64 && spmv_sell(*a->sell64, x, y, nullptr, nullptr)) return;
+  ensure_tiles(a);
+  const CsrView A = a->view();
+  if (!spmv_warp(A, EPI_AX, x, y, nullptr, nullptr, 0.0, nullptr, nullptr)) spmv_dev(A, x, y);
+}
+
+// squared norms of b - y0, b - (2 y0 - y1), b - (3 y0 - 3 y1 + y2): the residuals of the three warm-start
+// candidates q, 2q - q1, 3q - 3q1 + q2 given y_k = A q_k (y2 may be null: only the first two)
+__global__ void __launch_bounds__(kBlock)
+k_cand3(int64_t n, const double* __restrict__ b, const double* __restrict__ y0, const double* __restrict__ y1,
+        const double* __restrict__ y2, double* __restrict__ part) {
+  __shared__ double red[3 * 32];
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double bv = b[i], a0 = y0[i], a1 = y1[i];
+    const double r0 = bv - a0, r1 = bv - (2.0 * a0 - a1);
+    acc[0] += r0 * r0;
+    acc[1] += r1 * r1;
+    if (y2) { const double r2 = bv - (3.0 * a0 - 3.0 * a1 + y2[i]); acc[2] += r2 * r2; }
+  }
+  block_reduce<3>(acc, red);
+  if (threadIdx.x == 0) for (int k = 0; k < 3; ++k) part[3 * blockIdx.x + k] = acc[k];
+}
+
+void cand_norms3_dev(fs_csr* a, const double* b, const double* y0, const double* y1, const double* y2, double* out3) {
+  ensure_ws(a, 4 * (size_t)a->n);
+  const int64_t n = a->n;
+  const int g = std::min(vec_grid(n), 256);
+  k_cand3<<<g, kBlock, 0, stream()>>>(n, b, y0, y1, y2, a->partials.p);
+  FS_LAUNCH_CHECK();
+  std::vector<double> h(3 * (size_t)g);
+  FS_CUDA(cudaMemcpyAsync(h.data(), a->partials.p, sizeof(double) * 3 * g, cudaMemcpyDeviceToHost, stream()));
+  FS_CUDA(cudaStreamSynchronize(stream()));
+  out3[0] = out3[1] = out3[2] = 0.0;
+  for (int i = 0; i < g; ++i) for (int k = 0; k < 3; ++k) out3[k] += h[3 * i + k];
+}
+
 void lin3_dev(int64_t n, double a, const double* x, double b, const double* y, double* out) {
   k_lin3<<<vec_grid(n), kBlock, 0, stream()>>>(n, a, x, b, y, 0.0, nullptr, out);
   FS_LAUNCH_CHECK();

@@ -29,9 +29,14 @@ struct fs_stokes {
   fs::DBuf<unsigned char> is_dir, is_interior;
   fs::DBuf<double> ustar, div, rhs_red, p_red, p2_red, p_full, p2_full;
   bool have_p = false;
-  // previous solutions of the two pressure solves: the warm start may be extrapolated in time
-  fs::DBuf<double> p_prev, p2_prev, p_prev2, p2_prev2, q_try, q_try2;   // one and two steps back; candidates
-  int hist_p = 0, hist_p2 = 0;                                  // how many of them are valid
+  // history of one pressure solve: its solutions one and two steps back (q1, q2, nq of them valid) and
+  // their images y = K q (ny valid; recomputed on demand, never part of a checkpoint)
+  struct PressHist {
+    fs::DBuf<double> q1, q2, y1, y2;
+    int nq = 0, ny = 0;
+  };
+  PressHist h1, h2;                 // first / second projection of the step
+  fs::DBuf<double> y0, q_try;       // K q of the current solve; the chosen extrapolated guess
 };
 
 namespace fs {
@@ -69,10 +74,11 @@ __global__ void k_expand(int64_t N, const int* __restrict__ dof, const double* _
 }
 
 // Warm start: the previous step's solution q, or its extrapolation in time from the last two / three
-// steps (2 q - q1, 3 q - 3 q1 + q2), whichever has the smallest residual |b - K q|^2.  The candidates
-// are all evaluated: an SpMV each buys several PCG iterations while the flow evolves smoothly, and
-// nothing is lost when it does not.
-static void pressure_solve(fs_stokes* s, const double* d_vel, double* q, double* q1, double* q2, int* hist, double* p_full,
+// steps (2 q - q1, 3 q - 3 q1 + q2), whichever has the smallest residual |b - K q|.  K is linear, so
+// with y_k = K q_k kept from the earlier steps the three residual norms cost ONE SpMV (y0 = K q) and
+// one pass over four vectors: it buys 7-10 of ~27 PCG iterations while the flow evolves smoothly and
+// loses nothing when it does not (every solve still runs to rtol).
+static void pressure_solve(fs_stokes* s, const double* d_vel, double* q, fs_stokes::PressHist& H, double* p_full,
                            const fs_stokes_opts& o, int* iters, double* relres, double* max_div) {
   static const int extrap = [] { const char* e = std::getenv("FS_STOKES_EXTRAP"); return e ? std::atoi(e) : 2; }();
   fs_mesh* m = s->mesh;
@@ -84,27 +90,35 @@ static void pressure_solve(fs_stokes* s, const double* d_vel, double* q, double*
   FS_LAUNCH_CHECK();
   if (!o.warm_start || !s->have_p) {
     FS_CUDA(cudaMemsetAsync(q, 0, s->nd * sizeof(double), st));
-    *hist = 0;
+    H.nq = H.ny = 0;
   } else if (extrap > 0) {
     const size_t bytes = s->nd * sizeof(double);
-    int best = 0;   // 0: q, 1: linear, 2: quadratic (left in q_try)
-    if (*hist >= 1) {
-      double r_best = resid_norm2_dev(&s->k_red, s->rhs_red.p, q, s->div.p);
-      lin3_dev(s->nd, 2.0, q, -1.0, q1, s->q_try.p);
-      const double r_lin = resid_norm2_dev(&s->k_red, s->rhs_red.p, s->q_try.p, s->div.p);
-      if (r_lin < r_best) { best = 1; r_best = r_lin; }
-      if (*hist >= 2 && extrap >= 2) {
-        lin3_dev(s->nd, 3.0, q, -3.0, q1, s->q_try2.p);
-        lin3_dev(s->nd, 1.0, s->q_try2.p, 1.0, q2, s->q_try2.p);
-        const double r_quad = resid_norm2_dev(&s->k_red, s->rhs_red.p, s->q_try2.p, s->div.p);
-        if (r_quad < r_best) { best = 2; r_best = r_quad; }
+    int best = 0;   // 0: q, 1: linear, 2: quadratic
+    bool have_y0 = false;
+    if (H.nq >= 1) {
+      const bool quad = H.nq >= 2 && extrap >= 2;
+      spmv_best_dev(&s->k_red, q, s->y0.p);
+      have_y0 = true;
+      if (H.ny < 1) spmv_best_dev(&s->k_red, H.q1.p, H.y1.p);            // after a restore
+      if (quad && H.ny < 2) spmv_best_dev(&s->k_red, H.q2.p, H.y2.p);
+      double r3[3];
+      cand_norms3_dev(&s->k_red, s->rhs_red.p, s->y0.p, H.y1.p, quad ? H.y2.p : nullptr, r3);
+      if (r3[1] < r3[best]) best = 1;
+      if (quad && r3[2] < r3[best]) best = 2;
+      if (best == 1) lin3_dev(s->nd, 2.0, q, -1.0, H.q1.p, s->q_try.p);
+      if (best == 2) {
+        lin3_dev(s->nd, 3.0, q, -3.0, H.q1.p, s->q_try.p);
+        lin3_dev(s->nd, 1.0, s->q_try.p, 1.0, H.q2.p, s->q_try.p);
       }
     }
-    FS_CUDA(cudaMemcpyAsync(q2, q1, bytes, cudaMemcpyDeviceToDevice, st));
-    FS_CUDA(cudaMemcpyAsync(q1, q, bytes, cudaMemcpyDeviceToDevice, st));
-    if (best == 1) FS_CUDA(cudaMemcpyAsync(q, s->q_try.p, bytes, cudaMemcpyDeviceToDevice, st));
-    if (best == 2) FS_CUDA(cudaMemcpyAsync(q, s->q_try2.p, bytes, cudaMemcpyDeviceToDevice, st));
-    *hist = std::min(*hist + 1, 2);
+    // shift the history: (q1, y1) -> (q2, y2) by swapping the buffers, then q -> q1, y0 -> y1
+    std::swap(H.q1, H.q2);
+    std::swap(H.y1, H.y2);
+    FS_CUDA(cudaMemcpyAsync(H.q1.p, q, bytes, cudaMemcpyDeviceToDevice, st));
+    if (have_y0) std::swap(H.y1, s->y0);
+    H.ny = have_y0 ? 2 : 0;     // y1 = K q (just computed), y2 = the old y1 (valid or recomputed above)
+    H.nq = std::min(H.nq + 1, 2);
+    if (best) FS_CUDA(cudaMemcpyAsync(q, s->q_try.p, bytes, cudaMemcpyDeviceToDevice, st));
   }
   int it = cg_dev(&s->k_red, s->rhs_red.p, q, 1, o.rtol_pressure, o.maxit, o.precond, 1, relres);
   if (it < 0) throw Error(FS_ERR_NOCONV, "pressure CG did not converge within maxit");
@@ -187,9 +201,11 @@ int fs_stokes_create(fs_mesh* m, double DT, double nu, fs_stokes** out) {
   s->pat_red.contrib.release(); s->pat_red.seg_start.release(); s->pat_red.scatter.release();
   s->ustar.alloc(2 * N); s->div.alloc(N); s->rhs_red.alloc(nd);
   s->p_red.alloc(nd); s->p2_red.alloc(nd); s->p_full.alloc(N); s->p2_full.alloc(N);
-  s->p_prev.alloc(nd); s->p2_prev.alloc(nd); s->p_prev2.alloc(nd); s->p2_prev2.alloc(nd);
-  s->q_try.alloc(nd); s->q_try2.alloc(nd);
-  s->p_prev.zero(); s->p2_prev.zero(); s->p_prev2.zero(); s->p2_prev2.zero();
+  for (fs_stokes::PressHist* h : {&s->h1, &s->h2}) {
+    h->q1.alloc(nd); h->q2.alloc(nd); h->y1.alloc(nd); h->y2.alloc(nd);
+    h->q1.zero(); h->q2.zero();
+  }
+  s->y0.alloc(nd); s->q_try.alloc(nd);
   s->p_red.zero(); s->p2_red.zero(); s->p_full.zero(); s->p2_full.zero();
   fs::sync();
   *out = s.release();
@@ -236,7 +252,7 @@ int fs_stokes_step(fs_stokes* s, double* u, double B1, double B2, const fs_stoke
   dir_bcu_dev(m, s->ustar.p, B1, B2);
   mark();
   // Step 2+3: pressure correction and velocity update
-  pressure_solve(s, s->ustar.p, s->p_red.p, s->p_prev.p, s->p_prev2.p, &s->hist_p, s->p_full.p, o, &sts.iters_p1, &sts.relres_p1,
+  pressure_solve(s, s->ustar.p, s->p_red.p, s->h1, s->p_full.p, o, &sts.iters_p1, &sts.relres_p1,
                  o.final_div ? &sts.max_div_ustar : nullptr);
   mark();
   grad_update_dev(m, s->p_full.p, s->ustar.p, du, s->DT, nullptr);
@@ -244,7 +260,7 @@ int fs_stokes_step(fs_stokes* s, double* u, double B1, double B2, const fs_stoke
   dir_bcu_dev(m, du, B1, B2);
   mark();
   // second projection, interior nodes only, no BC re-imposition (:566-573)
-  pressure_solve(s, du, s->p2_red.p, s->p2_prev.p, s->p2_prev2.p, &s->hist_p2, s->p2_full.p, o, &sts.iters_p2, &sts.relres_p2, nullptr);
+  pressure_solve(s, du, s->p2_red.p, s->h2, s->p2_full.p, o, &sts.iters_p2, &sts.relres_p2, nullptr);
   mark();
   grad_update_dev(m, s->p2_full.p, du, du, s->DT, s->is_interior.p);
   s->have_p = true;
@@ -290,14 +306,15 @@ int fs_stokes_warm_state(fs_stokes* s, double* q, int set) {
   FS_REQUIRE(s && q, "NULL argument");
   const size_t nd = (size_t)s->nd;
   cudaStream_t st = stream();
-  double* bufs[6] = {s->p_red.p, s->p2_red.p, s->p_prev.p, s->p2_prev.p, s->p_prev2.p, s->p2_prev2.p};
-  double hist[2] = {(double)s->hist_p, (double)s->hist_p2};
+  double* bufs[6] = {s->p_red.p, s->p2_red.p, s->h1.q1.p, s->h2.q1.p, s->h1.q2.p, s->h2.q2.p};
+  double hist[2] = {(double)s->h1.nq, (double)s->h2.nq};
   if (set) {
     for (int k = 0; k < 6; ++k) FS_CUDA(cudaMemcpyAsync(bufs[k], q + k * nd, nd * sizeof(double), cudaMemcpyDefault, st));
     FS_CUDA(cudaMemcpyAsync(hist, q + 6 * nd, sizeof(hist), cudaMemcpyDefault, st));
     fs::sync();
-    s->hist_p = std::max(0, std::min(2, (int)hist[0]));
-    s->hist_p2 = std::max(0, std::min(2, (int)hist[1]));
+    s->h1.nq = std::max(0, std::min(2, (int)hist[0]));
+    s->h2.nq = std::max(0, std::min(2, (int)hist[1]));
+    s->h1.ny = s->h2.ny = 0;            // K q1, K q2 are recomputed by the next solve
     s->have_p = true;
   } else {
     for (int k = 0; k < 6; ++k) FS_CUDA(cudaMemcpyAsync(q + k * nd, bufs[k], nd * sizeof(double), cudaMemcpyDefault, st));
