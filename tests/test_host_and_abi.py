@@ -154,3 +154,18 @@ def test_refine_mesh():
     e = np.concatenate([t[:, [0, 1]], t[:, [1, 2]], t[:, [2, 0]]])
     E = len(np.unique(np.sort(e, axis=1), axis=0))
     assert len(n) - E + len(t) == 0
+
+
+def test_raster_argument_validation():
+    """Host-side checks of the output sink run before any device call."""
+    import fluidsim_b200 as fb
+    with pytest.raises(ValueError):
+        fb.colorize(np.zeros((4, 4), dtype=np.float32), 0.0, 1.0, cmap=np.zeros((10, 3), dtype=np.uint8))
+    with pytest.raises(ValueError):
+        fb.colorize(np.zeros((4, 4), dtype=np.float32), 0.0, 1.0, background=(0, 0, 0))
+    with pytest.raises(ValueError):
+        fb.splat_points(np.zeros((4, 4, 3), dtype=np.uint8), np.zeros((1, 2)))
+    with pytest.raises(ValueError):
+        fb.write_png("/dev/null", np.zeros((4, 4), dtype=np.uint8))
+    lut = fb.colormap_lut("gray")
+    assert np.array_equal(lut[:, 0], lut[:, 1]) and lut[0, 0] == 0 and lut[255, 0] == 255 and (np.diff(lut[:, 0].astype(int)) >= 0).all()
