@@ -74,9 +74,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Summary of the samples taken in [t_begin, t_end] (wall clock; all samples if the window holds none:
+        the sampler is started before the warm-up so that it is already streaming when the timed region begins)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -84,11 +86,14 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if (t_begin is None or t >= t_begin) and (t_end is None or t <= t_end + 0.1)]
+        if not rows:
+            rows = [r for _, r in self.rows]
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 9:
                 for n, v in zip(names, r[5:9]):
                     if v.lower().startswith("active"):
@@ -241,14 +246,15 @@ def run_ours(args):
     u_dev = torch.from_numpy(sim.u.copy()).cuda()
 
     # ---- device-resident arm: W warm-up steps, then exactly K timed steps
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()                      # streaming 100 ms samples from here on; summarised over the two timed regions
     for _ in range(args.warmup):
         sim.step(u_dev)
     barrier()
     u_snap = u_dev.clone()                  # loop state, so that the end-to-end arm repeats the same K steps
     warm_snap = sim.get_warm_state()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
+    t_clk0 = time.time()
     launches0 = fb.launch_count()
     _lib.call("fs_profile", 1)
     t_dev, iters = timed_steps(sim, u_dev, args.steps, _lib, barrier)
@@ -257,7 +263,6 @@ def run_ours(args):
     top_ms, top_n, top_bytes = C.c_double(0), C.c_int64(0), C.c_double(0)
     _lib.call("fs_profile_read_top", C.byref(top_ms), C.byref(top_n), C.byref(top_bytes))
     _lib.call("fs_profile", 0)
-    clk = clocks.stop() if rank == 0 else None
     t_dev = max_over_ranks(t_dev)
     value = world * args.steps / t_dev
 
@@ -273,6 +278,7 @@ def run_ours(args):
         sim.step(u_host)
     barrier()
     e2e = world * args.steps / max_over_ranks(time.perf_counter() - t0)
+    clk = clocks.stop(t_clk0, time.time()) if rank == 0 else None      # samples of the device arm and the end-to-end arm
 
     if dist is not None:
         dist.barrier()
