@@ -13,6 +13,7 @@ from .core import (Mesh, CsrMatrix, solve, buildStiffnessMatrix, buildFemSystem,
 from .stokes import StokesSolver, StokesColor, StokesFood, food_tracer_grid  # noqa: F401
 from .poisson import (PoissonProblem, HeatProblem, apply_periodic_bc, apply_dirichlet_rows,  # noqa: F401
                       add_identity_scaled)
+from .meshgen import triangulate, triangulate_poly, box_with_hole_pslg, read_poly_full  # noqa: F401
 from .raster import (raster_field, colorize, splat_points, colormap_lut, write_png, read_png, FrameSink)  # noqa: F401
 
 

@@ -169,3 +169,80 @@ def test_raster_argument_validation():
         fb.write_png("/dev/null", np.zeros((4, 4), dtype=np.uint8))
     lut = fb.colormap_lut("gray")
     assert np.array_equal(lut[:, 0], lut[:, 1]) and lut[0, 0] == 0 and lut[255, 0] == 255 and (np.diff(lut[:, 0].astype(int)) >= 0).all()
+
+
+# ---- mesh generation from a PSLG (`triangle -p -q30 -a...` is not available here) ----
+def _quality(P, T):
+    a, b, c = P[T[:, 0]], P[T[:, 1]], P[T[:, 2]]
+    area2 = (b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (c[:, 0] - a[:, 0]) * (b[:, 1] - a[:, 1])
+    l = np.sort(np.stack([np.linalg.norm(b - c, axis=1), np.linalg.norm(c - a, axis=1), np.linalg.norm(a - b, axis=1)], 1), axis=1)
+    return area2, np.degrees(np.arcsin(np.clip(np.abs(area2) / (l[:, 1] * l[:, 2]), 0, 1)))
+
+
+def _edges(T):
+    e = np.sort(np.concatenate([T[:, [0, 1]], T[:, [1, 2]], T[:, [2, 0]]]), axis=1)
+    return np.unique(e, axis=0, return_counts=True)
+
+
+@pytest.mark.parametrize("name", ["mesh2_1", "mesh5_1"])
+def test_meshgen_reproduces_the_reference_triangulation(name):
+    """Triangle's output is a conforming Delaunay triangulation: from the shipped nodes and boundary segments
+    the mesher must return exactly the reference's triangles (and add no point: the meshes already satisfy -q30)."""
+    import fluidsim_b200 as fb
+    g = load_golden(name + "_ops")
+    nodes, markers, tris = g["nodes"], g["markers"], g["tris"]
+    e, cnt = _edges(tris)
+    segs = e[cnt == 1]                                           # boundary edges = the .poly segments
+    smark = markers[segs[:, 0]]
+    assert np.array_equal(smark, markers[segs[:, 1]]) and set(smark) == {1, 2}
+    P, M, T, S, SM = fb.triangulate(nodes, markers, segs, smark, holes=[(0.5, 0.5)], min_angle=30.0)
+    assert np.array_equal(P, nodes) and np.array_equal(M, markers)
+    assert set(map(tuple, np.sort(T, axis=1).tolist())) == set(map(tuple, np.sort(tris, axis=1).tolist()))
+    assert (_quality(P, T)[0] > 0).all()                         # CCW
+
+
+def test_meshgen_quality_bounds_and_boundaries(tmp_path):
+    import fluidsim_b200 as fb
+    v, vm, s, sm, h = fb.box_with_hole_pslg(60)
+    amax = 5e-4
+    P, M, T, S, SM = fb.triangulate(v, vm, s, sm, h, min_angle=30.0, max_area=amax, curves={2: (0.5, 0.5, 0.25)})
+    area2, ang = _quality(P, T)
+    assert (area2 > 0).all() and ang.min() >= 30.0 - 1e-9 and 0.5 * area2.max() <= amax * (1 + 1e-12)
+    assert np.array_equal(P[:len(v)], v) and np.array_equal(M[:len(v)], vm)       # input vertices first, unchanged
+    # boundary: every output segment is an edge of exactly one triangle, and nothing else is a boundary edge
+    e, cnt = _edges(T)
+    bnd = set(map(tuple, e[cnt == 1].tolist()))
+    assert bnd == set(map(tuple, np.sort(S, axis=1).tolist())) and (cnt <= 2).all()
+    assert len(P) - len(e) + len(T) == 0                                          # Euler characteristic of an annulus
+    # markers: 1 on the box, 2 on the circle (new circle points were projected), 0 strictly inside
+    on_box = (np.abs(P[:, 0]) < 1e-14) | (np.abs(P[:, 0] - 1) < 1e-14) | (np.abs(P[:, 1]) < 1e-14) | (np.abs(P[:, 1] - 1) < 1e-14)
+    rad = np.hypot(P[:, 0] - 0.5, P[:, 1] - 0.5)
+    assert np.array_equal(M == 1, on_box) and np.abs(rad[M == 2] - 0.25).max() < 1e-14 and (rad[M == 0] > 0.25).all()
+    assert (M == 2).sum() >= 60 and np.array_equal(SM == 2, M[S[:, 0]] == 2)
+    # area = box minus the polygon actually meshed (between the 60-gon and the circle)
+    assert 1 - np.pi * 0.25 ** 2 < 0.5 * area2.sum() <= 1 - 0.5 * 60 * 0.25 ** 2 * np.sin(2 * np.pi / 60) + 1e-12
+    # the host-side set-up of the Stokes solver accepts the mesh; .node/.ele/.poly round trip
+    pairs = fb.filter_wall_pairs(P, fb.find_boundary_pairs(P))
+    sets = fb.index_sets(P, M)
+    assert len(pairs) > 5 and len(sets[0]) > 0 and len(sets[1]) == (M == 2).sum()
+    fb.write_node(str(tmp_path / "m.node"), P, M)
+    fb.write_ele(str(tmp_path / "m.ele"), T)
+    P2, M2 = fb.readNode(str(tmp_path / "m.node"))
+    assert np.array_equal(P2, P) and np.array_equal(M2, M) and np.array_equal(fb.readEle(str(tmp_path / "m.ele")), T)
+
+
+def test_meshgen_nonconvex_outline_and_poly_reader(tmp_path):
+    import fluidsim_b200 as fb
+    poly = tmp_path / "L.poly"
+    poly.write_text("6 2 0 1\n1 0 0 1\n2 1 0 1\n3 1 0.5 1\n4 0.5 0.5 1\n5 0.5 1 1\n6 0 1 1\n"
+                    "6 1\n1 1 2 1\n2 2 3 1\n3 3 4 1\n4 4 5 1\n5 5 6 1\n6 6 1 1\n0\n# an L-shaped domain, no holes\n")
+    v, vm, s, sm, h = fb.read_poly_full(str(poly))
+    assert v.shape == (6, 2) and len(h) == 0 and s.tolist()[0] == [0, 1] and (sm == 1).all() and (vm == 1).all()
+    P, M, T, S, SM = fb.triangulate_poly(str(poly), min_angle=28.0, max_area=2e-3)
+    area2, ang = _quality(P, T)
+    assert abs(0.5 * area2.sum() - 0.75) < 1e-12 and ang.min() >= 28.0 - 1e-9 and 0.5 * area2.max() <= 2e-3 * (1 + 1e-12)
+    cen = P[T].mean(1)
+    assert not ((cen[:, 0] > 0.5) & (cen[:, 1] > 0.5)).any()      # the notch is outside the domain
+    assert (M[(P[:, 0] > 0.51) & (P[:, 0] < 0.99) & (P[:, 1] > 0.01) & (P[:, 1] < 0.49)] == 0).all()
+    with pytest.raises(ValueError):
+        fb.triangulate(v, vm, s, sm, min_angle=40.0)
