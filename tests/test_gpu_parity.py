@@ -649,3 +649,18 @@ def test_amg_pcg_lagged_polling_with_a_much_easier_second_solve():
     A2 = mm.matrix(mm.stiffness_values())
     x2f, it2f, _ = A2.cg(b2, x0=x1, rtol=1e-10, precond=fb.PRECOND_AMG, project_mean=True)
     assert it2f == it2 and np.array_equal(x2, x2f)
+
+
+def test_generated_mesh_runs_through_the_stokes_step():
+    """A mesh from the PSLG mesher is a drop-in for the shipped ones: Stokes steps on it match the
+    restated oracle like the reference meshes do."""
+    v, vm, s, sm, h = fb.box_with_hole_pslg(60)
+    nodes, markers, tris, _, _ = fb.triangulate(v, vm, s, sm, h, min_angle=30.0, max_area=2e-3, curves={2: (0.5, 0.5, 0.25)})
+    sim = fb.StokesSolver(nodes, markers, tris, B1=-2.0, B2=-5.0, DT=0.05, v=0.1, rtol_pressure=1e-12, rtol_visc=1e-13)
+    o = R.RestatedStokes(nodes, markers, tris, B1=-2.0, B2=-5.0, DT=0.05, v=0.1)
+    assert sim.pairs == o.pairs and len(sim.pairs) > 5
+    for _ in range(5):
+        sim.step()
+        o.flow_step()
+    p, _ = sim.pressure()
+    assert rel(sim.u, o.u) <= 1e-9 and rel(p, o.p) <= 1e-9
