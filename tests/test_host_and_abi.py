@@ -246,3 +246,30 @@ def test_meshgen_nonconvex_outline_and_poly_reader(tmp_path):
     assert (M[(P[:, 0] > 0.51) & (P[:, 0] < 0.99) & (P[:, 1] > 0.01) & (P[:, 1] < 0.49)] == 0).all()
     with pytest.raises(ValueError):
         fb.triangulate(v, vm, s, sm, min_angle=40.0)
+
+
+def test_meshgen_two_holes_internal_segment_and_sharp_corner():
+    import fluidsim_b200 as fb
+    v, vm, s, sm, _ = fb.box_with_hole_pslg(40, centre=(0.3, 0.5), radius=0.15)
+    v2, _, s2, _, _ = fb.box_with_hole_pslg(30, centre=(0.72, 0.5), radius=0.1)
+    V = np.concatenate([v, v2[4:], [[0.1, 0.9], [0.9, 0.9]]])
+    VM = np.concatenate([vm, 3 * np.ones(30, dtype=np.int32), [0, 0]])
+    S = np.concatenate([s, s2[4:] - 4 + len(v), [[len(v) + 30, len(v) + 31]]])          # last: a constraint inside the domain
+    SM = np.concatenate([sm, 3 * np.ones(30, dtype=np.int32), [7]])
+    P, M, T, S2, SM2 = fb.triangulate(V, VM, S, SM, [(0.3, 0.5), (0.72, 0.5)], min_angle=30.0, max_area=1e-3)
+    area2, ang = _quality(P, T)
+    assert ang.min() >= 30.0 - 1e-9 and 0.5 * area2.max() <= 1e-3 * (1 + 1e-12) and (area2 > 0).all()
+    want = 1 - 0.5 * 40 * 0.15 ** 2 * np.sin(2 * np.pi / 40) - 0.5 * 30 * 0.1 ** 2 * np.sin(2 * np.pi / 30)
+    assert abs(0.5 * area2.sum() - want) < 1e-12
+    e, cnt = _edges(T)
+    es = set(map(tuple, e.tolist()))
+    assert all(tuple(sorted(x)) in es for x in S2.tolist())                              # every (sub)segment is an edge
+    assert np.allclose(P[M == 7, 1], 0.9) and (M == 7).sum() >= 1                        # points created on the constraint
+    assert len(P) - len(e) + len(T) == -1                                                # two holes
+    # a 20-degree input corner: the refinement terminates and leaves only the corner triangle below the bound
+    a = np.radians(20.0)
+    W = np.array([[0.0, 0.0], [1.0, 0.0], [np.cos(a), np.sin(a)]])
+    P, M, T, _, _ = fb.triangulate(W, np.ones(3, dtype=np.int32), np.array([[0, 1], [1, 2], [2, 0]]), np.ones(3, dtype=np.int32),
+                                   min_angle=30.0, max_area=2e-3)
+    area2, ang = _quality(P, T)
+    assert (ang < 30.0 - 1e-9).sum() == 1 and abs(ang.min() - 20.0) < 1e-9 and abs(0.5 * area2.sum() - 0.5 * np.sin(a)) < 1e-12
