@@ -5,7 +5,7 @@
 // Paths, chosen by size and preconditioner (cg_dev / fs_bicgstab):
 //   * n <= 8192: the whole CG (1 or 2 RHS) or BiCGStab solve in one CTA (k_cg_small, k_bicgstab_small)
 //   * Jacobi, 1 RHS: the persistent cooperative kernel of cg_persistent.cu
-//   * AMG: pcg_amg_impl below (V-cycle of amg.cu, SpMV of spmv_warp.cu)
+//   * AMG: pcg_amg_impl below (device-side scalars; V-cycle of amg.cu; A*p and the 2-RHS SpMV of spmv_sell.cu)
 //   * 2 RHS / fallback (FS_CG_MODE=multi): 3 kernels per iteration with device-side scalars:
 //       A: Ap = A p            + partial p.Ap          (matrix stream + p gather)
 //       B: x += a p; r -= a Ap + partial r.r, r.z      (z = Dinv r never stored)

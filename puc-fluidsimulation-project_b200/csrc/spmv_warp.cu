@@ -1,6 +1,7 @@
 // spmv_warp.cu -- the warp-granular CSR-stream SpMV of the persistent CG kernel (pass A of
-// cg_persistent.cu) as a stand-alone kernel with fused epilogues, used by the AMG V-cycle
-// and the AMG-preconditioned CG:
+// cg_persistent.cu) as a stand-alone kernel with fused epilogues: the unfolded AMG V-cycle
+// (FS_AMG_FOLD=0), the folded cycle without SELL copies (FS_AMG_SELL=0), initial residuals of the
+// Krylov solvers.  The default V-cycle and the AMG-PCG's A*p run on spmv_sell.cu instead.
 //   EPI_AX      y  = A x
 //   EPI_RESID   y  = b - A x
 //   EPI_JACOBI  y  = x + w D^-1 (b - A x)                      (y must not alias x)
