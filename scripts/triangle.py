@@ -9,7 +9,6 @@ Uses fluidsim_b200.meshgen (conforming Delaunay + Ruppert-style refinement).  A 
 of 0 takes its vertices from the `.node` file of the same stem."""
 import argparse, os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-import numpy as np
 import fluidsim_b200 as fb
 
 
