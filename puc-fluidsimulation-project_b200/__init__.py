@@ -14,7 +14,8 @@ from .stokes import StokesSolver, StokesColor, StokesFood, food_tracer_grid  # n
 from .poisson import (PoissonProblem, HeatProblem, apply_periodic_bc, apply_dirichlet_rows,  # noqa: F401
                       add_identity_scaled)
 from .meshgen import triangulate, triangulate_poly, box_with_hole_pslg, read_poly_full  # noqa: F401
-from .raster import (raster_field, colorize, splat_points, colormap_lut, write_png, read_png, FrameSink)  # noqa: F401
+from .raster import (raster_field, colorize, splat_points, colormap_lut, write_png, read_png, write_apng,  # noqa: F401
+                     read_apng, FrameSink)
 
 
 def launch_count() -> int:

@@ -102,6 +102,65 @@ def write_png(path, rgba):
         f.write(chunk(b"IEND", b""))
 
 
+def write_apng(path, frames, delay_ms=40, loops=0):
+    """Animated PNG (APNG) of equally sized RGBA frames: the movie the reference writes as mp4 through
+    matplotlib's ffmpeg writer (`scripts/good_visualization2.py:735-744`); ffmpeg is not available here, APNG needs
+    only zlib and plays in browsers.  frames: iterable of (H, W, 4) uint8 arrays."""
+    frames = [np.ascontiguousarray(f, dtype=np.uint8) for f in frames]
+    if not frames:
+        raise ValueError("no frames")
+    h, w = frames[0].shape[:2]
+    if any(f.shape != (h, w, 4) for f in frames):
+        raise ValueError("all frames must have the same (H, W, 4) shape")
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+
+    def deflate(rgba):
+        raw = np.empty((h, 1 + 4 * w), dtype=np.uint8)
+        raw[:, 0] = 0
+        raw[:, 1:] = rgba.reshape(h, 4 * w)
+        return zlib.compress(raw.tobytes(), 6)
+
+    seq = 0
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n")
+        f.write(chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 6, 0, 0, 0)))
+        f.write(chunk(b"acTL", struct.pack(">II", len(frames), int(loops))))
+        for k, fr in enumerate(frames):
+            f.write(chunk(b"fcTL", struct.pack(">IIIIIHHBB", seq, w, h, 0, 0, int(delay_ms), 1000, 0, 0)))
+            seq += 1
+            if k == 0:
+                f.write(chunk(b"IDAT", deflate(fr)))          # the first frame doubles as the still image
+            else:
+                f.write(chunk(b"fdAT", struct.pack(">I", seq) + deflate(fr)))
+                seq += 1
+        f.write(chunk(b"IEND", b""))
+
+
+def read_apng(path):
+    """Frames of a file written by write_apng (tests)."""
+    data = open(path, "rb").read()
+    pos, frames, w, h, n_decl = 8, [], 0, 0, 0
+    while pos < len(data):
+        n, tag = struct.unpack(">I4s", data[pos:pos + 8])
+        body = data[pos + 8:pos + 8 + n]
+        crc, = struct.unpack(">I", data[pos + 8 + n:pos + 12 + n])
+        if crc != (zlib.crc32(tag + body) & 0xFFFFFFFF):
+            raise ValueError(f"bad CRC in chunk {tag!r}")
+        if tag == b"IHDR":
+            w, h = struct.unpack(">II", body[:8])
+        elif tag == b"acTL":
+            n_decl = struct.unpack(">II", body)[0]
+        elif tag in (b"IDAT", b"fdAT"):
+            raw = np.frombuffer(zlib.decompress(body if tag == b"IDAT" else body[4:]), dtype=np.uint8).reshape(h, 1 + 4 * w)
+            frames.append(raw[:, 1:].reshape(h, w, 4).copy())
+        pos += 12 + n
+    if len(frames) != n_decl:
+        raise ValueError("frame count does not match the acTL chunk")
+    return frames
+
+
 def read_png(path):
     """Inverse of write_png for the files it writes (tests)."""
     data = open(path, "rb").read()
@@ -151,4 +210,11 @@ class FrameSink:
         path = os.path.join(self.directory, f"{self.prefix}_{self.count:06d}.png")
         write_png(path, self.render(field, vmin, vmax, **kw))
         self.count += 1
+        return path
+
+    def movie(self, path=None, delay_ms=40):
+        """Bundle the frames written so far into one animated PNG (the reference's mp4, without ffmpeg)."""
+        path = path or os.path.join(self.directory, f"{self.prefix}.apng")
+        names = [os.path.join(self.directory, f"{self.prefix}_{k:06d}.png") for k in range(self.count)]
+        write_apng(path, (read_png(n) for n in names), delay_ms=delay_ms)
         return path

@@ -191,3 +191,23 @@ def test_png_codec_roundtrip_and_colormaps(tmp_path):
         assert tuple(lut[0]) == first and tuple(lut[255]) == last
     with pytest.raises(ValueError):
         fb.colormap_lut("no-such-map")
+
+
+def test_apng_movie_roundtrip(tmp_path):
+    import struct
+    import fluidsim_b200 as fb
+    rng = np.random.default_rng(4)
+    frames = [rng.integers(0, 256, size=(24, 31, 4), dtype=np.uint8) for _ in range(5)]
+    path = str(tmp_path / "movie.apng")
+    fb.write_apng(path, frames, delay_ms=50)
+    back = fb.read_apng(path)                                  # also checks every chunk CRC and the acTL frame count
+    assert len(back) == 5 and all(np.array_equal(a, b) for a, b in zip(frames, back))
+    assert np.array_equal(fb.read_png(path), frames[0])        # a plain PNG reader sees the first frame
+    data = open(path, "rb").read()
+    i = data.index(b"fcTL")
+    seq, w, h, x0, y0, num, den = struct.unpack(">IIIIIHH", data[i + 4:i + 28])
+    assert (seq, w, h, x0, y0, num, den) == (0, 31, 24, 0, 0, 50, 1000)
+    with pytest.raises(ValueError):
+        fb.write_apng(path, [])
+    with pytest.raises(ValueError):
+        fb.write_apng(path, [frames[0], frames[1][:10]])
