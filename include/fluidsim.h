@@ -51,6 +51,13 @@ int fs_set_device(int device);
  * (cudaStream_t cast to void*; NULL = the library's own stream). */
 int fs_set_stream(void* cuda_stream);
 int fs_sync(void);
+/* Device-pointer arguments are read on the library's stream.  A caller that has just written such
+ * a buffer on ANOTHER stream (e.g. torch's current stream) must either synchronise, bind the library
+ * to that stream with fs_set_stream, or call fs_stream_wait(producer_stream) before the entry: it
+ * makes the library stream wait (on the device, no host block) for all work queued so far on the
+ * producer.  The Python mirror does this for every torch CUDA tensor it is handed.  Outputs need
+ * nothing: every entry returns after its work has completed. */
+int fs_stream_wait(void* producer_cuda_stream);
 /* number of kernels this library has launched since load (bench.py gpu_launches) */
 int64_t fs_launch_count(void);
 /* Serialise all ranks' kernels for profiling-free timing: record / read a CUDA
@@ -174,6 +181,8 @@ int fs_stokes_step(fs_stokes* s, double* u /* (n,2) in/out */, double B1, double
                    const fs_stokes_opts* opts, fs_stokes_stats* stats);
 /* p and p2 of the last step, mean-free, expanded to the N nodes */
 int fs_stokes_pressure(fs_stokes* s, double* p /* n or NULL */, double* p2 /* n or NULL */);
+/* restore those two fields (checkpoint resume; either may be NULL) */
+int fs_stokes_set_pressure(fs_stokes* s, const double* p /* n */, const double* p2 /* n */);
 /* the two operators, for inspection / parity (borrowed handles, do not destroy) */
 int fs_stokes_matrices(fs_stokes* s, fs_csr** a_visc, fs_csr** k_pressure, int32_t* dof /* n or NULL */);
 /* the CG warm-start state: the merged-dof pressures of the two solves of the last three steps (the
@@ -209,6 +218,37 @@ int fs_dist_connect(fs_dist* d, const void* all_handles /* world*64 bytes, host 
 int fs_dist_cg_begin(fs_dist* d, const double* b_own, int precond, double* local_sums2 /* host */);
 int fs_dist_cg_run(fs_dist* d, double bb_global, double rz_global, double* x_own, double rtol, int maxit,
                    int precond, int* iters, double* relres, double* ns_pass3 /* host, may be NULL */);
+
+/* ---- the whole Stokes step on a mesh cut into contiguous node blocks, one rank (process, GPU) per block
+ * (BASELINE config 5: the 32M-triangle annulus on 1/2/4/8 GPUs).  Same sequence as fs_stokes_step
+ * (code/StokesColor.py:537-575): 2-RHS viscous CG, BCs, divergence, AMG-preconditioned pressure CG, gradient
+ * update, BCs, second projection -- every kernel works on this rank's rows; halo values of the vectors that are
+ * read across block boundaries and the partial sums of every dot product travel as peer stores over NVLink
+ * issued from inside the kernels (CUDA-IPC arena, monotone sequence flags, deterministic rank-ordered sums);
+ * no host, NCCL or copy-engine call happens inside a step.
+ *   fs_pstokes_create  global = the replicated global state (fs_stokes_create on the whole mesh; may be destroyed
+ *                      afterwards); local_mesh = this rank's sub-mesh: all elements touching its nodes
+ *                      [node_split[rank], node_split[rank+1]), local numbering = owned nodes first (global order),
+ *                      then the other corners in ascending global id (l2g: local -> global, host), fs_bc_set done
+ *                      with the owned part of the index sets.  A periodic pair must lie inside one block.
+ *                      AMG levels with more than gather_rows rows (<=0: 100000) are partitioned like the mesh, the
+ *                      smaller ones are replicated.
+ *   fs_pstokes_ipc_handle / fs_pstokes_connect   exchange of the 64-byte IPC handles is the caller's job
+ *                      (torch.distributed.all_gather_object in the Python mirror); all_handles = world x 64 bytes.
+ *   fs_pstokes_step    u_own: this rank's rows of the velocity, (n_own,2), host or device, in/out.  Collective.
+ *   fs_pstokes_state   warm-start history of the two pressure solves (10*n_own_dofs + 4 doubles), read or restore. */
+typedef struct fs_pstokes fs_pstokes;
+int fs_pstokes_create(fs_stokes* global, fs_mesh* local_mesh, int rank, int world, const int64_t* node_split /* world+1, host */,
+                      const int32_t* l2g /* local nodes, host */, int gather_rows, fs_pstokes** out);
+int fs_pstokes_destroy(fs_pstokes* s);
+int fs_pstokes_sizes(const fs_pstokes* s, int64_t* n_own_nodes, int64_t* n_halo_nodes, int64_t* n_own_dofs, int64_t* n_halo_dofs,
+                     int32_t* levels_partitioned);
+int fs_pstokes_ipc_handle(fs_pstokes* s, void* handle64 /* 64 bytes, host */);
+int fs_pstokes_connect(fs_pstokes* s, const void* all_handles /* world*64 bytes, host */);
+int fs_pstokes_step(fs_pstokes* s, double* u_own /* (n_own,2) in/out */, double B1, double B2, const fs_stokes_opts* opts,
+                    fs_stokes_stats* stats);
+int fs_pstokes_pressure(fs_pstokes* s, double* p_own /* n_own or NULL */, double* p2_own);
+int fs_pstokes_state(fs_pstokes* s, double* buf, int set);
 
 /* ---- tracers and dye.
  * fs_locate: PointLocator.find, code/StokesColor.py:314-345 -- the 10 nearest

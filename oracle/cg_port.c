@@ -103,3 +103,126 @@ int cgport_cg(int64_t n, const int32_t* rowptr, const int32_t* colidx, const dou
   free(b); free(r); free(p); free(Ap); free(dinv);
   return it;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Multigrid-preconditioned CG: the CPU statement of the algorithm libfluidsim runs by default on
+ * large pressure systems (CG + one V(1,1) damped-Jacobi cycle of a smoothed-aggregation hierarchy
+ * per iteration).  The hierarchy (A_l, P_l, R_l = P_l^T as CSR, 1/diag(A_l), dense (pseudo-)inverse
+ * of the coarsest operator) is built by oracle/amg_cpu.py with scipy; this file only applies it.
+ * Used by bench.py --impl reference / cpu_baseline as the same-algorithm CPU arm.
+ */
+typedef struct cgport_level {
+  int64_t n;
+  const int32_t *a_rp, *a_ci; const double* a_v;     /* A_l            (n x n)        */
+  const int32_t *p_rp, *p_ci; const double* p_v;     /* P_l            (n x n_next)   */
+  const int32_t *r_rp, *r_ci; const double* r_v;     /* R_l = P_l^T    (n_next x n)   */
+  const double* dinv;
+  double *x, *b, *t;                                 /* work vectors of this level (n) */
+} cgport_level;
+
+static void vcycle(const cgport_level* L, int nlev, int l, const double* cinv, double omega, const double* b, double* x) {
+  const int64_t n = L[l].n;
+  if (l == nlev - 1) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+      const double* row = cinv + i * n;
+      double s = 0.0;
+      for (int64_t j = 0; j < n; ++j) s += row[j] * b[j];
+      x[i] = s;
+    }
+    return;
+  }
+  const cgport_level* lv = &L[l];
+  const cgport_level* nx = &L[l + 1];
+  double* t = lv->t;
+  /* pre-smooth from zero, residual */
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) x[i] = omega * lv->dinv[i] * b[i];
+  cgport_spmv(n, lv->a_rp, lv->a_ci, lv->a_v, x, t);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) t[i] = b[i] - t[i];
+  cgport_spmv(nx->n, lv->r_rp, lv->r_ci, lv->r_v, t, nx->b);
+  vcycle(L, nlev, l + 1, cinv, omega, nx->b, nx->x);
+  cgport_spmv(n, lv->p_rp, lv->p_ci, lv->p_v, nx->x, t);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) x[i] += t[i];
+  /* post-smooth */
+  cgport_spmv(n, lv->a_rp, lv->a_ci, lv->a_v, x, t);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) x[i] += omega * lv->dinv[i] * (b[i] - t[i]);
+}
+
+/* one application of the preconditioner z = M^-1 r (exposed for the tests) */
+void cgport_vcycle(const cgport_level* L, int nlev, const double* cinv, double omega, const double* r, double* z) {
+  vcycle(L, nlev, 0, cinv, omega, r, z);
+}
+
+int cgport_pcg_amg(const cgport_level* L, int nlev, const double* cinv, double omega, const double* b_in, double* x,
+                   double rtol, int maxit, int project_mean, double* relres) {
+  const int64_t n = L[0].n;
+  double* b = (double*)malloc(sizeof(double) * n);
+  double* r = (double*)malloc(sizeof(double) * n);
+  double* p = (double*)malloc(sizeof(double) * n);
+  double* Ap = (double*)malloc(sizeof(double) * n);
+  double* z = (double*)malloc(sizeof(double) * n);
+  double mean = 0.0;
+  if (project_mean) {
+#pragma omp parallel for reduction(+ : mean) schedule(static)
+    for (int64_t i = 0; i < n; ++i) mean += b_in[i];
+    mean /= (double)n;
+  }
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) b[i] = b_in[i] - mean;
+  cgport_spmv(n, L[0].a_rp, L[0].a_ci, L[0].a_v, x, Ap);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) r[i] = b[i] - Ap[i];
+  double bb = dot(n, b, b), rr = dot(n, r, r);
+  const double tol2 = rtol * rtol;
+  int it = 0;
+  if (bb > 0.0 && rr > tol2 * bb) {
+    vcycle(L, nlev, 0, cinv, omega, r, z);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) p[i] = z[i];
+    double rz = dot(n, r, z);
+    while (it < maxit) {
+      cgport_spmv(n, L[0].a_rp, L[0].a_ci, L[0].a_v, p, Ap);
+      const double pAp = dot(n, p, Ap);
+      const double alpha = pAp != 0.0 ? rz / pAp : 0.0;
+      double rr_new = 0.0;
+#pragma omp parallel for reduction(+ : rr_new) schedule(static)
+      for (int64_t i = 0; i < n; ++i) {
+        x[i] += alpha * p[i];
+        r[i] -= alpha * Ap[i];
+        rr_new += r[i] * r[i];
+      }
+      rr = rr_new;
+      ++it;
+      if (rr <= tol2 * bb) break;
+      vcycle(L, nlev, 0, cinv, omega, r, z);
+      const double rz_new = dot(n, r, z);
+      const double beta = rz != 0.0 ? rz_new / rz : 0.0;
+#pragma omp parallel for schedule(static)
+      for (int64_t i = 0; i < n; ++i) p[i] = z[i] + beta * p[i];
+      rz = rz_new;
+    }
+  }
+  if (project_mean) {
+    double m = 0.0;
+#pragma omp parallel for reduction(+ : m) schedule(static)
+    for (int64_t i = 0; i < n; ++i) m += x[i];
+    m /= (double)n;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) x[i] -= m;
+  }
+  if (relres) *relres = bb > 0.0 ? sqrt(rr / bb) : 0.0;
+  free(b); free(r); free(p); free(Ap); free(z);
+  return it;
+}
+
+void cgport_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}

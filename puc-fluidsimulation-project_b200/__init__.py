@@ -11,6 +11,8 @@ from .core import (Mesh, CsrMatrix, solve, buildStiffnessMatrix, buildFemSystem,
                    calculate_divergence, calculate_gradiant, PointLocator, mixing_index, mesh_for,
                    PRECOND_NONE, PRECOND_JACOBI, PRECOND_AMG, PRECOND_AUTO)
 from .stokes import StokesSolver, StokesColor, StokesFood, food_tracer_grid  # noqa: F401
+from .partitioned import PartitionedStokes  # noqa: F401
+from .hostmesh import node_block_split, sub_mesh, local_index_sets  # noqa: F401
 from .poisson import (PoissonProblem, HeatProblem, apply_periodic_bc, apply_dirichlet_rows,  # noqa: F401
                       add_identity_scaled)
 from .meshgen import triangulate, triangulate_poly, box_with_hole_pslg, read_poly_full  # noqa: F401

@@ -47,6 +47,7 @@ SIGNATURES = {
     "fs_set_device": (C.c_int, [C.c_int]),
     "fs_set_stream": (C.c_int, [c_vp]),
     "fs_sync": (C.c_int, []),
+    "fs_stream_wait": (C.c_int, [c_vp]),
     "fs_launch_count": (c_i64, []),
     "fs_timer_start": (C.c_int, []),
     "fs_timer_stop": (C.c_int, [P(C.c_float)]),
@@ -85,6 +86,7 @@ SIGNATURES = {
     "fs_stokes_destroy": (C.c_int, [c_vp]),
     "fs_stokes_step": (C.c_int, [c_vp, c_vp, c_dbl, c_dbl, P(StokesOpts), P(StokesStats)]),
     "fs_stokes_pressure": (C.c_int, [c_vp, c_vp, c_vp]),
+    "fs_stokes_set_pressure": (C.c_int, [c_vp, c_vp, c_vp]),
     "fs_stokes_matrices": (C.c_int, [c_vp, P(c_vp), P(c_vp), c_vp]),
     "fs_stokes_warm_state": (C.c_int, [c_vp, c_vp, C.c_int]),
     "fs_dist_create": (C.c_int, [C.c_int, C.c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, P(c_vp)]),
@@ -93,6 +95,14 @@ SIGNATURES = {
     "fs_dist_connect": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64]),
     "fs_dist_cg_begin": (C.c_int, [c_vp, c_vp, C.c_int, c_vp]),
     "fs_dist_cg_run": (C.c_int, [c_vp, c_dbl, c_dbl, c_vp, c_dbl, C.c_int, C.c_int, P(C.c_int), P(c_dbl), c_vp]),
+    "fs_pstokes_create": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp, C.c_int, P(c_vp)]),
+    "fs_pstokes_destroy": (C.c_int, [c_vp]),
+    "fs_pstokes_sizes": (C.c_int, [c_vp, P(c_i64), P(c_i64), P(c_i64), P(c_i64), P(c_i32)]),
+    "fs_pstokes_ipc_handle": (C.c_int, [c_vp, c_vp]),
+    "fs_pstokes_connect": (C.c_int, [c_vp, c_vp]),
+    "fs_pstokes_step": (C.c_int, [c_vp, c_vp, c_dbl, c_dbl, c_vp, c_vp]),
+    "fs_pstokes_pressure": (C.c_int, [c_vp, c_vp, c_vp]),
+    "fs_pstokes_state": (C.c_int, [c_vp, c_vp, C.c_int]),
     "fs_locate": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),
     "fs_advect_dye": (C.c_int, [c_vp, c_vp, c_vp, c_dbl, c_vp]),
     "fs_mixing_index": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
@@ -140,8 +150,23 @@ def _is_torch(x):
     return type(x).__module__.startswith("torch")
 
 
+class _Ptr(C.c_void_p):
+    """c_void_p that keeps the array it points into alive for as long as the argument object lives
+    (i.e. until the foreign call that receives it has returned)."""
+    _keep = None
+
+
+def _ptr_of(addr, owner):
+    p = _Ptr(addr)
+    p._keep = owner
+    return p
+
+
 def ptr(x, dtype=None, shape=None, name="array"):
-    """Raw pointer of a C-contiguous numpy array or torch tensor (None -> NULL)."""
+    """Pointer argument for a C-contiguous numpy array or torch tensor (None -> NULL).  The returned
+    object holds a reference to ``x``, so ``ptr(as_f64(v))`` is safe even when as_f64 had to copy.
+    For a torch CUDA tensor the library stream is first ordered after torch's current stream
+    (fs_stream_wait): the kernels that read the tensor cannot overtake the ones that produced it."""
     if x is None:
         return None
     if _is_torch(x):
@@ -154,7 +179,9 @@ def ptr(x, dtype=None, shape=None, name="array"):
                 raise TypeError(f"{name}: expected dtype {want}, got {x.dtype}")
         if shape is not None and tuple(x.shape) != tuple(shape):
             raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(x.shape)}")
-        return C.c_void_p(x.data_ptr())
+        if x.is_cuda:
+            call("fs_stream_wait", C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+        return _ptr_of(x.data_ptr(), x)
     if not isinstance(x, np.ndarray):
         raise TypeError(f"{name}: expected numpy.ndarray or torch.Tensor, got {type(x)}")
     if not x.flags["C_CONTIGUOUS"]:
@@ -163,7 +190,7 @@ def ptr(x, dtype=None, shape=None, name="array"):
         raise TypeError(f"{name}: expected dtype {np.dtype(dtype)}, got {x.dtype}")
     if shape is not None and tuple(x.shape) != tuple(shape):
         raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(x.shape)}")
-    return C.c_void_p(x.ctypes.data)
+    return _ptr_of(x.ctypes.data, x)
 
 
 def as_f64(x, name="array"):

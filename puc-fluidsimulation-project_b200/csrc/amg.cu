@@ -22,7 +22,7 @@
 //   (vectors and sums fp64).
 #include <cub/cub.cuh>
 
-#include "internal.cuh"
+#include "dist.cuh"
 
 namespace fs {
 
@@ -58,6 +58,18 @@ struct Amg {
   cudaEvent_t* top_ev = nullptr; // transient: events around the finest up-sweep (amg_apply's top_ev)
   int sub_rows = 0;             // matrices with at most this many rows use the lanes-per-row CSR kernel
   int applications = 0;
+  // Partitioned application (dist.cuh, pstokes.cu): levels [0, Lp) are cut into contiguous row blocks, one per
+  // rank -- each rank keeps only its rows of R~ and [G | P~], columns renumbered to [own | halo] -- and level Lp
+  // and below are replicated: the restriction into level Lp is computed block-wise and stored into every rank.
+  bool part_f32 = true;
+  struct Part {
+    DistCtx* ctx = nullptr;
+    int rank = 0, world = 1, Lp = 0;
+    std::vector<std::vector<int64_t>> split;     // [0..Lp] row split of each level
+    std::vector<std::unique_ptr<Space>> space;   // [1..Lp] (entry 0 unused: level 0's space belongs to the caller)
+    const Space* space0 = nullptr;
+    std::vector<DVec> vb, vx;                    // [1..Lp] right-hand side / solution of each level inside the arena
+  } part;
   ~Amg() { if (graph) cudaGraphExecDestroy(graph); }
 };
 
@@ -442,8 +454,36 @@ static double env_num(const char* name, double dflt) {
   return e ? std::atof(e) : dflt;
 }
 
-Amg* amg_setup(fs_csr* fine) {
+// first-row split of the coarse level from the fine one: coarse ids follow their aggregates' leaders, so
+// the aggregates touched by the rows below split[r] are (up to stragglers) the ids below max(agg[0..split[r])) + 1
+static std::vector<int64_t> coarse_split(const int* agg, const std::vector<int64_t>& split, int nc) {
+  cudaStream_t st = stream();
+  const int world = (int)split.size() - 1;
+  std::vector<int64_t> cs(world + 1, 0);
+  DBuf<int> out(1);
+  for (int r = 1; r < world; ++r) {
+    const int k = (int)split[r];
+    if (k <= 0) { cs[r] = 0; continue; }
+    size_t bytes = 0;
+    FS_CUDA(cub::DeviceReduce::Max(nullptr, bytes, agg, out.p, k, st));
+    DBuf<char> tmp(bytes);
+    FS_CUDA(cub::DeviceReduce::Max(tmp.p, bytes, agg, out.p, k, st));
+    count_launch();
+    cs[r] = std::min<int64_t>(nc, (int64_t)out.to_host()[0] + 1);
+  }
+  cs[world] = nc;
+  for (int r = 1; r <= world; ++r) cs[r] = std::max(cs[r], cs[r - 1]);
+  return cs;
+}
+
+Amg* amg_setup(fs_csr* fine, const AmgPartSpec* ps) {
   std::unique_ptr<Amg> amg(new Amg());
+  if (ps) {
+    amg->part.rank = ps->rank;
+    amg->part.world = ps->world;
+    amg->part.split.push_back(ps->split0);
+    FS_REQUIRE((int)ps->split0.size() == ps->world + 1 && ps->split0.back() == fine->n, "bad fine-level split");
+  }
   amg->omega = env_num("FS_AMG_OMEGA", amg->omega);
   amg->omega_p = env_num("FS_AMG_OMEGA_P", amg->omega_p);
   amg->theta = env_num("FS_AMG_THETA", amg->theta);
@@ -492,6 +532,10 @@ Amg* amg_setup(fs_csr* fine) {
       }
     }
     if (nc >= cur.n * 0.8) break;                      // coarsening stalled
+    // partitioned cycle: this level is cut into row blocks iff it is the finest or larger than gather_rows
+    const size_t lidx = amg->L.size() - 1;
+    const bool part_l = ps && amg->part.split.size() == lidx + 1 && (lidx == 0 || cur.n > ps->gather_rows);
+    if (part_l) amg->part.split.push_back(coarse_split(agg.p, amg->part.split[lidx], nc));
     // smoothed prolongator, its transpose, and the Galerkin operator P^T (A P)
     {
       const size_t m = (size_t)Av.nnz + cur.n;
@@ -522,13 +566,18 @@ Amg* amg_setup(fs_csr* fine) {
         FS_LAUNCH_CHECK();
         coo_to_csr(ukeys, uv, mu, cur.n, cur.n + nc, cur.U);
         coo_to_csr(rkeys, rv, mr, nc, cur.n, cur.Rt);
-        if (amg->sell) {
-          sell_build(cur.U, fp32, cur.Us, cur.n);
-          sell_build(cur.Rt, fp32, cur.Rts);
+        if (part_l) {
+          // the global CSR forms stay until amg_part_finalize has cut this rank's rows out of them
+          FS_REQUIRE(amg->sell, "the partitioned cycle needs the SELL layout (FS_AMG_SELL=1)");
+        } else {
+          if (amg->sell) {
+            sell_build(cur.U, fp32, cur.Us, cur.n);
+            sell_build(cur.Rt, fp32, cur.Rts);
+          }
+          auto drop = [](fs_csr& M) { M.vals.release(); M.colidx_own.release(); M.rowptr_own.release(); M.rowptr = M.colidx = nullptr; };
+          if (amg->sell && cur.n > amg->sub_rows) drop(cur.U); else ensure_tiles(&cur.U);
+          if (amg->sell && nc > amg->sub_rows) drop(cur.Rt); else ensure_tiles(&cur.Rt);
         }
-        auto drop = [](fs_csr& M) { M.vals.release(); M.colidx_own.release(); M.rowptr_own.release(); M.rowptr = M.colidx = nullptr; };
-        if (amg->sell && cur.n > amg->sub_rows) drop(cur.U); else ensure_tiles(&cur.U);
-        if (amg->sell && nc > amg->sub_rows) drop(cur.Rt); else ensure_tiles(&cur.Rt);
       }
     }
     if (amg->folded) {   // the folded cycle does not touch P / P^T again
@@ -543,6 +592,13 @@ Amg* amg_setup(fs_csr* fine) {
     jacobi_prepare(&nxt->A);
     amg->L.push_back(std::move(nxt));
   }
+  if (ps) {
+    FS_REQUIRE(amg->folded, "the partitioned cycle needs the folded form (FS_AMG_FOLD=1)");
+    amg->part.Lp = (int)amg->part.split.size() - 1;
+    FS_REQUIRE(amg->part.Lp >= 1 && amg->part.Lp < (int)amg->L.size(),
+               "partitioned AMG: the coarsest level must be replicated (raise gather_rows or refine the mesh)");
+    amg->part_f32 = fp32;
+  }
   if (fp32) {
     // mixed precision: the cycle streams fp32 copies of all its matrices (vectors stay fp64)
     auto to32 = [&](const fs_csr& M) {
@@ -552,7 +608,9 @@ Amg* amg_setup(fs_csr* fine) {
       k_to_f32<<<div_up(W.nnz, 256), 256, 0, stream()>>>(W.vals.p, W.nnz, W.vals32.p);
       FS_LAUNCH_CHECK();
     };
-    for (auto& l : amg->L) {
+    for (size_t li = 0; li < amg->L.size(); ++li) {
+      auto& l = amg->L[li];
+      if (ps && (int)li < amg->part.Lp) continue;   // fp64 CSR kept for the row-block extraction
       if (!amg->folded) to32(l->mat());
       if (l->P.nnz) { to32(l->P); to32(l->PT); }
       if (l->U.nnz) {   // only the fp32 copies of the folded operators are ever read
@@ -808,6 +866,160 @@ int amg_apply(Amg* amg, const double* r, double* z, bool x0_ready, double* rz_pa
     amg->graph_failed = true;   // run the cycle eagerly from now on
   }
   return cycle();
+}
+
+// ---------------------------------------------------------------- partitioned cycle
+int amg_part_levels(const Amg* amg) { return amg->part.Lp; }
+const std::vector<int64_t>& amg_part_split(const Amg* amg, int level) { return amg->part.split.at(level); }
+
+static Space make_gather_space(const std::vector<int64_t>& split, int rank, int world) {
+  Space sp;
+  sp.split = split;
+  sp.gather = true;
+  sp.own_lo = split[rank];
+  sp.n_own = split[rank + 1] - split[rank];
+  sp.n_halo = 0;
+  sp.cap = (split[world] + 31) / 32 * 32;
+  for (int q = 0; q < world; ++q) {
+    if (q == rank) continue;
+    if (sp.n_own > 0) sp.to[sp.n_to++] = (signed char)q;                       // my block goes to everybody
+    if (split[q + 1] > split[q]) sp.from[sp.n_from++] = (signed char)q;        // and I wait for every non-empty block
+  }
+  return sp;
+}
+
+size_t amg_part_collect(Amg* amg, HaloCollector& c0) {
+  Amg::Part& P = amg->part;
+  const int Lp = P.Lp;
+  FS_REQUIRE(Lp >= 1, "amg_part_collect: the hierarchy was not set up for a partitioned cycle");
+  std::vector<HaloCollector> col(Lp);   // col[l] for 1 <= l < Lp
+  for (int l = 0; l < Lp; ++l) {
+    AmgLevel& lv = *amg->L[l];
+    const int n = lv.n;
+    const CsrView U = lv.U.view(), Rt = lv.Rt.view();
+    HaloCollector& cl = (l == 0) ? c0 : col[l];
+    cl.add_matrix(U, P.split[l], P.split[l], 0, n);                             // G part reads b_l
+    cl.add_matrix(Rt, P.split[l + 1], P.split[l], 0, n);                        // R~ reads b_l, rows = next level's blocks
+    if (l + 1 < Lp) col[l + 1].add_matrix(U, P.split[l], P.split[l + 1], n, (int64_t)n + amg->L[l + 1]->n);   // P~ part reads x_{l+1}
+  }
+  P.space.clear();
+  P.space.resize(Lp + 1);
+  size_t bytes = 0;
+  for (int l = 1; l < Lp; ++l) {
+    P.space[l].reset(new Space());
+    P.space[l]->split = P.split[l];
+    col[l].finish(*P.space[l], P.rank, P.world);
+    bytes += 2 * (((size_t)P.space[l]->cap * sizeof(double) + 255) / 256 * 256);
+  }
+  P.space[Lp].reset(new Space(make_gather_space(P.split[Lp], P.rank, P.world)));
+  bytes += ((size_t)P.space[Lp]->cap * sizeof(double) + 255) / 256 * 256;
+  return bytes;
+}
+
+void amg_part_finalize(Amg* amg, const Space& space0, DistCtx& ctx) {
+  Amg::Part& P = amg->part;
+  const int Lp = P.Lp, rank = P.rank;
+  P.ctx = &ctx;
+  P.space0 = &space0;
+  P.vb.assign(Lp + 1, DVec{});
+  P.vx.assign(Lp + 1, DVec{});
+  for (int l = 1; l < Lp; ++l) { P.vb[l] = ctx.carve(*P.space[l], 1); P.vx[l] = ctx.carve(*P.space[l], 1); }
+  P.vb[Lp] = ctx.carve(*P.space[Lp], 1);
+  auto drop = [](fs_csr& M) {
+    M.vals.release(); M.vals32.release(); M.colidx_own.release(); M.rowptr_own.release();
+    M.rowptr = M.colidx = nullptr; M.nnz = 0;
+  };
+  for (int l = 0; l < Lp; ++l) {
+    AmgLevel& lv = *amg->L[l];
+    const Space& sl = (l == 0) ? space0 : *P.space[l];
+    const Space* sn = P.space[l + 1].get();           // next level's space (gather space for l + 1 == Lp)
+    {
+      fs_csr loc;
+      extract_rows(lv.U.view(), P.split[l][rank], P.split[l][rank + 1], sl, lv.n, sn, loc);
+      sell_build(loc, amg->part_f32, lv.Us, (int)(sl.n_own + sl.n_halo));
+    }
+    {
+      fs_csr loc;
+      const int64_t r0 = P.split[l + 1][rank], r1 = P.split[l + 1][rank + 1];
+      if (r1 > r0) {
+        extract_rows(lv.Rt.view(), r0, r1, sl, lv.n, nullptr, loc);
+        sell_build(loc, amg->part_f32, lv.Rts);
+      }
+    }
+    drop(lv.U);
+    drop(lv.Rt);
+  }
+  // level 0 borrowed the caller's global fine matrix: nothing in the folded cycle reads it again
+  amg->L[0]->Aref = nullptr;
+  FS_CUDA(cudaStreamSynchronize(stream()));
+  if (std::getenv("FS_AMG_VERBOSE")) {
+    std::fprintf(stderr, "[amg rank %d] partitioned levels %d:", rank, Lp);
+    for (int l = 0; l < Lp; ++l) {
+      const Space& sl = (l == 0) ? space0 : *P.space[l];
+      std::fprintf(stderr, " L%d own %lld halo %lld send %d |", l, (long long)sl.n_own, (long long)sl.n_halo, sl.n_send);
+    }
+    std::fprintf(stderr, " gathered level: %lld rows (own %lld)\n", (long long)P.split[Lp].back(), (long long)P.space[Lp]->n_own);
+  }
+}
+
+// b_c = R~ b (own block; pushed) ; recurse ; x = [G | P~] [b; x_c] (own rows; pushed for the level above)
+static int vcycle_folded_dist(Amg& amg, int l, const DVec& bv, double* x, double* dot_part) {
+  Amg::Part& P = amg.part;
+  DistCtx& ctx = *P.ctx;
+  const int Lp = P.Lp;
+  if (l == Lp) {                       // replicated tail: wait for every rank's block of b, then the usual cycle
+    ctx.wait(P.vb[l]);
+    vcycle_folded(amg, (size_t)l, P.vb[l].p, x, nullptr);
+    return 0;
+  }
+  AmgLevel& lv = *amg.L[l];
+  const bool next_part = l + 1 < Lp;
+  const DVec& nb = P.vb[l + 1];
+  if (lv.Rts.nslices) {
+    double* y = next_part ? nb.p : nb.p + P.split[l + 1][P.rank];
+    spmv_sell_dist(lv.Rts, bv.p, y, nullptr, nullptr, ctx.comm, ctx.wait_of(&bv));
+  }
+  ctx.push(nb);
+  double* xc = next_part ? P.vx[l + 1].p : amg.L[l + 1]->x.p;
+  vcycle_folded_dist(amg, l + 1, nb, xc, nullptr);
+  const int g = spmv_sell_dist(lv.Us, bv.p, x, xc, dot_part, ctx.comm, ctx.wait_of(&bv, next_part ? &P.vx[l + 1] : nullptr));
+  if (l >= 1) ctx.push(P.vx[l]);
+  return dot_part ? g : 0;
+}
+
+int amg_apply_dist(Amg* amg, const DVec& r, double* z, double* rz_part) {
+  static const bool use_graph = env_num("FS_AMG_GRAPH", 1) != 0;
+  cudaStream_t st = stream();
+  ++amg->applications;
+  if (use_graph && amg->graph && amg->graph_r == r.p && amg->graph_z == z && amg->graph_part == rz_part) {
+    FS_CUDA(cudaGraphLaunch(amg->graph, st));
+    count_launch();
+    return amg->graph_nparts;
+  }
+  if (use_graph && amg->applications >= 2 && !amg->graph_failed) {
+    if (amg->graph) { cudaGraphExecDestroy(amg->graph); amg->graph = nullptr; }
+    cudaGraph_t g = nullptr;
+    FS_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    bool ok = true;
+    int nparts = 0;
+    try { nparts = vcycle_folded_dist(*amg, 0, r, z, rz_part); } catch (...) { ok = false; }
+    cudaError_t e = cudaStreamEndCapture(st, &g);
+    if (ok && e == cudaSuccess && g) {
+      cudaGraphExec_t ex = nullptr;
+      if (cudaGraphInstantiate(&ex, g, 0) == cudaSuccess) {
+        amg->graph = ex; amg->graph_r = r.p; amg->graph_z = z; amg->graph_x0 = false;
+        amg->graph_part = rz_part; amg->graph_nparts = nparts;
+        cudaGraphDestroy(g);
+        FS_CUDA(cudaGraphLaunch(amg->graph, st));
+        count_launch();
+        return nparts;
+      }
+    }
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+    amg->graph_failed = true;
+  }
+  return vcycle_folded_dist(*amg, 0, r, z, rz_part);
 }
 
 int amg_levels(const Amg* amg, int* sizes, int cap) {

@@ -230,7 +230,7 @@ void divergence_dev(fs_mesh* m, const double* d_u, double* d_div, double* d_div_
   const int B = 256;
   k_div_elem<<<div_up(m->T, B), B, 0, st>>>((const double2*)m->coords.p, m->tris.p, (const double2*)d_u, m->T, m->elem_a.p);
   FS_LAUNCH_CHECK();
-  k_div_node<<<div_up(m->N, B), B, 0, st>>>(m->inc_ptr.p, m->inc.p, m->elem_a.p, m->area_sum.p, m->N, d_div, d_div_sum);
+  k_div_node<<<div_up(m->n_eval(), B), B, 0, st>>>(m->inc_ptr.p, m->inc.p, m->elem_a.p, m->area_sum.p, m->n_eval(), d_div, d_div_sum);
   FS_LAUNCH_CHECK();
 }
 
@@ -242,8 +242,8 @@ static void grad_elem(fs_mesh* m, const double* d_p) {
 
 void gradient_dev(fs_mesh* m, const double* d_p, double* d_gx, double* d_gy) {
   grad_elem(m, d_p);
-  k_grad_node<0><<<div_up(m->N, 256), 256, 0, stream()>>>(m->inc_ptr.p, m->inc.p, m->elem_a.p, m->elem_c.p, m->area_sum.p,
-                                                           m->N, d_gx, d_gy, nullptr, nullptr, 0.0, nullptr);
+  k_grad_node<0><<<div_up(m->n_eval(), 256), 256, 0, stream()>>>(m->inc_ptr.p, m->inc.p, m->elem_a.p, m->elem_c.p, m->area_sum.p,
+                                                           m->n_eval(), d_gx, d_gy, nullptr, nullptr, 0.0, nullptr);
   FS_LAUNCH_CHECK();
 }
 
@@ -251,12 +251,12 @@ void grad_update_dev(fs_mesh* m, const double* d_p, const double* d_ui, double* 
                      const unsigned char* d_interior_flag) {
   grad_elem(m, d_p);
   if (d_interior_flag)
-    k_grad_node<2><<<div_up(m->N, 256), 256, 0, stream()>>>(m->inc_ptr.p, m->inc.p, m->elem_a.p, m->elem_c.p, m->area_sum.p,
-                                                             m->N, nullptr, nullptr, (const double2*)d_ui, (double2*)d_uo, DT,
+    k_grad_node<2><<<div_up(m->n_eval(), 256), 256, 0, stream()>>>(m->inc_ptr.p, m->inc.p, m->elem_a.p, m->elem_c.p, m->area_sum.p,
+                                                             m->n_eval(), nullptr, nullptr, (const double2*)d_ui, (double2*)d_uo, DT,
                                                              d_interior_flag);
   else
-    k_grad_node<1><<<div_up(m->N, 256), 256, 0, stream()>>>(m->inc_ptr.p, m->inc.p, m->elem_a.p, m->elem_c.p, m->area_sum.p,
-                                                             m->N, nullptr, nullptr, (const double2*)d_ui, (double2*)d_uo, DT,
+    k_grad_node<1><<<div_up(m->n_eval(), 256), 256, 0, stream()>>>(m->inc_ptr.p, m->inc.p, m->elem_a.p, m->elem_c.p, m->area_sum.p,
+                                                             m->n_eval(), nullptr, nullptr, (const double2*)d_ui, (double2*)d_uo, DT,
                                                              nullptr);
   FS_LAUNCH_CHECK();
 }

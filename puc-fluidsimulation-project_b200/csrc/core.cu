@@ -140,6 +140,20 @@ int fs_sync(void) {
   FS_API_END
 }
 
+// Order the library stream after everything queued so far on `producer` (the caller's stream that
+// wrote a device-pointer argument): event record + stream wait, no host block.
+int fs_stream_wait(void* producer) {
+  FS_API_BEGIN
+  cudaStream_t ps = (cudaStream_t)producer;
+  cudaStream_t st = stream();
+  if (ps == st) return FS_OK;
+  static thread_local cudaEvent_t ev = nullptr;
+  if (!ev) FS_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  FS_CUDA(cudaEventRecord(ev, ps));
+  FS_CUDA(cudaStreamWaitEvent(st, ev, 0));
+  FS_API_END
+}
+
 int64_t fs_launch_count(void) { return g_launches.load(); }
 
 int fs_timer_start(void) {

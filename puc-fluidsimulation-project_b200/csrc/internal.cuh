@@ -225,6 +225,11 @@ namespace fs { struct Locator; struct Amg; void amg_free(Amg*); }
 
 struct fs_mesh {
   int64_t N = 0, T = 0;
+  // Sub-mesh of a partitioned run: only nodes [0, n_active) are owned; the node passes of divergence /
+  // gradient evaluate (and write) those alone -- the remaining nodes are halo copies whose incident
+  // elements are incomplete and whose vector entries belong to other ranks.  -1: all nodes.
+  int64_t n_active = -1;
+  int64_t n_eval() const { return n_active >= 0 ? n_active : N; }
   fs::DBuf<double> coords;    // (N,2)
   fs::DBuf<int> tris;         // (T,3)
   fs::DBuf<int> markers;      // (N)
@@ -280,7 +285,8 @@ int spmv_sell_grid(const fs_sell& S);   // grid (= dot partials per column) of s
 void spmv_sell2(const fs_sell& S, const double* x, double* y, double* dot_partials, const int* done);
 // any-matrix fallback: y = A [x; x2] (columns >= nsplit gather from x2; x2 null: y = A x)
 void spmv_sub(const CsrView& A, const double* x, double* y, const double* x2, int nsplit);
-Amg* amg_setup(fs_csr* fine);
+struct AmgPartSpec;
+Amg* amg_setup(fs_csr* fine, const AmgPartSpec* part = nullptr);   // part: row-block partitioned cycle (dist.cuh)
 // x0_ready: the caller has written w D^-1 r into the buffer given by amg_presmooth_target (unfolded
 // cycle only).  rz_part (optional): room for per-CTA partial sums of r.z; the return value is how
 // many were written by the cycle's last kernel (0: the caller computes r.z itself).

@@ -14,94 +14,9 @@
 //     (deterministic, no atomics); the host polls a "done" flag every chunk.
 #include <algorithm>
 
-#include "internal.cuh"
+#include "reduce.cuh"
 
 namespace fs {
-
-constexpr int kBlock = 256;
-constexpr int kMaxBlocks = 1024;   // partial arrays are sized for this
-
-template <int R>
-__device__ __forceinline__ void load_vec(const double* __restrict__ p, int64_t i, double (&o)[R]) {
-  if (R == 1) o[0] = p[i];
-  else { double2 t = reinterpret_cast<const double2*>(p)[i]; o[0] = t.x; o[R - 1] = t.y; }
-}
-template <int R>
-__device__ __forceinline__ void load_vec_ldg(const double* __restrict__ p, int64_t i, double (&o)[R]) {
-  if (R == 1) o[0] = __ldg(p + i);
-  else { double2 t = __ldg(reinterpret_cast<const double2*>(p) + i); o[0] = t.x; o[R - 1] = t.y; }
-}
-template <int R>
-__device__ __forceinline__ void store_vec(double* __restrict__ p, int64_t i, const double (&o)[R]) {
-  if (R == 1) p[i] = o[0];
-  else reinterpret_cast<double2*>(p)[i] = make_double2(o[0], o[R - 1]);
-}
-
-// block-wide deterministic sum of K values per thread -> out[0..K) valid in thread 0
-template <int K>
-__device__ __forceinline__ void block_reduce(double (&v)[K], double* smem /* K*32 */) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-#pragma unroll
-  for (int k = 0; k < K; ++k)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
-  if (lane == 0)
-#pragma unroll
-    for (int k = 0; k < K; ++k) smem[k * 32 + warp] = v[k];
-  __syncthreads();
-  if (warp == 0) {
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      double t = (lane < nw) ? smem[k * 32 + lane] : 0.0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      v[k] = t;
-    }
-  }
-  __syncthreads();
-}
-
-// every block re-reduces the partial array (nblk x K) in the same fixed order (thread-strided
-// sums with the loads issued together, warp xor trees, then the warps in ascending order);
-// result broadcast to all threads through shared memory.
-template <int K>
-__device__ __forceinline__ void reduce_partials(const double* __restrict__ part, int nblk, double (&out)[K],
-                                                double* smem /* K */) {
-  __shared__ double scr[32 * K];
-  const int t = threadIdx.x, lane = t & 31, w = t >> 5, nw = blockDim.x >> 5;
-  double acc[K];
-#pragma unroll
-  for (int k = 0; k < K; ++k) acc[k] = 0.0;
-  for (int b0 = t; b0 < nblk; b0 += 4 * blockDim.x) {
-    double v[4][K];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int b = b0 + j * blockDim.x;
-#pragma unroll
-      for (int k = 0; k < K; ++k) v[j][k] = (b < nblk) ? part[(size_t)b * K + k] : 0.0;
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int k = 0; k < K; ++k) acc[k] += v[j][k];
-  }
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-    if (lane == 0) scr[w * K + k] = acc[k];
-  }
-  __syncthreads();
-  if (t < K) {
-    double s = 0.0;
-    for (int q = 0; q < nw; ++q) s += scr[q * K + t];
-    smem[t] = s;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < K; ++k) out[k] = smem[k];
-  __syncthreads();
-}
 
 // ---- SpMV: LPR lanes per row, R interleaved right-hand sides -------------------
 template <int R, int LPR, bool DOT>
@@ -460,7 +375,7 @@ __global__ void __launch_bounds__(kBlock)
 k_cg_update_p(int64_t n, const double* __restrict__ r, const double* __restrict__ dinv, double* __restrict__ p,
               const double* __restrict__ part_b, int nblk_b, CgScal sc, int slot, double tol2) {
   __shared__ double sm[2 * R];
-  if (sc.flags[0]) return;
+  if (block_done(sc.flags)) return;   // block 0 of THIS launch may set the flag: one read per CTA
   double v[2 * R], beta[R];
   reduce_partials<2 * R>(part_b, nblk_b, v, sm);
 #pragma unroll
@@ -924,7 +839,7 @@ __global__ void __launch_bounds__(kBlock)
 k_pcg_p(int64_t n, const double* __restrict__ z, double* __restrict__ p, const double* __restrict__ partB, int nB,
         const double* __restrict__ partRZ, int nRZ, double* __restrict__ sc, int slot, int* __restrict__ flags) {
   __shared__ double sm[1];
-  if (flags[0]) return;
+  if (block_done(flags)) return;      // block 0 of THIS launch may set the flag: one read per CTA
   double rr[1], rzn[1];
   reduce_partials<1>(partB, nB, rr, sm);
   reduce_partials<1>(partRZ, nRZ, rzn, sm);

@@ -16,7 +16,7 @@
 // y = A x or A [x; x2] (columns >= nsplit read x2), optional per-CTA partials of x.y.
 #include <cub/cub.cuh>
 
-#include "internal.cuh"
+#include "dist.cuh"
 
 namespace fs {
 
@@ -126,9 +126,21 @@ __device__ __forceinline__ double sell_part4(const float* __restrict__ vp, const
   return acc;
 }
 
-template <bool SPLIT, bool DOT, bool F32>
-__global__ void __launch_bounds__(kST, (SPLIT && F32 && DOT) ? 8 : 6) k_spmv_sell(SellArgs a) {
+// DIST (partitioned step, pstokes.cu): x / x2 are [own | halo] vectors whose halo entries are written by the
+// neighbouring ranks; the kernel returns at once when the running solve has converged and otherwise
+// waits for the halo flags of its input channels before the first gather (dist.cuh).
+struct DistSell {
+  Comm c;
+  HaloWait w;
+};
+
+template <bool SPLIT, bool DOT, bool F32, bool DIST>
+__global__ void __launch_bounds__(kST, (SPLIT && F32 && DOT) ? 8 : 6) k_spmv_sell(SellArgs a, DistSell d) {
   __shared__ double red[kSW];
+  if (DIST) {
+    if (d.c.done && *d.c.done) return;
+    halo_wait(d.c, d.w);
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nwarps = gridDim.x * kSW;
   double dacc = 0.0;
@@ -171,10 +183,11 @@ __global__ void __launch_bounds__(kST, (SPLIT && F32 && DOT) ? 8 : 6) k_spmv_sel
 }
 
 // two interleaved right-hand sides (x, y are (n,2) row-major), fp64 values: the viscous 2-RHS CG
-template <bool DOT>
-__global__ void __launch_bounds__(kST, 4) k_spmv_sell2(SellArgs a, const int* __restrict__ done) {
+template <bool DOT, bool DIST>
+__global__ void __launch_bounds__(kST, 4) k_spmv_sell2(SellArgs a, const int* __restrict__ done, DistSell d) {
   __shared__ double red[2 * kSW];
   if (done && *done) return;
+  if (DIST) halo_wait(d.c, d.w);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nwarps = gridDim.x * kSW;
   const double2* __restrict__ x2v = reinterpret_cast<const double2*>(a.x);
@@ -309,28 +322,45 @@ void sell_build(const fs_csr& A, bool f32, fs_sell& out, int nsplit) {
 }
 
 template <bool SPLIT, bool DOT>
-static void launch_sell(const SellArgs& args, int grid) {
-  if (args.v32) k_spmv_sell<SPLIT, DOT, true><<<grid, kST, 0, stream()>>>(args);
-  else k_spmv_sell<SPLIT, DOT, false><<<grid, kST, 0, stream()>>>(args);
+static void launch_sell(const SellArgs& args, int grid, const DistSell* d) {
+  static const DistSell none{};
+  if (d) {
+    if (args.v32) k_spmv_sell<SPLIT, DOT, true, true><<<grid, kST, 0, stream()>>>(args, *d);
+    else k_spmv_sell<SPLIT, DOT, false, true><<<grid, kST, 0, stream()>>>(args, *d);
+  } else {
+    if (args.v32) k_spmv_sell<SPLIT, DOT, true, false><<<grid, kST, 0, stream()>>>(args, none);
+    else k_spmv_sell<SPLIT, DOT, false, false><<<grid, kST, 0, stream()>>>(args, none);
+  }
 }
 
 // y = S x, or S [x; x2] for a matrix built in split form.  Returns the grid (= number of dot
 // partials when asked for), 0 if S is empty.
-int spmv_sell(const fs_sell& S, const double* x, double* y, const double* x2, double* dot_partials) {
+static int spmv_sell_impl(const fs_sell& S, const double* x, double* y, const double* x2, double* dot_partials,
+                          const DistSell* d) {
   if (!S.nslices) return 0;
   FS_REQUIRE((S.nsplit >= 0) == (x2 != nullptr), "spmv_sell: split form and second vector must come together");
   const int per_sm = (x2 && S.v32.p && dot_partials) ? 8 : 6;   // the finest up-sweep runs at 32 registers
   const int grid = std::max(1, std::min(div_up(S.nslices, kSW), sm_count() * per_sm));
   SellArgs args{S.n, S.nslices, S.sptr.p, S.wg.p, S.cols.p, S.v32.p, S.v64.p, x, x2, y, dot_partials};
   if (x2) {
-    if (dot_partials) launch_sell<true, true>(args, grid);
-    else launch_sell<true, false>(args, grid);
+    if (dot_partials) launch_sell<true, true>(args, grid, d);
+    else launch_sell<true, false>(args, grid, d);
   } else {
-    if (dot_partials) launch_sell<false, true>(args, grid);
-    else launch_sell<false, false>(args, grid);
+    if (dot_partials) launch_sell<false, true>(args, grid, d);
+    else launch_sell<false, false>(args, grid, d);
   }
   FS_LAUNCH_CHECK();
   return grid;
+}
+
+int spmv_sell(const fs_sell& S, const double* x, double* y, const double* x2, double* dot_partials) {
+  return spmv_sell_impl(S, x, y, x2, dot_partials, nullptr);
+}
+
+int spmv_sell_dist(const fs_sell& S, const double* x, double* y, const double* x2, double* dot_partials, const Comm& c,
+                   const HaloWait& w) {
+  DistSell d{c, w};
+  return spmv_sell_impl(S, x, y, x2, dot_partials, &d);
 }
 
 int spmv_sell_grid(const fs_sell& S) { return std::max(1, std::min(div_up(S.nslices, kSW), sm_count() * 4)); }
@@ -340,8 +370,20 @@ void spmv_sell2(const fs_sell& S, const double* x, double* y, double* dot_partia
   FS_REQUIRE(S.nslices && S.v64.p && S.nsplit < 0, "spmv_sell2: needs a one-part fp64 SELL matrix");
   const int grid = spmv_sell_grid(S);
   SellArgs args{S.n, S.nslices, S.sptr.p, nullptr, S.cols.p, nullptr, S.v64.p, x, nullptr, y, dot_partials};
-  if (dot_partials) k_spmv_sell2<true><<<grid, kST, 0, stream()>>>(args, done);
-  else k_spmv_sell2<false><<<grid, kST, 0, stream()>>>(args, done);
+  static const DistSell none{};
+  if (dot_partials) k_spmv_sell2<true, false><<<grid, kST, 0, stream()>>>(args, done, none);
+  else k_spmv_sell2<false, false><<<grid, kST, 0, stream()>>>(args, done, none);
+  FS_LAUNCH_CHECK();
+}
+
+void spmv_sell2_dist(const fs_sell& S, const double* x, double* y, double* dot_partials, const int* done, const Comm& c,
+                     const HaloWait& w) {
+  FS_REQUIRE(S.nslices && S.v64.p && S.nsplit < 0, "spmv_sell2: needs a one-part fp64 SELL matrix");
+  const int grid = spmv_sell_grid(S);
+  SellArgs args{S.n, S.nslices, S.sptr.p, nullptr, S.cols.p, nullptr, S.v64.p, x, nullptr, y, dot_partials};
+  DistSell d{c, w};
+  if (dot_partials) k_spmv_sell2<true, true><<<grid, kST, 0, stream()>>>(args, done, d);
+  else k_spmv_sell2<false, true><<<grid, kST, 0, stream()>>>(args, done, d);
   FS_LAUNCH_CHECK();
 }
 

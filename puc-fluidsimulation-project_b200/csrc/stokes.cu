@@ -26,6 +26,9 @@ struct fs_stokes {
   fs::Pattern pat_red;
   fs::DBuf<int> dof;      // (N) node -> merged dof
   int64_t nd = 0;
+  fs::DBuf<int> rep;      // (nd) dof -> its representative (smallest) node
+  fs::DBuf<int> ex_ptr, ex_dof, ex_node;   // dofs with merged-in nodes: CSR list of those nodes, ascending
+  int64_t n_ex = 0;
   fs::DBuf<unsigned char> is_dir, is_interior;
   fs::DBuf<double> ustar, div, rhs_red, p_red, p2_red, p_full, p2_full;
   bool have_p = false;
@@ -60,12 +63,25 @@ __global__ void k_visc_vals(CsrView K, double dtnu, const unsigned char* __restr
   }
 }
 
-// rhs_red[dof[n]] += M[n] * (-(1/DT) * div[n])   (code/StokesColor.py:554 then mass-weighting)
-__global__ void k_pressure_rhs(int64_t N, const int* __restrict__ dof, const double* __restrict__ mass,
+// rhs_red[d] = sum over the nodes n merged into dof d of M[n] * (-(1/DT) * div[n])
+// (code/StokesColor.py:554 then mass-weighting).  No atomics: the dof's representative (smallest node
+// id) is gathered first, the few merged-in nodes are added in ascending node order by one thread per
+// dof that has any -- the same bits on every run however many nodes share a dof.
+__global__ void k_pressure_rhs(int64_t nd, const int* __restrict__ rep, const double* __restrict__ mass,
                                const double* __restrict__ div, double s, double* __restrict__ rhs_red) {
-  int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  atomicAdd(&rhs_red[dof[n]], mass[n] * (s * div[n]));
+  int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (d >= nd) return;
+  const int n = rep[d];
+  rhs_red[d] = mass[n] * (s * div[n]);
+}
+__global__ void k_pressure_rhs_extra(int64_t n_ex, const int* __restrict__ ex_ptr, const int* __restrict__ ex_dof,
+                                     const int* __restrict__ ex_node, const double* __restrict__ mass,
+                                     const double* __restrict__ div, double s, double* __restrict__ rhs_red) {
+  int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j >= n_ex) return;
+  double v = rhs_red[ex_dof[j]];
+  for (int k = ex_ptr[j]; k < ex_ptr[j + 1]; ++k) { const int n = ex_node[k]; v += mass[n] * (s * div[n]); }
+  rhs_red[ex_dof[j]] = v;
 }
 
 __global__ void k_expand(int64_t N, const int* __restrict__ dof, const double* __restrict__ q, double* __restrict__ p) {
@@ -85,9 +101,13 @@ static void pressure_solve(fs_stokes* s, const double* d_vel, double* q, fs_stok
   cudaStream_t st = stream();
   divergence_dev(m, d_vel, s->div.p, nullptr);
   if (max_div) *max_div = max_abs_dev(s->div.p, m->N);
-  s->rhs_red.zero();
-  k_pressure_rhs<<<div_up(m->N, 256), 256, 0, st>>>(m->N, s->dof.p, m->mass.p, s->div.p, -(1.0 / s->DT), s->rhs_red.p);
+  k_pressure_rhs<<<div_up(s->nd, 256), 256, 0, st>>>(s->nd, s->rep.p, m->mass.p, s->div.p, -(1.0 / s->DT), s->rhs_red.p);
   FS_LAUNCH_CHECK();
+  if (s->n_ex) {
+    k_pressure_rhs_extra<<<div_up(s->n_ex, 128), 128, 0, st>>>(s->n_ex, s->ex_ptr.p, s->ex_dof.p, s->ex_node.p, m->mass.p,
+                                                             s->div.p, -(1.0 / s->DT), s->rhs_red.p);
+    FS_LAUNCH_CHECK();
+  }
   if (!o.warm_start || !s->have_p) {
     FS_CUDA(cudaMemsetAsync(q, 0, s->nd * sizeof(double), st));
     H.nq = H.ny = 0;
@@ -125,6 +145,12 @@ static void pressure_solve(fs_stokes* s, const double* d_vel, double* q, fs_stok
   *iters = it;
   k_expand<<<div_up(m->N, 256), 256, 0, st>>>(m->N, s->dof.p, q, p_full);
   FS_LAUNCH_CHECK();
+}
+
+// what the partitioned step (pstokes.cu) cuts its blocks out of
+void stokes_global_view(fs_stokes* s, fs_mesh** mesh, fs_csr** a_visc, fs_csr** k_red, double* DT, double* nu, std::vector<int>& dof) {
+  *mesh = s->mesh; *a_visc = &s->a_visc; *k_red = &s->k_red; *DT = s->DT; *nu = s->nu;
+  dof = s->dof.to_host();
 }
 
 }  // namespace fs
@@ -191,6 +217,22 @@ int fs_stokes_create(fs_mesh* m, double DT, double nu, fs_stokes** out) {
   s->nd = nd;
   s->dof.alloc(N);
   s->dof.upload(dof.data(), N);
+  {
+    std::vector<int> rep(nd), cnt(nd, 0);
+    for (int64_t i = 0; i < N; ++i) { if (newid[i] >= 0) rep[newid[i]] = (int)i; else ++cnt[dof[i]]; }
+    std::vector<int> ex_dof, ex_ptr(1, 0), slot(nd, -1);
+    for (int d = 0; d < nd; ++d) if (cnt[d]) { slot[d] = (int)ex_dof.size(); ex_dof.push_back(d); ex_ptr.push_back(ex_ptr.back() + cnt[d]); }
+    std::vector<int> ex_node(ex_ptr.back()), fill(ex_ptr.begin(), ex_ptr.end() - 1);
+    for (int64_t i = 0; i < N; ++i) if (newid[i] < 0) ex_node[fill[slot[dof[i]]]++] = (int)i;   // ascending node id
+    s->rep.alloc(nd); s->rep.upload(rep.data(), nd);
+    s->n_ex = (int64_t)ex_dof.size();
+    if (s->n_ex) {
+      s->ex_ptr.alloc(ex_ptr.size()); s->ex_ptr.upload(ex_ptr.data(), ex_ptr.size());
+      s->ex_dof.alloc(ex_dof.size()); s->ex_dof.upload(ex_dof.data(), ex_dof.size());
+      s->ex_node.alloc(ex_node.size()); s->ex_node.upload(ex_node.data(), ex_node.size());
+    }
+    fs::sync();   // the host vectors above go out of scope
+  }
   fs::sync();
   build_pattern(m->tris.p, m->T, nd, s->dof.p, s->pat_red);
   s->k_red.n = nd; s->k_red.nnz = s->pat_red.nnz;
@@ -285,6 +327,16 @@ int fs_stokes_pressure(fs_stokes* s, double* p, double* p2) {
   const int64_t N = s->mesh->N;
   if (p) FS_CUDA(cudaMemcpyAsync(p, s->p_full.p, N * sizeof(double), cudaMemcpyDefault, stream()));
   if (p2) FS_CUDA(cudaMemcpyAsync(p2, s->p2_full.p, N * sizeof(double), cudaMemcpyDefault, stream()));
+  fs::sync();
+  FS_API_END
+}
+
+int fs_stokes_set_pressure(fs_stokes* s, const double* p, const double* p2) {
+  FS_API_BEGIN
+  FS_REQUIRE(s, "NULL argument");
+  const int64_t N = s->mesh->N;
+  if (p) FS_CUDA(cudaMemcpyAsync(s->p_full.p, p, N * sizeof(double), cudaMemcpyDefault, stream()));
+  if (p2) FS_CUDA(cudaMemcpyAsync(s->p2_full.p, p2, N * sizeof(double), cudaMemcpyDefault, stream()));
   fs::sync();
   FS_API_END
 }

@@ -102,17 +102,32 @@ class StokesSolver:
     def _state_arrays(self):
         return {"u": self.u}
 
+    @staticmethod
+    def _npz_path(path):
+        path = str(path)
+        return path if path.endswith(".npz") else path + ".npz"
+
     def save_state(self, path):
-        """Write the complete loop state (velocity, CG warm-start vectors, and the dye / tracer
-        arrays of the subclasses) to an .npz file."""
-        np.savez(path, warm=self.get_warm_state(), **self._state_arrays())
+        """Write the complete loop state (velocity, CG warm-start vectors, the two pressure fields of the
+        last step, and the dye / tracer arrays of the subclasses) to ``path`` (``.npz`` is appended when
+        missing, by save and load alike)."""
+        p, p2 = self.pressure()
+        np.savez(self._npz_path(path), warm=self.get_warm_state(), p_full=p, p2_full=p2, **self._state_arrays())
 
     def load_state(self, path):
         """Restore a state written by save_state; the run continues bit for bit."""
-        z = np.load(path)
+        z = np.load(self._npz_path(path))
         for k, arr in self._state_arrays().items():
             arr[...] = z[k]
         self.set_warm_state(z["warm"])
+        if "p_full" in z.files:
+            self.set_pressure(z["p_full"], z["p2_full"])
+
+    def set_pressure(self, p, p2):
+        """Restore the nodal pressure fields that pressure() returns (checkpoint resume)."""
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        p2 = np.ascontiguousarray(p2, dtype=np.float64)
+        call("fs_stokes_set_pressure", self._h, ptr(p, np.float64, (self.N,)), ptr(p2, np.float64, (self.N,)))
 
     def pressure(self):
         p = np.empty(self.N)
