@@ -9,14 +9,20 @@ One "step" = one pass of the operator-split Stokes step (code/StokesColor.py:537
 CG, interior update -- on the square-with-hole mesh n_theta=2048 x n_r=1024
 (T=4 194 304, N=2 099 200), pusher squirmer B1=-2 B2=-5, nu=0.1, DT=0.05.
 
-N>1 (torchrun, one rank per GPU): the B1/B2 sweep of config 4 -- every rank advances
-its own squirmer configuration on its own copy of the mesh, no data-path collective
-("scaling": "weak"); value = steps of all ranks / max-over-ranks time.
+N>1 (torchrun, one rank per GPU): weak scaling of the PARTITIONED step (BASELINE config 5): the mesh grows
+with N (N x 4M triangles: 2048x2048, 4096x2048, 4096x4096 = the 32M-triangle config at N=8), is cut into
+N contiguous blocks of rings, and every rank advances its block -- halo values and dot products travel as
+peer stores over NVLink from inside the kernels (csrc/dist.cuh).  value = N x (steps/s of the big mesh),
+i.e. 4M-triangle-equivalent steps per second, so the metric keeps its meaning across N; the line also
+carries check_rel_err_vs_1gpu (the partitioned solver against the single-GPU one on a 262k-triangle mesh).
+--sweep keeps the old N>1 behaviour (independent (B1,B2) configurations, no collective).
 
---impl reference times the reference's CPU path.  The literal reference (dense numpy)
-cannot hold a 4M-triangle mesh (N x N doubles = 32 TB), so the arm runs the oracle's
-CPU port of the same algorithm (oracle/cg_port.c, OpenMP, all host threads) on a bounded
-sample and extrapolates with the iteration counts of the GPU run (profiles/bench_iters.json).
+--impl reference times the reference's CPU path.  The literal reference (dense numpy LU) cannot hold a
+4M-triangle mesh (N x N doubles = 32 TB), so the arm runs the oracle's multi-threaded CPU statement of the
+same step (oracle/cpu_step.py + oracle/cg_port.c, OpenMP, all host threads) with the SAME algorithm as the
+GPU arm (AMG-preconditioned pressure CG): W + K complete, measured steps, nothing extrapolated.  A single
+measured step with the Jacobi-CG (the closest sparse analogue of the reference's own solve) is reported next
+to it as cpu_baseline_jacobi.
 """
 from __future__ import annotations
 
@@ -33,12 +39,10 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version at VERSION/INFO)
 
 N_THETA, N_R = 2048, 1024
 PARAMS = dict(B1=-2.0, B2=-5.0, DT=0.05, v=0.1)
 RTOL_P, RTOL_V = 1e-10, 1e-12
-ITERS_FILE = os.path.join(ROOT, "profiles", "bench_iters.json")
 TRAFFIC_FILE = os.path.join(ROOT, "profiles", "spmv_traffic.json")
 
 
@@ -110,80 +114,104 @@ def measured_peak():
 
 
 # ------------------------------------------------------------------------------ CPU baseline
-def cpu_baseline_sample(rowptr, colidx, vals, nodes, tris, iters_per_step, n_cg=60):
-    """Oracle port on the host cores: n_cg Jacobi-CG iterations of the pressure operator
-    (oracle/cg_port.c, OpenMP) + one divergence + one gradient (oracle/restated.py, numpy),
-    extrapolated to one Stokes step = iters_per_step CG iterations + 3 div + 2 grad."""
-    from oracle import cgport, restated as R
-    nd = len(rowptr) - 1
-    rng = np.random.default_rng(0)
-    b = rng.standard_normal(nd)
-    cgport.cg(rowptr, colidx, vals, b, rtol=0.0, maxit=10, project_mean=True)     # warm (thread start-up)
+def load_hostmesh():
+    """The numpy-only mesh helpers of the package, loaded by path: the CPU arm must not load libfluidsim.so."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("fs_hostmesh", os.path.join(ROOT, "puc-fluidsimulation-project_b200", "hostmesh.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_steps(nodes, markers, tris, precond, warmup, steps, threads, budget_s=None):
+    """W + K complete Stokes steps of the oracle's CPU statement (oracle/cpu_step.py), measured.  Stops early
+    (after at least one timed step) once budget_s seconds of timed work are spent."""
+    from oracle import cpu_step
     t0 = time.perf_counter()
-    _, it, _ = cgport.cg(rowptr, colidx, vals, b, rtol=0.0, maxit=n_cg, project_mean=True)
-    t_iter = (time.perf_counter() - t0) / max(it, 1)
-    u = rng.standard_normal((nodes.shape[0], 2))
-    t0 = time.perf_counter()
-    R.divergence(nodes, tris, u)
-    t_div = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    R.gradient(nodes, tris, u[:, 0].copy())
-    t_grad = time.perf_counter() - t0
-    t_step = iters_per_step * t_iter + 3 * t_div + 2 * t_grad
-    return {"value": 1.0 / t_step, "unit": "steps/s", "cores": cgport.threads(), "kind": "port",
-            "sample": f"{it} Jacobi-CG iterations of the 4M-tri pressure operator (oracle/cg_port.c, OpenMP) "
-                      f"+ 1 divergence + 1 gradient (oracle/restated.py); extrapolated to {iters_per_step:.0f} "
-                      f"CG iterations + 3 div + 2 grad per step",
-            "ms_per_cg_iter": 1e3 * t_iter, "s_div": t_div, "s_grad": t_grad,
-            "cg_iter_gbs": (12.0 * len(colidx) + 92.0 * nd) / t_iter / 1e9}
+    sim = cpu_step.CpuStokes(nodes, markers, tris, B1=PARAMS["B1"], B2=PARAMS["B2"], DT=PARAMS["DT"], v=PARAMS["v"],
+                             precond=precond, rtol_pressure=RTOL_P, rtol_visc=RTOL_V, threads=threads)
+    t_setup = time.perf_counter() - t0
+    for _ in range(warmup):
+        sim.step()
+    iters, times = [], []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        iters.append(tuple(int(v) for v in sim.step()))
+        times.append(time.perf_counter() - t0)
+        if budget_s is not None and sum(times) >= budget_s:
+            break
+    return {"s_per_step": float(np.mean(times)), "steps_timed": len(times), "warmup": warmup, "cg_iters_per_step": iters,
+            "setup_s": t_setup}
+
+
+def cpu_baseline_line(res, precond, threads, nt, nr):
+    algo = ("AMG-preconditioned pressure CG (same algorithm as the GPU arm)" if precond == "amg" else
+            "Jacobi-preconditioned pressure CG (closest sparse analogue of the reference's dense solve)")
+    return {"value": 1.0 / res["s_per_step"], "unit": "steps/s", "cores": threads, "kind": "port",
+            "sample": f"{res['steps_timed']} complete measured Stokes steps after {res['warmup']} warm-up steps on the "
+                      f"{2 * nt * nr}-triangle mesh, oracle/cpu_step.py + oracle/cg_port.c (OpenMP): {algo}; "
+                      f"2-RHS-equivalent viscous Jacobi-CG, sparse div/grad; nothing extrapolated",
+            "ms_per_step": 1e3 * res["s_per_step"], "cg_iters_per_step": res["cg_iters_per_step"], "setup_s": res["setup_s"]}
 
 
 def run_reference(args):
-    """--impl reference: CPU only (rank 0)."""
+    """--impl reference: CPU only (rank 0).  Does not import the product."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import restated as R
-    import fluidsim_b200.mesh as fmesh     # host-only helpers (generator, pair finder); no GPU call
-    nodes, markers, tris = fmesh.square_with_hole(args.n_theta, args.n_r)
-    pairs = fmesh.filter_wall_pairs(nodes, fmesh.find_boundary_pairs(nodes))
-    ps = R.PressureSystem(nodes, tris, pairs)
-    iters = 2 * 9000.0
-    src = "default estimate"
-    if os.path.exists(ITERS_FILE):
-        j = json.load(open(ITERS_FILE))
-        iters = float(j["iters_per_step"])
-        src = "profiles/bench_iters.json (GPU run)"
-    vals = []
-    for _ in range(args.warmup + args.steps):
-        vals.append(cpu_baseline_sample(ps.rowptr, ps.colidx, ps.vals, nodes, tris, iters))
-    vals = vals[args.warmup:]
-    best = max(vals, key=lambda d: d["value"])
-    v = float(np.mean([d["value"] for d in vals]))
-    best["value"] = v
-    best["sample"] += f"; iteration count from {src}"
+    hm = load_hostmesh()
+    threads = host_threads()                      # torchrun exports OMP_NUM_THREADS=1: set the count explicitly
+    # weak scaling: the CPU arm advances ONE 4M-triangle share of the N x 4M-triangle mesh (the metric is in
+    # 4M-triangle-equivalent steps/s, and the host does not grow with N)
+    nodes, markers, tris = hm.square_with_hole(args.n_theta, args.n_r)
+    res = cpu_steps(nodes, markers, tris, "amg", args.warmup, args.steps, threads)
+    cpu = cpu_baseline_line(res, "amg", threads, args.n_theta, args.n_r)
+    v = cpu["value"]
     out = {"impl": "reference", "metric": "stokes_steps_per_sec_4M_tri", "value": v, "unit": "steps/s",
-           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v,
+           "n_gpus": args.gpus, "steps": res["steps_timed"], "warmup": args.warmup, "ms_per_step": 1e3 / v,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": workload_config(args, iters_note=src), "cpu_baseline": best,
+           "config": workload_config(args, world=1, parallelism=f"CPU, {threads} OpenMP threads; one 4M-triangle share of the "
+                                     f"N x 4M-triangle mesh of the GPU arm"),
+           "cpu_baseline": cpu,
            "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
+    if not args.no_extra:
+        rj = cpu_steps(nodes, markers, tris, "jacobi", 0, 1, threads)
+        out["cpu_baseline_jacobi"] = cpu_baseline_line(rj, "jacobi", threads, args.n_theta, args.n_r)
+    out["product_loaded"] = any(m.startswith("fluidsim_b200") for m in sys.modules)      # must stay False: CPU arm only
     emit(out)
 
 
-def workload_config(args, **extra):
-    cfg = {"workload": f"stokes_step square-with-hole n_theta={args.n_theta} n_r={args.n_r} "
-                       f"(T={2 * args.n_theta * args.n_r}, N={args.n_theta * (args.n_r + 1)}), pusher B1=-2 B2=-5, "
-                       f"nu=0.1, DT=0.05",
-           "solver": f"pressure: CG + smoothed-aggregation AMG V(1,1), cycle folded to two SELL-32 SpMVs per level "
+WEAK_SHAPES = {1: (2048, 1024), 2: (2048, 2048), 4: (4096, 2048), 8: (4096, 4096)}
+
+
+def workload_config(args, world=1, **extra):
+    nt, nr = (args.n_theta, args.n_r) if world == 1 else weak_shape(args, world)
+    cfg = {"workload": f"stokes_step square-with-hole n_theta={nt} n_r={nr} "
+                       f"(T={2 * nt * nr}, N={nt * (nr + 1)}), pusher B1=-2 B2=-5, nu=0.1, DT=0.05",
+           "solver": f"pressure: fp64 CG preconditioned by a smoothed-aggregation AMG V(1,1) cycle whose operators are stored in "
+                     f"fp32 (vectors, sums and the CG itself fp64), cycle folded to two SELL-32 SpMVs per level "
                      f"[--precond amg] or Jacobi persistent CG [--precond jacobi], rtol_pressure={RTOL_P:g}; "
                      f"viscous: 2-RHS Jacobi CG rtol={RTOL_V:g}; pressure warm start = best of the previous solution and its "
                      f"linear / quadratic extrapolation in time (every solve still runs to rtol)",
            "l2": "inputs larger than L2 (per PCG iteration: A 190 MB fp64 SELL + V-cycle operators ~440 MB fp32 SELL "
-                 "+ 5 vectors 84 MB > 126 MB), no flush needed",
+                 "+ 5 vectors 84 MB > 126 MB per GPU), no flush needed",
            "steps_from": "t=0 (u=0 + squirmer BC); warm-up steps advance the same trajectory"}
     cfg.update(extra)
     return cfg
+
+
+def weak_shape(args, world):
+    if args.n_theta != N_THETA or args.n_r != N_R:          # explicit per-GPU share: grow radially
+        return args.n_theta, args.n_r * world
+    return WEAK_SHAPES[world]
 
 
 # ------------------------------------------------------------------------------ GPU arm
@@ -235,43 +263,79 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    nodes, markers, tris = fb.square_with_hole(args.n_theta, args.n_r)
-    B1, B2 = sweep_params(rank, world) if world > 1 else (PARAMS["B1"], PARAMS["B2"])
+    partitioned = world > 1 and not args.sweep
     precond = {"amg": fb.PRECOND_AMG, "jacobi": fb.PRECOND_JACOBI}[args.precond]
-    sim = fb.StokesSolver(nodes, markers, tris, B1=B1, B2=B2, DT=PARAMS["DT"], v=PARAMS["v"],
-                          rtol_pressure=RTOL_P, rtol_visc=RTOL_V, precond=precond)
-    N = sim.N
-    _, kp, _ = sim.matrices()
-    nd, nnz = kp.n, kp.nnz
-    u_dev = torch.from_numpy(sim.u.copy()).cuda()
+    kw = dict(DT=PARAMS["DT"], v=PARAMS["v"], rtol_pressure=RTOL_P, rtol_visc=RTOL_V)
+    check = None
+    if partitioned:
+        # cross-check first (small mesh): the partitioned solver against the single-GPU one, same steps
+        cn, cm, ct = fb.square_with_hole(512, 256)
+        pc = fb.PartitionedStokes(cn, cm, ct, rank=rank, world=world, dist=dist, align=512, gather_rows=5000,
+                                  B1=PARAMS["B1"], B2=PARAMS["B2"], **kw)
+        uc = torch.from_numpy(pc.u.copy()).cuda()
+        itc = []
+        for _ in range(5):
+            st = pc.step(uc)
+            itc.append((st.iters_visc, st.iters_p1, st.iters_p2))
+        ug = pc.gather(uc)
+        if rank == 0:
+            ref = fb.StokesSolver(cn, cm, ct, B1=PARAMS["B1"], B2=PARAMS["B2"], precond=fb.PRECOND_AMG, **kw)
+            ur = torch.from_numpy(ref.u.copy()).cuda()
+            it1 = []
+            for _ in range(5):
+                st = ref.step(ur)
+                it1.append((st.iters_visc, st.iters_p1, st.iters_p2))
+            ur = ur.cpu().numpy()
+            check = {"value": float(np.linalg.norm(ug - ur) / np.linalg.norm(ur)), "mesh": "square-with-hole 512x256 (262144 triangles)",
+                     "steps": 5, "cg_iters_partitioned": itc, "cg_iters_1gpu": it1, "levels_partitioned": pc.levels_partitioned}
+            del ref, ur
+        del pc, uc
+        barrier()
+        nt, nr = weak_shape(args, world)
+        nodes, markers, tris = fb.square_with_hole(nt, nr)
+        t0 = time.perf_counter()
+        sim = fb.PartitionedStokes(nodes, markers, tris, rank=rank, world=world, dist=dist, align=nt,
+                                   B1=PARAMS["B1"], B2=PARAMS["B2"], **kw)
+        t_setup = time.perf_counter() - t0
+        N = sim.n_own
+        nd, nnz = sim.n_own_dofs, None
+        u_dev = torch.from_numpy(sim.u.copy()).cuda()
+        get_state, set_state = sim.get_state, sim.set_state
+    else:
+        nodes, markers, tris = fb.square_with_hole(args.n_theta, args.n_r)
+        B1, B2 = sweep_params(rank, world) if world > 1 else (PARAMS["B1"], PARAMS["B2"])
+        t0 = time.perf_counter()
+        sim = fb.StokesSolver(nodes, markers, tris, B1=B1, B2=B2, precond=precond, **kw)
+        t_setup = time.perf_counter() - t0
+        N = sim.N
+        _, kp, _ = sim.matrices()
+        nd, nnz = kp.n, kp.nnz
+        u_dev = torch.from_numpy(sim.u.copy()).cuda()
+        get_state, set_state = sim.get_warm_state, sim.set_warm_state
 
-    # ---- device-resident arm: W warm-up steps, then exactly K timed steps
+    # ---- device-resident arm: W warm-up steps, then exactly K timed steps (no profiling events inside)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()                      # streaming 100 ms samples from here on; summarised over the two timed regions
     for _ in range(args.warmup):
         sim.step(u_dev)
     barrier()
-    u_snap = u_dev.clone()                  # loop state, so that the end-to-end arm repeats the same K steps
-    warm_snap = sim.get_warm_state()
+    u_snap = u_dev.clone()                  # loop state, so that the other arms repeat the same K steps
+    warm_snap = get_state()
     t_clk0 = time.time()
     launches0 = fb.launch_count()
-    _lib.call("fs_profile", 1)
+    _lib.call("fs_profile", 0)
     t_dev, iters = timed_steps(sim, u_dev, args.steps, _lib, barrier)
     launches = fb.launch_count() - launches0
-    pms, samples = read_profile(_lib)
-    top_ms, top_n, top_bytes = C.c_double(0), C.c_int64(0), C.c_double(0)
-    _lib.call("fs_profile_read_top", C.byref(top_ms), C.byref(top_n), C.byref(top_bytes))
-    _lib.call("fs_profile", 0)
     t_dev = max_over_ranks(t_dev)
     value = world * args.steps / t_dev
 
     # ---- end-to-end arm: the same K steps through the host-buffer C-ABI call (pinned numpy view):
-    # every step copies u host->device and device->host inside the timed region
+    # every step copies this rank's u host->device and device->host inside the timed region
     u_pin = torch.empty((N, 2), dtype=torch.float64).pin_memory()
     u_pin.copy_(u_snap.cpu())
     u_host = u_pin.numpy()
-    sim.set_warm_state(warm_snap)
+    set_state(warm_snap)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -279,6 +343,22 @@ def run_ours(args):
     barrier()
     e2e = world * args.steps / max_over_ranks(time.perf_counter() - t0)
     clk = clocks.stop(t_clk0, time.time()) if rank == 0 else None      # samples of the device arm and the end-to-end arm
+
+    # ---- sampled pass (NOT part of value): per-kernel event timing for the roofline
+    pms = samples = None
+    top_ms, top_n, top_bytes = C.c_double(0), C.c_int64(0), C.c_double(0)
+    us_iter_part = None
+    if partitioned:
+        us_iter_part = max_over_ranks(sim.profile_pcg(40))
+    else:
+        u_prof = u_snap.clone()
+        set_state(warm_snap)
+        _lib.call("fs_profile", 1)
+        timed_steps(sim, u_prof, args.steps, _lib, barrier)
+        pms, samples = read_profile(_lib)
+        _lib.call("fs_profile_read_top", C.byref(top_ms), C.byref(top_n), C.byref(top_bytes))
+        _lib.call("fs_profile", 0)
+        del u_prof
 
     if dist is not None:
         dist.barrier()
@@ -292,16 +372,27 @@ def run_ours(args):
         _lib.call("fs_sync")
 
     peak, peak_src = measured_peak()
-    spmv_bytes = 12.0 * nnz + 20.0 * nd
-    cg_bytes = 12.0 * nnz + 92.0 * nd + 16.0 * nd      # Jacobi PCG iteration: + dinv read in passes B and C
     it_arr = np.array(iters, dtype=np.float64)
     out_extra = {}
-    if args.precond == "amg":
+    if partitioned:
+        # per-rank algorithmic bytes of one AMG-PCG iteration at 4M triangles per GPU: A*p (SELL fp64)
+        # 210 MB + folded V-cycle operators and vectors ~440 MB + the two PCG vector kernels 151 MB
+        it_bytes = 801e6
+        roof = {"bound": "hbm", "kernel": "whole AMG-PCG iteration per rank (k_spmv_sell A*p + folded V-cycle SpMVs + k_ppcg_xr / k_ppcg_p, "
+                                          "halo pushes and all-reduces inside the kernels), fixed-count run timed with CUDA events",
+                "achieved": it_bytes / (us_iter_part * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": it_bytes / (us_iter_part * 1e-6) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": it_bytes, "us_per_launch": us_iter_part,
+                "note": "per-rank figure; one 'launch' = one PCG iteration (11 kernels + 1 graph)"}
+        out_extra["check_rel_err_vs_1gpu"] = check
+        out_extra["setup_s"] = t_setup
+    elif args.precond == "amg":
         # dominant kernel of this configuration: k_spmv_sell, the SELL-32 SpMV that runs the CG's A*p (fp64
         # values) and every large operator of the folded V-cycle (fp32 values).  Its longest launch is the
         # finest level's up-sweep z = [G | SP] [r; x_c] (+ fused r.z): timed with its own CUDA event pair on
-        # every 8th PCG iteration of the timed region (that cycle runs outside its CUDA graph); the A*p
-        # launch is bracketed by events in every iteration.
+        # every 8th PCG iteration of the sampled pass (that cycle runs outside its CUDA graph); the A*p
+        # launch is bracketed by events in every iteration of the sampled pass.
+        spmv_bytes = 12.0 * nnz + 20.0 * nd
         t_spmv = pms[0] / samples / 1e3
         ap_bytes = 12.0 * nnz + 16.25 * nd      # values + columns, slice pointers (8 B / 32 rows), p gathered, A*p written
         traffic = json.load(open(TRAFFIC_FILE)) if os.path.exists(TRAFFIC_FILE) else {}
@@ -321,13 +412,14 @@ def run_ours(args):
         else:   # unfolded cycle (FS_AMG_FOLD=0): the CG's A*p is the largest launch
             roof = dict(ap_line, bound="hbm", peak=peak, unit="GB/s", peak_source=peak_src,
                         frac_of_8TBps_spec=ap_bytes / t_spmv / 8e12)
-        roof["us_per_pcg_iteration"] = {"A*p": 1e6 * t_spmv, "V-cycle": 1e3 * pms[1] / samples,
-                                        "vector ops + dots": 1e3 * pms[2] / samples}
-        jac_iters = float(json.load(open(ITERS_FILE))["iters_per_step"]) if os.path.exists(ITERS_FILE) else 16000.0
-        visc_iters = float(it_arr[:, 0].mean())
+        us_it = {"A*p": 1e6 * t_spmv, "V-cycle": 1e3 * pms[1] / samples, "vector ops + dots": 1e3 * pms[2] / samples}
+        us_it["total"] = sum(us_it.values())
+        roof["us_per_pcg_iteration"] = us_it
+        roof["note"] = "timed in a separate sampled pass over the same K steps (events inside the solver); value is timed without them"
     if args.precond == "amg" and not args.no_extra and world == 1:
-        # the Jacobi-preconditioned persistent CG kernel on the same operator: the path's HBM-roofline
-        # kernel and the same algorithm as the CPU baseline (2000 fixed iterations, not part of `value`)
+        # the Jacobi-preconditioned persistent CG kernel on the same operator: the path's HBM-roofline kernel
+        # (2000 fixed iterations, not part of `value`)
+        cg_bytes = 12.0 * nnz + 92.0 * nd + 16.0 * nd      # Jacobi PCG iteration: + dinv read in passes B and C
         b = torch.randn(nd, dtype=torch.float64, device="cuda")
         x = torch.zeros_like(b)
         it_c, rr_c = C.c_int(0), C.c_double(0)
@@ -346,19 +438,18 @@ def run_ours(args):
             "spmv_pass_GBs": spmv_bytes / (pj[0] / sj / 1e3) / 1e9,
             "spmv_pass_frac": spmv_bytes / (pj[0] / sj / 1e3) / 1e9 / peak,
             "note": "frac can exceed 1: the five CG vectors are kept L2-resident (evict_last), DRAM traffic is below the algorithmic bytes"}
-        # same-algorithm value: the Stokes step with the Jacobi persistent CG (what the CPU baseline runs)
-        simj = fb.StokesSolver(nodes, markers, tris, B1=B1, B2=B2, DT=PARAMS["DT"], v=PARAMS["v"],
-                               rtol_pressure=RTOL_P, rtol_visc=RTOL_V, precond=fb.PRECOND_JACOBI)
+        # same step with the Jacobi persistent CG (the closest analogue of the reference's own solve)
+        simj = fb.StokesSolver(nodes, markers, tris, B1=B1, B2=B2, precond=fb.PRECOND_JACOBI, **kw)
         uj = torch.from_numpy(simj.u.copy()).cuda()
         for _ in range(args.warmup):          # same point of the trajectory as the timed AMG steps
             simj.step(uj)
         tj, itj = timed_steps(simj, uj, 2, _lib, barrier)
         out_extra["value_jacobi_pcg"] = {"value": 2 / tj, "unit": "steps/s", "cg_iters_per_step": itj,
-                                         "note": "same algorithm as cpu_baseline / the reference arm"}
-        jac_iters = float(np.mean([i[1] + i[2] for i in itj]))
-        visc_iters = float(np.mean([i[0] for i in itj]))
+                                         "note": "same algorithm as cpu_baseline_jacobi"}
         del simj, uj
-    elif args.precond == "jacobi":
+    elif args.precond == "jacobi" and not partitioned:
+        spmv_bytes = 12.0 * nnz + 20.0 * nd
+        cg_bytes = 12.0 * nnz + 92.0 * nd + 16.0 * nd
         t_spmv = pms[0] / samples / 1e3
         t_it = pms.sum() / samples / 1e3
         n_launch = 2 * args.steps
@@ -373,26 +464,35 @@ def run_ours(args):
                 "spmv_pass_GBs": spmv_bytes / t_spmv / 1e9, "spmv_pass_frac": spmv_bytes / t_spmv / 1e9 / peak,
                 "frac_of_8TBps_spec": cg_bytes / t_it / 8e12,
                 "note": "frac can exceed 1: the five CG vectors are kept L2-resident (evict_last), DRAM traffic is below the algorithmic bytes"}
-        jac_iters = float((it_arr[:, 1] + it_arr[:, 2]).mean())
-        visc_iters = float(it_arr[:, 0].mean())
-    try:
-        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        json.dump({"iters_per_step": jac_iters, "algorithm": "Jacobi PCG", "n_theta": args.n_theta, "n_r": args.n_r,
-                   "rtol_pressure": RTOL_P}, open(os.path.join(ROOT, "gpurun_out", "bench_iters.json"), "w"))
-    except OSError:
-        pass
     cpu = None
     if world == 1 and not args.no_cpu:
-        rp, ci, vv = kp.arrays()
-        cpu = cpu_baseline_sample(rp, ci, vv, nodes, tris, jac_iters + 2 * visc_iters)
+        del sim, u_dev, u_snap
+        torch.cuda.empty_cache()
+        threads = host_threads()
+        hm_nodes, hm_markers, hm_tris = nodes, markers, tris
+        # bounded sample: complete CPU steps at the same point of the trajectory is not needed for a rate -- 2 warm-up
+        # steps (the transient of the warm start), then measured steps until ~20 s of CPU work are spent
+        res = cpu_steps(hm_nodes, hm_markers, hm_tris, "amg", 2, 12, threads, budget_s=20.0)
+        cpu = cpu_baseline_line(res, "amg", threads, args.n_theta, args.n_r)
+    if world == 1:
+        par = "single GPU"
+    elif partitioned:
+        par = (f"mesh cut into {world} contiguous blocks of rings, one per GPU: row-block partitioned operators (A_visc, Z^T K Z, AMG "
+               f"levels above 100k rows; smaller levels replicated), halo values pushed over NVLink peer memory from inside the "
+               f"producing kernels, dot products all-reduced inside the PCG vector kernels (deterministic, rank order); one reduction "
+               f"wave + 7 halo exchanges per PCG iteration; setup replicated")
+    else:
+        par = f"{world} independent squirmer (B1,B2) configs, one per GPU, no collective"
     out = {"metric": "stokes_steps_per_sec_4M_tri", "value": value, "unit": "steps/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": workload_config(args, precond=args.precond, cg_iters_per_step=iters,
-                                     parallelism=("single GPU" if world == 1 else
-                                                  f"{world} independent squirmer (B1,B2) configs, one per GPU, no collective")),
+           "config": workload_config(args, world=world if partitioned else 1, precond=args.precond, cg_iters_per_step=iters,
+                                     parallelism=par,
+                                     value_note=(f"value = {world} x steps/s of the {world} x 4M-triangle mesh (4M-triangle-equivalent steps/s)"
+                                                 if partitioned else "value = steps/s")),
            "roofline": roof, "cpu_baseline": cpu,
-           "e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": 16 * N, "d2h_bytes_per_step": 16 * N},
+           "e2e": {"value": e2e, "unit": "steps/s", "h2d_bytes_per_step": 16 * N * (world if partitioned else 1),
+                   "d2h_bytes_per_step": 16 * N * (world if partitioned else 1)},
            "gpu_launches": int(launches), "clocks": clk}
     out.update(out_extra)
     emit(out)
@@ -429,6 +529,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the Jacobi persistent-CG legs (roofline_persistent_cg, value_jacobi_pcg); profiling runs")
+    ap.add_argument("--sweep", action="store_true",
+                    help="N>1: independent (B1,B2) configurations, one per GPU (config 4), instead of the partitioned step")
     ap.add_argument("--precond", default="amg", choices=["amg", "jacobi"],
                     help="pressure-CG preconditioner of the timed steps (default: amg, the fastest)")
     args = ap.parse_args()

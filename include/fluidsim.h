@@ -248,6 +248,9 @@ int fs_pstokes_connect(fs_pstokes* s, const void* all_handles /* world*64 bytes,
 int fs_pstokes_step(fs_pstokes* s, double* u_own /* (n_own,2) in/out */, double B1, double B2, const fs_stokes_opts* opts,
                     fs_stokes_stats* stats);
 int fs_pstokes_pressure(fs_pstokes* s, double* p_own /* n_own or NULL */, double* p2_own);
+/* profiling aid: `iters` PCG iterations (no convergence test) on the last pressure right-hand side, timed with
+ * CUDA events; collective */
+int fs_pstokes_profile_pcg(fs_pstokes* s, int iters, double* us_per_iter);
 int fs_pstokes_state(fs_pstokes* s, double* buf, int set);
 
 /* ---- tracers and dye.

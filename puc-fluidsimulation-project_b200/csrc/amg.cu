@@ -936,7 +936,9 @@ void amg_part_finalize(Amg* amg, const Space& space0, DistCtx& ctx) {
     {
       fs_csr loc;
       extract_rows(lv.U.view(), P.split[l][rank], P.split[l][rank + 1], sl, lv.n, sn, loc);
-      sell_build(loc, amg->part_f32, lv.Us, (int)(sl.n_own + sl.n_halo));
+      const int nsplit = (int)(sl.n_own + sl.n_halo);
+      sell_build(loc, amg->part_f32, lv.Us, nsplit);
+      sell_mark_boundary(lv.Us, loc, (int)sl.n_own, nsplit, sn->gather ? -1 : (int)sn->n_own);
     }
     {
       fs_csr loc;
@@ -944,6 +946,7 @@ void amg_part_finalize(Amg* amg, const Space& space0, DistCtx& ctx) {
       if (r1 > r0) {
         extract_rows(lv.Rt.view(), r0, r1, sl, lv.n, nullptr, loc);
         sell_build(loc, amg->part_f32, lv.Rts);
+        sell_mark_boundary(lv.Rts, loc, (int)sl.n_own, 0x7fffffff, -1);
       }
     }
     drop(lv.U);
@@ -975,15 +978,18 @@ static int vcycle_folded_dist(Amg& amg, int l, const DVec& bv, double* x, double
   AmgLevel& lv = *amg.L[l];
   const bool next_part = l + 1 < Lp;
   const DVec& nb = P.vb[l + 1];
+  // the restriction stores the rows of b_{l+1} that other ranks read (all of them for the replicated level) into
+  // their copies itself; a rank without coarse rows has nothing to compute or to send
   if (lv.Rts.nslices) {
     double* y = next_part ? nb.p : nb.p + P.split[l + 1][P.rank];
-    spmv_sell_dist(lv.Rts, bv.p, y, nullptr, nullptr, ctx.comm, ctx.wait_of(&bv));
+    const PushSpec ps = ctx.push_spec(nb);
+    spmv_sell_dist(lv.Rts, bv.p, y, nullptr, nullptr, ctx.comm, ctx.wait_of(&bv), &ps);
   }
-  ctx.push(nb);
   double* xc = next_part ? P.vx[l + 1].p : amg.L[l + 1]->x.p;
   vcycle_folded_dist(amg, l + 1, nb, xc, nullptr);
-  const int g = spmv_sell_dist(lv.Us, bv.p, x, xc, dot_part, ctx.comm, ctx.wait_of(&bv, next_part ? &P.vx[l + 1] : nullptr));
-  if (l >= 1) ctx.push(P.vx[l]);
+  PushSpec ps;
+  if (l >= 1) ps = ctx.push_spec(P.vx[l]);
+  const int g = spmv_sell_dist(lv.Us, bv.p, x, xc, dot_part, ctx.comm, ctx.wait_of(&bv, next_part ? &P.vx[l + 1] : nullptr), &ps);
   return dot_part ? g : 0;
 }
 

@@ -133,6 +133,37 @@ void HaloCollector::finish(Space& sp, int rank, int world) {
     sp.send_peer.alloc(sp.n_send); sp.send_peer.upload(peers.data(), sp.n_send);
     sp.send_dst.alloc(sp.n_send); sp.send_dst.upload(dsts.data(), sp.n_send);
   }
+  {
+    // fused-push plan: send entries grouped by own row, rows described per 32-row slice
+    const int nsl = (int)((sp.n_own + 31) / 32);
+    std::vector<int> order(sp.n_send);
+    for (int k = 0; k < sp.n_send; ++k) order[k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return rows[a] < rows[b]; });
+    std::vector<unsigned> smask(std::max(nsl, 1), 0u);
+    std::vector<int> sbase(std::max(nsl, 1), 0), uptr(1, 0), upeer(sp.n_send), udst(sp.n_send);
+    int prev_row = -1, nu = 0;
+    for (int k = 0; k < sp.n_send; ++k) {
+      const int e = order[k], r = rows[e];
+      if (r != prev_row) {
+        if (!smask[r >> 5]) sbase[r >> 5] = nu;
+        smask[r >> 5] |= 1u << (r & 31);
+        if (prev_row >= 0) uptr.push_back(k);
+        ++nu;
+        prev_row = r;
+      }
+      upeer[k] = peers[e];
+      udst[k] = dsts[e];
+    }
+    uptr.push_back(sp.n_send);
+    sp.smask.alloc(smask.size()); sp.smask.upload(smask.data(), smask.size());
+    sp.sbase.alloc(sbase.size()); sp.sbase.upload(sbase.data(), sbase.size());
+    sp.uptr.alloc(uptr.size()); sp.uptr.upload(uptr.data(), uptr.size());
+    if (sp.n_send) {
+      sp.upeer.alloc(sp.n_send); sp.upeer.upload(upeer.data(), sp.n_send);
+      sp.udst.alloc(sp.n_send); sp.udst.upload(udst.data(), sp.n_send);
+    }
+    FS_CUDA(cudaStreamSynchronize(stream()));   // the host vectors above go out of scope
+  }
   FS_CUDA(cudaStreamSynchronize(stream()));
   keys.clear();
   keys.shrink_to_fit();
@@ -245,6 +276,13 @@ __global__ void k_halo_wait(Comm c, HaloWait w) {
   halo_wait(c, w);
 }
 
+// FS_DIST_DEBUG_SKIP (timing experiments only; results are wrong): bit 0 = no halo pushes, bit 1 = no halo waits,
+// bit 2 = reductions stay local
+static int debug_skip() {
+  static const int v = [] { const char* e = std::getenv("FS_DIST_DEBUG_SKIP"); return e ? std::atoi(e) : 0; }();
+  return v;
+}
+
 void DistCtx::init(int rank_, int world_, size_t vector_bytes) {
   FS_REQUIRE(world_ >= 1 && world_ <= kMaxRanks && rank_ >= 0 && rank_ < world_, "bad rank / world (at most 8 ranks)");
   rank = rank_;
@@ -300,11 +338,12 @@ void DistCtx::connect(const void* all_handles) {
     comm.flag_peer[q] = reinterpret_cast<unsigned long long*>((char*)peer_base[q] + kCtlFlagOff);
   }
   connected = true;
+  if (debug_skip() & 4) comm.world = 1;
 }
 
 void DistCtx::push(const DVec& v) {
   const Space& sp = *v.sp;
-  if (world == 1 || sp.n_to == 0) return;
+  if (world == 1 || sp.n_to == 0 || (debug_skip() & 1)) return;
   PushArgs a;
   a.src = v.p;
   a.stride = v.stride;
@@ -330,9 +369,29 @@ void DistCtx::push(const DVec& v) {
   FS_LAUNCH_CHECK();
 }
 
+PushSpec DistCtx::push_spec(const DVec& v) const {
+  PushSpec ps;
+  const Space& sp = *v.sp;
+  if (world == 1 || sp.n_to == 0 || (debug_skip() & 1)) return ps;
+  FS_REQUIRE(v.stride == 1, "fused pushes are for scalar vectors");
+  ps.enabled = 1;
+  ps.channel = v.channel;
+  ps.vec_off = v.off;
+  for (int q = 0; q < world; ++q) ps.peer_base[q] = (char*)peer_base[q];
+  ps.n_to = sp.n_to;
+  for (int k = 0; k < sp.n_to; ++k) ps.to[k] = sp.to[k];
+  if (sp.gather) {
+    ps.gather = 1;
+    ps.row0 = (int)sp.own_lo;
+  } else {
+    ps.smask = sp.smask.p; ps.sbase = sp.sbase.p; ps.uptr = sp.uptr.p; ps.upeer = sp.upeer.p; ps.udst = sp.udst.p;
+  }
+  return ps;
+}
+
 HaloWait DistCtx::wait_of(const DVec* a, const DVec* b) const {
   HaloWait w;
-  if (world == 1) return w;
+  if (world == 1 || (debug_skip() & 2)) return w;
   for (const DVec* v : {a, b}) {
     if (!v || !v->sp || v->sp->n_from == 0) continue;
     const int k = w.nch++;

@@ -73,6 +73,27 @@ struct PushArgs {
   int row0 = 0, n_rows = 0;
 };
 
+// Fused push: the producer kernel of a halo'd vector stores its boundary rows into the neighbours' halo slots
+// itself (no separate push kernel, no launch gap) and the CTA that finishes last releases the channel's flags.
+// The send rows of a space are described per 32-row slice: smask[s] has a bit for every row of the slice that
+// is read by another rank, sbase[s] indexes the slice's first such row in uptr, and uptr / upeer / udst list the
+// (rank, slot) destinations of every send row.
+struct PushSpec {
+  int enabled = 0;
+  int gather = 0;                   // replicated space: row r goes to row row0 + r of every rank in `to`
+  int row0 = 0;
+  int channel = 0;
+  const unsigned* smask = nullptr;
+  const int* sbase = nullptr;
+  const int* uptr = nullptr;
+  const int* upeer = nullptr;
+  const int* udst = nullptr;
+  size_t vec_off = 0;
+  char* peer_base[kMaxRanks] = {nullptr};
+  int n_to = 0;
+  signed char to[kMaxRanks] = {0};
+};
+
 // ---- host side ------------------------------------------------------------------------------------
 // An index space (mesh nodes, or the rows of one AMG level) cut into contiguous blocks, one per rank.
 // Every rank knows the halo lists of ALL ranks (they are derived from replicated global matrices), so
@@ -85,6 +106,8 @@ struct Space {
   DBuf<int> halo_dev;                       // this rank's list on the device (column remap)
   DBuf<int> send_row, send_peer, send_dst;  // own row -> slot send_dst of rank send_peer (sorted by peer, row)
   int n_send = 0;
+  DBuf<unsigned> smask;                     // fused-push plan (see PushSpec), built from the send list
+  DBuf<int> sbase, uptr, upeer, udst;
   int n_to = 0, n_from = 0;
   signed char to[kMaxRanks] = {0}, from[kMaxRanks] = {0};
   bool gather = false;                      // replicated space: vectors are full length, global numbering,
@@ -121,6 +144,7 @@ struct DistCtx {
   DVec carve(const Space& sp, int stride);
   void connect(const void* all_handles);    // world x 64-byte IPC handles (own entry ignored)
   void push(const DVec& v);                 // k_halo_push: own boundary rows -> the neighbours' halo slots + flags
+  PushSpec push_spec(const DVec& v) const;  // the same exchange, performed by the kernel that produces v (stride 1)
   void wait(const DVec& v);                 // stand-alone wait kernel (for consumers without a built-in wait)
   HaloWait wait_of(const DVec* a, const DVec* b = nullptr) const;
   void check(const char* where);            // throws FS_ERR_INTERNAL if a wait has timed out (synchronises)
@@ -162,8 +186,11 @@ void amg_part_finalize(Amg* amg, const Space& space0, DistCtx& ctx);
 // one V-cycle z = M^-1 r on this rank's rows; r is an arena vector whose halo has been pushed
 int amg_apply_dist(Amg* amg, const DVec& r, double* z, double* rz_part);
 
+// mark the slices of S (built from the local CSR `loc`) that read halo entries: columns in [n_own_a, nsplit) of the
+// first vector, or >= nsplit + n_own_b of the second (n_own_b < 0: the second vector has no halo part)
+void sell_mark_boundary(fs_sell& S, const fs_csr& loc, int n_own_a, int nsplit, int n_own_b);
 int spmv_sell_dist(const fs_sell& S, const double* x, double* y, const double* x2, double* dot_partials, const Comm& c,
-                   const HaloWait& w);
+                   const HaloWait& w, const PushSpec* push = nullptr);
 void spmv_sell2_dist(const fs_sell& S, const double* x, double* y, double* dot_partials, const int* done, const Comm& c,
                      const HaloWait& w);
 
@@ -276,6 +303,47 @@ __device__ __forceinline__ void rank_allreduce(const Comm& c, double (&v)[K], un
 #pragma unroll
   for (int k = 0; k < K; ++k) v[k] = s_sum[k];
   __syncthreads();
+}
+
+// ---- fused push (PushSpec) ----
+// the thread that has just produced row `row` of the vector; returns true if anything was stored remotely
+__device__ __forceinline__ bool push_row(const PushSpec& ps, int row, double v) {
+  if (ps.gather) {
+    for (int j = 0; j < ps.n_to; ++j)
+      dist_st_sys_f64(reinterpret_cast<double*>(ps.peer_base[ps.to[j]] + ps.vec_off) + (ps.row0 + row), v);
+    return ps.n_to > 0;
+  }
+  const int s = row >> 5, l = row & 31;
+  const unsigned m = __ldg(ps.smask + s);
+  if (!((m >> l) & 1u)) return false;
+  const int idx = __ldg(ps.sbase + s) + __popc(m & ((1u << l) - 1u));
+  for (int k = __ldg(ps.uptr + idx); k < __ldg(ps.uptr + idx + 1); ++k)
+    dist_st_sys_f64(reinterpret_cast<double*>(ps.peer_base[__ldg(ps.upeer + k)] + ps.vec_off) + __ldg(ps.udst + k), v);
+  return true;
+}
+// End of a producer kernel WITHOUT a reduction: every CTA calls it (all threads); the CTA that arrives last
+// releases the flags with the current sequence number.
+__device__ __forceinline__ void push_finish(const Comm& c, const PushSpec& ps, bool pushed, unsigned long long stamp) {
+  if (pushed) __threadfence_system();
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned prev = atomicAdd(c.done_ctr + 8 + ps.channel, 1u);
+    s_last = (prev == gridDim.x - 1);
+    if (s_last) c.done_ctr[8 + ps.channel] = 0;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x < ps.n_to) {
+    __threadfence_system();
+    dist_st_release_sys(c.flag_peer[ps.to[threadIdx.x]] + (size_t)ps.channel * kMaxRanks + c.rank, stamp);
+  }
+}
+// the same for a kernel that already knows it is the last block (reducing kernels: after dist_seq_bump)
+__device__ __forceinline__ void push_release(const Comm& c, const PushSpec& ps, unsigned long long stamp) {
+  __threadfence_system();
+  for (int j = 0; j < ps.n_to; ++j)
+    dist_st_release_sys(c.flag_peer[ps.to[j]] + (size_t)ps.channel * kMaxRanks + c.rank, stamp);
 }
 
 // Called by every CTA at the END of a reducing kernel: true in exactly one thread (thread 0 of the CTA that

@@ -278,6 +278,11 @@ struct fs_sell {
   DBuf<int> cols;
   DBuf<float> v32;        // exactly one of v32 / v64 is filled
   DBuf<double> v64;
+  // partitioned step: slices that read halo entries of their input vectors (bit per slice + list); the DIST kernel
+  // does all other slices first and waits for the neighbours' halo flags only before these
+  DBuf<unsigned> bmask;
+  DBuf<int> blist;
+  int n_blist = 0;
 };
 void sell_build(const fs_csr& A, bool f32, fs_sell& out, int nsplit = -1);
 int spmv_sell(const fs_sell& S, const double* x, double* y, const double* x2, double* dot_partials);

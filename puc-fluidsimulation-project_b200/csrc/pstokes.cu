@@ -109,7 +109,7 @@ k_ppcg_init(const double* __restrict__ partRZ, int nrz, const double* __restrict
 __global__ void __launch_bounds__(kBlock)
 k_ppcg_xr(int64_t n, const double* __restrict__ p, const double* __restrict__ Ap, double* __restrict__ x, double* __restrict__ r,
           const double* __restrict__ partA, int nblkA, const double* __restrict__ sc, int slot, const int* __restrict__ flags,
-          double* __restrict__ partB, Comm c) {
+          double* __restrict__ partB, Comm c, PushSpec ps) {
   __shared__ double red[32];
   __shared__ double sm[1];
   if (block_done(flags)) return;
@@ -120,22 +120,29 @@ k_ppcg_xr(int64_t n, const double* __restrict__ p, const double* __restrict__ Ap
   const double rz = sc[slot];
   const double alpha = (pAp[0] != 0.0) ? rz / pAp[0] : 0.0;
   double acc[1] = {0.0};
+  bool pushed = false;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const double rn = r[i] - alpha * Ap[i];
     x[i] += alpha * p[i];
     r[i] = rn;
     acc[0] += rn * rn;
+    if (ps.enabled) pushed |= push_row(ps, (int)i, rn);      // the new residual's boundary rows go to the neighbours now
   }
   block_reduce<1>(acc, red);
   if (threadIdx.x == 0) partB[blockIdx.x] = acc[0];
-  if (dist_last_block(c, 0)) dist_seq_bump(c);
+  if (pushed) __threadfence_system();
+  if (dist_last_block(c, 0)) {
+    dist_seq_bump(c);
+    if (ps.enabled) push_release(c, ps, seq + 1);
+  }
 }
 
 // convergence test, beta, p = z + beta p.  Every CTA takes the same decision from the all-reduced sums; the
 // CTA that finishes last publishes the scalars (so the flag cannot change under a CTA of the same launch).
 __global__ void __launch_bounds__(kBlock)
 k_ppcg_p(int64_t n, const double* __restrict__ z, double* __restrict__ p, const double* __restrict__ partB, int nB,
-         const double* __restrict__ partRZ, int nRZ, double* __restrict__ sc, int slot, int* __restrict__ flags, Comm c) {
+         const double* __restrict__ partRZ, int nRZ, double* __restrict__ sc, int slot, int* __restrict__ flags, Comm c,
+         PushSpec ps) {
   __shared__ double sm[1];
   if (block_done(flags)) return;
   double v[2], t[1];
@@ -147,17 +154,23 @@ k_ppcg_p(int64_t n, const double* __restrict__ z, double* __restrict__ p, const 
   rank_allreduce<2>(c, v, seq + 1);
   const double rz_old = sc[slot];
   const bool conv = v[0] <= sc[4] * sc[2];
+  bool pushed = false;
   if (!conv) {
     const double beta = rz_old != 0.0 ? v[1] / rz_old : 0.0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-      p[i] = z[i] + beta * p[i];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      const double pn = z[i] + beta * p[i];
+      p[i] = pn;
+      if (ps.enabled) pushed |= push_row(ps, (int)i, pn);
+    }
   }
+  if (pushed) __threadfence_system();
   if (dist_last_block(c, 1)) {
     sc[slot ^ 1] = v[1];
     sc[3] = v[0];
     flags[1] += 1;
     if (conv) flags[0] = 1;
     dist_seq_bump(c);
+    if (ps.enabled && !conv) push_release(c, ps, seq + 1);
   }
 }
 
@@ -307,6 +320,10 @@ __global__ void k_expand_l(int64_t n, const int* __restrict__ ldof, const double
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) p[i] = q[ldof[i]];
 }
+__global__ void k_fill_pattern(int64_t n, int64_t g0, double* __restrict__ v) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) v[i] = (double)((g0 + i) % 13) - 6.0 + 0.25 * (double)((g0 + i) % 5);
+}
 __global__ void k_flag_l(const int* __restrict__ idx, int64_t n, unsigned char* __restrict__ flag) {
   const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (k < n) flag[idx[k]] = 1;
@@ -406,14 +423,14 @@ static int ppcg_amg(fs_pstokes* s, const double* b_in, DVec& X, double rtol, int
     ctx.push(s->P);
     const int unchecked = std::max(0, std::min(std::min(s->hint, s->hint_prev) - 3, maxit));
     int queued = 0, hflags[2] = {0, 0};
+    const PushSpec psR = ctx.push_spec(s->R), psP = ctx.push_spec(s->P);
+    const HaloWait wP = ctx.wait_of(&s->P);
     while (queued < maxit) {
       const int slot = queued & 1;
-      const int ga = spmv_sell_dist(s->k_red, p, Ap, nullptr, partA, cm, ctx.wait_of(&s->P));
-      k_ppcg_xr<<<g, kBlock, 0, st>>>(n, p, Ap, X.p, r, partA, ga, sc, slot, flags, partB, cm); FS_LAUNCH_CHECK();
-      ctx.push(s->R);
+      const int ga = spmv_sell_dist(s->k_red, p, Ap, nullptr, partA, cm, wP);
+      k_ppcg_xr<<<g, kBlock, 0, st>>>(n, p, Ap, X.p, r, partA, ga, sc, slot, flags, partB, cm, psR); FS_LAUNCH_CHECK();
       nrz = amg_apply_dist(s->amg, s->R, z, partRZ);
-      k_ppcg_p<<<g, kBlock, 0, st>>>(n, z, p, partB, g, partRZ, nrz, sc, slot, flags, cm); FS_LAUNCH_CHECK();
-      ctx.push(s->P);
+      k_ppcg_p<<<g, kBlock, 0, st>>>(n, z, p, partB, g, partRZ, nrz, sc, slot, flags, cm, psP); FS_LAUNCH_CHECK();
       ++queued;
       if (queued > unchecked) {
         FS_CUDA(cudaMemcpyAsync(hflags, flags, sizeof(hflags), cudaMemcpyDeviceToHost, st));
@@ -691,6 +708,7 @@ int fs_pstokes_create(fs_stokes* glob, fs_mesh* lmesh, int rank, int world, cons
     fs_csr loc;
     extract_rows(gk->view(), dsplit[rank], dsplit[rank + 1], s->dofs, nd, nullptr, loc);
     sell_build(loc, false, s->k_red);
+    sell_mark_boundary(s->k_red, loc, (int)s->dofs.n_own, 0x7fffffff, -1);
   }
   // ---- local node -> local dof (own dofs first, then the dof halo list)
   {
@@ -793,6 +811,39 @@ int fs_pstokes_step(fs_pstokes* s, double* u_own, double B1, double B2, const fs
   fs::sync();
   ctx.check("fs_pstokes_step");
   if (stats) *stats = sts;
+  FS_API_END
+}
+
+// Profiling aid: `iters` PCG iterations on the right-hand side of the last pressure solve (x0 = 0, no convergence
+// test), timed with a CUDA event pair on the library stream.  Collective.
+int fs_pstokes_profile_pcg(fs_pstokes* s, int iters, double* us_per_iter) {
+  FS_API_BEGIN
+  FS_REQUIRE(s && us_per_iter && iters > 0, "bad arguments");
+  cudaStream_t st = stream();
+  cudaEvent_t e0, e1;
+  FS_CUDA(cudaEventCreate(&e0));
+  FS_CUDA(cudaEventCreate(&e1));
+  const int hint = s->hint, hint_prev = s->hint_prev;
+  k_fill_pattern<<<div_up(s->dofs.n_own, 256), 256, 0, st>>>(s->dofs.n_own, s->dofs.own_lo, s->rhs.p);   // synthetic right-hand side
+  FS_LAUNCH_CHECK();
+  for (int pass = 0; pass < 3; ++pass) {       // passes 0, 1 warm up (graph capture), pass 2 is timed
+    FS_CUDA(cudaMemsetAsync(s->QTRY.p, 0, s->dofs.n_own * sizeof(double), st));
+    barrier_dev(s);
+    s->hint = s->hint_prev = iters + 3;
+    FS_CUDA(cudaEventRecord(e0, st));
+    double rr = 0.0;
+    ppcg_amg(s, s->rhs.p, s->QTRY, 0.0, iters, &rr);
+    FS_CUDA(cudaEventRecord(e1, st));
+    FS_CUDA(cudaEventSynchronize(e1));
+  }
+  float ms = 0.f;
+  FS_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  *us_per_iter = 1e3 * ms / iters;
+  s->hint = hint; s->hint_prev = hint_prev;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  barrier_dev(s);
+  fs::sync();
   FS_API_END
 }
 

@@ -129,22 +129,41 @@ __device__ __forceinline__ double sell_part4(const float* __restrict__ vp, const
 // DIST (partitioned step, pstokes.cu): x / x2 are [own | halo] vectors whose halo entries are written by the
 // neighbouring ranks; the kernel returns at once when the running solve has converged and otherwise
 // waits for the halo flags of its input channels before the first gather (dist.cuh).
+// Two passes: the slices that read no halo entry first, then -- after the neighbours' flags have arrived -- the few
+// that do, so the transfer latency hides behind the interior work.  With a PushSpec the kernel also stores the
+// rows other ranks read into their halo slots as it produces them, and its last CTA releases the channel's flags.
 struct DistSell {
   Comm c;
   HaloWait w;
+  PushSpec ps;
+  const unsigned* bmask = nullptr;
+  const int* blist = nullptr;
+  int n_blist = 0;
 };
 
 template <bool SPLIT, bool DOT, bool F32, bool DIST>
-__global__ void __launch_bounds__(kST, (SPLIT && F32 && DOT) ? 8 : 6) k_spmv_sell(SellArgs a, DistSell d) {
+__global__ void __launch_bounds__(kST, (SPLIT && F32 && DOT && !DIST) ? 8 : 6) k_spmv_sell(SellArgs a, DistSell d) {
   __shared__ double red[kSW];
   if (DIST) {
     if (d.c.done && *d.c.done) return;
-    halo_wait(d.c, d.w);
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nwarps = gridDim.x * kSW;
   double dacc = 0.0;
-  for (int s = blockIdx.x * kSW + warp; s < a.nslices; s += nwarps) {
+  bool pushed = false;
+  const int npass = (DIST && d.n_blist > 0) ? 2 : 1;
+  for (int pass = 0; pass < npass; ++pass) {
+  if (DIST && pass == 1) {
+    if (blockIdx.x * kSW >= d.n_blist) break;      // none of this CTA's warps has a boundary slice
+    halo_wait(d.c, d.w);
+  }
+  const int count = (DIST && pass == 1) ? d.n_blist : a.nslices;
+  for (int si = blockIdx.x * kSW + warp; si < count; si += nwarps) {
+    int s = si;
+    if (DIST && npass == 2) {
+      if (pass == 0) { if ((__ldg(d.bmask + (si >> 5)) >> (si & 31)) & 1u) continue; }
+      else s = __ldg(d.blist + si);
+    }
     const long long off = __ldg(a.sptr + s);
     const int W = (int)((__ldg(a.sptr + s + 1) - off) >> 5);
     const int Wg = SPLIT ? __ldg(a.wg + s) : W;
@@ -168,7 +187,9 @@ __global__ void __launch_bounds__(kST, (SPLIT && F32 && DOT) ? 8 : 6) k_spmv_sel
     if (row < a.n) {
       a.y[row] = acc;
       if (DOT) dacc += __ldg(a.x + row) * acc;
+      if (DIST && d.ps.enabled) pushed |= push_row(d.ps, row, acc);
     }
+  }
   }
   if (DOT) {
     for (int o = 16; o > 0; o >>= 1) dacc += __shfl_xor_sync(0xffffffffu, dacc, o);
@@ -180,6 +201,7 @@ __global__ void __launch_bounds__(kST, (SPLIT && F32 && DOT) ? 8 : 6) k_spmv_sel
       a.part[blockIdx.x] = sum;
     }
   }
+  if (DIST && d.ps.enabled) push_finish(d.c, d.ps, pushed, dist_seq(d.c));
 }
 
 // two interleaved right-hand sides (x, y are (n,2) row-major), fp64 values: the viscous 2-RHS CG
@@ -336,12 +358,13 @@ static void launch_sell(const SellArgs& args, int grid, const DistSell* d) {
 // y = S x, or S [x; x2] for a matrix built in split form.  Returns the grid (= number of dot
 // partials when asked for), 0 if S is empty.
 static int spmv_sell_impl(const fs_sell& S, const double* x, double* y, const double* x2, double* dot_partials,
-                          const DistSell* d) {
+                          DistSell* d) {
   if (!S.nslices) return 0;
   FS_REQUIRE((S.nsplit >= 0) == (x2 != nullptr), "spmv_sell: split form and second vector must come together");
-  const int per_sm = (x2 && S.v32.p && dot_partials) ? 8 : 6;   // the finest up-sweep runs at 32 registers
+  const int per_sm = (x2 && S.v32.p && dot_partials && !d) ? 8 : 6;   // the finest up-sweep runs at 32 registers
   const int grid = std::max(1, std::min(div_up(S.nslices, kSW), sm_count() * per_sm));
   SellArgs args{S.n, S.nslices, S.sptr.p, S.wg.p, S.cols.p, S.v32.p, S.v64.p, x, x2, y, dot_partials};
+  if (d && d->w.nch && S.n_blist > 0) { d->bmask = S.bmask.p; d->blist = S.blist.p; d->n_blist = S.n_blist; }
   if (x2) {
     if (dot_partials) launch_sell<true, true>(args, grid, d);
     else launch_sell<true, false>(args, grid, d);
@@ -358,9 +381,41 @@ int spmv_sell(const fs_sell& S, const double* x, double* y, const double* x2, do
 }
 
 int spmv_sell_dist(const fs_sell& S, const double* x, double* y, const double* x2, double* dot_partials, const Comm& c,
-                   const HaloWait& w) {
-  DistSell d{c, w};
+                   const HaloWait& w, const PushSpec* push) {
+  DistSell d;
+  d.c = c;
+  d.w = w;
+  if (push) d.ps = *push;
   return spmv_sell_impl(S, x, y, x2, dot_partials, &d);
+}
+
+// ---- boundary slices ---------------------------------------------------------------------------
+__global__ void k_mark_boundary(CsrView A, int n_own_a, int nsplit, int n_own_b, unsigned* __restrict__ bmask) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= A.n) return;
+  bool halo = false;
+  for (int k = A.rowptr[row]; k < A.rowptr[row + 1]; ++k) {
+    const int c = A.colidx[k];
+    if (c < nsplit) halo |= (c >= n_own_a);
+    else halo |= (n_own_b >= 0 && c - nsplit >= n_own_b);
+  }
+  if (halo) atomicOr(bmask + (row >> 10), 1u << ((row >> 5) & 31));
+}
+
+void sell_mark_boundary(fs_sell& S, const fs_csr& loc, int n_own_a, int nsplit, int n_own_b) {
+  const int nsl = S.nslices;
+  if (!nsl) return;
+  const int nw = div_up(nsl, 32);
+  S.bmask.alloc(nw);
+  S.bmask.zero();
+  k_mark_boundary<<<div_up(loc.n, 256), 256, 0, stream()>>>(loc.view(), n_own_a, nsplit, n_own_b, S.bmask.p);
+  FS_LAUNCH_CHECK();
+  std::vector<unsigned> h = S.bmask.to_host();
+  std::vector<int> list;
+  for (int s = 0; s < nsl; ++s) if ((h[s >> 5] >> (s & 31)) & 1u) list.push_back(s);
+  S.n_blist = (int)list.size();
+  if (S.n_blist) { S.blist.alloc(list.size()); S.blist.upload(list.data(), list.size()); }
+  FS_CUDA(cudaStreamSynchronize(stream()));
 }
 
 int spmv_sell_grid(const fs_sell& S) { return std::max(1, std::min(div_up(S.nslices, kSW), sm_count() * 4)); }
@@ -381,7 +436,9 @@ void spmv_sell2_dist(const fs_sell& S, const double* x, double* y, double* dot_p
   FS_REQUIRE(S.nslices && S.v64.p && S.nsplit < 0, "spmv_sell2: needs a one-part fp64 SELL matrix");
   const int grid = spmv_sell_grid(S);
   SellArgs args{S.n, S.nslices, S.sptr.p, nullptr, S.cols.p, nullptr, S.v64.p, x, nullptr, y, dot_partials};
-  DistSell d{c, w};
+  DistSell d;
+  d.c = c;
+  d.w = w;
   if (dot_partials) k_spmv_sell2<true, true><<<grid, kST, 0, stream()>>>(args, done, d);
   else k_spmv_sell2<false, true><<<grid, kST, 0, stream()>>>(args, done, d);
   FS_LAUNCH_CHECK();

@@ -101,6 +101,12 @@ class PartitionedStokes:
             raise ValueError("state size mismatch")
         call("fs_pstokes_state", self._h, ptr(q), 1)
 
+    def profile_pcg(self, iters=40):
+        """µs per AMG-PCG iteration on the last pressure right-hand side (fixed iteration count; collective)."""
+        us = C.c_double(0)
+        call("fs_pstokes_profile_pcg", self._h, int(iters), C.byref(us))
+        return us.value
+
     def gather(self, x_own):
         """All ranks' blocks of a nodal array, concatenated (host; for checks and output)."""
         x_own = np.ascontiguousarray(x_own.cpu().numpy() if _lib._is_torch(x_own) else x_own)

@@ -10,7 +10,6 @@ GPU with the single-GPU kernel and compares (small meshes).
 """
 import argparse, ctypes as C, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ["NCCL_DEBUG"] = "WARN"
 import numpy as np, torch
 import fluidsim_b200 as fb
 from fluidsim_b200 import _lib, parallel as par

@@ -21,6 +21,7 @@ ap.add_argument("--warmup", type=int, default=0)
 ap.add_argument("--gather-rows", type=int, default=100000)
 ap.add_argument("--rtol", type=float, default=1e-10)
 ap.add_argument("--check", action="store_true")
+ap.add_argument("--profile-pcg", type=int, default=0, help="also time this many PCG iterations at a fixed count")
 args = ap.parse_args()
 
 rank, world, local, dist = par.init_distributed()
@@ -51,6 +52,9 @@ out = {"n_gpus": world, "n_theta": args.n_theta, "n_r": args.n_r, "triangles": i
        "ms_per_step": 1e3 * tmax / max(args.steps, 1), "cg_iters_per_step": iters, "setup_s": t_setup,
        "levels_partitioned": ps.levels_partitioned, "n_own": ps.n_own, "n_halo_nodes": ps.n_halo_nodes,
        "n_own_dofs": ps.n_own_dofs, "n_halo_dofs": ps.n_halo_dofs, "launches_per_step": (fb.launch_count() - l0) / max(args.steps, 1)}
+if args.profile_pcg:
+    out["us_per_pcg_iteration_fixed"] = ps.profile_pcg(args.profile_pcg)
+    out["debug_skip"] = os.environ.get("FS_DIST_DEBUG_SKIP", "0")
 if args.check:
     ug = ps.gather(u)
     pg = ps.gather(ps.pressure()[0])

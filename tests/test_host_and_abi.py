@@ -2,6 +2,7 @@
 sets, synthetic mesh, CSR row surgery) and the C-ABI surface.  No compute call is made:
 without a GPU every compute entry point must fail loudly (there is no CPU fallback)."""
 import ctypes
+import ctypes as C
 import os
 import re
 
@@ -11,6 +12,7 @@ import pytest
 import fluidsim_b200 as fb
 from fluidsim_b200 import _lib
 from conftest import ROOT, load_golden, MESHES
+from oracle import restated as R
 
 
 def test_every_declared_symbol_is_exported():
@@ -273,3 +275,99 @@ def test_meshgen_two_holes_internal_segment_and_sharp_corner():
                                    min_angle=30.0, max_area=2e-3)
     area2, ang = _quality(P, T)
     assert (ang < 30.0 - 1e-9).sum() == 1 and abs(ang.min() - 20.0) < 1e-9 and abs(0.5 * area2.sum() - 0.5 * np.sin(a)) < 1e-12
+
+
+# ---- round 2: host-side partition helpers, keep-alive pointers, CPU reference arm ---------------------
+def test_ptr_keeps_converted_temporaries_alive():
+    """ptr(as_f64(x)) must hold the converted copy until the call has returned."""
+    import gc
+    from fluidsim_b200 import _lib
+    x = np.arange(12, dtype=np.float32).reshape(6, 2)[::2]          # needs a copy: wrong dtype, strided
+    p = _lib.ptr(_lib.as_f64(x))
+    gc.collect()
+    assert p._keep is not None and p._keep.dtype == np.float64 and p._keep.flags["C_CONTIGUOUS"]
+    assert p.value == p._keep.ctypes.data
+    got = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(6,))
+    assert np.array_equal(got, np.asarray(x, dtype=np.float64).ravel())
+
+
+def test_sub_mesh_local_numbering_and_sums():
+    """The sub-mesh of a node block reproduces the whole-mesh nodal sums on its owned nodes bit for bit
+    (same elements, same order) and numbers own nodes first, halo nodes in ascending global id."""
+    nodes, markers, tris = fb.square_with_hole(64, 24)
+    N = len(nodes)
+    split = fb.node_block_split(N, 3, align=64)
+    assert split[0] == 0 and split[-1] == N and all(b % 64 == 0 for b in split[:-1])
+    u = np.random.default_rng(5).standard_normal((N, 2))
+    div_g = R.divergence(nodes, tris, u)
+    mass_g = R.lumped_mass(nodes, tris)
+    seen = np.zeros(len(tris), dtype=int)
+    for r in range(3):
+        lo, hi = split[r], split[r + 1]
+        ln, lm, lt, l2g, eids = fb.sub_mesh(nodes, markers, tris, lo, hi)
+        n_own = hi - lo
+        assert np.array_equal(l2g[:n_own], np.arange(lo, hi)) and np.all(np.diff(l2g[n_own:]) > 0)
+        assert np.array_equal(l2g[lt], tris[eids]) and np.array_equal(ln, nodes[l2g]) and np.array_equal(lm, markers[l2g])
+        assert np.all(np.diff(eids) > 0)
+        seen[eids] += 1
+        assert np.array_equal(R.divergence(ln, lt, u[l2g])[:n_own], div_g[lo:hi])
+        assert np.array_equal(R.lumped_mass(ln, lt)[:n_own], mass_g[lo:hi])
+    assert seen.min() >= 1                                          # every element belongs to at least one block
+
+
+def test_local_index_sets_and_cut_pairs():
+    nodes, markers, tris = fb.square_with_hole(64, 24)
+    pairs = fb.filter_wall_pairs(nodes, fb.find_boundary_pairs(nodes))
+    wall, inner, _, interior = fb.index_sets(nodes, markers)
+    N = len(nodes)
+    split = fb.node_block_split(N, 2, align=64)
+    tot = 0
+    for r in range(2):
+        lo, hi = split[r], split[r + 1]
+        w, i, it, pr = fb.local_index_sets(lo, hi, wall, inner, interior, pairs)
+        assert np.array_equal(w + lo, wall[(wall >= lo) & (wall < hi)])
+        assert np.array_equal(i + lo, inner[(inner >= lo) & (inner < hi)])
+        tot += len(pr)
+        for m, s in pr:
+            assert (m + lo, s + lo) in pairs
+    assert tot == len(pairs)                                        # all pairs sit on the outer ring: one block has them all
+    a, b = pairs[0]
+    cut = (min(a, b) + max(a, b)) // 2 + 1                          # a block boundary between the two nodes of a pair
+    with pytest.raises(ValueError):
+        fb.local_index_sets(0, cut, wall, inner, interior, pairs)
+
+
+def test_cpu_step_matches_restated_oracle():
+    """oracle/cpu_step.py (the CPU arm of bench.py): sparse div/grad operators and both pressure solvers against
+    the restated oracle's direct solves."""
+    from oracle import cpu_step
+    nodes, markers, tris = fb.square_with_hole(128, 32)
+    Dx, Dy = cpu_step.grad_operators(nodes, tris)
+    u = np.random.default_rng(0).standard_normal((len(nodes), 2))
+    d0 = R.divergence(nodes, tris, u)
+    assert np.abs(d0 - (Dx @ u[:, 0] + Dy @ u[:, 1])).max() <= 1e-13 * np.abs(d0).max()
+    gx, gy = R.gradient(nodes, tris, u[:, 0])
+    assert np.abs(gx - Dx @ u[:, 0]).max() <= 1e-13 * np.abs(gx).max() and np.abs(gy - Dy @ u[:, 0]).max() <= 1e-13 * np.abs(gy).max()
+    ref = R.RestatedStokes(nodes, markers, tris, B1=-2.0, B2=-5.0)
+    sims = {p: cpu_step.CpuStokes(nodes, markers, tris, B1=-2.0, B2=-5.0, precond=p) for p in ("amg", "jacobi")}
+    for _ in range(4):
+        ref.flow_step()
+        for p, s in sims.items():
+            it = s.step()
+            assert np.linalg.norm(s.u - ref.u) <= 1e-9 * np.linalg.norm(ref.u), p
+            assert np.linalg.norm(s.p - ref.p) <= 1e-7 * np.linalg.norm(ref.p), p
+    assert sims["amg"].iters[1] < 60 < sims["jacobi"].iters[1]
+
+
+def test_bench_reference_arm_runs_without_the_product():
+    import json, subprocess, sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--n-theta", "128", "--n-r", "32",
+                        "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, OMP_NUM_THREADS="1"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    out = json.loads(lines[0])
+    assert out["impl"] == "reference" and out["product_loaded"] is False and out["gpu_launches"] == 0
+    assert out["steps"] == 2 and out["cpu_baseline"]["kind"] == "port" and out["cpu_baseline"]["cores"] >= 1
+    assert out["value"] > 0 and out["e2e"]["h2d_bytes_per_step"] == 0 and "cpu_baseline_jacobi" in out

@@ -75,6 +75,36 @@ def _worker(rank, world, port, q):
     assert np.array_equal(yl, yg[lo:hi]) or np.abs(yl - yg[lo:hi]).max() < 1e-12 * np.abs(yg).max()
     # dot product by allreduce
     assert abs(par.allreduce(float(yl @ xl[:hi - lo]), "sum", d) - float(yg @ x)) < 1e-9 * abs(float(yg @ x))
+    # --- partitioned Stokes step, host logic: node blocks, sub-meshes, local index sets; the nodal operator
+    # evaluated block by block (oracle arithmetic on the sub-mesh, halo velocities taken from the owner)
+    # reproduces the whole-mesh result bit for bit
+    from fluidsim_b200 import node_block_split, sub_mesh, local_index_sets, index_sets
+    N = len(nodes)
+    split = node_block_split(N, world, align=64)
+    lo, hi = split[rank], split[rank + 1]
+    ln, lm, lt, l2g, eids = sub_mesh(nodes, markers, tris, lo, hi)
+    wall, inner, _, interior = index_sets(nodes, markers)
+    lw, li, lint, lpairs = local_index_sets(lo, hi, wall, inner, interior, pairs)
+    u_full = np.random.default_rng(7).standard_normal((N, 2))               # same on both ranks
+    u_loc = np.zeros((len(l2g), 2))
+    u_loc[:hi - lo] = u_full[lo:hi]
+    need = [None] * world
+    dist.all_gather_object(need, l2g[hi - lo:])                             # halo node ids of every rank
+    answers = [None] * world
+    mine = {peer: u_full[ids[(ids >= lo) & (ids < hi)]] for peer, ids in enumerate(need) if peer != rank}
+    dist.all_gather_object(answers, mine)
+    halo = l2g[hi - lo:]
+    for peer in range(world):
+        if peer == rank:
+            continue
+        sel = (halo >= split[peer]) & (halo < split[peer + 1])
+        u_loc[(hi - lo) + np.nonzero(sel)[0]] = answers[peer][rank]
+    div_blocks = [None] * world
+    dist.all_gather_object(div_blocks, R.divergence(ln, lt, u_loc)[:hi - lo])
+    assert np.array_equal(np.concatenate(div_blocks), R.divergence(nodes, tris, u_full))
+    counts = [None] * world
+    dist.all_gather_object(counts, (len(lw), len(li), len(lint), len(lpairs)))
+    assert tuple(np.sum(counts, axis=0)) == (len(wall), len(inner), len(interior), len(pairs))
     dist.barrier()
     dist.destroy_process_group()
     q.put((rank, "ok"))
