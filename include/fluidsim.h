@@ -251,6 +251,9 @@ int fs_pstokes_pressure(fs_pstokes* s, double* p_own /* n_own or NULL */, double
 /* profiling aid: `iters` PCG iterations (no convergence test) on the last pressure right-hand side, timed with
  * CUDA events; collective */
 int fs_pstokes_profile_pcg(fs_pstokes* s, int iters, double* us_per_iter);
+/* FS_DIST_TRACE=1 (environment, read at creation): CTA 0 of the partitioned kernels logs {tag, %globaltimer ns} events;
+ * this copies them out (pairs of uint64) and resets the log */
+int fs_pstokes_trace(fs_pstokes* s, uint64_t* out /* 2*cap */, int64_t cap, int64_t* n);
 int fs_pstokes_state(fs_pstokes* s, double* buf, int set);
 
 /* ---- tracers and dye.

@@ -27,6 +27,7 @@
 namespace fs {
 
 struct AmgLevel {
+  int part_nsplit = 0;      // partitioned cycle: width of the [own | halo] right-hand side this rank's rows of U refer to
   fs_csr A;                 // operator of this level (level 0 borrows the fine matrix)
   const fs_csr* Aref = nullptr;
   int n = 0;
@@ -929,6 +930,18 @@ void amg_part_finalize(Amg* amg, const Space& space0, DistCtx& ctx) {
     M.vals.release(); M.vals32.release(); M.colidx_own.release(); M.rowptr_own.release();
     M.rowptr = M.colidx = nullptr; M.nnz = 0;
   };
+  // Operators with at most sub_rows local rows stay in CSR form for the lanes-per-row kernel (these levels are latency
+  // bound: one wave of short chains; their halo exchange runs as separate push / wait kernels), the large ones become
+  // SELL-32 with the exchange fused into the kernel (spmv_sell.cu).
+  auto keep_csr = [&](fs_csr& dst, fs_csr& src) {
+    dst.n = src.n; dst.nnz = src.nnz;
+    dst.rowptr_own = std::move(src.rowptr_own); dst.colidx_own = std::move(src.colidx_own);
+    dst.rowptr = dst.rowptr_own.p; dst.colidx = dst.colidx_own.p;
+    dst.vals32.alloc(std::max<int64_t>(dst.nnz, 1));
+    if (dst.nnz) { k_to_f32<<<div_up(dst.nnz, 256), 256, 0, stream()>>>(src.vals.p, dst.nnz, dst.vals32.p); FS_LAUNCH_CHECK(); }
+    FS_CUDA(cudaStreamSynchronize(stream()));
+    ensure_tiles(&dst);
+  };
   for (int l = 0; l < Lp; ++l) {
     AmgLevel& lv = *amg->L[l];
     const Space& sl = (l == 0) ? space0 : *P.space[l];
@@ -936,21 +949,29 @@ void amg_part_finalize(Amg* amg, const Space& space0, DistCtx& ctx) {
     {
       fs_csr loc;
       extract_rows(lv.U.view(), P.split[l][rank], P.split[l][rank + 1], sl, lv.n, sn, loc);
+      drop(lv.U);
       const int nsplit = (int)(sl.n_own + sl.n_halo);
-      sell_build(loc, amg->part_f32, lv.Us, nsplit);
-      sell_mark_boundary(lv.Us, loc, (int)sl.n_own, nsplit, sn->gather ? -1 : (int)sn->n_own);
+      if (l >= 1 && loc.n <= amg->sub_rows) keep_csr(lv.U, loc);
+      else {
+        sell_build(loc, amg->part_f32, lv.Us, nsplit);
+        sell_mark_boundary(lv.Us, loc, (int)sl.n_own, nsplit, sn->gather ? -1 : (int)sn->n_own, l >= 1 ? &sl : nullptr);
+      }
+      lv.part_nsplit = nsplit;
     }
     {
       fs_csr loc;
       const int64_t r0 = P.split[l + 1][rank], r1 = P.split[l + 1][rank + 1];
-      if (r1 > r0) {
-        extract_rows(lv.Rt.view(), r0, r1, sl, lv.n, nullptr, loc);
-        sell_build(loc, amg->part_f32, lv.Rts);
-        sell_mark_boundary(lv.Rts, loc, (int)sl.n_own, 0x7fffffff, -1);
+      const bool have = r1 > r0;
+      if (have) extract_rows(lv.Rt.view(), r0, r1, sl, lv.n, nullptr, loc);
+      drop(lv.Rt);
+      if (have) {
+        if (loc.n <= amg->sub_rows) keep_csr(lv.Rt, loc);
+        else {
+          sell_build(loc, amg->part_f32, lv.Rts);
+          sell_mark_boundary(lv.Rts, loc, (int)sl.n_own, 0x7fffffff, -1, sn);
+        }
       }
     }
-    drop(lv.U);
-    drop(lv.Rt);
   }
   // level 0 borrowed the caller's global fine matrix: nothing in the folded cycle reads it again
   amg->L[0]->Aref = nullptr;
@@ -980,17 +1001,28 @@ static int vcycle_folded_dist(Amg& amg, int l, const DVec& bv, double* x, double
   const DVec& nb = P.vb[l + 1];
   // the restriction stores the rows of b_{l+1} that other ranks read (all of them for the replicated level) into
   // their copies itself; a rank without coarse rows has nothing to compute or to send
+  double* y = next_part ? nb.p : nb.p + P.split[l + 1][P.rank];
   if (lv.Rts.nslices) {
-    double* y = next_part ? nb.p : nb.p + P.split[l + 1][P.rank];
     const PushSpec ps = ctx.push_spec(nb);
-    spmv_sell_dist(lv.Rts, bv.p, y, nullptr, nullptr, ctx.comm, ctx.wait_of(&bv), &ps);
+    spmv_sell_dist(lv.Rts, bv.p, y, nullptr, nullptr, ctx.comm, ctx.wait_of(&bv), &ps, 10 + 2 * l);
+  } else if (lv.Rt.rowptr) {          // small block: lanes-per-row CSR kernel between a wait and a push kernel
+    ctx.wait(bv);
+    spmv_sub(lv.Rt.view32(), bv.p, y, nullptr, 0);
+    ctx.push(nb);
   }
   double* xc = next_part ? P.vx[l + 1].p : amg.L[l + 1]->x.p;
   vcycle_folded_dist(amg, l + 1, nb, xc, nullptr);
-  PushSpec ps;
-  if (l >= 1) ps = ctx.push_spec(P.vx[l]);
-  const int g = spmv_sell_dist(lv.Us, bv.p, x, xc, dot_part, ctx.comm, ctx.wait_of(&bv, next_part ? &P.vx[l + 1] : nullptr), &ps);
-  return dot_part ? g : 0;
+  if (lv.Us.nslices) {
+    PushSpec ps;
+    if (l >= 1) ps = ctx.push_spec(P.vx[l]);
+    const int g = spmv_sell_dist(lv.Us, bv.p, x, xc, dot_part, ctx.comm, ctx.wait_of(&bv, next_part ? &P.vx[l + 1] : nullptr), &ps, 11 + 2 * l);
+    return dot_part ? g : 0;
+  }
+  ctx.wait(bv);
+  if (next_part) ctx.wait(P.vx[l + 1]);
+  spmv_sub(lv.U.view32(), bv.p, x, xc, lv.part_nsplit);
+  ctx.push(P.vx[l]);
+  return 0;
 }
 
 int amg_apply_dist(Amg* amg, const DVec& r, double* z, double* rz_part) {

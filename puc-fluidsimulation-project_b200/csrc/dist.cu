@@ -155,6 +155,13 @@ void HaloCollector::finish(Space& sp, int rank, int world) {
       udst[k] = dsts[e];
     }
     uptr.push_back(sp.n_send);
+    sp.h_urow.clear();
+    for (int k = 0, pr = -1; k < sp.n_send; ++k) { const int r = rows[order[k]]; if (r != pr) { sp.h_urow.push_back(r); pr = r; } }
+    sp.h_uptr = uptr; sp.h_upeer = upeer; sp.h_udst = udst;
+    std::vector<int> slist;
+    for (int sl = 0; sl < nsl; ++sl) if (smask[sl]) slist.push_back(sl);
+    sp.n_slist = (int)slist.size();
+    if (sp.n_slist) { sp.slist.alloc(slist.size()); sp.slist.upload(slist.data(), slist.size()); }
     sp.smask.alloc(smask.size()); sp.smask.upload(smask.data(), smask.size());
     sp.sbase.alloc(sbase.size()); sp.sbase.upload(sbase.data(), sbase.size());
     sp.uptr.alloc(uptr.size()); sp.uptr.upload(uptr.data(), uptr.size());
@@ -256,18 +263,16 @@ __global__ void __launch_bounds__(512) k_halo_push(PushArgs a, Comm c) {
       for (int s = 0; s < a.stride; ++s) dist_st_sys_f64(dst + s, __ldcg(src + s));
     }
   }
-  __threadfence_system();
-  __shared__ int s_last;
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0) {       // see push_finish (dist.cuh) for the ordering argument
+    dist_fence_sys();
     const unsigned prev = atomicAdd(c.done_ctr + 8 + a.channel, 1u);
-    s_last = (prev == gridDim.x - 1);
-    if (s_last) c.done_ctr[8 + a.channel] = 0;
-  }
-  __syncthreads();
-  if (s_last && threadIdx.x < a.n_to) {
-    __threadfence_system();
-    dist_st_release_sys(c.flag_peer[a.to[threadIdx.x]] + (size_t)a.channel * kMaxRanks + c.rank, seq);
+    if (prev == gridDim.x - 1) {
+      c.done_ctr[8 + a.channel] = 0;
+      dist_fence_sys();
+      for (int j = 0; j < a.n_to; ++j)
+        dist_st_sys_u64(c.flag_peer[a.to[j]] + (size_t)a.channel * kMaxRanks + c.rank, seq);
+    }
   }
 }
 
@@ -307,6 +312,16 @@ void DistCtx::init(int rank_, int world_, size_t vector_bytes) {
   comm.flag_local = reinterpret_cast<unsigned long long*>(arena.p + kCtlFlagOff);
   comm.red_peer[rank] = comm.red_local;
   comm.flag_peer[rank] = comm.flag_local;
+  if (const char* e = std::getenv("FS_DIST_TRACE")) {
+    if (std::atoi(e) > 0) {
+      comm.trace_cap = 1u << 16;
+      trace.alloc(2 * (size_t)comm.trace_cap);
+      trace_n.alloc(1);
+      trace_n.zero();
+      comm.trace = trace.p;
+      comm.trace_n = trace_n.p;
+    }
+  }
   if (const char* e = std::getenv("FS_DIST_TIMEOUT_MS")) comm.timeout_ns = (unsigned long long)std::atof(e) * 1000000ull;
   connected = (world == 1);
   FS_CUDA(cudaStreamSynchronize(stream()));
@@ -385,6 +400,7 @@ PushSpec DistCtx::push_spec(const DVec& v) const {
     ps.row0 = (int)sp.own_lo;
   } else {
     ps.smask = sp.smask.p; ps.sbase = sp.sbase.p; ps.uptr = sp.uptr.p; ps.upeer = sp.upeer.p; ps.udst = sp.udst.p;
+    ps.slist = sp.slist.p; ps.n_slist = sp.n_slist;
   }
   return ps;
 }

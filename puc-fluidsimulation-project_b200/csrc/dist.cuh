@@ -46,6 +46,10 @@ struct Comm {
   unsigned long long* red_peer[kMaxRanks] = {nullptr};
   unsigned long long* flag_peer[kMaxRanks] = {nullptr};
   unsigned long long timeout_ns = 20000000000ull;
+  // optional event trace (FS_DIST_TRACE=1): CTA 0 / thread 0 of the partitioned kernels appends {tag, %globaltimer}
+  unsigned long long* trace = nullptr;
+  unsigned* trace_n = nullptr;
+  unsigned trace_cap = 0;
 };
 
 // which channels a consumer kernel has to see before its first halo read
@@ -84,6 +88,8 @@ struct PushSpec {
   int row0 = 0;
   int channel = 0;
   const unsigned* smask = nullptr;
+  const int* slist = nullptr;       // the slices with a non-zero mask
+  int n_slist = 0;
   const int* sbase = nullptr;
   const int* uptr = nullptr;
   const int* upeer = nullptr;
@@ -107,7 +113,9 @@ struct Space {
   DBuf<int> send_row, send_peer, send_dst;  // own row -> slot send_dst of rank send_peer (sorted by peer, row)
   int n_send = 0;
   DBuf<unsigned> smask;                     // fused-push plan (see PushSpec), built from the send list
-  DBuf<int> sbase, uptr, upeer, udst;
+  DBuf<int> sbase, uptr, upeer, udst, slist;
+  int n_slist = 0;
+  std::vector<int> h_urow, h_uptr, h_upeer, h_udst;   // host copy of the plan: send rows ascending, their destinations
   int n_to = 0, n_from = 0;
   signed char to[kMaxRanks] = {0}, from[kMaxRanks] = {0};
   bool gather = false;                      // replicated space: vectors are full length, global numbering,
@@ -133,6 +141,8 @@ struct DistCtx {
   DBuf<int> err;
   DBuf<unsigned> done_ctr;
   DBuf<int> flags;                          // {converged, iterations, -, -} of the running solve
+  DBuf<unsigned long long> trace;
+  DBuf<unsigned> trace_n;
   int next_channel = 0;
   Comm comm;
   bool connected = false;
@@ -188,9 +198,11 @@ int amg_apply_dist(Amg* amg, const DVec& r, double* z, double* rz_part);
 
 // mark the slices of S (built from the local CSR `loc`) that read halo entries: columns in [n_own_a, nsplit) of the
 // first vector, or >= nsplit + n_own_b of the second (n_own_b < 0: the second vector has no halo part)
-void sell_mark_boundary(fs_sell& S, const fs_csr& loc, int n_own_a, int nsplit, int n_own_b);
+// ... or whose rows are send rows of the output space `out` (may be null); for those the per-lane destinations are
+// tabulated next to the slice list (fs_sell::btab) so that the kernel needs no look-up chain before its remote stores
+void sell_mark_boundary(fs_sell& S, const fs_csr& loc, int n_own_a, int nsplit, int n_own_b, const Space* out);
 int spmv_sell_dist(const fs_sell& S, const double* x, double* y, const double* x2, double* dot_partials, const Comm& c,
-                   const HaloWait& w, const PushSpec* push = nullptr);
+                   const HaloWait& w, const PushSpec* push = nullptr, int trace_tag = 0);
 void spmv_sell2_dist(const fs_sell& S, const double* x, double* y, double* dot_partials, const int* done, const Comm& c,
                      const HaloWait& w);
 
@@ -216,6 +228,13 @@ __device__ __forceinline__ unsigned long long dist_ld_sys_u64(const unsigned lon
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a) : "memory");
   return v;
 }
+__device__ __forceinline__ void dist_trace(const Comm& c, unsigned tag) {
+  if (c.trace && blockIdx.x == 0 && threadIdx.x == 0) {
+    const unsigned k = atomicAdd(c.trace_n, 1u);
+    if (k < c.trace_cap) { c.trace[2 * k] = tag; c.trace[2 * k + 1] = dist_gtime(); }
+  }
+}
+
 __device__ __forceinline__ void dist_st_sys_f64(double* a, double v) {
   asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(a), "d"(v) : "memory");
 }
@@ -321,29 +340,29 @@ __device__ __forceinline__ bool push_row(const PushSpec& ps, int row, double v) 
     dist_st_sys_f64(reinterpret_cast<double*>(ps.peer_base[__ldg(ps.upeer + k)] + ps.vec_off) + __ldg(ps.udst + k), v);
   return true;
 }
-// End of a producer kernel WITHOUT a reduction: every CTA calls it (all threads); the CTA that arrives last
-// releases the flags with the current sequence number.
-__device__ __forceinline__ void push_finish(const Comm& c, const PushSpec& ps, bool pushed, unsigned long long stamp) {
-  if (pushed) __threadfence_system();
-  __shared__ int s_last;
+__device__ __forceinline__ void dist_fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+__device__ __forceinline__ void dist_fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+// After the send rows have been produced: each of the n_cta CTAs that own send rows calls it (all threads); the one
+// that arrives last releases the flags with `stamp`.  No per-thread fences: the CTA barrier orders every thread's
+// remote stores before thread 0's release fence (cumulativity), the arrival counter chains the CTAs' fences, and the
+// last CTA's fence orders all of them before the flag stores.  (__threadfence_system() is a sequentially-consistent
+// fence and was measured at 12-15 us per pushing thread after NVLink stores; acq_rel is what a release needs.)
+__device__ __forceinline__ void push_finish(const Comm& c, const PushSpec& ps, bool /*pushed*/, unsigned long long stamp, int n_cta,
+                                            unsigned trace_tag = 0) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
+    if (trace_tag) dist_trace(c, trace_tag);
+    dist_fence_sys();
+    if (trace_tag) dist_trace(c, trace_tag + 1);
     const unsigned prev = atomicAdd(c.done_ctr + 8 + ps.channel, 1u);
-    s_last = (prev == gridDim.x - 1);
-    if (s_last) c.done_ctr[8 + ps.channel] = 0;
+    if (prev == (unsigned)n_cta - 1) {
+      c.done_ctr[8 + ps.channel] = 0;
+      dist_fence_sys();
+      for (int j = 0; j < ps.n_to; ++j)
+        dist_st_sys_u64(c.flag_peer[ps.to[j]] + (size_t)ps.channel * kMaxRanks + c.rank, stamp);
+    }
   }
-  __syncthreads();
-  if (s_last && threadIdx.x < ps.n_to) {
-    __threadfence_system();
-    dist_st_release_sys(c.flag_peer[ps.to[threadIdx.x]] + (size_t)ps.channel * kMaxRanks + c.rank, stamp);
-  }
-}
-// the same for a kernel that already knows it is the last block (reducing kernels: after dist_seq_bump)
-__device__ __forceinline__ void push_release(const Comm& c, const PushSpec& ps, unsigned long long stamp) {
-  __threadfence_system();
-  for (int j = 0; j < ps.n_to; ++j)
-    dist_st_release_sys(c.flag_peer[ps.to[j]] + (size_t)ps.channel * kMaxRanks + c.rank, stamp);
 }
 
 // Called by every CTA at the END of a reducing kernel: true in exactly one thread (thread 0 of the CTA that
@@ -353,14 +372,14 @@ __device__ __forceinline__ bool dist_last_block(const Comm& c, int ctr) {
   __syncthreads();
   bool last = false;
   if (threadIdx.x == 0) {
-    __threadfence();
+    dist_fence_gpu();
     const unsigned prev = atomicAdd(c.done_ctr + ctr, 1u);
-    if (prev == gridDim.x - 1) { c.done_ctr[ctr] = 0; last = true; }
+    if (prev == gridDim.x - 1) { c.done_ctr[ctr] = 0; last = true; dist_fence_gpu(); }
   }
   return last;
 }
 __device__ __forceinline__ void dist_seq_bump(const Comm& c) {
-  __threadfence();
+  dist_fence_gpu();
   atomicAdd(c.seq, 1ull);
 }
 #endif  // __CUDACC__

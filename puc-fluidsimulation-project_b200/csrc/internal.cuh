@@ -283,6 +283,7 @@ struct fs_sell {
   DBuf<unsigned> bmask;
   DBuf<int> blist;
   int n_blist = 0;
+  DBuf<int2> btab;        // per boundary slice and lane: up to two destinations (rank << 28 | slot; -1 none; .y = -2: look up)
 };
 void sell_build(const fs_csr& A, bool f32, fs_sell& out, int nsplit = -1);
 int spmv_sell(const fs_sell& S, const double* x, double* y, const double* x2, double* dot_partials);

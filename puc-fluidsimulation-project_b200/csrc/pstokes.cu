@@ -113,28 +113,45 @@ k_ppcg_xr(int64_t n, const double* __restrict__ p, const double* __restrict__ Ap
   __shared__ double red[32];
   __shared__ double sm[1];
   if (block_done(flags)) return;
+  dist_trace(c, 20);
   double pAp[1];
   reduce_partials<1>(partA, nblkA, pAp, sm);
   const unsigned long long seq = dist_seq(c);
+  dist_trace(c, 21);
   rank_allreduce<1>(c, pAp, seq + 1);
+  dist_trace(c, 22);
   const double rz = sc[slot];
   const double alpha = (pAp[0] != 0.0) ? rz / pAp[0] : 0.0;
   double acc[1] = {0.0};
-  bool pushed = false;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  // one warp per 32-row slice; the slices with rows that other ranks read come first: their new residuals are stored
+  // into the neighbours' halo slots and the flags released while the rest of the vector is still being updated
+  const int lane = threadIdx.x & 31;
+  const int gw = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5), nw = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
+  const int nsl = (int)((n + 31) >> 5);
+  auto upd = [&](int64_t i, bool send) -> bool {
     const double rn = r[i] - alpha * Ap[i];
     x[i] += alpha * p[i];
     r[i] = rn;
     acc[0] += rn * rn;
-    if (ps.enabled) pushed |= push_row(ps, (int)i, rn);      // the new residual's boundary rows go to the neighbours now
+    return send ? push_row(ps, (int)i, rn) : false;
+  };
+  if (ps.enabled && blockIdx.x * (kBlock / 32) < ps.n_slist) {
+    bool pushed = false;
+    for (int j = gw; j < ps.n_slist; j += nw) {
+      const int64_t i = ((int64_t)__ldg(ps.slist + j) << 5) + lane;
+      if (i < n) pushed |= upd(i, true);
+    }
+    push_finish(c, ps, pushed, seq + 1, min((int)gridDim.x, (ps.n_slist + kBlock / 32 - 1) / (kBlock / 32)));
+  }
+  for (int sl = gw; sl < nsl; sl += nw) {
+    if (ps.enabled && __ldg(ps.smask + sl)) continue;
+    const int64_t i = ((int64_t)sl << 5) + lane;
+    if (i < n) upd(i, false);
   }
   block_reduce<1>(acc, red);
   if (threadIdx.x == 0) partB[blockIdx.x] = acc[0];
-  if (pushed) __threadfence_system();
-  if (dist_last_block(c, 0)) {
-    dist_seq_bump(c);
-    if (ps.enabled) push_release(c, ps, seq + 1);
-  }
+  dist_trace(c, 23);
+  if (dist_last_block(c, 0)) dist_seq_bump(c);
 }
 
 // convergence test, beta, p = z + beta p.  Every CTA takes the same decision from the all-reduced sums; the
@@ -151,26 +168,37 @@ k_ppcg_p(int64_t n, const double* __restrict__ z, double* __restrict__ p, const 
   reduce_partials<1>(partRZ, nRZ, t, sm);
   v[1] = t[0];
   const unsigned long long seq = dist_seq(c);
+  dist_trace(c, 31);
   rank_allreduce<2>(c, v, seq + 1);
+  dist_trace(c, 32);
   const double rz_old = sc[slot];
   const bool conv = v[0] <= sc[4] * sc[2];
-  bool pushed = false;
   if (!conv) {
     const double beta = rz_old != 0.0 ? v[1] / rz_old : 0.0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-      const double pn = z[i] + beta * p[i];
-      p[i] = pn;
-      if (ps.enabled) pushed |= push_row(ps, (int)i, pn);
+    const int lane = threadIdx.x & 31;
+    const int gw = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5), nw = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
+    const int nsl = (int)((n + 31) >> 5);
+    if (ps.enabled && blockIdx.x * (kBlock / 32) < ps.n_slist) {        // rows the neighbours read: first, sent as produced
+      bool pushed = false;
+      for (int j = gw; j < ps.n_slist; j += nw) {
+        const int64_t i = ((int64_t)__ldg(ps.slist + j) << 5) + lane;
+        if (i < n) { const double pn = z[i] + beta * p[i]; p[i] = pn; pushed |= push_row(ps, (int)i, pn); }
+      }
+      push_finish(c, ps, pushed, seq + 1, min((int)gridDim.x, (ps.n_slist + kBlock / 32 - 1) / (kBlock / 32)));
+    }
+    for (int sl = gw; sl < nsl; sl += nw) {
+      if (ps.enabled && __ldg(ps.smask + sl)) continue;
+      const int64_t i = ((int64_t)sl << 5) + lane;
+      if (i < n) p[i] = z[i] + beta * p[i];
     }
   }
-  if (pushed) __threadfence_system();
+  dist_trace(c, 33);
   if (dist_last_block(c, 1)) {
     sc[slot ^ 1] = v[1];
     sc[3] = v[0];
     flags[1] += 1;
     if (conv) flags[0] = 1;
     dist_seq_bump(c);
-    if (ps.enabled && !conv) push_release(c, ps, seq + 1);
   }
 }
 
@@ -427,7 +455,7 @@ static int ppcg_amg(fs_pstokes* s, const double* b_in, DVec& X, double rtol, int
     const HaloWait wP = ctx.wait_of(&s->P);
     while (queued < maxit) {
       const int slot = queued & 1;
-      const int ga = spmv_sell_dist(s->k_red, p, Ap, nullptr, partA, cm, wP);
+      const int ga = spmv_sell_dist(s->k_red, p, Ap, nullptr, partA, cm, wP, nullptr, 1);
       k_ppcg_xr<<<g, kBlock, 0, st>>>(n, p, Ap, X.p, r, partA, ga, sc, slot, flags, partB, cm, psR); FS_LAUNCH_CHECK();
       nrz = amg_apply_dist(s->amg, s->R, z, partRZ);
       k_ppcg_p<<<g, kBlock, 0, st>>>(n, z, p, partB, g, partRZ, nrz, sc, slot, flags, cm, psP); FS_LAUNCH_CHECK();
@@ -708,7 +736,7 @@ int fs_pstokes_create(fs_stokes* glob, fs_mesh* lmesh, int rank, int world, cons
     fs_csr loc;
     extract_rows(gk->view(), dsplit[rank], dsplit[rank + 1], s->dofs, nd, nullptr, loc);
     sell_build(loc, false, s->k_red);
-    sell_mark_boundary(s->k_red, loc, (int)s->dofs.n_own, 0x7fffffff, -1);
+    sell_mark_boundary(s->k_red, loc, (int)s->dofs.n_own, 0x7fffffff, -1, nullptr);
   }
   // ---- local node -> local dof (own dofs first, then the dof halo list)
   {
@@ -844,6 +872,23 @@ int fs_pstokes_profile_pcg(fs_pstokes* s, int iters, double* us_per_iter) {
   cudaEventDestroy(e1);
   barrier_dev(s);
   fs::sync();
+  FS_API_END
+}
+
+// FS_DIST_TRACE=1: copy out (and reset) the event trace: pairs {tag, ns}.  Returns the number of events in *n.
+int fs_pstokes_trace(fs_pstokes* s, uint64_t* out, int64_t cap, int64_t* n) {
+  FS_API_BEGIN
+  FS_REQUIRE(s && n, "NULL argument");
+  *n = 0;
+  if (!s->ctx.comm.trace) return FS_OK;
+  fs::sync();
+  unsigned cnt = s->ctx.trace_n.to_host()[0];
+  cnt = std::min<unsigned>(cnt, s->ctx.comm.trace_cap);
+  const int64_t m = std::min<int64_t>(cnt, cap);
+  if (out && m) FS_CUDA(cudaMemcpy(out, s->ctx.trace.p, (size_t)m * 16, cudaMemcpyDeviceToHost));
+  s->ctx.trace_n.zero();
+  fs::sync();
+  *n = m;
   FS_API_END
 }
 

@@ -129,16 +129,22 @@ __device__ __forceinline__ double sell_part4(const float* __restrict__ vp, const
 // DIST (partitioned step, pstokes.cu): x / x2 are [own | halo] vectors whose halo entries are written by the
 // neighbouring ranks; the kernel returns at once when the running solve has converged and otherwise
 // waits for the halo flags of its input channels before the first gather (dist.cuh).
-// Two passes: the slices that read no halo entry first, then -- after the neighbours' flags have arrived -- the few
-// that do, so the transfer latency hides behind the interior work.  With a PushSpec the kernel also stores the
-// rows other ranks read into their halo slots as it produces them, and its last CTA releases the channel's flags.
+// Boundary first: the few slices that read halo entries or whose rows other ranks read ("boundary slices", listed in
+// blist) are done at the START of the kernel -- wait for the input flags, compute, store the rows into the
+// neighbours' halo slots, and the last boundary CTA releases the output channel's flags -- while all other CTAs are
+// already streaming the interior.  The flags are thus on their way one whole kernel before the consumer needs them,
+// and the consumer's own wait (same scheme) finds them set: the transfer latency hides behind the interior work.
+// A producer for a replicated level (gather) sends every row; it releases its flags at the end.
 struct DistSell {
   Comm c;
   HaloWait w;
   PushSpec ps;
   const unsigned* bmask = nullptr;
   const int* blist = nullptr;
+  const int2* btab = nullptr;
   int n_blist = 0;
+  int nb_cta = 0;
+  int tag = 0;
 };
 
 template <bool SPLIT, bool DOT, bool F32, bool DIST>
@@ -146,23 +152,31 @@ __global__ void __launch_bounds__(kST, (SPLIT && F32 && DOT && !DIST) ? 8 : 6) k
   __shared__ double red[kSW];
   if (DIST) {
     if (d.c.done && *d.c.done) return;
+    dist_trace(d.c, d.tag * 10 + 0);
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nwarps = gridDim.x * kSW;
   double dacc = 0.0;
   bool pushed = false;
-  const int npass = (DIST && d.n_blist > 0) ? 2 : 1;
-  for (int pass = 0; pass < npass; ++pass) {
-  if (DIST && pass == 1) {
-    if (blockIdx.x * kSW >= d.n_blist) break;      // none of this CTA's warps has a boundary slice
+  // the first nb CTAs do the boundary slices and nothing else, the others share the interior
+  const bool two = DIST && d.n_blist > 0;
+  const int nb = two ? d.nb_cta : 0;
+  const bool bcta = two && (int)blockIdx.x < nb;
+  if (bcta) {
     halo_wait(d.c, d.w);
+    dist_trace(d.c, d.tag * 10 + 1);
   }
-  const int count = (DIST && pass == 1) ? d.n_blist : a.nslices;
-  for (int si = blockIdx.x * kSW + warp; si < count; si += nwarps) {
+  const int count = bcta ? d.n_blist : a.nslices;
+  const int first = (bcta ? blockIdx.x : blockIdx.x - nb) * kSW + warp;
+  const int nwarps = (bcta ? nb : (int)gridDim.x - nb) * kSW;
+  {
+  for (int si = first; si < count; si += nwarps) {
     int s = si;
-    if (DIST && npass == 2) {
-      if (pass == 0) { if ((__ldg(d.bmask + (si >> 5)) >> (si & 31)) & 1u) continue; }
-      else s = __ldg(d.blist + si);
+    int2 dst = make_int2(-1, -1);
+    if (two) {
+      if (bcta) {
+        s = __ldg(d.blist + si);
+        if (d.btab) dst = __ldg(d.btab + ((size_t)si << 5) + lane);
+      } else if ((__ldg(d.bmask + (si >> 5)) >> (si & 31)) & 1u) continue;
     }
     const long long off = __ldg(a.sptr + s);
     const int W = (int)((__ldg(a.sptr + s + 1) - off) >> 5);
@@ -187,9 +201,21 @@ __global__ void __launch_bounds__(kST, (SPLIT && F32 && DOT && !DIST) ? 8 : 6) k
     if (row < a.n) {
       a.y[row] = acc;
       if (DOT) dacc += __ldg(a.x + row) * acc;
-      if (DIST && d.ps.enabled) pushed |= push_row(d.ps, row, acc);
+      if (DIST && d.ps.enabled) {
+        if (d.ps.gather) pushed |= push_row(d.ps, row, acc);
+        else if (bcta) {
+          if (dst.y == -2) pushed |= push_row(d.ps, row, acc);
+          else {
+            if (dst.x >= 0) dist_st_sys_f64(reinterpret_cast<double*>(d.ps.peer_base[dst.x >> 28] + d.ps.vec_off) + (dst.x & 0x0fffffff), acc);
+            if (dst.y >= 0) dist_st_sys_f64(reinterpret_cast<double*>(d.ps.peer_base[dst.y >> 28] + d.ps.vec_off) + (dst.y & 0x0fffffff), acc);
+          }
+        }
+      }
     }
   }
+  if (bcta && d.ps.enabled && !d.ps.gather)
+    push_finish(d.c, d.ps, pushed, dist_seq(d.c), nb, d.tag * 10 + 4);      // the send rows all sit in boundary slices
+  if (bcta) dist_trace(d.c, d.tag * 10 + 2);
   }
   if (DOT) {
     for (int o = 16; o > 0; o >>= 1) dacc += __shfl_xor_sync(0xffffffffu, dacc, o);
@@ -201,7 +227,8 @@ __global__ void __launch_bounds__(kST, (SPLIT && F32 && DOT && !DIST) ? 8 : 6) k
       a.part[blockIdx.x] = sum;
     }
   }
-  if (DIST && d.ps.enabled) push_finish(d.c, d.ps, pushed, dist_seq(d.c));
+  if (DIST && d.ps.enabled && d.ps.gather) push_finish(d.c, d.ps, pushed, dist_seq(d.c), (int)gridDim.x);
+  if (DIST) dist_trace(d.c, d.tag * 10 + 3);
 }
 
 // two interleaved right-hand sides (x, y are (n,2) row-major), fp64 values: the viscous 2-RHS CG
@@ -362,9 +389,17 @@ static int spmv_sell_impl(const fs_sell& S, const double* x, double* y, const do
   if (!S.nslices) return 0;
   FS_REQUIRE((S.nsplit >= 0) == (x2 != nullptr), "spmv_sell: split form and second vector must come together");
   const int per_sm = (x2 && S.v32.p && dot_partials && !d) ? 8 : 6;   // the finest up-sweep runs at 32 registers
-  const int grid = std::max(1, std::min(div_up(S.nslices, kSW), sm_count() * per_sm));
+  int grid = std::max(1, std::min(div_up(S.nslices, kSW), sm_count() * per_sm));
   SellArgs args{S.n, S.nslices, S.sptr.p, S.wg.p, S.cols.p, S.v32.p, S.v64.p, x, x2, y, dot_partials};
-  if (d && d->w.nch && S.n_blist > 0) { d->bmask = S.bmask.p; d->blist = S.blist.p; d->n_blist = S.n_blist; }
+  int grid_add = 0;
+  if (d && (d->w.nch || (d->ps.enabled && !d->ps.gather)) && S.n_blist > 0) {
+    d->bmask = S.bmask.p; d->blist = S.blist.p; d->n_blist = S.n_blist;
+    d->btab = (d->ps.enabled && !d->ps.gather) ? S.btab.p : nullptr;
+    d->nb_cta = std::max(1, std::min(div_up(S.n_blist, kSW), sm_count() * 2));   // dedicated boundary CTAs, scheduled first
+    grid_add = d->nb_cta;
+  }
+  if (d && d->ps.enabled && !d->ps.gather && S.n_blist == 0) d->ps.enabled = 0;   // nothing to send from these rows
+  if (grid_add) grid = std::max(grid, grid_add + 1);      // at least one interior CTA; the total stays one resident wave
   if (x2) {
     if (dot_partials) launch_sell<true, true>(args, grid, d);
     else launch_sell<true, false>(args, grid, d);
@@ -381,19 +416,21 @@ int spmv_sell(const fs_sell& S, const double* x, double* y, const double* x2, do
 }
 
 int spmv_sell_dist(const fs_sell& S, const double* x, double* y, const double* x2, double* dot_partials, const Comm& c,
-                   const HaloWait& w, const PushSpec* push) {
+                   const HaloWait& w, const PushSpec* push, int trace_tag) {
   DistSell d;
   d.c = c;
   d.w = w;
+  d.tag = trace_tag;
   if (push) d.ps = *push;
   return spmv_sell_impl(S, x, y, x2, dot_partials, &d);
 }
 
 // ---- boundary slices ---------------------------------------------------------------------------
-__global__ void k_mark_boundary(CsrView A, int n_own_a, int nsplit, int n_own_b, unsigned* __restrict__ bmask) {
+__global__ void k_mark_boundary(CsrView A, int n_own_a, int nsplit, int n_own_b, const unsigned* __restrict__ out_smask,
+                                unsigned* __restrict__ bmask) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= A.n) return;
-  bool halo = false;
+  bool halo = out_smask && ((out_smask[row >> 5] >> (row & 31)) & 1u);    // the row itself is read by another rank
   for (int k = A.rowptr[row]; k < A.rowptr[row + 1]; ++k) {
     const int c = A.colidx[k];
     if (c < nsplit) halo |= (c >= n_own_a);
@@ -402,21 +439,40 @@ __global__ void k_mark_boundary(CsrView A, int n_own_a, int nsplit, int n_own_b,
   if (halo) atomicOr(bmask + (row >> 10), 1u << ((row >> 5) & 31));
 }
 
-void sell_mark_boundary(fs_sell& S, const fs_csr& loc, int n_own_a, int nsplit, int n_own_b) {
+void sell_mark_boundary(fs_sell& S, const fs_csr& loc, int n_own_a, int nsplit, int n_own_b, const Space* out) {
   const int nsl = S.nslices;
   if (!nsl) return;
   const int nw = div_up(nsl, 32);
+  const bool sends = out && !out->gather && out->n_send > 0;
   S.bmask.alloc(nw);
   S.bmask.zero();
-  k_mark_boundary<<<div_up(loc.n, 256), 256, 0, stream()>>>(loc.view(), n_own_a, nsplit, n_own_b, S.bmask.p);
+  k_mark_boundary<<<div_up(loc.n, 256), 256, 0, stream()>>>(loc.view(), n_own_a, nsplit, n_own_b, sends ? out->smask.p : nullptr, S.bmask.p);
   FS_LAUNCH_CHECK();
   std::vector<unsigned> h = S.bmask.to_host();
   std::vector<int> list;
   for (int s = 0; s < nsl; ++s) if ((h[s >> 5] >> (s & 31)) & 1u) list.push_back(s);
   S.n_blist = (int)list.size();
   if (S.n_blist) { S.blist.alloc(list.size()); S.blist.upload(list.data(), list.size()); }
+  if (sends && S.n_blist) {
+    std::vector<int2> tab((size_t)S.n_blist * 32, make_int2(-1, -1));
+    for (int j = 0; j < S.n_blist; ++j)
+      for (int l = 0; l < 32; ++l) {
+        const int row = list[j] * 32 + l;
+        auto it = std::lower_bound(out->h_urow.begin(), out->h_urow.end(), row);
+        if (it == out->h_urow.end() || *it != row) continue;
+        const size_t u = it - out->h_urow.begin();
+        const int k0 = out->h_uptr[u], k1 = out->h_uptr[u + 1];
+        int2& e = tab[(size_t)j * 32 + l];
+        if (k1 - k0 > 2 || out->h_udst[k0] >= (1 << 28)) { e.y = -2; continue; }
+        e.x = (out->h_upeer[k0] << 28) | out->h_udst[k0];
+        if (k1 - k0 == 2) e.y = (out->h_upeer[k0 + 1] << 28) | out->h_udst[k0 + 1];
+      }
+    S.btab.alloc(tab.size());
+    S.btab.upload(tab.data(), tab.size());
+  }
   FS_CUDA(cudaStreamSynchronize(stream()));
 }
+
 
 int spmv_sell_grid(const fs_sell& S) { return std::max(1, std::min(div_up(S.nslices, kSW), sm_count() * 4)); }
 

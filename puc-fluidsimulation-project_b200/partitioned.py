@@ -107,6 +107,13 @@ class PartitionedStokes:
         call("fs_pstokes_profile_pcg", self._h, int(iters), C.byref(us))
         return us.value
 
+    def trace(self, cap=1 << 16):
+        """Event log of the partitioned kernels (FS_DIST_TRACE=1): (n,2) uint64 array of {tag, ns}; resets the log."""
+        buf = np.zeros((cap, 2), dtype=np.uint64)
+        n = C.c_int64(0)
+        call("fs_pstokes_trace", self._h, ptr(buf), cap, C.byref(n))
+        return buf[:n.value]
+
     def gather(self, x_own):
         """All ranks' blocks of a nodal array, concatenated (host; for checks and output)."""
         x_own = np.ascontiguousarray(x_own.cpu().numpy() if _lib._is_torch(x_own) else x_own)

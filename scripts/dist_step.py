@@ -53,7 +53,11 @@ out = {"n_gpus": world, "n_theta": args.n_theta, "n_r": args.n_r, "triangles": i
        "levels_partitioned": ps.levels_partitioned, "n_own": ps.n_own, "n_halo_nodes": ps.n_halo_nodes,
        "n_own_dofs": ps.n_own_dofs, "n_halo_dofs": ps.n_halo_dofs, "launches_per_step": (fb.launch_count() - l0) / max(args.steps, 1)}
 if args.profile_pcg:
+    ps.trace()                                  # reset the event log
     out["us_per_pcg_iteration_fixed"] = ps.profile_pcg(args.profile_pcg)
+    tr = ps.trace()
+    if len(tr):
+        np.save(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", f"trace_rank{rank}.npy"), tr)
     out["debug_skip"] = os.environ.get("FS_DIST_DEBUG_SKIP", "0")
 if args.check:
     ug = ps.gather(u)
