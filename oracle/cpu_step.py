@@ -55,7 +55,10 @@ class _Csr:
 
 class CpuStokes:
     def __init__(self, nodes, markers, tris, B1=-2.0, B2=0.0, DT=0.05, v=0.1, precond="amg",
-                 rtol_pressure=1e-10, rtol_visc=1e-12, H=1.0, tol=1e-6, threads=None):
+                 rtol_pressure=1e-10, rtol_visc=1e-12, H=1.0, tol=1e-6, threads=None, exact_ops=False):
+        # exact_ops: divergence / gradient by restated.divergence / restated.gradient (the element sums of the
+        # reference in the reference's order) instead of the pre-assembled sparse operators
+        self.exact_ops = exact_ops
         if threads:
             cgport.load().cgport_set_threads(int(threads))
         self.nodes, self.markers, self.tris = nodes, markers, np.asarray(tris)
@@ -83,9 +86,13 @@ class CpuStokes:
         self.iters = (0, 0, 0)
 
     def divergence(self, u):
+        if self.exact_ops:
+            return R.divergence(self.nodes, self.tris, u)
         return self.Dx.dot(u[:, 0]) + self.Dy.dot(u[:, 1])
 
     def gradient(self, p):
+        if self.exact_ops:
+            return R.gradient(self.nodes, self.tris, p)
         return self.Dx.dot(p), self.Dy.dot(p)
 
     def _visc(self, rhs):

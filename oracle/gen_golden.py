@@ -202,7 +202,7 @@ def gen_trajectory(mesh, tag, B1, B2, DT, v, steps=100, dye=True, food=False):
     print(msg, f"({time.time() - t0:.0f}s)")
 
 
-def gen_poisson_heat(mesh, heat_steps=50):
+def gen_poisson_heat(mesh, heat_steps=1000):      # BASELINE config 2: 1000 time steps
     """Literal poisson.py / heatEq.py module bodies re-enacted with the reference
     functions (code/poisson.py:216-285, code/heatEq.py:219-333), fp32 coordinates."""
     ns = L.load_functions("poisson.py")
@@ -260,7 +260,7 @@ def gen_poisson_heat(mesh, heat_steps=50):
     ur = R.heat_reapply(np.zeros(N), nodes, markers, pa)
     assert np.array_equal(u, ur)
     heat = {"heat_u_init": u.copy()}
-    snaps = [0, 1, 9, heat_steps - 1]
+    snaps = sorted({0, 1, 9, min(99, heat_steps - 1), heat_steps - 1})
     for n in range(heat_steps):
         rhs = u + DT * b * 0
         u = np.linalg.solve(Ah, rhs)
@@ -292,4 +292,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "--heat-only":      # regenerate the Poisson / heat fixtures alone
+        for m in MESHES:
+            gen_poisson_heat(m)
+    else:
+        main()
