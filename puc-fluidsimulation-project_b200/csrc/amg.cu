@@ -572,8 +572,14 @@ Amg* amg_setup(fs_csr* fine, const AmgPartSpec* ps) {
           FS_REQUIRE(amg->sell, "the partitioned cycle needs the SELL layout (FS_AMG_SELL=1)");
         } else {
           if (amg->sell) {
-            sell_build(cur.U, fp32, cur.Us, cur.n);
-            sell_build(cur.Rt, fp32, cur.Rts);
+            // SELL-C-sigma (rows sorted by length inside windows of sigma rows) removes the padding -- 35 % for R~, 10 % for
+            // [G | P~] -- but was measured slower or equal on the B200 (V-cycle 153.3 -> 155.6 us with sigma = 1024 on R~,
+            // 162.5 us with U sorted too, profiles/r02_ab_l2hint_sigma.txt): these kernels are bound by the latency of the
+            // dependent stream -> gather chain, not by bytes, and sorting costs gather locality.  Off by default.
+            static const int sigma = (int)env_num("FS_SELL_SIGMA", 0);
+            static const int sigma_u = (int)env_num("FS_SELL_SIGMA_U", 0);
+            sell_build(cur.U, fp32, cur.Us, cur.n, sigma_u);
+            sell_build(cur.Rt, fp32, cur.Rts, -1, sigma);
           }
           auto drop = [](fs_csr& M) { M.vals.release(); M.colidx_own.release(); M.rowptr_own.release(); M.rowptr = M.colidx = nullptr; };
           if (amg->sell && cur.n > amg->sub_rows) drop(cur.U); else ensure_tiles(&cur.U);

@@ -278,6 +278,8 @@ struct fs_sell {
   DBuf<int> cols;
   DBuf<float> v32;        // exactly one of v32 / v64 is filled
   DBuf<double> v64;
+  DBuf<int> perm;         // SELL-C-sigma: slot (32 s + lane) holds row perm[slot] (rows sorted by length inside windows
+                          // of sigma rows, so a slice pads to its own longest row only); empty: identity
   // partitioned step: slices that read halo entries of their input vectors (bit per slice + list); the DIST kernel
   // does all other slices first and waits for the neighbours' halo flags only before these
   DBuf<unsigned> bmask;
@@ -285,7 +287,7 @@ struct fs_sell {
   int n_blist = 0;
   DBuf<int2> btab;        // per boundary slice and lane: up to two destinations (rank << 28 | slot; -1 none; .y = -2: look up)
 };
-void sell_build(const fs_csr& A, bool f32, fs_sell& out, int nsplit = -1);
+void sell_build(const fs_csr& A, bool f32, fs_sell& out, int nsplit = -1, int sigma = 0);
 int spmv_sell(const fs_sell& S, const double* x, double* y, const double* x2, double* dot_partials);
 int spmv_sell_grid(const fs_sell& S);   // grid (= dot partials per column) of spmv_sell2
 void spmv_sell2(const fs_sell& S, const double* x, double* y, double* dot_partials, const int* done);

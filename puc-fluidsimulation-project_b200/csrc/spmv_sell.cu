@@ -34,22 +34,32 @@ struct SellArgs {
   const double* x2;
   double* y;
   double* part;
+  int l2hint;
+  const int* perm;      // SELL-C-sigma row of every slot (null: identity)
 };
 
-// streamed once per launch: read-only path, no L1 allocation (the L1 is for the gathered vectors)
-__device__ __forceinline__ float ld_stream(const float* a) {
+// streamed once per launch: read-only path, no L1 allocation (the L1 is for the gathered vectors), and an L2
+// evict-first hint: one PCG iteration streams ~630 MB of matrix entries through a 126 MB L2 that should rather keep
+// the ~100 MB of CG / multigrid vectors between the kernels that produce and consume them (FS_L2_HINT=0: no hint)
+__device__ __forceinline__ uint64_t sell_policy(int hint) {
+  uint64_t p;
+  if (hint) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float ld_stream(const float* a, uint64_t pol) {
   float v;
-  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(a));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(a), "l"(pol));
   return v;
 }
-__device__ __forceinline__ double ld_stream(const double* a) {
+__device__ __forceinline__ double ld_stream(const double* a, uint64_t pol) {
   double v;
-  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(a));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(a), "l"(pol));
   return v;
 }
-__device__ __forceinline__ int ld_stream(const int* a) {
+__device__ __forceinline__ int ld_stream(const int* a, uint64_t pol) {
   int v;
-  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(a));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
   return v;
 }
 
@@ -65,11 +75,11 @@ __device__ __forceinline__ double sell_mac(VT v, double xv, double acc) {
 
 template <int U, class VT>
 __device__ __forceinline__ double sell_batch(const VT* __restrict__ vp, const int* __restrict__ cp, const double* __restrict__ x,
-                                             double acc) {
+                                             double acc, uint64_t pol) {
   VT vv[U];
   int cc[U];
 #pragma unroll
-  for (int j = 0; j < U; ++j) { vv[j] = ld_stream(vp + (j << 5)); cc[j] = ld_stream(cp + (j << 5)); }
+  for (int j = 0; j < U; ++j) { vv[j] = ld_stream(vp + (j << 5), pol); cc[j] = ld_stream(cp + (j << 5), pol); }
   double xx[U];
 #pragma unroll
   for (int j = 0; j < U; ++j) xx[j] = __ldg(x + cc[j]);
@@ -81,14 +91,14 @@ __device__ __forceinline__ double sell_batch(const VT* __restrict__ vp, const in
 // guarded batch for the last rem < U entries
 template <int U, class VT>
 __device__ __forceinline__ double sell_tail(const VT* __restrict__ vp, const int* __restrict__ cp, int rem,
-                                            const double* __restrict__ x, double acc) {
+                                            const double* __restrict__ x, double acc, uint64_t pol) {
   VT vv[U];
   int cc[U];
 #pragma unroll
   for (int j = 0; j < U; ++j) {
     const bool ok = j < rem;
-    vv[j] = ok ? ld_stream(vp + (j << 5)) : VT(0);
-    cc[j] = ok ? ld_stream(cp + (j << 5)) : 0;
+    vv[j] = ok ? ld_stream(vp + (j << 5), pol) : VT(0);
+    cc[j] = ok ? ld_stream(cp + (j << 5), pol) : 0;
   }
   double xx[U];
 #pragma unroll
@@ -100,17 +110,17 @@ __device__ __forceinline__ double sell_tail(const VT* __restrict__ vp, const int
 
 template <class VT>
 __device__ __forceinline__ double sell_part(const VT* __restrict__ vp, const int* __restrict__ cp, int W,
-                                            const double* __restrict__ x, double acc) {
+                                            const double* __restrict__ x, double acc, uint64_t pol) {
   int k = 0;
-  for (; k + 8 <= W; k += 8, vp += 256, cp += 256) acc = sell_batch<8, VT>(vp, cp, x, acc);
+  for (; k + 8 <= W; k += 8, vp += 256, cp += 256) acc = sell_batch<8, VT>(vp, cp, x, acc, pol);
   if (sizeof(VT) == 8) {
     // fp64 (the CG's A*p, rows of ~7): the last 1..7 entries as ONE guarded batch -- a second dependent
     // load / gather round costs more than the guards
-    if (k < W) acc = sell_tail<7, VT>(vp, cp, W - k, x, acc);
+    if (k < W) acc = sell_tail<7, VT>(vp, cp, W - k, x, acc, pol);
   } else {
     // fp32 two-part operators: 4 unguarded + up to 3 guarded keeps the kernel inside 40 registers
-    if (k + 4 <= W) { acc = sell_batch<4, VT>(vp, cp, x, acc); k += 4; vp += 128; cp += 128; }
-    if (k < W) acc = sell_tail<3, VT>(vp, cp, W - k, x, acc);
+    if (k + 4 <= W) { acc = sell_batch<4, VT>(vp, cp, x, acc, pol); k += 4; vp += 128; cp += 128; }
+    if (k < W) acc = sell_tail<3, VT>(vp, cp, W - k, x, acc, pol);
   }
   return acc;
 }
@@ -119,10 +129,10 @@ __device__ __forceinline__ double sell_part(const VT* __restrict__ vp, const int
 // kernel fits 32 registers and all 64 warps of an SM are resident (measured: 50.9 us against 53.8 us at 40
 // registers / 48 warps; the deeper rows of the coarser levels prefer the 8-wide batches)
 __device__ __forceinline__ double sell_part4(const float* __restrict__ vp, const int* __restrict__ cp, int W,
-                                             const double* __restrict__ x, double acc) {
+                                             const double* __restrict__ x, double acc, uint64_t pol) {
   int k = 0;
-  for (; k + 4 <= W; k += 4, vp += 128, cp += 128) acc = sell_batch<4, float>(vp, cp, x, acc);
-  if (k < W) acc = sell_tail<3, float>(vp, cp, W - k, x, acc);
+  for (; k + 4 <= W; k += 4, vp += 128, cp += 128) acc = sell_batch<4, float>(vp, cp, x, acc, pol);
+  if (k < W) acc = sell_tail<3, float>(vp, cp, W - k, x, acc, pol);
   return acc;
 }
 
@@ -155,6 +165,7 @@ __global__ void __launch_bounds__(kST, (SPLIT && F32 && DOT && !DIST) ? 8 : 6) k
     dist_trace(d.c, d.tag * 10 + 0);
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t pol = sell_policy(a.l2hint);
   double dacc = 0.0;
   bool pushed = false;
   // the first nb CTAs do the boundary slices and nothing else, the others share the interior
@@ -186,19 +197,20 @@ __global__ void __launch_bounds__(kST, (SPLIT && F32 && DOT && !DIST) ? 8 : 6) k
     if (F32) {
       const float* __restrict__ vp = a.v32 + off + lane;
       if (SPLIT && DOT) {   // the finest up-sweep
-        acc = sell_part4(vp, cp, Wg, a.x, acc);
-        acc = sell_part4(vp + ((long long)Wg << 5), cp + ((long long)Wg << 5), W - Wg, a.x2, acc);
+        acc = sell_part4(vp, cp, Wg, a.x, acc, pol);
+        acc = sell_part4(vp + ((long long)Wg << 5), cp + ((long long)Wg << 5), W - Wg, a.x2, acc, pol);
       } else {
-        acc = sell_part<float>(vp, cp, Wg, a.x, acc);
-        if (SPLIT) acc = sell_part<float>(vp + ((long long)Wg << 5), cp + ((long long)Wg << 5), W - Wg, a.x2, acc);
+        acc = sell_part<float>(vp, cp, Wg, a.x, acc, pol);
+        if (SPLIT) acc = sell_part<float>(vp + ((long long)Wg << 5), cp + ((long long)Wg << 5), W - Wg, a.x2, acc, pol);
       }
     } else {
       const double* __restrict__ vp = a.v64 + off + lane;
-      acc = sell_part<double>(vp, cp, Wg, a.x, acc);
-      if (SPLIT) acc = sell_part<double>(vp + ((long long)Wg << 5), cp + ((long long)Wg << 5), W - Wg, a.x2, acc);
+      acc = sell_part<double>(vp, cp, Wg, a.x, acc, pol);
+      if (SPLIT) acc = sell_part<double>(vp + ((long long)Wg << 5), cp + ((long long)Wg << 5), W - Wg, a.x2, acc, pol);
     }
-    const int row = (s << 5) + lane;
-    if (row < a.n) {
+    const int slot = (s << 5) + lane;
+    if (slot < a.n) {
+      const int row = a.perm ? __ldg(a.perm + slot) : slot;
       a.y[row] = acc;
       if (DOT) dacc += __ldg(a.x + row) * acc;
       if (DIST && d.ps.enabled) {
@@ -231,6 +243,136 @@ __global__ void __launch_bounds__(kST, (SPLIT && F32 && DOT && !DIST) ? 8 : 6) k
   if (DIST) dist_trace(d.c, d.tag * 10 + 3);
 }
 
+// ---- bulk-async (TMA) staged variant -----------------------------------------------------------------
+// The register-staged kernel above issues, per batch, a round of stream loads (values + columns), waits, issues the
+// gathers, waits again: two dependent memory round trips per batch, and the registers that hold a batch in flight cap
+// the occupancy.  Here every warp owns a ring of kBS stages in shared memory; lane 0 keeps kBS chunks of the warp's
+// slice stream (8 entries per lane: 1 KB of columns + 1 or 2 KB of values, contiguous in the SELL layout) in flight with
+// cp.async.bulk (1-D TMA, L2 evict-first hint) completing on one mbarrier per stage, and the lanes only read the landed
+// chunk from shared memory, gather and accumulate -- one round trip on the critical path, no staging registers.
+constexpr int kBK = 8;          // entries per lane and chunk
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+template <bool SPLIT, bool DOT, bool F32, int kBS, int MINB>
+__global__ void __launch_bounds__(kST, MINB) k_spmv_sell_bulk(SellArgs a) {
+  using VT = typename std::conditional<F32, float, double>::type;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ double red[kSW];
+  __shared__ __align__(8) unsigned long long bars[kSW * kBS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = gridDim.x * kSW;
+  constexpr int kColB = kBK * 32 * 4, kValB = kBK * 32 * (int)sizeof(VT), kStageB = kColB + kValB;
+  unsigned char* ring = smem_raw + (size_t)warp * kBS * kStageB;
+  const unsigned ring_s = smem_u32(ring);
+  const unsigned bar0 = smem_u32(bars + warp * kBS);
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  if (lane == 0) {
+    for (int k = 0; k < kBS; ++k) mbar_init(bar0 + 8 * k, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+  // producer cursor (kept identical in all lanes; lane 0 issues)
+  int p_slice = blockIdx.x * kSW + warp, p_k = 0, p_W = 0, p_n = 0;
+  long long p_off = 0;
+  auto issue = [&]() -> bool {
+    while (p_slice < a.nslices) {
+      if (p_k == 0) {
+        p_off = __ldg(a.sptr + p_slice);
+        p_W = (int)((__ldg(a.sptr + p_slice + 1) - p_off) >> 5);
+      }
+      if (p_k < p_W) break;
+      p_slice += nwarps;       // empty slice: nothing to stream
+      p_k = 0;
+    }
+    if (p_slice >= a.nslices) return false;
+    const int cnt = min(kBK, p_W - p_k);
+    const int st = p_n % kBS;
+    if (lane == 0) {
+      const unsigned bar = bar0 + 8 * st, dst = ring_s + st * kStageB;
+      const long long e0 = p_off + ((long long)p_k << 5);
+      mbar_expect_tx(bar, (unsigned)(cnt * 32 * (4 + (int)sizeof(VT))));
+      bulk_g2s(dst, a.cols + e0, (unsigned)(cnt * 128), bar, pol);
+      bulk_g2s(dst + kColB, (F32 ? (const void*)(a.v32 + e0) : (const void*)(a.v64 + e0)), (unsigned)(cnt * 32 * (int)sizeof(VT)), bar, pol);
+    }
+    p_k += cnt;
+    if (p_k >= p_W) { p_slice += nwarps; p_k = 0; }
+    ++p_n;
+    return true;
+  };
+  for (int k = 0; k < kBS; ++k) issue();
+  double dacc = 0.0;
+  int c_n = 0;
+  for (int s = blockIdx.x * kSW + warp; s < a.nslices; s += nwarps) {
+    const long long off = __ldg(a.sptr + s);
+    const int W = (int)((__ldg(a.sptr + s + 1) - off) >> 5);
+    const int Wg = SPLIT ? __ldg(a.wg + s) : W;
+    double acc = 0.0;
+    for (int k0 = 0; k0 < W; k0 += kBK) {
+      const int st = c_n % kBS;
+      mbar_wait(bar0 + 8 * st, (unsigned)((c_n / kBS) & 1));
+      const int* sc = reinterpret_cast<const int*>(ring + st * kStageB) + lane;
+      const VT* sv = reinterpret_cast<const VT*>(ring + st * kStageB + kColB) + lane;
+      const int cnt = min(kBK, W - k0);
+      double xx[kBK];
+      if (cnt == kBK) {
+#pragma unroll
+        for (int j = 0; j < kBK; ++j) xx[j] = __ldg(((!SPLIT || k0 + j < Wg) ? a.x : a.x2) + sc[j << 5]);
+#pragma unroll
+        for (int j = 0; j < kBK; ++j) acc = sell_mac<VT>(sv[j << 5], xx[j], acc);     // values straight from shared memory
+      } else {
+#pragma unroll
+        for (int j = 0; j < kBK; ++j) xx[j] = __ldg(((!SPLIT || k0 + j < Wg) ? a.x : a.x2) + (j < cnt ? sc[j << 5] : 0));
+#pragma unroll
+        for (int j = 0; j < kBK; ++j) acc = sell_mac<VT>(j < cnt ? sv[j << 5] : VT(0), xx[j], acc);
+      }
+      __syncwarp();                                                     // every lane is done with the stage
+      if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue();                                                          // refill it
+      ++c_n;
+    }
+    const int slot = (s << 5) + lane;
+    if (slot < a.n) {
+      const int row = a.perm ? __ldg(a.perm + slot) : slot;
+      a.y[row] = acc;
+      if (DOT) dacc += __ldg(a.x + row) * acc;
+    }
+  }
+  if (DOT) {
+    for (int o = 16; o > 0; o >>= 1) dacc += __shfl_xor_sync(0xffffffffu, dacc, o);
+    if (lane == 0) red[warp] = dacc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double sum = 0.0;
+      for (int k = 0; k < kSW; ++k) sum += red[k];
+      a.part[blockIdx.x] = sum;
+    }
+  }
+}
+
 // two interleaved right-hand sides (x, y are (n,2) row-major), fp64 values: the viscous 2-RHS CG
 template <bool DOT, bool DIST>
 __global__ void __launch_bounds__(kST, 4) k_spmv_sell2(SellArgs a, const int* __restrict__ done, DistSell d) {
@@ -239,6 +381,7 @@ __global__ void __launch_bounds__(kST, 4) k_spmv_sell2(SellArgs a, const int* __
   if (DIST) halo_wait(d.c, d.w);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nwarps = gridDim.x * kSW;
+  const uint64_t pol = sell_policy(a.l2hint);
   const double2* __restrict__ x2v = reinterpret_cast<const double2*>(a.x);
   double d0 = 0.0, d1 = 0.0;
   for (int s = blockIdx.x * kSW + warp; s < a.nslices; s += nwarps) {
@@ -253,8 +396,8 @@ __global__ void __launch_bounds__(kST, 4) k_spmv_sell2(SellArgs a, const int* __
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const bool ok = k0 + j < W;
-        vv[j] = ok ? ld_stream(vp + (j << 5)) : 0.0;
-        cc[j] = ok ? ld_stream(cp + (j << 5)) : 0;
+        vv[j] = ok ? ld_stream(vp + (j << 5), pol) : 0.0;
+        cc[j] = ok ? ld_stream(cp + (j << 5), pol) : 0;
       }
       double2 xx[4];
 #pragma unroll
@@ -289,11 +432,13 @@ __device__ __forceinline__ int row_split(const CsrView& A, int rs, int len, int 
 }
 
 // per slice: 32 * (max first-part length + max second-part length); nsplit = INT_MAX: one part
-__global__ void k_sell_width(CsrView A, int nslices, int nsplit, long long* __restrict__ w32, int* __restrict__ wg) {
+__global__ void k_sell_width(CsrView A, int nslices, int nsplit, const int* __restrict__ perm, long long* __restrict__ w32,
+                             int* __restrict__ wg) {
   const int s = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (s > nslices) return;
   int lg = 0, lp = 0;
-  const int row = (s << 5) + lane;
+  const int slot = (s << 5) + lane;
+  const int row = (s < nslices && slot < A.n) ? (perm ? perm[slot] : slot) : A.n;
   if (s < nslices && row < A.n) {
     const int rs = A.rowptr[row], len = A.rowptr[row + 1] - rs;
     lg = row_split(A, rs, len, nsplit);
@@ -310,14 +455,15 @@ __global__ void k_sell_width(CsrView A, int nslices, int nsplit, long long* __re
 }
 
 template <bool F32>
-__global__ void k_sell_fill(CsrView A, int nslices, int nsplit, const long long* __restrict__ sptr, const int* __restrict__ wg,
-                            int* __restrict__ cols, float* __restrict__ v32, double* __restrict__ v64) {
+__global__ void k_sell_fill(CsrView A, int nslices, int nsplit, const int* __restrict__ perm, const long long* __restrict__ sptr,
+                            const int* __restrict__ wg, int* __restrict__ cols, float* __restrict__ v32, double* __restrict__ v64) {
   const int s = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (s >= nslices) return;
   const long long off = sptr[s];
   const int W = (int)((sptr[s + 1] - off) >> 5);
   const int Wg = wg ? wg[s] : W;
-  const int row = (s << 5) + lane;
+  const int slot = (s << 5) + lane;
+  const int row = slot < A.n ? (perm ? perm[slot] : slot) : A.n;
   int rs = 0, len = 0, lg = 0;
   if (row < A.n) { rs = A.rowptr[row]; len = A.rowptr[row + 1] - rs; lg = row_split(A, rs, len, nsplit); }
   for (int k = 0; k < W; ++k) {
@@ -337,16 +483,39 @@ void sell_free(fs_sell* s) { delete s; }
 
 // nsplit >= 0: two-part slices (columns < nsplit first, padded per slice; the second part's columns
 // are stored relative to nsplit), for y = A [x; x2] without a per-entry select.
-void sell_build(const fs_csr& A, bool f32, fs_sell& out, int nsplit) {
+__global__ void k_sigma_keys(const int* __restrict__ rowptr, int n, int sigma, unsigned long long* __restrict__ keys, int* __restrict__ rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned len = (unsigned)(rowptr[i + 1] - rowptr[i]);
+  keys[i] = ((unsigned long long)(unsigned)(i / sigma) << 32) | (0xffffffffu - len);   // window, then longest first (stable: row order)
+  rows[i] = i;
+}
+
+void sell_build(const fs_csr& A, bool f32, fs_sell& out, int nsplit, int sigma) {
   cudaStream_t st = stream();
   const int n = (int)A.n;
   const int nslices = div_up(n, 32);
   const bool split = nsplit >= 0;
+  const int* perm = nullptr;
+  if (sigma > 32 && n > sigma) {
+    DBuf<unsigned long long> keys(n), keys2(n);
+    DBuf<int> rows(n);
+    out.perm.alloc(n);
+    k_sigma_keys<<<div_up(n, 256), 256, 0, st>>>(A.rowptr, n, sigma, keys.p, rows.p);
+    FS_LAUNCH_CHECK();
+    size_t bytes = 0;
+    FS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys.p, keys2.p, rows.p, out.perm.p, n, 0, 64, st));
+    DBuf<char> tmp(bytes);
+    FS_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, keys.p, keys2.p, rows.p, out.perm.p, n, 0, 64, st));
+    count_launch(2);
+    FS_CUDA(cudaStreamSynchronize(st));
+    perm = out.perm.p;
+  }
   DBuf<long long> w32((size_t)nslices + 1);
   out.sptr.alloc((size_t)nslices + 1);
   if (split) out.wg.alloc((size_t)nslices);
   const int g = (int)div_up(((int64_t)nslices + 1) * 32, 256);
-  k_sell_width<<<g, 256, 0, st>>>(A.view(), nslices, split ? nsplit : 0x7fffffff, w32.p, split ? out.wg.p : nullptr);
+  k_sell_width<<<g, 256, 0, st>>>(A.view(), nslices, split ? nsplit : 0x7fffffff, perm, w32.p, split ? out.wg.p : nullptr);
   FS_LAUNCH_CHECK();
   size_t bytes = 0;
   FS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, w32.p, out.sptr.p, nslices + 1, st));
@@ -364,10 +533,15 @@ void sell_build(const fs_csr& A, bool f32, fs_sell& out, int nsplit) {
   out.cols.alloc((size_t)total);
   if (f32) out.v32.alloc((size_t)total); else out.v64.alloc((size_t)total);
   const int ns = split ? nsplit : 0x7fffffff;
-  if (f32) k_sell_fill<true><<<g, 256, 0, st>>>(A.view(), nslices, ns, out.sptr.p, out.wg.p, out.cols.p, out.v32.p, nullptr);
-  else k_sell_fill<false><<<g, 256, 0, st>>>(A.view(), nslices, ns, out.sptr.p, out.wg.p, out.cols.p, nullptr, out.v64.p);
+  if (f32) k_sell_fill<true><<<g, 256, 0, st>>>(A.view(), nslices, ns, perm, out.sptr.p, out.wg.p, out.cols.p, out.v32.p, nullptr);
+  else k_sell_fill<false><<<g, 256, 0, st>>>(A.view(), nslices, ns, perm, out.sptr.p, out.wg.p, out.cols.p, nullptr, out.v64.p);
   FS_LAUNCH_CHECK();
   FS_CUDA(cudaStreamSynchronize(st));
+}
+
+static int l2_hint() {
+  static const int v = [] { const char* e = std::getenv("FS_L2_HINT"); return e ? std::atoi(e) : 1; }();
+  return v;
 }
 
 template <bool SPLIT, bool DOT>
@@ -384,13 +558,56 @@ static void launch_sell(const SellArgs& args, int grid, const DistSell* d) {
 
 // y = S x, or S [x; x2] for a matrix built in split form.  Returns the grid (= number of dot
 // partials when asked for), 0 if S is empty.
+// FS_SELL_TMA=1: the bulk-async staged kernel for the single-GPU SpMVs
+template <bool SPLIT, bool DOT, bool F32, int kBS, int MINB>
+static int launch_bulk_cfg(const SellArgs& args) {
+  constexpr int vb = F32 ? 4 : 8;
+  const size_t smem = (size_t)kSW * kBS * (kBK * 32 * (4 + vb));
+  static int per_sm = -1;
+  if (per_sm < 0) {
+    FS_CUDA(cudaFuncSetAttribute(k_spmv_sell_bulk<SPLIT, DOT, F32, kBS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_spmv_sell_bulk<SPLIT, DOT, F32, kBS, MINB>, kST, smem));
+    per_sm = std::max(per_sm, 1);
+  }
+  const int grid = std::max(1, std::min(div_up(args.nslices, kSW), sm_count() * per_sm));
+  k_spmv_sell_bulk<SPLIT, DOT, F32, kBS, MINB><<<grid, kST, smem, stream()>>>(args);
+  FS_LAUNCH_CHECK();
+  return grid;
+}
+
+static int sell_tma_mode();
+template <bool SPLIT, bool DOT, bool F32>
+static int launch_bulk(const SellArgs& args) {
+  switch (sell_tma_mode()) {
+    case 2: return launch_bulk_cfg<SPLIT, DOT, F32, 2, (F32 ? 6 : 4)>(args);      // 2 stages, many warps
+    case 3: return launch_bulk_cfg<SPLIT, DOT, F32, 3, (F32 ? 4 : 3)>(args);
+    default: return launch_bulk_cfg<SPLIT, DOT, F32, 4, (F32 ? 3 : 2)>(args);     // 4 stages, 24 / 16 warps per SM
+  }
+}
+
+static int sell_tma_mode() {
+  static const int v = [] { const char* e = std::getenv("FS_SELL_TMA"); return e ? std::atoi(e) : 0; }();
+  return v;
+}
+
 static int spmv_sell_impl(const fs_sell& S, const double* x, double* y, const double* x2, double* dot_partials,
                           DistSell* d) {
   if (!S.nslices) return 0;
   FS_REQUIRE((S.nsplit >= 0) == (x2 != nullptr), "spmv_sell: split form and second vector must come together");
+  if (!d && sell_tma_mode() && S.nslices >= 4096) {
+    SellArgs args{S.n, S.nslices, S.sptr.p, S.wg.p, S.cols.p, S.v32.p, S.v64.p, x, x2, y, dot_partials, 1, S.perm.p};
+    const bool f32 = S.v32.p != nullptr;
+    if (x2) {
+      if (dot_partials) return f32 ? launch_bulk<true, true, true>(args) : launch_bulk<true, true, false>(args);
+      return f32 ? launch_bulk<true, false, true>(args) : launch_bulk<true, false, false>(args);
+    }
+    if (dot_partials) return f32 ? launch_bulk<false, true, true>(args) : launch_bulk<false, true, false>(args);
+    return f32 ? launch_bulk<false, false, true>(args) : launch_bulk<false, false, false>(args);
+  }
   const int per_sm = (x2 && S.v32.p && dot_partials && !d) ? 8 : 6;   // the finest up-sweep runs at 32 registers
   int grid = std::max(1, std::min(div_up(S.nslices, kSW), sm_count() * per_sm));
-  SellArgs args{S.n, S.nslices, S.sptr.p, S.wg.p, S.cols.p, S.v32.p, S.v64.p, x, x2, y, dot_partials};
+  SellArgs args{S.n, S.nslices, S.sptr.p, S.wg.p, S.cols.p, S.v32.p, S.v64.p, x, x2, y, dot_partials, l2_hint(), S.perm.p};
+  FS_REQUIRE(!(d && S.perm.p), "SELL-C-sigma matrices are not used by the partitioned kernels");
   int grid_add = 0;
   if (d && (d->w.nch || (d->ps.enabled && !d->ps.gather)) && S.n_blist > 0) {
     d->bmask = S.bmask.p; d->blist = S.blist.p; d->n_blist = S.n_blist;
@@ -480,7 +697,7 @@ int spmv_sell_grid(const fs_sell& S) { return std::max(1, std::min(div_up(S.nsli
 void spmv_sell2(const fs_sell& S, const double* x, double* y, double* dot_partials, const int* done) {
   FS_REQUIRE(S.nslices && S.v64.p && S.nsplit < 0, "spmv_sell2: needs a one-part fp64 SELL matrix");
   const int grid = spmv_sell_grid(S);
-  SellArgs args{S.n, S.nslices, S.sptr.p, nullptr, S.cols.p, nullptr, S.v64.p, x, nullptr, y, dot_partials};
+  SellArgs args{S.n, S.nslices, S.sptr.p, nullptr, S.cols.p, nullptr, S.v64.p, x, nullptr, y, dot_partials, l2_hint(), nullptr};
   static const DistSell none{};
   if (dot_partials) k_spmv_sell2<true, false><<<grid, kST, 0, stream()>>>(args, done, none);
   else k_spmv_sell2<false, false><<<grid, kST, 0, stream()>>>(args, done, none);
@@ -491,7 +708,7 @@ void spmv_sell2_dist(const fs_sell& S, const double* x, double* y, double* dot_p
                      const HaloWait& w) {
   FS_REQUIRE(S.nslices && S.v64.p && S.nsplit < 0, "spmv_sell2: needs a one-part fp64 SELL matrix");
   const int grid = spmv_sell_grid(S);
-  SellArgs args{S.n, S.nslices, S.sptr.p, nullptr, S.cols.p, nullptr, S.v64.p, x, nullptr, y, dot_partials};
+  SellArgs args{S.n, S.nslices, S.sptr.p, nullptr, S.cols.p, nullptr, S.v64.p, x, nullptr, y, dot_partials, l2_hint(), nullptr};
   DistSell d;
   d.c = c;
   d.w = w;

@@ -38,4 +38,18 @@ if has 4; then
       -k regex:k_cg_persistent -c 1 --csv --log-file $out/${tag}_cg_dram_nocachectl.csv \
       python scripts/prof_cg.py 200 > $out/${tag}_ncu_dram.log 2>&1
 fi
+if has 5; then   # roofline records of the rest of the path: DRAM bytes and duration per launch (4M triangles, 4M tracers)
+  python scripts/prof_path.py > $out/${tag}_plain_path.log 2>&1 || { echo "plain path run failed"; tail -5 $out/${tag}_plain_path.log; exit 1; }
+  ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread \
+      --clock-control none --kernel-name-base demangled \
+      -k regex:"k_element_stiffness|k_assemble|k_div_elem|k_div_node|k_grad_elem|k_grad_node|k_locate|k_advect|k_tracer_step|k_backtrace" \
+      -c 60 --csv --log-file $out/${tag}_path_kernels.csv python scripts/prof_path.py > $out/${tag}_ncu_path.log 2>&1
+  tail -2 $out/${tag}_ncu_path.log
+fi
+if has 6; then   # A/B: the bulk-async (TMA) staged SELL kernel against the register-staged one (same launches)
+  FS_SELL_TMA=2 python scripts/prof_amg.py 6 > $out/${tag}_plain_amg_tma.log 2>&1 || { echo "plain amg (tma) failed"; exit 1; }
+  FS_SELL_TMA=2 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"k_spmv_sell_bulk<.bool.(0|1), .bool.1" --launch-skip 6 -c 2 \
+      -o $out/${tag}_spmv_sell_bulk -f python scripts/prof_amg.py 6 > $out/${tag}_ncu_spmv_tma.log 2>&1
+  tail -2 $out/${tag}_ncu_spmv_tma.log
+fi
 echo "profile.sh done: $steps"

@@ -119,5 +119,55 @@ if os.path.exists(f"{G}/{tag}_cg_dram_nocachectl.csv"):
                     "how": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --cache-control none (single pass, no replay, caches left alone)"})
     os.system(f"cp {G}/{tag}_cg_dram_nocachectl.csv {P}/{tag}_cg_dram_nocachectl.csv")
 
+# 5) the rest of the path (assembly, div / grad, locator, tracers): DRAM bytes and duration per launch -> roofline fractions
+if os.path.exists(f"{G}/{tag}_path_kernels.csv"):
+    rows = [r for r in csv.reader(open(f"{G}/{tag}_path_kernels.csv")) if len(r) > 10]
+    hdr = rows[0]
+    ki, mi, ui, vi, idi = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Unit"), hdr.index("Metric Value"), hdr.index("ID")
+    per = collections.OrderedDict()
+    for r in rows[1:]:
+        try: v = float(r[vi].replace(",", ""))
+        except ValueError: continue
+        if r[mi].startswith("dram__bytes"): v *= UNIT.get(r[ui], 1)
+        if r[mi] == "gpu__time_duration.sum": v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(r[ui], 1e-3)
+        per.setdefault((r[idi], r[ki].split("(")[0]), {})[r[mi]] = v
+    agg = collections.OrderedDict()
+    for (_, k), d in per.items():
+        a = agg.setdefault(k, [0, 0.0, 0.0, 0.0, 0.0])
+        a[0] += 1; a[1] += d.get("gpu__time_duration.sum", 0); a[2] += d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0)
+        a[3] = d.get("launch__registers_per_thread", 0); a[4] += d.get("sm__warps_active.avg.pct_of_peak_sustained_active", 0)
+    peak = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"] if os.path.exists("MEASURED_PEAKS.json") else 6650.0
+    # algorithmic bytes per launch on the 4M-triangle mesh (T = 4 194 304, N = 2 099 200, nnz = 14 690 826)
+    T, N, NNZ, P4 = 4194304, 2099200, 14690826, 4000000
+    ALG = {"k_element_stiffness": 12 * T + 16 * N + 72 * T, "k_assemble": 72 * T + 36 * T + 4 * NNZ + 8 * NNZ,
+           "k_div_elem": 12 * T + 16 * N + 16 * N + 8 * T, "k_div_node": 4 * N + 12 * T + 8 * T + 8 * N + 8 * N,
+           "k_grad_elem": 12 * T + 16 * N + 8 * N + 16 * T, "k_grad_node": 4 * N + 12 * T + 16 * T + 8 * N + 16 * N,
+           "k_tracer_step": (16 + 16 + 4 + 4 + 4 + 4) * P4, "k_advect_dye": 16 * N + 16 * N + 8 * N + 8 * N, "k_locate_knn": 16 * N + 4 * N}
+    with open(f"{P}/{tag}_path_kernels.txt", "w") as f:
+        f.write("# ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,... --clock-control none python scripts/prof_path.py\n"
+                "# 4M-triangle mesh (N = 2 099 200), 4M tracers; per launch, mean over the captured launches (cold cache, serialised)\n"
+                f"# roofline: algorithmic bytes (DESIGN.md section 4) / duration against the measured copy bandwidth {peak:.1f} GB/s\n")
+        f.write(f"{'kernel':40s} {'launches':>8s} {'us':>9s} {'DRAM MB':>9s} {'alg MB':>9s} {'alg GB/s':>9s} {'frac':>6s} {'regs':>5s} {'warps %':>8s}\n")
+        for k, (n, t, b, regs, wa) in agg.items():
+            base = k.split("<")[0].replace("void ", "").replace("fs::", "").strip()
+            alg = next((v for kk, v in ALG.items() if base.startswith(kk)), None)
+            us, mb = t / n, b / n / 1e6
+            gbs = (alg / (us * 1e-6) / 1e9) if alg else float("nan")
+            f.write(f"{k[:40]:40s} {n:8d} {us:9.1f} {mb:9.1f} {(alg or 0)/1e6:9.1f} {gbs:9.0f} {gbs/peak:6.2f} {int(regs):5d} {wa/n:8.1f}\n")
+    print(open(f"{P}/{tag}_path_kernels.txt").read())
+
+# 6) A/B of the bulk-async (TMA) staged SELL kernel against the register-staged one
+if os.path.exists(f"{G}/{tag}_spmv_sell_bulk.ncu-rep"):
+    h, u, rs = raw_page(f"{G}/{tag}_spmv_sell_bulk.ncu-rep")
+    with open(f"{P}/{tag}_spmv_sell_bulk_ncu_full.txt", "w") as f:
+        f.write("# FS_SELL_TMA=2 ncu --set full --clock-control none --import-source on --kernel-name-base demangled "
+                "-k regex:'k_spmv_sell_bulk<.bool.(0|1), .bool.1' --launch-skip 6 -c 2 python scripts/prof_amg.py 6\n"
+                "# the same two launches as in the k_spmv_sell capture next to this file, run by the cp.async.bulk + mbarrier staged\n"
+                "# kernel (2 stages per warp, 6 CTAs per SM for fp32 / 4 for fp64): compare duration, DRAM throughput, stall reasons\n")
+        for r in rs:
+            write_full(h, u, r, f)
+            f.write("\n")
+    print(open(f"{P}/{tag}_spmv_sell_bulk_ncu_full.txt").read())
+
 json.dump(traffic, open(TRAFFIC, "w"), indent=1)
 print(open(TRAFFIC).read())
