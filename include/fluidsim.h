@@ -219,6 +219,19 @@ int fs_dist_cg_begin(fs_dist* d, const double* b_own, int precond, double* local
 int fs_dist_cg_run(fs_dist* d, double bb_global, double rz_global, double* x_own, double rtol, int maxit,
                    int precond, int* iters, double* relres, double* ns_pass3 /* host, may be NULL */);
 
+/* ---- B configurations of a squirmer (B1,B2) sweep on one GPU in one call (BASELINE config 4).  The configurations
+ * share the mesh and therefore A_visc and Z^T K Z; B1, B2 enter only through makeDirBCU (code/StokesColor.py:419).
+ * fs_stokes_step_batch runs every kernel of the step once for all of them (grid.y = configuration, the single-CTA
+ * Krylov solvers as one CTA per configuration).  Small meshes (N <= 8192, the shipped ones); warm start = each
+ * configuration's previous pressures.  u: (B,N,2) in/out, b1b2: (B,2), iters: (B,3) {viscous, p, p2} or NULL.
+ * fs_tracer_step_batch: fs_tracer_step for all B tracer sets (pts (B,P,2), status / hint (B,P), u (B,N,2), eaten (B)). */
+typedef struct fs_stokes_batch fs_stokes_batch;
+int fs_stokes_batch_create(fs_stokes* s, int32_t n_configs, fs_stokes_batch** out);
+int fs_stokes_batch_destroy(fs_stokes_batch* b);
+int fs_stokes_step_batch(fs_stokes_batch* b, double* u, const double* b1b2, const fs_stokes_opts* opts, int32_t* iters);
+int fs_tracer_step_batch(fs_mesh* m, int32_t n_configs, double* pts, int32_t* status, int32_t* hint_ids, int64_t n_pts,
+                         const double* u, double DT, double L, double cx, double cy, double rcap, int64_t* eaten /* (B) host */);
+
 /* ---- the whole Stokes step on a mesh cut into contiguous node blocks, one rank (process, GPU) per block
  * (BASELINE config 5: the 32M-triangle annulus on 1/2/4/8 GPUs).  Same sequence as fs_stokes_step
  * (code/StokesColor.py:537-575): 2-RHS viscous CG, BCs, divergence, AMG-preconditioned pressure CG, gradient

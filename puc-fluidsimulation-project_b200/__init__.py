@@ -10,7 +10,7 @@ from .mesh import (readNode, readEle, readPoly, write_node, write_ele, find_boun
 from .core import (Mesh, CsrMatrix, solve, buildStiffnessMatrix, buildFemSystem, buildLumpedMassMatrix,  # noqa: F401
                    calculate_divergence, calculate_gradiant, PointLocator, mixing_index, mesh_for,
                    PRECOND_NONE, PRECOND_JACOBI, PRECOND_AMG, PRECOND_AUTO)
-from .stokes import StokesSolver, StokesColor, StokesFood, food_tracer_grid  # noqa: F401
+from .stokes import StokesSolver, StokesColor, StokesFood, StokesSweep, food_tracer_grid  # noqa: F401
 from .partitioned import PartitionedStokes  # noqa: F401
 from .hostmesh import node_block_split, sub_mesh, local_index_sets  # noqa: F401
 from .poisson import (PoissonProblem, HeatProblem, apply_periodic_bc, apply_dirichlet_rows,  # noqa: F401

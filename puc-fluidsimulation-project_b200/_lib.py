@@ -95,6 +95,10 @@ SIGNATURES = {
     "fs_dist_connect": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64]),
     "fs_dist_cg_begin": (C.c_int, [c_vp, c_vp, C.c_int, c_vp]),
     "fs_dist_cg_run": (C.c_int, [c_vp, c_dbl, c_dbl, c_vp, c_dbl, C.c_int, C.c_int, P(C.c_int), P(c_dbl), c_vp]),
+    "fs_stokes_batch_create": (C.c_int, [c_vp, c_i32, P(c_vp)]),
+    "fs_stokes_batch_destroy": (C.c_int, [c_vp]),
+    "fs_stokes_step_batch": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "fs_tracer_step_batch": (C.c_int, [c_vp, c_i32, c_vp, c_vp, c_vp, c_i64, c_vp, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_vp]),
     "fs_pstokes_create": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp, C.c_int, P(c_vp)]),
     "fs_pstokes_destroy": (C.c_int, [c_vp]),
     "fs_pstokes_sizes": (C.c_int, [c_vp, P(c_i64), P(c_i64), P(c_i64), P(c_i64), P(c_i32)]),

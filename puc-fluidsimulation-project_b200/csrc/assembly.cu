@@ -136,8 +136,10 @@ __global__ void k_node_sum(const int* __restrict__ inc_ptr, const unsigned* __re
 }
 
 // calculate_divergence element part, code/StokesColor.py:145-160
+// (blockIdx.y = configuration of a batched sweep: own fields on the shared mesh, strides bs_* between configurations)
 __global__ void k_div_elem(const double2* __restrict__ coords, const int* __restrict__ tris,
-                           const double2* __restrict__ u, int64_t T, double* __restrict__ lump) {
+                           const double2* __restrict__ u, int64_t T, double* __restrict__ lump, int64_t bs_n = 0) {
+  u += blockIdx.y * bs_n; lump += blockIdx.y * T;
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= T) return;
   int a = tris[3 * e], b = tris[3 * e + 1], c = tris[3 * e + 2];
@@ -154,7 +156,9 @@ __global__ void k_div_elem(const double2* __restrict__ coords, const int* __rest
 
 __global__ void k_div_node(const int* __restrict__ inc_ptr, const unsigned* __restrict__ inc,
                            const double* __restrict__ lump, const double* __restrict__ area_sum, int64_t N,
-                           double* __restrict__ div, double* __restrict__ div_sum) {
+                           double* __restrict__ div, double* __restrict__ div_sum, int64_t bs_n = 0, int64_t bs_t = 0) {
+  lump += blockIdx.y * bs_t;
+  if (div) div += blockIdx.y * bs_n;
   int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (n >= N) return;
   double s = 0.0;
@@ -166,7 +170,8 @@ __global__ void k_div_node(const int* __restrict__ inc_ptr, const unsigned* __re
 // calculate_gradiant element part, code/StokesColor.py:235-253
 __global__ void k_grad_elem(const double2* __restrict__ coords, const int* __restrict__ tris,
                             const double* __restrict__ p, int64_t T, double* __restrict__ lx,
-                            double* __restrict__ ly) {
+                            double* __restrict__ ly, int64_t bs_n = 0) {
+  p += blockIdx.y * bs_n; lx += blockIdx.y * T; ly += blockIdx.y * T;
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= T) return;
   int a = tris[3 * e], b = tris[3 * e + 1], c = tris[3 * e + 2];
@@ -188,7 +193,9 @@ __global__ void k_grad_node(const int* __restrict__ inc_ptr, const unsigned* __r
                             const double* __restrict__ lx, const double* __restrict__ ly,
                             const double* __restrict__ area_sum, int64_t N, double* __restrict__ gx,
                             double* __restrict__ gy, const double2* __restrict__ ui, double2* __restrict__ uo,
-                            double DT, const unsigned char* __restrict__ is_interior) {
+                            double DT, const unsigned char* __restrict__ is_interior, int64_t bs_n = 0, int64_t bs_t = 0) {
+  lx += blockIdx.y * bs_t; ly += blockIdx.y * bs_t;
+  if (MODE != 0) { ui += blockIdx.y * bs_n; uo += blockIdx.y * bs_n; }
   int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (n >= N) return;
   if (MODE == 2 && !is_interior[n]) return;
@@ -273,13 +280,15 @@ __global__ void k_inner_trig(const double2* __restrict__ coords, const int* __re
   s2[k] = sin(2 * th);
 }
 
-__global__ void k_per_bcu_par(const int* __restrict__ pairs, int64_t np, double2* __restrict__ u) {
+__global__ void k_per_bcu_par(const int* __restrict__ pairs, int64_t np, double2* __restrict__ u, int64_t bs_n = 0) {
+  u += blockIdx.y * bs_n;
   int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (k >= np) return;
   u[pairs[2 * k + 1]] = u[pairs[2 * k]];
 }
 
-__global__ void k_per_bcu_seq(const int* __restrict__ pairs, int64_t np, double2* __restrict__ u) {
+__global__ void k_per_bcu_seq(const int* __restrict__ pairs, int64_t np, double2* __restrict__ u, int64_t bs_n = 0) {
+  u += blockIdx.y * bs_n;
   if (blockIdx.x == 0 && threadIdx.x == 0)
     for (int64_t k = 0; k < np; ++k) u[pairs[2 * k + 1]] = u[pairs[2 * k]];
 }
@@ -292,7 +301,9 @@ __global__ void k_scalar_per_seq(const int* __restrict__ pairs, int64_t np, doub
 // makeDirBCU, code/StokesColor.py:405-427
 __global__ void k_dir_bcu(const int* __restrict__ wall, int64_t nw, const int* __restrict__ inner, int64_t ni,
                           const double* __restrict__ s, const double* __restrict__ c, const double* __restrict__ s2,
-                          double B1, double B2, double2* __restrict__ u) {
+                          double B1, double B2, double2* __restrict__ u, const double* __restrict__ b12 = nullptr, int64_t bs_n = 0) {
+  u += blockIdx.y * bs_n;
+  if (b12) { B1 = b12[2 * blockIdx.y]; B2 = b12[2 * blockIdx.y + 1]; }     // batched sweep: (B1, B2) per configuration
   int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (k < nw) u[wall[k]] = make_double2(0.0, 0.0);
   else if (k < nw + ni) {
@@ -337,6 +348,46 @@ void dir_bcu_dev(fs_mesh* m, double* d_u, double B1, double B2) {
   k_dir_bcu<<<div_up(tot, 128), 128, 0, stream()>>>(m->wall.p, m->n_wall, m->inner.p, m->n_inner, m->inner_sin.p,
                                                      m->inner_cos.p, m->inner_sin2.p, B1, B2, (double2*)d_u);
   FS_LAUNCH_CHECK();
+}
+
+// ---- the same operators for B configurations at once (shared mesh, fields strided by N / T) ----
+void divergence_batch_dev(fs_mesh* m, int B, const double* d_u, double* d_div, double* d_lump) {
+  ensure_geom(m);
+  cudaStream_t st = stream();
+  k_div_elem<<<dim3(div_up(m->T, 256), B), 256, 0, st>>>((const double2*)m->coords.p, m->tris.p, (const double2*)d_u, m->T, d_lump, m->N);
+  FS_LAUNCH_CHECK();
+  k_div_node<<<dim3(div_up(m->n_eval(), 256), B), 256, 0, st>>>(m->inc_ptr.p, m->inc.p, d_lump, m->area_sum.p, m->n_eval(), d_div, nullptr, m->N, m->T);
+  FS_LAUNCH_CHECK();
+}
+void grad_update_batch_dev(fs_mesh* m, int B, const double* d_p, const double* d_ui, double* d_uo, double DT,
+                           const unsigned char* d_interior_flag, double* d_lx, double* d_ly) {
+  ensure_geom(m);
+  cudaStream_t st = stream();
+  k_grad_elem<<<dim3(div_up(m->T, 256), B), 256, 0, st>>>((const double2*)m->coords.p, m->tris.p, d_p, m->T, d_lx, d_ly, m->N);
+  FS_LAUNCH_CHECK();
+  const dim3 g(div_up(m->n_eval(), 256), B);
+  if (d_interior_flag)
+    k_grad_node<2><<<g, 256, 0, st>>>(m->inc_ptr.p, m->inc.p, d_lx, d_ly, m->area_sum.p, m->n_eval(), nullptr, nullptr, (const double2*)d_ui,
+                                      (double2*)d_uo, DT, d_interior_flag, m->N, m->T);
+  else
+    k_grad_node<1><<<g, 256, 0, st>>>(m->inc_ptr.p, m->inc.p, d_lx, d_ly, m->area_sum.p, m->n_eval(), nullptr, nullptr, (const double2*)d_ui,
+                                      (double2*)d_uo, DT, nullptr, m->N, m->T);
+  FS_LAUNCH_CHECK();
+}
+void bcu_batch_dev(fs_mesh* m, int B, double* d_u, const double* d_b12) {
+  FS_REQUIRE(m->bc_ready, "fs_bc_set has not been called");
+  cudaStream_t st = stream();
+  if (m->n_pairs) {
+    if (pairs_independent(m->pairs_host)) k_per_bcu_par<<<dim3(div_up(m->n_pairs, 128), B), 128, 0, st>>>(m->pairs.p, m->n_pairs, (double2*)d_u, m->N);
+    else k_per_bcu_seq<<<dim3(1, B), 32, 0, st>>>(m->pairs.p, m->n_pairs, (double2*)d_u, m->N);
+    FS_LAUNCH_CHECK();
+  }
+  const int64_t tot = m->n_wall + m->n_inner;
+  if (tot) {
+    k_dir_bcu<<<dim3(div_up(tot, 128), B), 128, 0, st>>>(m->wall.p, m->n_wall, m->inner.p, m->n_inner, m->inner_sin.p, m->inner_cos.p,
+                                                        m->inner_sin2.p, 0.0, 0.0, (double2*)d_u, d_b12, m->N);
+    FS_LAUNCH_CHECK();
+  }
 }
 
 }  // namespace fs

@@ -262,6 +262,10 @@ void per_bcu_dev(fs_mesh* m, double* d_u);
 void dir_bcu_dev(fs_mesh* m, double* d_u, double B1, double B2);
 void grad_update_dev(fs_mesh* m, const double* d_p, const double* d_ui, double* d_uo, double DT,
                      const unsigned char* d_interior_flag /* null: all nodes */);
+void divergence_batch_dev(fs_mesh* m, int B, const double* d_u, double* d_div, double* d_lump);
+void grad_update_batch_dev(fs_mesh* m, int B, const double* d_p, const double* d_ui, double* d_uo, double DT,
+                           const unsigned char* d_interior_flag, double* d_lx, double* d_ly);
+void bcu_batch_dev(fs_mesh* m, int B, double* d_u, const double* d_b12);   // makePerBCU + makeDirBCU with (B1, B2) per configuration
 void jacobi_prepare(fs_csr* a);
 void ensure_tiles(fs_csr* a);
 // warp-granular SpMV with fused epilogues (spmv_warp.cu); returns the grid used or 0 if unsupported
@@ -311,6 +315,9 @@ void cg_persistent_launch(const CsrView& A, double* x, double* r, double* p, dou
 // CG on device pointers; returns iterations, writes relres.
 int cg_dev(fs_csr* a, const double* d_b, double* d_x, int nrhs, double rtol, int maxit, int precond,
            int project_mean, double* relres);
+void cg_small_batch_dev(fs_csr* a, const double* d_b, double* d_x, int nrhs, int B, double rtol, int maxit, int precond,
+                        int project_mean, double* ws, double* out, int* flags);
+int cg_small_limit();
 void spmv_dev(const CsrView& A, const double* d_x, double* d_y);
 double resid_norm2_dev(fs_csr* a, const double* b, const double* x, double* work);   // |b - A x|^2
 void spmv_best_dev(fs_csr* a, const double* x, double* y);                          // y = A x, fastest layout at hand

@@ -503,6 +503,12 @@ k_cg_small(CsrView A, const double* __restrict__ dinv, const double* __restrict_
            int* __restrict__ flags) {
   __shared__ double red[32];
   const int n = A.n, t = threadIdx.x, nt = blockDim.x;
+  // batch: CTA c solves system c (same matrix; right-hand side, solution, workspace and results c-th in their arrays)
+  b_in += (size_t)blockIdx.x * n * R;
+  x += (size_t)blockIdx.x * n * R;
+  ws += (size_t)blockIdx.x * 4 * n * R;
+  out += (size_t)blockIdx.x * 2 * R;
+  flags += (size_t)blockIdx.x * 2;
   double *r = ws, *p = r + (size_t)n * R, *Ap = p + (size_t)n * R, *b = Ap + (size_t)n * R;
   auto csum = [&](double v) -> double {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -649,6 +655,19 @@ static int cg_small(fs_csr* a, const double* d_b, double* d_x, double rtol, int 
   if (relres) *relres = worst;
   return hf[0] ? hf[1] : -hf[1] - 1;
 }
+
+// B independent systems with the same (small) matrix: one launch, one CTA per system.  x holds the initial guesses.
+// ws: B*4*n*nrhs doubles, out: B*2*nrhs, flags: B*2 ints (device).  No host synchronisation.
+void cg_small_batch_dev(fs_csr* a, const double* d_b, double* d_x, int nrhs, int B, double rtol, int maxit, int precond,
+                        int project_mean, double* ws, double* out, int* flags) {
+  FS_REQUIRE(a->n <= kSmallCgN, "cg_small_batch_dev: the matrix is too large for the single-CTA solver");
+  const double* dinv = nullptr;
+  if (precond == FS_PRECOND_JACOBI) { jacobi_prepare(a); dinv = a->dinv.p; }
+  if (nrhs == 1) k_cg_small<1><<<B, 1024, 0, stream()>>>(a->view(), dinv, d_b, d_x, ws, rtol * rtol, maxit, project_mean, out, flags);
+  else k_cg_small<2><<<B, 1024, 0, stream()>>>(a->view(), dinv, d_b, d_x, ws, rtol * rtol, maxit, project_mean, out, flags);
+  FS_LAUNCH_CHECK();
+}
+int cg_small_limit() { return kSmallCgN; }
 
 // FS_CG_MODE=multi forces the 3-kernels-per-iteration path (A/B testing); default persistent
 static int cg_mode() {

@@ -68,7 +68,8 @@ __global__ void k_visc_vals(CsrView K, double dtnu, const unsigned char* __restr
 // id) is gathered first, the few merged-in nodes are added in ascending node order by one thread per
 // dof that has any -- the same bits on every run however many nodes share a dof.
 __global__ void k_pressure_rhs(int64_t nd, const int* __restrict__ rep, const double* __restrict__ mass,
-                               const double* __restrict__ div, double s, double* __restrict__ rhs_red) {
+                               const double* __restrict__ div, double s, double* __restrict__ rhs_red, int64_t bs_n = 0) {
+  div += blockIdx.y * bs_n; rhs_red += blockIdx.y * nd;
   int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (d >= nd) return;
   const int n = rep[d];
@@ -76,7 +77,9 @@ __global__ void k_pressure_rhs(int64_t nd, const int* __restrict__ rep, const do
 }
 __global__ void k_pressure_rhs_extra(int64_t n_ex, const int* __restrict__ ex_ptr, const int* __restrict__ ex_dof,
                                      const int* __restrict__ ex_node, const double* __restrict__ mass,
-                                     const double* __restrict__ div, double s, double* __restrict__ rhs_red) {
+                                     const double* __restrict__ div, double s, double* __restrict__ rhs_red, int64_t bs_n = 0,
+                                     int64_t bs_nd = 0) {
+  div += blockIdx.y * bs_n; rhs_red += blockIdx.y * bs_nd;
   int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (j >= n_ex) return;
   double v = rhs_red[ex_dof[j]];
@@ -84,7 +87,9 @@ __global__ void k_pressure_rhs_extra(int64_t n_ex, const int* __restrict__ ex_pt
   rhs_red[ex_dof[j]] = v;
 }
 
-__global__ void k_expand(int64_t N, const int* __restrict__ dof, const double* __restrict__ q, double* __restrict__ p) {
+__global__ void k_expand(int64_t N, const int* __restrict__ dof, const double* __restrict__ q, double* __restrict__ p,
+                         int64_t bs_nd = 0) {
+  q += blockIdx.y * bs_nd; p += blockIdx.y * N;            // blockIdx.y = configuration of a batched sweep
   int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (n < N) p[n] = q[dof[n]];
 }
@@ -327,6 +332,101 @@ int fs_stokes_pressure(fs_stokes* s, double* p, double* p2) {
   const int64_t N = s->mesh->N;
   if (p) FS_CUDA(cudaMemcpyAsync(p, s->p_full.p, N * sizeof(double), cudaMemcpyDefault, stream()));
   if (p2) FS_CUDA(cudaMemcpyAsync(p2, s->p2_full.p, N * sizeof(double), cudaMemcpyDefault, stream()));
+  fs::sync();
+  FS_API_END
+}
+
+// ---- B configurations of a (B1, B2) sweep that share the mesh and therefore A_visc and Z^T K Z (BASELINE config 4):
+// every kernel of the step runs once for all of them (grid.y = configuration; the single-CTA Krylov solvers as one
+// CTA per configuration), instead of B launch-latency-bound step sequences.  B1, B2 enter only through makeDirBCU
+// (code/StokesColor.py:419).  Small meshes only (the shipped ones): the solves use the one-CTA CG.
+struct fs_stokes_batch {
+  fs_stokes* s = nullptr;
+  int B = 0;
+  fs::DBuf<double> ustar, div, lump_a, lump_c, rhs, q1, q2, p_full, ws, out, b12;
+  fs::DBuf<int> flags;
+};
+
+int fs_stokes_batch_create(fs_stokes* s, int32_t B, fs_stokes_batch** out) {
+  FS_API_BEGIN
+  FS_REQUIRE(s && out && B >= 1 && B <= 65535, "bad arguments");
+  *out = nullptr;
+  const int64_t N = s->mesh->N, T = s->mesh->T, nd = s->nd;
+  FS_REQUIRE(N <= cg_small_limit(), "fs_stokes_batch: the mesh is too large for the batched single-CTA solvers; "
+                                    "advance the configurations one by one (fs_stokes_step) or partition the mesh (fs_pstokes_*)");
+  std::unique_ptr<fs_stokes_batch> b(new fs_stokes_batch());
+  b->s = s; b->B = B;
+  b->ustar.alloc((size_t)B * 2 * N); b->div.alloc((size_t)B * N); b->lump_a.alloc((size_t)B * T); b->lump_c.alloc((size_t)B * T);
+  b->rhs.alloc((size_t)B * nd); b->q1.alloc((size_t)B * nd); b->q2.alloc((size_t)B * nd); b->p_full.alloc((size_t)B * N);
+  b->ws.alloc((size_t)B * 4 * 2 * N); b->out.alloc((size_t)B * 4); b->flags.alloc((size_t)B * 2); b->b12.alloc((size_t)B * 2);
+  b->q1.zero(); b->q2.zero();
+  fs::sync();
+  *out = b.release();
+  FS_API_END
+}
+
+int fs_stokes_batch_destroy(fs_stokes_batch* b) {
+  FS_API_BEGIN
+  if (b) { cudaStreamSynchronize(stream()); delete b; }
+  FS_API_END
+}
+
+int fs_stokes_step_batch(fs_stokes_batch* b, double* u, const double* b1b2, const fs_stokes_opts* opts, int32_t* iters) {
+  FS_API_BEGIN
+  FS_REQUIRE(b && u && b1b2, "NULL argument");
+  fs_stokes_opts o;
+  fs_stokes_default_opts(&o);
+  if (opts) o = *opts;
+  fs_stokes* s = b->s;
+  fs_mesh* m = s->mesh;
+  const int B = b->B;
+  const int64_t N = m->N, nd = s->nd;
+  cudaStream_t st = stream();
+  Out<double> ou(u, (size_t)B * 2 * N, true);
+  double* du = ou.d;
+  FS_CUDA(cudaMemcpyAsync(b->b12.p, b1b2, (size_t)B * 2 * sizeof(double), cudaMemcpyDefault, st));
+  const int pre_p = (o.precond == FS_PRECOND_NONE) ? FS_PRECOND_NONE : FS_PRECOND_JACOBI;
+  std::vector<int> hf((size_t)B * 2);
+  auto read_iters = [&](int col) {
+    FS_CUDA(cudaMemcpyAsync(hf.data(), b->flags.p, hf.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+    FS_CUDA(cudaStreamSynchronize(st));
+    for (int c = 0; c < B; ++c) {
+      if (!hf[2 * c]) throw Error(FS_ERR_NOCONV, "fs_stokes_step_batch: a solve did not converge within maxit");
+      if (iters) iters[3 * c + col] = hf[2 * c + 1];
+    }
+  };
+  // viscous solve (2 right-hand sides per configuration), started from u
+  FS_CUDA(cudaMemcpyAsync(b->ustar.p, du, (size_t)B * 2 * N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  cg_small_batch_dev(&s->a_visc, du, b->ustar.p, 2, B, o.rtol_visc, o.maxit, pre_p, 0, b->ws.p, b->out.p, b->flags.p);
+  if (iters) read_iters(0);
+  bcu_batch_dev(m, B, b->ustar.p, b->b12.p);
+  auto pressure = [&](const double* vel, double* q, int col) {
+    divergence_batch_dev(m, B, vel, b->div.p, b->lump_a.p);
+    k_pressure_rhs<<<dim3(div_up(nd, 256), B), 256, 0, st>>>(nd, s->rep.p, m->mass.p, b->div.p, -(1.0 / s->DT), b->rhs.p, N);
+    FS_LAUNCH_CHECK();
+    if (s->n_ex) {
+      k_pressure_rhs_extra<<<dim3(div_up(s->n_ex, 128), B), 128, 0, st>>>(s->n_ex, s->ex_ptr.p, s->ex_dof.p, s->ex_node.p, m->mass.p,
+                                                                        b->div.p, -(1.0 / s->DT), b->rhs.p, N, nd);
+      FS_LAUNCH_CHECK();
+    }
+    if (!o.warm_start) FS_CUDA(cudaMemsetAsync(q, 0, (size_t)B * nd * sizeof(double), st));
+    cg_small_batch_dev(&s->k_red, b->rhs.p, q, 1, B, o.rtol_pressure, o.maxit, pre_p, 1, b->ws.p, b->out.p, b->flags.p);
+    if (iters) read_iters(col);
+    k_expand<<<dim3(div_up(N, 256), B), 256, 0, st>>>(N, s->dof.p, q, b->p_full.p, nd);
+    FS_LAUNCH_CHECK();
+  };
+  pressure(b->ustar.p, b->q1.p, 1);
+  grad_update_batch_dev(m, B, b->p_full.p, b->ustar.p, du, s->DT, nullptr, b->lump_a.p, b->lump_c.p);
+  bcu_batch_dev(m, B, du, b->b12.p);
+  pressure(du, b->q2.p, 2);
+  grad_update_batch_dev(m, B, b->p_full.p, du, du, s->DT, s->is_interior.p, b->lump_a.p, b->lump_c.p);
+  ou.commit();
+  if (!iters) {          // without per-solve reads: at least the last solve of every configuration must have converged
+    FS_CUDA(cudaMemcpyAsync(hf.data(), b->flags.p, hf.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+    FS_CUDA(cudaStreamSynchronize(st));
+    for (int c = 0; c < B; ++c)
+      if (!hf[2 * c]) throw Error(FS_ERR_NOCONV, "fs_stokes_step_batch: a pressure solve did not converge within maxit");
+  }
   fs::sync();
   FS_API_END
 }

@@ -371,7 +371,9 @@ k_locate_exact(LocView V, const double2* __restrict__ pts, int64_t P, int* __res
 __global__ void __launch_bounds__(128)
 k_tracer_step(LocView V, const double2* __restrict__ u, double2* __restrict__ pts, int* __restrict__ status,
               int* __restrict__ hint, int64_t P, double DT, double L, double cx, double cy, double rcap,
-              unsigned long long* __restrict__ eaten) {
+              unsigned long long* __restrict__ eaten, int64_t u_stride) {
+  // blockIdx.y = configuration of a batched sweep (own velocity field and tracer set on the shared mesh)
+  u += blockIdx.y * u_stride; pts += blockIdx.y * P; status += blockIdx.y * P; hint += blockIdx.y * P; eaten += blockIdx.y;
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int st = 0;
   if (i < P) {
@@ -597,11 +599,33 @@ int fs_tracer_step(fs_mesh* m, double* pts, int32_t* status, int32_t* hint_ids, 
   DBuf<unsigned long long> cnt(1);
   cnt.zero();
   k_tracer_step<<<div_up(P, 128), 128, 0, stream()>>>(V, (const double2*)iu.d, (double2*)op.d, os.d, oh.d, P, DT, L, cx,
-                                                       cy, rcap, cnt.p);
+                                                       cy, rcap, cnt.p, 0);
   FS_LAUNCH_CHECK();
   op.commit(); os.commit(); oh.commit();
   unsigned long long h = cnt.to_host()[0];
   if (eaten) *eaten = (int64_t)h;
+  FS_API_END
+}
+
+// B configurations of a sweep in one launch: pts (B,P,2), status / hint (B,P), u (B,N,2), eaten (B) host
+int fs_tracer_step_batch(fs_mesh* m, int32_t B, double* pts, int32_t* status, int32_t* hint_ids, int64_t P, const double* u,
+                         double DT, double L, double cx, double cy, double rcap, int64_t* eaten) {
+  FS_API_BEGIN
+  FS_REQUIRE(m && u && B >= 1 && (P == 0 || (pts && status && hint_ids)), "bad arguments");
+  if (P == 0) { if (eaten) for (int c = 0; c < B; ++c) eaten[c] = 0; return FS_OK; }
+  FS_REQUIRE(B <= 65535, "at most 65535 configurations per call");
+  LocView V = loc_view(m);
+  In<double> iu(u, (size_t)B * 2 * m->N);
+  Out<double> op(pts, (size_t)B * 2 * P, true);
+  Out<int> os(status, (size_t)B * P, true), oh(hint_ids, (size_t)B * P, true);
+  DBuf<unsigned long long> cnt(B);
+  cnt.zero();
+  k_tracer_step<<<dim3(div_up(P, 128), B), 128, 0, stream()>>>(V, (const double2*)iu.d, (double2*)op.d, os.d, oh.d, P, DT, L, cx,
+                                                                cy, rcap, cnt.p, m->N);
+  FS_LAUNCH_CHECK();
+  op.commit(); os.commit(); oh.commit();
+  std::vector<unsigned long long> h = cnt.to_host();
+  if (eaten) for (int c = 0; c < B; ++c) eaten[c] = (int64_t)h[c];
   FS_API_END
 }
 

@@ -204,3 +204,68 @@ class StokesFood(StokesSolver):
     def step_all(self):
         st = self.step()
         return st, self.tracer_step()
+
+
+class StokesSweep:
+    """BASELINE config 4 on one GPU: B squirmer configurations (B1, B2) on one mesh advanced TOGETHER -- the operators
+    are shared (B1, B2 enter only through makeDirBCU, code/StokesColor.py:419), so every kernel of the step runs once
+    for all configurations (fs_stokes_step_batch) and the passive-tracer step of code/StokesFood.py:482-503 once for
+    all tracer sets (fs_tracer_step_batch).  Arrays carry a leading configuration axis; numpy or torch cuda tensors."""
+
+    def __init__(self, nodes_coords, nodes_boundary_markers, triangles, configs, DT=0.01, v=1.0, grid_density=25,
+                 tracer_points=None, device_arrays=False, **kw):
+        self.configs = [(float(a), float(b)) for a, b in configs]
+        self.B = len(self.configs)
+        self.base = StokesSolver(nodes_coords, nodes_boundary_markers, triangles, B1=self.configs[0][0], B2=self.configs[0][1],
+                                 DT=DT, v=v, **kw)
+        self.N, self.DT, self.mesh = self.base.N, DT, self.base.mesh
+        self.b12 = np.ascontiguousarray(self.configs, dtype=np.float64)
+        h = C.c_void_p()
+        call("fs_stokes_batch_create", self.base._h, self.B, C.byref(h))
+        self._h = h
+        self.u = np.zeros((self.B, self.N, 2))
+        for c, (B1, B2) in enumerate(self.configs):                   # code/StokesColor.py:482-483 per configuration
+            self.mesh.make_dir_bcu(self.u[c], B1, B2)
+        pts = (food_tracer_grid(grid_density, self.base.L, self.base.H, StokesFood.SQUIRMER_RADIUS)
+               if tracer_points is None else np.ascontiguousarray(tracer_points, dtype=np.float64))
+        self.num_tracers = pts.shape[0]
+        if device_arrays:
+            import torch
+            self.u = torch.from_numpy(self.u).cuda()
+            one = torch.from_numpy(pts).cuda()
+            self.tracer_points = one.unsqueeze(0).repeat(self.B, 1, 1).contiguous()
+            self.tracer_status = torch.zeros((self.B, self.num_tracers), dtype=torch.int32, device="cuda")
+            self._hint = torch.full((self.B, self.num_tracers), -1, dtype=torch.int32, device="cuda")
+        else:
+            self.tracer_points = np.ascontiguousarray(np.broadcast_to(pts, (self.B,) + pts.shape))
+            self.tracer_status = np.zeros((self.B, self.num_tracers), dtype=np.int32)
+            self._hint = np.full((self.B, self.num_tracers), -1, dtype=np.int32)
+        self.iters = np.zeros((self.B, 3), dtype=np.int32)
+        self.num_eaten = np.zeros(self.B, dtype=np.int64)
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.lib.fs_stokes_batch_destroy(self._h)
+        except Exception:
+            pass
+
+    def step(self, want_iters=False):
+        """One flow step of every configuration (code/StokesColor.py:540-575), in place on self.u."""
+        call("fs_stokes_step_batch", self._h, ptr(self.u, np.float64, (self.B, self.N, 2), "u"), ptr(self.b12),
+             C.byref(self.base.opts), ptr(self.iters) if want_iters else None)
+        return self.iters if want_iters else None
+
+    def tracer_step(self):
+        """code/StokesFood.py:482-503 for every configuration's tracer set; returns the eaten counts (B,)."""
+        s = StokesFood
+        call("fs_tracer_step_batch", self.mesh._h, self.B, ptr(self.tracer_points, np.float64, (self.B, self.num_tracers, 2), "pts"),
+             ptr(self.tracer_status, np.int32, (self.B, self.num_tracers), "status"),
+             ptr(self._hint, np.int32, (self.B, self.num_tracers), "hint"), self.num_tracers,
+             ptr(self.u, np.float64, (self.B, self.N, 2), "u"), float(self.DT), float(self.base.L), float(s.SQUIRMER_CENTER[0]),
+             float(s.SQUIRMER_CENTER[1]), float(s.CAPTURE_RADIUS), ptr(self.num_eaten))
+        return self.num_eaten
+
+    def step_all(self):
+        self.step()
+        return self.tracer_step()

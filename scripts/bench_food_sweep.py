@@ -18,6 +18,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=200)
 ap.add_argument("--configs", type=int, default=64)
 ap.add_argument("--grid", type=int, default=2257)      # g x g tracer grid minus the body: 3.86M tracers
+ap.add_argument("--batched", action="store_true",
+                help="advance this rank's configurations TOGETHER (fs_stokes_step_batch / fs_tracer_step_batch): one launch "
+                     "sequence per step for all of them instead of one per configuration")
+ap.add_argument("--group", type=int, default=16, help="--batched: configurations per batch (memory: 24 B x tracers each)")
 args = ap.parse_args()
 rank, world, local, dist = par.init_distributed()
 torch.cuda.set_device(local)
@@ -32,6 +36,15 @@ torch.cuda.synchronize()
 if dist is not None:
     dist.barrier()
 t0 = time.perf_counter()
+if args.batched:
+    for k0 in range(0, len(mine), args.group):
+        grp = mine[k0:k0 + args.group]
+        sw = fb.StokesSweep(g["nodes"], g["markers"], g["tris"], grp, DT=0.01, v=1.0, tracer_points=pts0, device_arrays=True)
+        for _ in range(args.steps):
+            eaten = sw.step_all()
+        results += [(b1, b2, int(e) / P) for (b1, b2), e in zip(grp, eaten)]
+        del sw
+    mine = []
 for (B1, B2) in mine:
     sim = fb.StokesSolver(g["nodes"], g["markers"], g["tris"], B1=B1, B2=B2, DT=0.01, v=1.0)
     u = torch.from_numpy(sim.u.copy()).cuda()
@@ -50,6 +63,7 @@ tot_eaten = par.allreduce(sum(r[2] for r in results), "sum", dist)
 if rank == 0:
     n_cfg = min(args.configs, 64)
     print(json.dumps({"workload": f"StokesFood sweep: {n_cfg} (B1,B2) configs x {P} tracers, mesh5.1, {args.steps} steps each",
+                      "mode": f"batched, {args.group} configurations per launch sequence" if args.batched else "one configuration at a time",
                       "n_gpus": world, "seconds": dt, "config_steps_per_s": n_cfg * args.steps / dt,
                       "tracer_updates_per_s": n_cfg * args.steps * P / dt,
                       "ms_per_config_step": 1e3 * dt * world / (n_cfg * args.steps),
