@@ -110,6 +110,9 @@ int fs_scatter_map(const fs_mesh* m, int32_t* scatter /* (t,9): entry (i,j) at i
  *   constant g_const.  fs_centroids gives the centroids in the same arithmetic. */
 int fs_assemble_stiffness(fs_mesh* m, double* vals /* nnz */);
 int fs_lumped_mass(fs_mesh* m, double* mass /* n */);
+/* build_mass_and_convection, code/StokesColor.py:286-312 (defined by the reference, used by its convection drafts):
+ * consistent mass (area/12 (1 + delta_ij)) and convection (area/3 u_c . grad phi_j) on the structural pattern */
+int fs_assemble_mass_convection(fs_mesh* m, const double* u /* (n,2) */, double* m_vals /* nnz */, double* c_vals /* nnz */);
 int fs_centroids(fs_mesh* m, int f32_arith, double* cx /* t */, double* cy /* t */);
 int fs_assemble_fem(fs_mesh* m, int f32_arith, const double* g_centroid, double g_const,
                     double* vals /* nnz */, double* b /* n */);
@@ -132,6 +135,8 @@ int fs_bc_set(fs_mesh* m, const int32_t* wall, int64_t n_wall, const int32_t* in
               const int32_t* interior, int64_t n_interior);
 int fs_make_per_bcu(fs_mesh* m, double* u /* (n,2) */);
 int fs_make_dir_bcu(fs_mesh* m, double* u /* (n,2) */, double B1, double B2);
+/* rotating inner cylinder (scripts/stokes_report.py:1155-1171): u = omega x (r - centre) on the inner boundary, 0 on the walls */
+int fs_make_rot_bcu(fs_mesh* m, double* u /* (n,2) */, double omega, double cx, double cy);
 int fs_reapply_scalar_bc(fs_mesh* m, double* u /* n */, const int32_t* pairs_all, int64_t n_pairs_all,
                          double wall_value, double inner_value);
 
@@ -168,6 +173,9 @@ typedef struct fs_stokes_opts {
   int precond;           /* FS_PRECOND_* of the pressure solves    (default AUTO) */
   int warm_start;        /* start pressure CG from the previous step's p / p2 (default 1) */
   int final_div;         /* also evaluate final_div (:575) and its max-norm (default 0) */
+  int bc_mode;           /* Dirichlet data of the inner boundary: 0 = squirmer (B1,B2), makeDirBCU :405-427 (default);
+                            1 = rotating cylinder u = omega x r about (0.5,0.5), scripts/stokes_report.py:1155-1171 */
+  double omega;          /* bc_mode 1: angular velocity of this step (the caller ramps it, :1159-1162) */
 } fs_stokes_opts;
 typedef struct fs_stokes_stats {
   int iters_visc, iters_p1, iters_p2;
@@ -281,6 +289,8 @@ int fs_pstokes_state(fs_pstokes* s, double* buf, int set);
 int fs_locate(fs_mesh* m, const double* pts /* (P,2) */, int64_t n_pts, int32_t* ids /* P */);
 int fs_advect_dye(fs_mesh* m, double* c /* n */, const double* u /* (n,2) */, double DT,
                   int32_t* ids_out /* n or NULL */);
+/* explicit dye diffusion of scripts/good_visualization2.py:704-715: c <- clip(c + DT*D*(K c), 0, 1), K = stiffness handle */
+int fs_dye_diffuse(fs_csr* K, double* c /* n */, double DT, double D);
 int fs_mixing_index(fs_mesh* m, const double* c, const double* mass, const int32_t* mask_idx,
                     int64_t n_mask, double* out3);
 int fs_locate_exact(fs_mesh* m, const double* pts, int64_t n_pts, int32_t* hint_ids /* P in/out */);

@@ -278,6 +278,43 @@ def gen_poisson_heat(mesh, heat_steps=1000):      # BASELINE config 2: 1000 time
     print(f"[{mesh}] poisson/heat: N={N} pairs={len(pf)} fem b gap {gap_b:.1e} OK")
 
 
+def gen_variants(mesh="mesh5.1"):
+    """Fixtures for the draft-script physics variants.  build_mass_and_convection is a function of
+    code/StokesColor.py and is executed literally; the rotating-cylinder data, the dye diffusion and the pressure
+    smoothing are inline script statements (scripts/stokes_report.py, scripts/good_visualization2.py), restated."""
+    ns = L.load_functions("StokesColor.py")
+    npth, epth = L.mesh_paths(mesh)
+    with L.quiet():
+        nodes, markers = ns["readNode"](npth)
+        tris = ns["readEle"](epth)
+    N = nodes.shape[0]
+    rng = np.random.default_rng(11)
+    u = rng.standard_normal((N, 2))
+    M, Cm = ns["build_mass_and_convection"](nodes, tris, u)
+    rp, ci, scatter = R.csr_pattern(N, tris)
+    mv, cv = R.mass_convection(nodes, tris, u, rp, ci, scatter)
+    Md = sp.csr_matrix((mv, ci, rp), shape=(N, N)).toarray()
+    Cd = sp.csr_matrix((cv, ci, rp), shape=(N, N)).toarray()
+    assert np.array_equal(Md, M), "consistent mass not bit-exact"
+    gap_c = np.abs(Cd - Cm).max() / np.abs(Cm).max()
+    assert gap_c <= 1e-15, gap_c                      # np.dot of 2-vectors: BLAS summation / FMA
+    wall, inner, _, _ = R.index_sets(nodes, markers)
+    urot = rng.standard_normal((N, 2))
+    omega = R.ramp_omega(37)
+    R.rotating_cylinder_bcu(urot, nodes, wall, inner, omega)
+    kvals = R.assemble_stiffness(nodes, tris, rp, ci, scatter)
+    K = sp.csr_matrix((kvals, ci, rp), shape=(N, N))
+    c_adv = rng.uniform(0.0, 1.0, N)
+    c_dif = R.dye_diffuse(c_adv, K, 0.05, 1e-3)
+    p_raw = rng.standard_normal(N)
+    p_s = R.helmholtz_smooth(K.toarray(), p_raw, ref=3, alpha=0.01)
+    np.savez_compressed(os.path.join(OUT, mesh.replace(".", "_") + "_variants.npz"),
+                        u=u, M_vals=mv, C_vals_literal=sp.csr_matrix(Cm)[np.repeat(np.arange(N), np.diff(rp)), ci].A1,
+                        C_vals=cv, gap_c=gap_c, urot_in=rng.standard_normal((N, 2)) * 0 + 7.0, urot=urot, omega=omega,
+                        c_adv=c_adv, c_dif=c_dif, DT=0.05, D=1e-3, p_raw=p_raw, p_smooth=p_s, ref=3, alpha=0.01)
+    print(f"[{mesh}] variants: mass bit-exact, convection gap {gap_c:.1e} OK")
+
+
 def main():
     if not L.available():
         sys.exit("reference checkout not found; fixtures can only be generated in the authoring container")
@@ -289,11 +326,14 @@ def main():
     gen_trajectory("mesh5.1", "food_pusher", -2.0, -5.0, 0.01, 1.0, steps=100, dye=False, food=True)
     gen_trajectory("mesh5.1", "food_neutral", -2.0, 0.0, 0.01, 1.0, steps=100, dye=False, food=True)
     gen_trajectory("mesh_fine.1", "color_puller", -2.0, 5.0, 0.05, 0.1, steps=20)
+    gen_variants()
 
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "--heat-only":      # regenerate the Poisson / heat fixtures alone
         for m in MESHES:
             gen_poisson_heat(m)
+    elif len(sys.argv) > 1 and sys.argv[1] == "--variants-only":
+        gen_variants()
     else:
         main()

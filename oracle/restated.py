@@ -342,19 +342,27 @@ class RestatedStokes:
         x += self._visc_lu.solve(rhs - self.A_visc @ x)
         return x
 
+    omega = None      # set to an angular velocity: rotating-cylinder data instead of the squirmer's (stokes_report.py:1155-1171)
+
+    def _dirichlet(self, v):
+        if self.omega is None:
+            make_dir_bcu(v, self.nodes, self.wall, self.inner_b, self.B1, self.B2)
+        else:
+            rotating_cylinder_bcu(v, self.nodes, self.wall, self.inner_b, self.omega)
+
     def flow_step(self):
         DT, nodes, tris = self.DT, self.nodes, self.tris
         u = self.u
         us = np.stack([self._visc_solve(u[:, 0].copy()), self._visc_solve(u[:, 1].copy())], axis=1)
         make_per_bcu(us, self.pairs)
-        make_dir_bcu(us, nodes, self.wall, self.inner_b, self.B1, self.B2)
+        self._dirichlet(us)
         self.div_u_star = divergence(nodes, tris, us)
         p = self.psys.solve(-(1.0 / DT) * self.div_u_star)
         gx, gy = gradient(nodes, tris, p)
         u[:, 0] = us[:, 0] - DT * gx
         u[:, 1] = us[:, 1] - DT * gy
         make_per_bcu(u, self.pairs)
-        make_dir_bcu(u, nodes, self.wall, self.inner_b, self.B1, self.B2)
+        self._dirichlet(u)
         p2 = self.psys.solve(-(1.0 / DT) * divergence(nodes, tris, u))
         g2x, g2y = gradient(nodes, tris, p2)
         u[self.interior, 0] -= DT * g2x[self.interior]
@@ -670,3 +678,59 @@ def splat_points(rgba, points, status, colors, radius_px, extent=(0.0, 1.0, 0.0,
                     rgba[yy, xx, :3] = colors[k]
                     rgba[yy, xx, 3] = 255
     return rgba
+
+
+# --------------------------------------------------------------------------- physics variants of the draft scripts
+def ramp_omega(step, target=5.0, ramp_up_steps=200):
+    """scripts/stokes_report.py:1156-1162."""
+    return target * (step + 1) / ramp_up_steps if step < ramp_up_steps else target
+
+
+def rotating_cylinder_bcu(u, nodes, wall, inner, omega, center=(0.5, 0.5)):
+    """scripts/stokes_report.py:1150-1171 (the Dirichlet data the script's loop writes: walls at rest, the inner
+    boundary moving tangentially with angular velocity omega)."""
+    u[wall] = 0.0
+    rx = nodes[inner, 0] - center[0]
+    ry = nodes[inner, 1] - center[1]
+    u[inner, 0] = -ry * omega
+    u[inner, 1] = rx * omega
+
+
+def mass_convection(nodes, tris, u, rowptr, colidx, scatter):
+    """build_mass_and_convection, code/StokesColor.py:286-312, on the structural pattern: consistent mass and
+    convection values, contributions added in ascending element order, (i, j) i-major (like the dense loop)."""
+    tris = np.asarray(tris)
+    det, yd, xd = _geom(nodes, tris)
+    keep = np.abs(det) >= 1e-14
+    area = 0.5 * np.abs(det)
+    uc = ((u[tris[:, 0]] + u[tris[:, 1]]) + u[tris[:, 2]]) / 3.0            # u[idx].mean(axis=0)
+    den = 2 * np.abs(det)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        gx, gy = yd / den[:, None], xd / den[:, None]
+    conv_j = (area / 3)[:, None] * (uc[:, 0:1] * gx + uc[:, 1:2] * gy)       # (T,3): depends on j only
+    keC = np.repeat(conv_j[:, None, :], 3, axis=1).reshape(-1, 9)
+    w = np.where(np.eye(3, dtype=bool), 2.0, 1.0).reshape(1, 9)
+    keM = (area / 12.0)[:, None] * w
+    m_vals = np.bincount(scatter[keep].ravel(), weights=keM[keep].ravel(), minlength=len(colidx))
+    c_vals = np.bincount(scatter[keep].ravel(), weights=keC[keep].ravel(), minlength=len(colidx))
+    return m_vals, c_vals
+
+
+def dye_diffuse(c_adv, K, DT, D):
+    """scripts/good_visualization2.py:704-715: explicit update with the stiffness matrix, clipped to [0, 1]
+    (sign as in the script)."""
+    return np.clip(c_adv + DT * D * (K @ c_adv), 0.0, 1.0)
+
+
+def helmholtz_smooth(K_dense, p_raw, ref, alpha=0.01):
+    """scripts/stokes_report.py:1187-1196: p = solve(I + alpha K with row / column `ref` replaced by e_ref, p_raw with
+    p_raw[ref] = 0), then the mean removed."""
+    n = len(p_raw)
+    S = np.eye(n) + alpha * K_dense
+    S[ref, :] = 0.0
+    S[:, ref] = 0.0
+    S[ref, ref] = 1.0
+    pr = p_raw.copy()
+    pr[ref] = 0.0
+    p = np.linalg.solve(S, pr)
+    return p - p.mean()

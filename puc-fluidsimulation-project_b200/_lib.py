@@ -30,7 +30,8 @@ class FluidsimError(RuntimeError):
 
 class StokesOpts(C.Structure):
     _fields_ = [("rtol_visc", c_dbl), ("rtol_pressure", c_dbl), ("maxit", C.c_int),
-                ("precond", C.c_int), ("warm_start", C.c_int), ("final_div", C.c_int)]
+                ("precond", C.c_int), ("warm_start", C.c_int), ("final_div", C.c_int),
+                ("bc_mode", C.c_int), ("omega", c_dbl)]
 
 
 class StokesStats(C.Structure):
@@ -65,6 +66,9 @@ SIGNATURES = {
     "fs_scatter_map": (C.c_int, [c_vp, c_vp]),
     "fs_assemble_stiffness": (C.c_int, [c_vp, c_vp]),
     "fs_lumped_mass": (C.c_int, [c_vp, c_vp]),
+    "fs_assemble_mass_convection": (C.c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "fs_make_rot_bcu": (C.c_int, [c_vp, c_vp, c_dbl, c_dbl, c_dbl]),
+    "fs_dye_diffuse": (C.c_int, [c_vp, c_vp, c_dbl, c_dbl]),
     "fs_centroids": (C.c_int, [c_vp, C.c_int, c_vp, c_vp]),
     "fs_assemble_fem": (C.c_int, [c_vp, C.c_int, c_vp, c_dbl, c_vp, c_vp]),
     "fs_divergence": (C.c_int, [c_vp, c_vp, c_vp]),

@@ -228,6 +228,24 @@ class Mesh:
     def make_dir_bcu(self, u, B1, B2):
         call("fs_make_dir_bcu", self._h, ptr(u, np.float64, (self.N, 2), "u"), float(B1), float(B2))
 
+    def make_rot_bcu(self, u, omega, center=(0.5, 0.5)):
+        """Rotating inner cylinder, scripts/stokes_report.py:1155-1171 (in place)."""
+        call("fs_make_rot_bcu", self._h, ptr(u, np.float64, (self.N, 2), "u"), float(omega), float(center[0]), float(center[1]))
+
+    def mass_convection(self, u):
+        """build_mass_and_convection(nodes, triangles, u), code/StokesColor.py:286-312 -> (M, C) as CsrMatrix handles."""
+        u = as_f64(u)
+        mv = np.empty(self.nnz, dtype=np.float64)
+        cv = np.empty(self.nnz, dtype=np.float64)
+        call("fs_assemble_mass_convection", self._h, ptr(u, np.float64, (self.N, 2), "u"), ptr(mv), ptr(cv))
+        return self.matrix(mv), self.matrix(cv)
+
+    def dye_diffuse(self, c, DT, D):
+        """scripts/good_visualization2.py:704-715: c <- clip(c + DT*D*(A_stiffness @ c), 0, 1), in place."""
+        if getattr(self, "_K", None) is None:
+            self._K = self.stiffness()
+        call("fs_dye_diffuse", self._K._h, ptr(c, np.float64, (self.N,), "c"), float(DT), float(D))
+
     def reapply_scalar_bc(self, u, pairs_all, wall_value, inner_value):
         pr = np.ascontiguousarray(np.asarray(pairs_all, dtype=np.int32).reshape(-1, 2))
         call("fs_reapply_scalar_bc", self._h, ptr(u, np.float64, (self.N,), "u"), ptr(pr), len(pr),
@@ -340,6 +358,11 @@ class PointLocator:
 
     def find_many(self, pts):
         return self._mesh.locate(pts)
+
+
+def build_mass_and_convection(nodes, triangles, u):
+    """code/StokesColor.py:286-312 -> (M, C) CsrMatrix handles (the reference returns dense matrices)."""
+    return mesh_for(nodes, triangles).mass_convection(u)
 
 
 def mixing_index(c, mass, mask=None, mesh: Mesh | None = None):

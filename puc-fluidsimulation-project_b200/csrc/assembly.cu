@@ -350,6 +350,62 @@ void dir_bcu_dev(fs_mesh* m, double* d_u, double B1, double B2) {
   FS_LAUNCH_CHECK();
 }
 
+// ---- physics variants of the reference's draft scripts ----------------------------------
+// rotating inner cylinder: u = omega x r on the inner boundary, 0 on the walls (scripts/stokes_report.py:1155-1171)
+__global__ void k_rot_bcu(const double2* __restrict__ coords, const int* __restrict__ wall, int64_t nw, const int* __restrict__ inner,
+                          int64_t ni, double omega, double cx, double cy, double2* __restrict__ u) {
+  int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k < nw) u[wall[k]] = make_double2(0.0, 0.0);
+  else if (k < nw + ni) {
+    const int idx = inner[k - nw];
+    const double2 p = coords[idx];
+    const double rx = p.x - cx, ry = p.y - cy;
+    u[idx] = make_double2(-ry * omega, rx * omega);
+  }
+}
+void rot_bcu_dev(fs_mesh* m, double* d_u, double omega, double cx, double cy) {
+  FS_REQUIRE(m->bc_ready, "fs_bc_set has not been called");
+  const int64_t tot = m->n_wall + m->n_inner;
+  if (tot == 0) return;
+  k_rot_bcu<<<div_up(tot, 128), 128, 0, stream()>>>((const double2*)m->coords.p, m->wall.p, m->n_wall, m->inner.p, m->n_inner, omega, cx, cy,
+                                                     (double2*)d_u);
+  FS_LAUNCH_CHECK();
+}
+
+// consistent mass and convection element matrices of build_mass_and_convection, code/StokesColor.py:286-312
+__global__ void k_elem_mass_conv(const double2* __restrict__ coords, const int* __restrict__ tris, const double2* __restrict__ u,
+                                 int64_t T, double* __restrict__ keM, double* __restrict__ keC) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= T) return;
+  const int a = tris[3 * e], b = tris[3 * e + 1], c = tris[3 * e + 2];
+  const double2 p1 = coords[a], p2 = coords[b], p3 = coords[c];
+  const double det = p1.x * (p2.y - p3.y) + p2.x * (p3.y - p1.y) + p3.x * (p1.y - p2.y);
+  const bool skip = fabs(det) < 1e-14;
+  const double area = 0.5 * fabs(det);
+  const double2 ua = u[a], ub = u[b], uc = u[c];
+  const double ucx = ((ua.x + ub.x) + uc.x) / 3.0, ucy = ((ua.y + ub.y) + uc.y) / 3.0;      // u[idx].mean(axis=0)
+  const double den = 2 * fabs(det);
+  const double gx[3] = {(p2.y - p3.y) / den, (p3.y - p1.y) / den, (p1.y - p2.y) / den};
+  const double gy[3] = {(p3.x - p2.x) / den, (p1.x - p3.x) / den, (p2.x - p1.x) / den};
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      keM[9 * e + 3 * i + j] = skip ? 0.0 : (area / 12.0) * (i != j ? 1.0 : 2.0);
+      keC[9 * e + 3 * i + j] = skip ? 0.0 : (area / 3) * (ucx * gx[j] + ucy * gy[j]);
+    }
+}
+
+// c <- clip(c + DT D (K c), 0, 1): the explicit dye "diffusion" of scripts/good_visualization2.py:704-715 (sign as in the script)
+__global__ void k_dye_diffuse(CsrView K, const double* __restrict__ c, double s, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K.n) return;
+  double lap = 0.0;
+  for (int k = K.rowptr[i]; k < K.rowptr[i + 1]; ++k) lap += K.vals[k] * c[K.colidx[k]];
+  const double v = c[i] + s * lap;
+  out[i] = fmin(fmax(v, 0.0), 1.0);
+}
+
 // ---- the same operators for B configurations at once (shared mesh, fields strided by N / T) ----
 void divergence_batch_dev(fs_mesh* m, int B, const double* d_u, double* d_div, double* d_lump) {
   ensure_geom(m);
@@ -408,6 +464,44 @@ int fs_assemble_stiffness(fs_mesh* m, double* vals) {
   Out<double> o(vals, m->pat.nnz);
   assemble_on_pattern(m->pat, m->ke.p, o.d);
   o.commit();
+  fs::sync();
+  FS_API_END
+}
+
+int fs_assemble_mass_convection(fs_mesh* m, const double* u, double* m_vals, double* c_vals) {
+  FS_API_BEGIN
+  FS_REQUIRE(m && u && m_vals && c_vals, "NULL argument");
+  In<double> iu(u, 2 * m->N);
+  DBuf<double> keM((size_t)9 * m->T), keC((size_t)9 * m->T);
+  k_elem_mass_conv<<<div_up(m->T, 256), 256, 0, stream()>>>((const double2*)m->coords.p, m->tris.p, (const double2*)iu.d, m->T, keM.p, keC.p);
+  FS_LAUNCH_CHECK();
+  Out<double> om(m_vals, m->pat.nnz), oc(c_vals, m->pat.nnz);
+  assemble_on_pattern(m->pat, keM.p, om.d);
+  assemble_on_pattern(m->pat, keC.p, oc.d);
+  om.commit(); oc.commit();
+  fs::sync();
+  FS_API_END
+}
+
+int fs_make_rot_bcu(fs_mesh* m, double* u, double omega, double cx, double cy) {
+  FS_API_BEGIN
+  FS_REQUIRE(m && u, "NULL argument");
+  Out<double> o(u, 2 * m->N, true);
+  rot_bcu_dev(m, o.d, omega, cx, cy);
+  o.commit();
+  fs::sync();
+  FS_API_END
+}
+
+int fs_dye_diffuse(fs_csr* K, double* c, double DT, double D) {
+  FS_API_BEGIN
+  FS_REQUIRE(K && c, "NULL argument");
+  Out<double> oc(c, K->n, true);
+  DBuf<double> tmp(K->n);
+  k_dye_diffuse<<<div_up(K->n, 256), 256, 0, stream()>>>(K->view(), oc.d, DT * D, tmp.p);
+  FS_LAUNCH_CHECK();
+  FS_CUDA(cudaMemcpyAsync(oc.d, tmp.p, K->n * sizeof(double), cudaMemcpyDeviceToDevice, stream()));
+  oc.commit();
   fs::sync();
   FS_API_END
 }

@@ -260,6 +260,7 @@ void divergence_dev(fs_mesh* m, const double* d_u, double* d_div, double* d_div_
 void gradient_dev(fs_mesh* m, const double* d_p, double* d_gx, double* d_gy);
 void per_bcu_dev(fs_mesh* m, double* d_u);
 void dir_bcu_dev(fs_mesh* m, double* d_u, double B1, double B2);
+void rot_bcu_dev(fs_mesh* m, double* d_u, double omega, double cx, double cy);
 void grad_update_dev(fs_mesh* m, const double* d_p, const double* d_ui, double* d_uo, double DT,
                      const unsigned char* d_interior_flag /* null: all nodes */);
 void divergence_batch_dev(fs_mesh* m, int B, const double* d_u, double* d_div, double* d_lump);

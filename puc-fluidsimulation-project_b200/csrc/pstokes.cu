@@ -822,13 +822,17 @@ int fs_pstokes_step(fs_pstokes* s, double* u_own, double B1, double B2, const fs
   int it = visc_solve(s, o.rtol_visc, o.maxit, &sts.relres_visc);
   if (it < 0) throw Error(FS_ERR_NOCONV, "partitioned viscous CG did not converge within maxit");
   sts.iters_visc = it;
+  auto dirichlet = [&](double* v) {
+    if (o.bc_mode == 1) rot_bcu_dev(m, v, o.omega, 0.5, 0.5);
+    else dir_bcu_dev(m, v, B1, B2);
+  };
   per_bcu_dev(m, s->USTAR.p);
-  dir_bcu_dev(m, s->USTAR.p, B1, B2);
+  dirichlet(s->USTAR.p);
   ctx.push(s->USTAR);
   pressure_solve(s, s->USTAR, s->Q1, s->h1, s->p_loc.p, o, &sts.iters_p1, &sts.relres_p1);
   grad_update_dev(m, s->p_loc.p, s->USTAR.p, s->U.p, s->DT, nullptr);
   per_bcu_dev(m, s->U.p);
-  dir_bcu_dev(m, s->U.p, B1, B2);
+  dirichlet(s->U.p);
   ctx.push(s->U);
   pressure_solve(s, s->U, s->Q2, s->h2, s->p2_loc.p, o, &sts.iters_p2, &sts.relres_p2);
   grad_update_dev(m, s->p2_loc.p, s->U.p, s->U.p, s->DT, s->is_interior.p);

@@ -173,6 +173,8 @@ int fs_stokes_default_opts(fs_stokes_opts* o) {
   o->precond = FS_PRECOND_AUTO;
   o->warm_start = 1;
   o->final_div = 0;
+  o->bc_mode = 0;
+  o->omega = 0.0;
   FS_API_END
 }
 
@@ -295,8 +297,12 @@ int fs_stokes_step(fs_stokes* s, double* u, double B1, double B2, const fs_stoke
   int it = cg_dev(&s->a_visc, du, s->ustar.p, 2, o.rtol_visc, o.maxit, pre_visc, 0, &sts.relres_visc);
   if (it < 0) throw Error(FS_ERR_NOCONV, "viscous CG did not converge within maxit");
   sts.iters_visc = it;
+  auto dirichlet = [&](double* v) {            // squirmer slip velocity, or the rotating-cylinder variant
+    if (o.bc_mode == 1) rot_bcu_dev(m, v, o.omega, 0.5, 0.5);
+    else dir_bcu_dev(m, v, B1, B2);
+  };
   per_bcu_dev(m, s->ustar.p);
-  dir_bcu_dev(m, s->ustar.p, B1, B2);
+  dirichlet(s->ustar.p);
   mark();
   // Step 2+3: pressure correction and velocity update
   pressure_solve(s, s->ustar.p, s->p_red.p, s->h1, s->p_full.p, o, &sts.iters_p1, &sts.relres_p1,
@@ -304,7 +310,7 @@ int fs_stokes_step(fs_stokes* s, double* u, double B1, double B2, const fs_stoke
   mark();
   grad_update_dev(m, s->p_full.p, s->ustar.p, du, s->DT, nullptr);
   per_bcu_dev(m, du);
-  dir_bcu_dev(m, du, B1, B2);
+  dirichlet(du);
   mark();
   // second projection, interior nodes only, no BC re-imposition (:566-573)
   pressure_solve(s, du, s->p2_red.p, s->h2, s->p2_full.p, o, &sts.iters_p2, &sts.relres_p2, nullptr);

@@ -178,3 +178,19 @@ class HeatProblem(PoissonProblem):
         self.iters = it
         self.reapply(self.u)
         return self.u
+
+
+def helmholtz_smooth(K: CsrMatrix, p_raw, ref, alpha=0.01, rtol=1e-13):
+    """The stabilised-pressure variant of scripts/stokes_report.py:1187-1196: solve (I + alpha K) p = p_raw with row and
+    column ``ref`` replaced by the unit vector (p[ref] = 0), then remove the mean.  The system is SPD: CG on the device."""
+    n = K.n
+    rowptr, colidx, vals = K.arrays()
+    rows = np.repeat(np.arange(n), np.diff(rowptr))
+    v = alpha * vals + (rows == colidx)
+    kill = (rows == ref) | (colidx == ref)
+    v = np.where(kill, (rows == colidx).astype(np.float64), v)
+    S = CsrMatrix.from_arrays(rowptr, colidx, v)
+    b = np.array(p_raw, dtype=np.float64)
+    b[ref] = 0.0
+    p, _, _ = S.cg(b, rtol=rtol)
+    return p - p.mean()

@@ -21,7 +21,7 @@ from .core import CsrMatrix, Mesh
 class StokesSolver:
     def __init__(self, nodes_coords, nodes_boundary_markers, triangles, B1=-2.0, B2=0.0, DT=0.05, v=0.1,
                  L=1.0, H=1.0, tol=1e-6, rtol_pressure=1e-10, rtol_visc=1e-12, precond=3, warm_start=True,
-                 maxit=200000, final_div=False):
+                 maxit=200000, final_div=False, bc="squirmer", omega=0.0):
         self.nodes_coords = np.ascontiguousarray(nodes_coords, dtype=np.float64)
         self.nodes_boundary_markers = np.ascontiguousarray(nodes_boundary_markers, dtype=np.int32)
         self.triangles = np.ascontiguousarray(triangles, dtype=np.int32)
@@ -45,6 +45,11 @@ class StokesSolver:
         self.opts.warm_start = 1 if warm_start else 0
         self.opts.maxit = maxit
         self.opts.final_div = 1 if final_div else 0
+        # bc = "rotating": the rotating-cylinder variant of scripts/stokes_report.py:1155-1171; set self.omega before
+        # every step (the script ramps it: target * (step + 1) / 200)
+        if bc not in ("squirmer", "rotating"):
+            raise ValueError("bc must be 'squirmer' or 'rotating'")
+        self.bc, self.omega = bc, float(omega)
         self.stats = StokesStats()
         self.M_lumped_diag = self.mesh.lumped_mass()
         # code/StokesColor.py:482-483
@@ -60,8 +65,11 @@ class StokesSolver:
 
     # -- the reference's global-reading helpers
     def makeDirBCU(self, u):
-        """code/StokesColor.py:405-427 (in place)."""
-        self.mesh.make_dir_bcu(u, self.B1, self.B2)
+        """code/StokesColor.py:405-427 (in place); the rotating-cylinder data for bc="rotating"."""
+        if self.bc == "rotating":
+            self.mesh.make_rot_bcu(u, self.omega)
+        else:
+            self.mesh.make_dir_bcu(u, self.B1, self.B2)
 
     def makePerBCU(self, u):
         """code/StokesColor.py:429-431 (in place)."""
@@ -79,6 +87,8 @@ class StokesSolver:
         """Advance ``u`` (default: self.u) in place; numpy (host, staged) or torch cuda tensor."""
         if u is None:
             u = self.u
+        self.opts.bc_mode = 1 if self.bc == "rotating" else 0
+        self.opts.omega = self.omega
         call("fs_stokes_step", self._h, ptr(u, np.float64, (self.N, 2), "u"), float(self.B1), float(self.B2),
              C.byref(self.opts), C.byref(self.stats))
         return self.stats
@@ -155,10 +165,14 @@ class StokesColor(StokesSolver):
         """code/StokesColor.py:347-389 (in place on c)."""
         self.mesh.advect_dye(c, u, DT)
 
+    dye_diffusivity = 0.0      # > 0: the explicit dye diffusion of scripts/good_visualization2.py:704-715 after the advection
+
     def step_all(self):
         """One pass of the reference loop body, code/StokesColor.py:538-585."""
         st = self.step()
         self.advect_semilagrange(self.c, self.u, self.DT)
+        if self.dye_diffusivity > 0:
+            self.mesh.dye_diffuse(self.c, self.DT, self.dye_diffusivity)
         I, mu, var = self.mesh.mixing_index(self.c, self.M_lumped_diag, self.inner)
         self.progress = 1.0 - var / (self.var0 + 1e-16)
         return st, self.progress

@@ -810,3 +810,51 @@ def test_batched_sweep_matches_one_by_one():
     for step in range(15):
         ed = sd.step_all()
     assert np.array_equal(ed, eaten) and rel(sd.u.cpu().numpy(), sw.u) <= 1e-12
+
+
+# ---- physics variants of the reference's draft scripts ------------------------------------------
+def test_mass_convection_rotating_bc_dye_diffusion_smoothing():
+    g = load_golden("mesh5_1_ops")
+    v = load_golden("mesh5_1_variants")
+    m = fb.Mesh(g["nodes"], g["tris"], g["markers"])
+    # build_mass_and_convection, code/StokesColor.py:286-312 (fixture: the literal function's dense output)
+    M, Cm = m.mass_convection(v["u"])
+    assert np.array_equal(M.arrays()[2], v["M_vals"])
+    assert np.abs(Cm.arrays()[2] - v["C_vals_literal"]).max() <= 1e-15 * np.abs(v["C_vals_literal"]).max() + 1e-300
+    assert np.abs(Cm.arrays()[2] - v["C_vals"]).max() <= 1e-15 * np.abs(v["C_vals"]).max()
+    M2, C2 = fb.build_mass_and_convection(g["nodes"], g["tris"], v["u"])
+    assert np.array_equal(M2.arrays()[2], v["M_vals"])
+    # rotating cylinder, scripts/stokes_report.py:1155-1171
+    wall, inner, _, interior = fb.index_sets(g["nodes"], g["markers"])
+    m.set_bc(wall, inner, [], interior)
+    u = v["urot"].copy()
+    u[wall] = 3.0
+    u[inner] = -4.0
+    m.make_rot_bcu(u, float(v["omega"]))
+    assert np.array_equal(u, v["urot"])
+    # dye diffusion, scripts/good_visualization2.py:704-715
+    c = v["c_adv"].copy()
+    m.dye_diffuse(c, float(v["DT"]), float(v["D"]))
+    assert np.abs(c - v["c_dif"]).max() <= 1e-15 and c.min() >= 0.0 and c.max() <= 1.0
+    # pressure pin + Helmholtz smoothing, scripts/stokes_report.py:1187-1196
+    p = fb.helmholtz_smooth(m.stiffness(), v["p_raw"], int(v["ref"]), float(v["alpha"]))
+    assert rel(p, v["p_smooth"]) <= 1e-10
+
+
+def test_rotating_cylinder_flow_vs_restated_oracle():
+    """The operator-split step with the rotating-cylinder Dirichlet data and the script's ramp (target 5, 200 steps)."""
+    g = load_golden("mesh5_1_ops")
+    sim = fb.StokesSolver(g["nodes"], g["markers"], g["tris"], DT=0.01, v=1.0, bc="rotating", omega=R.ramp_omega(0),
+                          rtol_pressure=1e-12)
+    ref = R.RestatedStokes(g["nodes"], g["markers"], g["tris"], DT=0.01, v=1.0)
+    ref.omega = R.ramp_omega(0)
+    ref.u[:] = 0.0
+    ref._dirichlet(ref.u)
+    assert np.array_equal(sim.u, ref.u)
+    for step in range(25):
+        sim.omega = ref.omega = R.ramp_omega(step)
+        sim.step()
+        ref.flow_step()
+        assert rel(sim.u, ref.u) <= 1e-9, step
+    speed = np.hypot(sim.u[:, 0], sim.u[:, 1])
+    assert speed[sim.inner_boundary_indices].max() > 0.1 and np.abs(sim.u[sim.wall_node_indices]).max() == 0.0

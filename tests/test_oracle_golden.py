@@ -216,3 +216,22 @@ def test_apng_movie_roundtrip(tmp_path):
         fb.write_apng(path, [])
     with pytest.raises(ValueError):
         fb.write_apng(path, [frames[0], frames[1][:10]])
+
+
+def test_variants_golden():
+    """SURVEY 8 f4 fixtures: the restated mass / convection assembly against the literal build_mass_and_convection
+    output stored in the fixture, and the restated inline statements against their stored results."""
+    g = load_golden("mesh5_1_ops")
+    v = load_golden("mesh5_1_variants")
+    mv, cv = R.mass_convection(g["nodes"], g["tris"], v["u"], g["rowptr"], g["colidx"], g["scatter"])
+    assert np.array_equal(mv, v["M_vals"]) and np.array_equal(cv, v["C_vals"])
+    assert np.abs(cv - v["C_vals_literal"]).max() <= 1e-15 * np.abs(cv).max()
+    wall, inner, _, _ = R.index_sets(g["nodes"], g["markers"])
+    u = v["urot"].copy()
+    u[wall] = 1.0
+    u[inner] = 2.0
+    R.rotating_cylinder_bcu(u, g["nodes"], wall, inner, float(v["omega"]))
+    assert np.array_equal(u, v["urot"]) and float(v["omega"]) == R.ramp_omega(37) == 5.0 * 38 / 200
+    K = sp.csr_matrix((g["K"], g["colidx"], g["rowptr"]))
+    assert np.array_equal(R.dye_diffuse(v["c_adv"], K, float(v["DT"]), float(v["D"])), v["c_dif"])
+    assert np.allclose(R.helmholtz_smooth(K.toarray(), v["p_raw"], int(v["ref"]), float(v["alpha"])), v["p_smooth"], rtol=0, atol=1e-13)
