@@ -1011,10 +1011,8 @@ static int vcycle_folded_dist(Amg& amg, int l, const DVec& bv, double* x, double
   if (lv.Rts.nslices) {
     const PushSpec ps = ctx.push_spec(nb);
     spmv_sell_dist(lv.Rts, bv.p, y, nullptr, nullptr, ctx.comm, ctx.wait_of(&bv), &ps, 10 + 2 * l);
-  } else if (lv.Rt.rowptr) {          // small block: lanes-per-row CSR kernel between a wait and a push kernel
-    ctx.wait(bv);
-    spmv_sub(lv.Rt.view32(), bv.p, y, nullptr, 0);
-    ctx.push(nb);
+  } else if (lv.Rt.rowptr) {          // small block: lanes-per-row CSR kernel with the wait and the push inside
+    spmv_sub_dist(lv.Rt.view32(), bv.p, y, nullptr, 0, ctx.comm, ctx.wait_of(&bv), ctx.push_spec(nb));
   }
   double* xc = next_part ? P.vx[l + 1].p : amg.L[l + 1]->x.p;
   vcycle_folded_dist(amg, l + 1, nb, xc, nullptr);
@@ -1024,10 +1022,8 @@ static int vcycle_folded_dist(Amg& amg, int l, const DVec& bv, double* x, double
     const int g = spmv_sell_dist(lv.Us, bv.p, x, xc, dot_part, ctx.comm, ctx.wait_of(&bv, next_part ? &P.vx[l + 1] : nullptr), &ps, 11 + 2 * l);
     return dot_part ? g : 0;
   }
-  ctx.wait(bv);
-  if (next_part) ctx.wait(P.vx[l + 1]);
-  spmv_sub(lv.U.view32(), bv.p, x, xc, lv.part_nsplit);
-  ctx.push(P.vx[l]);
+  spmv_sub_dist(lv.U.view32(), bv.p, x, xc, lv.part_nsplit, ctx.comm, ctx.wait_of(&bv, next_part ? &P.vx[l + 1] : nullptr),
+                ctx.push_spec(P.vx[l]));
   return 0;
 }
 

@@ -203,6 +203,8 @@ int amg_apply_dist(Amg* amg, const DVec& r, double* z, double* rz_part);
 void sell_mark_boundary(fs_sell& S, const fs_csr& loc, int n_own_a, int nsplit, int n_own_b, const Space* out);
 int spmv_sell_dist(const fs_sell& S, const double* x, double* y, const double* x2, double* dot_partials, const Comm& c,
                    const HaloWait& w, const PushSpec* push = nullptr, int trace_tag = 0);
+void spmv_sub_dist(const CsrView& A, const double* x, double* y, const double* x2, int nsplit, const Comm& c, const HaloWait& w,
+                   const PushSpec& ps);
 void spmv_sell2_dist(const fs_sell& S, const double* x, double* y, double* dot_partials, const int* done, const Comm& c,
                      const HaloWait& w);
 
@@ -235,6 +237,13 @@ __device__ __forceinline__ void dist_trace(const Comm& c, unsigned tag) {
   }
 }
 
+// the same from thread 0 of the LAST CTA of the grid (an interior CTA of the boundary-first kernels): kernel end
+__device__ __forceinline__ void dist_trace_last(const Comm& c, unsigned tag) {
+  if (c.trace && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+    const unsigned k = atomicAdd(c.trace_n, 1u);
+    if (k < c.trace_cap) { c.trace[2 * k] = tag; c.trace[2 * k + 1] = dist_gtime(); }
+  }
+}
 __device__ __forceinline__ void dist_st_sys_f64(double* a, double v) {
   asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(a), "d"(v) : "memory");
 }

@@ -125,8 +125,11 @@ k_ppcg_xr(int64_t n, const double* __restrict__ p, const double* __restrict__ Ap
   double acc[1] = {0.0};
   // one warp per 32-row slice; the slices with rows that other ranks read come first: their new residuals are stored
   // into the neighbours' halo slots and the flags released while the rest of the vector is still being updated
-  const int lane = threadIdx.x & 31;
-  const int gw = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5), nw = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
+  // (the first nb CTAs do nothing else, the others share the rest: nobody carries boundary work on top of a full share)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kW = kBlock / 32;
+  const int per_warp = max(1, (int)((n + 31) >> 5) / (2 * (int)gridDim.x * kW));      // half an interior warp's share
+  const int nb = ps.enabled ? min((int)gridDim.x / 2, (ps.n_slist + kW * per_warp - 1) / (kW * per_warp)) : 0;
   const int nsl = (int)((n + 31) >> 5);
   auto upd = [&](int64_t i, bool send) -> bool {
     const double rn = r[i] - alpha * Ap[i];
@@ -135,22 +138,24 @@ k_ppcg_xr(int64_t n, const double* __restrict__ p, const double* __restrict__ Ap
     acc[0] += rn * rn;
     return send ? push_row(ps, (int)i, rn) : false;
   };
-  if (ps.enabled && blockIdx.x * (kBlock / 32) < ps.n_slist) {
+  if ((int)blockIdx.x < nb) {
     bool pushed = false;
-    for (int j = gw; j < ps.n_slist; j += nw) {
+    for (int j = blockIdx.x * kW + warp; j < ps.n_slist; j += nb * kW) {
       const int64_t i = ((int64_t)__ldg(ps.slist + j) << 5) + lane;
       if (i < n) pushed |= upd(i, true);
     }
-    push_finish(c, ps, pushed, seq + 1, min((int)gridDim.x, (ps.n_slist + kBlock / 32 - 1) / (kBlock / 32)));
-  }
-  for (int sl = gw; sl < nsl; sl += nw) {
-    if (ps.enabled && __ldg(ps.smask + sl)) continue;
-    const int64_t i = ((int64_t)sl << 5) + lane;
-    if (i < n) upd(i, false);
+    push_finish(c, ps, pushed, seq + 1, nb);
+  } else {
+    for (int sl = ((int)blockIdx.x - nb) * kW + warp; sl < nsl; sl += ((int)gridDim.x - nb) * kW) {
+      if (nb && __ldg(ps.smask + sl)) continue;
+      const int64_t i = ((int64_t)sl << 5) + lane;
+      if (i < n) upd(i, false);
+    }
   }
   block_reduce<1>(acc, red);
   if (threadIdx.x == 0) partB[blockIdx.x] = acc[0];
   dist_trace(c, 23);
+  dist_trace_last(c, 26);
   if (dist_last_block(c, 0)) dist_seq_bump(c);
 }
 
@@ -175,24 +180,28 @@ k_ppcg_p(int64_t n, const double* __restrict__ z, double* __restrict__ p, const 
   const bool conv = v[0] <= sc[4] * sc[2];
   if (!conv) {
     const double beta = rz_old != 0.0 ? v[1] / rz_old : 0.0;
-    const int lane = threadIdx.x & 31;
-    const int gw = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5), nw = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kW = kBlock / 32;
+    const int per_warp = max(1, (int)((n + 31) >> 5) / (2 * (int)gridDim.x * kW));      // half an interior warp's share
+    const int nb = ps.enabled ? min((int)gridDim.x / 2, (ps.n_slist + kW * per_warp - 1) / (kW * per_warp)) : 0;
     const int nsl = (int)((n + 31) >> 5);
-    if (ps.enabled && blockIdx.x * (kBlock / 32) < ps.n_slist) {        // rows the neighbours read: first, sent as produced
+    if ((int)blockIdx.x < nb) {                                         // rows the neighbours read: dedicated CTAs, sent as produced
       bool pushed = false;
-      for (int j = gw; j < ps.n_slist; j += nw) {
+      for (int j = blockIdx.x * kW + warp; j < ps.n_slist; j += nb * kW) {
         const int64_t i = ((int64_t)__ldg(ps.slist + j) << 5) + lane;
         if (i < n) { const double pn = z[i] + beta * p[i]; p[i] = pn; pushed |= push_row(ps, (int)i, pn); }
       }
-      push_finish(c, ps, pushed, seq + 1, min((int)gridDim.x, (ps.n_slist + kBlock / 32 - 1) / (kBlock / 32)));
-    }
-    for (int sl = gw; sl < nsl; sl += nw) {
-      if (ps.enabled && __ldg(ps.smask + sl)) continue;
-      const int64_t i = ((int64_t)sl << 5) + lane;
-      if (i < n) p[i] = z[i] + beta * p[i];
+      push_finish(c, ps, pushed, seq + 1, nb);
+    } else {
+      for (int sl = ((int)blockIdx.x - nb) * kW + warp; sl < nsl; sl += ((int)gridDim.x - nb) * kW) {
+        if (nb && __ldg(ps.smask + sl)) continue;
+        const int64_t i = ((int64_t)sl << 5) + lane;
+        if (i < n) p[i] = z[i] + beta * p[i];
+      }
     }
   }
   dist_trace(c, 33);
+  dist_trace_last(c, 36);
   if (dist_last_block(c, 1)) {
     sc[slot ^ 1] = v[1];
     sc[3] = v[0];
@@ -461,12 +470,11 @@ static int ppcg_amg(fs_pstokes* s, const double* b_in, DVec& X, double rtol, int
       k_ppcg_p<<<g, kBlock, 0, st>>>(n, z, p, partB, g, partRZ, nrz, sc, slot, flags, cm, psP); FS_LAUNCH_CHECK();
       ++queued;
       if (queued > unchecked) {
-        FS_CUDA(cudaMemcpyAsync(hflags, flags, sizeof(hflags), cudaMemcpyDeviceToHost, st));
-        FS_CUDA(cudaStreamSynchronize(st));
-        if (hflags[0]) break;
         int e = 0;   // a time-out ends the solve instead of queueing maxit empty iterations
-        FS_CUDA(cudaMemcpy(&e, ctx.err.p, sizeof(int), cudaMemcpyDeviceToHost));
-        if (e) break;
+        FS_CUDA(cudaMemcpyAsync(hflags, flags, sizeof(hflags), cudaMemcpyDeviceToHost, st));
+        FS_CUDA(cudaMemcpyAsync(&e, ctx.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        FS_CUDA(cudaStreamSynchronize(st));
+        if (hflags[0] || e) break;
       }
     }
     double hsc[5];
@@ -478,8 +486,8 @@ static int ppcg_amg(fs_pstokes* s, const double* b_in, DVec& X, double rtol, int
     rr = hsc[3];
     if (done) { s->hint_prev = s->hint; s->hint = it; }
     FS_CUDA(cudaMemsetAsync(flags, 0, 4 * sizeof(int), st));   // the kernels below must not see "converged"
+    if (!done) ctx.check("partitioned pressure CG");             // (a time-out is reported; otherwise the step's final check suffices)
   }
-  ctx.check("partitioned pressure CG");
   // x <- x - mean(x); publish its boundary values (the caller expands it to the nodes)
   k_dotk<1><<<g, kBlock, 0, st>>>(n, X.p, nullptr, nullptr, nullptr, part); FS_LAUNCH_CHECK();
   allreduce_k(s, part, g, 1, red + 3);
@@ -536,12 +544,12 @@ static int visc_solve(fs_pstokes* s, double rtol, int maxit, double* relres) {
       slot ^= 1;
     }
     launched += todo;
-    poll();
     int e = 0;
-    FS_CUDA(cudaMemcpy(&e, ctx.err.p, sizeof(int), cudaMemcpyDeviceToHost));
+    FS_CUDA(cudaMemcpyAsync(&e, ctx.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    poll();
     if (e) break;
   }
-  ctx.check("partitioned viscous CG");
+  if (!hs.f[0]) ctx.check("partitioned viscous CG");
   FS_CUDA(cudaMemsetAsync(flags, 0, 4 * sizeof(int), st));
   double worst = 0.0;
   for (int c = 0; c < 2; ++c) if (hs.d[4 + c] > 0.0) worst = std::max(worst, std::sqrt(hs.d[6 + c] / hs.d[4 + c]));

@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(kST, (SPLIT && F32 && DOT && !DIST) ? 8 : 6) k
     }
   }
   if (DIST && d.ps.enabled && d.ps.gather) push_finish(d.c, d.ps, pushed, dist_seq(d.c), (int)gridDim.x);
-  if (DIST) dist_trace(d.c, d.tag * 10 + 3);
+  if (DIST) { dist_trace(d.c, d.tag * 10 + 3); dist_trace_last(d.c, d.tag * 10 + 6); }
 }
 
 // ---- bulk-async (TMA) staged variant -----------------------------------------------------------------
@@ -612,7 +612,10 @@ static int spmv_sell_impl(const fs_sell& S, const double* x, double* y, const do
   if (d && (d->w.nch || (d->ps.enabled && !d->ps.gather)) && S.n_blist > 0) {
     d->bmask = S.bmask.p; d->blist = S.blist.p; d->n_blist = S.n_blist;
     d->btab = (d->ps.enabled && !d->ps.gather) ? S.btab.p : nullptr;
-    d->nb_cta = std::max(1, std::min(div_up(S.n_blist, kSW), sm_count() * 2));   // dedicated boundary CTAs, scheduled first
+    // dedicated boundary CTAs, scheduled first.  Their warps take about half as many slices as an interior warp, so the
+    // flags leave in the first half of the kernel (the consumer is a later kernel) without idling a third of the SMs
+    const int per_warp = std::max(1, S.nslices / (2 * grid * kSW));
+    d->nb_cta = std::max(1, std::min(div_up(S.n_blist, kSW * per_warp), grid / 2));
     grid_add = d->nb_cta;
   }
   if (d && d->ps.enabled && !d->ps.gather && S.n_blist == 0) d->ps.enabled = 0;   // nothing to send from these rows

@@ -16,7 +16,7 @@
 // (very long rows): LPR lanes per row, same gather options.
 // A warp owns 32-row mini-tiles; values/columns of the next mini-tile are in flight in registers
 // while the current one is multiplied and reduced through the warp's shared-memory slice.
-#include "internal.cuh"
+#include "dist.cuh"
 
 namespace fs {
 
@@ -161,8 +161,21 @@ __global__ void __launch_bounds__(kWT, 2) k_spmv_warp(SpmvWarpArgs a) {
 
 // LPR lanes per row (4..32), lane-strided partial sums combined by an xor tree: deterministic, any
 // row length; y = A x or A [x; x2]
-template <int LPR, bool F32>
-__global__ void __launch_bounds__(256) k_spmv_sub(SpmvWarpArgs a) {
+// DIST (partitioned cycle, small levels): wait for the input channels' halo flags first, store the rows other ranks
+// read into their halo slots as they are produced, and let the last CTA release the output channel's flags --
+// one launch instead of wait kernel + SpMV + push kernel.
+struct DistSub {
+  Comm c;
+  HaloWait w;
+  PushSpec ps;
+};
+
+template <int LPR, bool F32, bool DIST>
+__global__ void __launch_bounds__(256) k_spmv_sub(SpmvWarpArgs a, DistSub d) {
+  if (DIST) {
+    if (d.c.done && *d.c.done) return;
+    halo_wait(d.c, d.w);
+  }
   const int row = (int)((blockIdx.x * 256ll + threadIdx.x) / LPR), sub = threadIdx.x % LPR;
   double s = 0.0;
   if (row < a.A.n) {
@@ -187,31 +200,48 @@ __global__ void __launch_bounds__(256) k_spmv_sub(SpmvWarpArgs a) {
   }
 #pragma unroll
   for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (row < a.A.n && sub == 0) a.y[row] = s;
+  if (row < a.A.n && sub == 0) {
+    a.y[row] = s;
+    if (DIST && d.ps.enabled) push_row(d.ps, row, s);
+  }
+  if (DIST && d.ps.enabled) push_finish(d.c, d.ps, true, dist_seq(d.c), (int)gridDim.x);
 }
 
 template <int LPR>
-static void launch_sub(const SpmvWarpArgs& args) {
+static void launch_sub(const SpmvWarpArgs& args, const DistSub* d = nullptr) {
   const int grid = (int)div_up((int64_t)args.A.n * LPR, 256);
-  if (args.A.vals32) k_spmv_sub<LPR, true><<<grid, 256, 0, stream()>>>(args);
-  else k_spmv_sub<LPR, false><<<grid, 256, 0, stream()>>>(args);
+  static const DistSub none{};
+  if (d) {
+    if (args.A.vals32) k_spmv_sub<LPR, true, true><<<grid, 256, 0, stream()>>>(args, *d);
+    else k_spmv_sub<LPR, false, true><<<grid, 256, 0, stream()>>>(args, *d);
+  } else {
+    if (args.A.vals32) k_spmv_sub<LPR, true, false><<<grid, 256, 0, stream()>>>(args, none);
+    else k_spmv_sub<LPR, false, false><<<grid, 256, 0, stream()>>>(args, none);
+  }
   FS_LAUNCH_CHECK();
 }
 
 // y = A [x; x2] (x2 may be null: plain y = A x) for any CSR matrix.  Lanes per row: about a quarter of
 // the mean row length (each lane keeps four entries in flight), so that small matrices still
 // spread over the whole machine in one wave.
-void spmv_sub(const CsrView& A, const double* x, double* y, const double* x2, int nsplit) {
+static void spmv_sub_impl(const CsrView& A, const double* x, double* y, const double* x2, int nsplit, const DistSub* d) {
   SpmvWarpArgs args{A, x, y, nullptr, nullptr, 0.0, nullptr, nullptr, 0, 0};
   args.x2 = x2;
   args.nsplit = x2 ? nsplit : 0x7fffffff;
   static const double per_lane = [] { const char* e = std::getenv("FS_SUB_PER_LANE"); return e ? std::atof(e) : 4.0; }();
   const double avg = A.n > 0 ? (double)A.nnz / A.n : 0.0;
   const double lanes = avg / per_lane;
-  if (lanes <= 4.0) launch_sub<4>(args);
-  else if (lanes <= 8.0) launch_sub<8>(args);
-  else if (lanes <= 16.0) launch_sub<16>(args);
-  else launch_sub<32>(args);
+  if (lanes <= 4.0) launch_sub<4>(args, d);
+  else if (lanes <= 8.0) launch_sub<8>(args, d);
+  else if (lanes <= 16.0) launch_sub<16>(args, d);
+  else launch_sub<32>(args, d);
+}
+void spmv_sub(const CsrView& A, const double* x, double* y, const double* x2, int nsplit) { spmv_sub_impl(A, x, y, x2, nsplit, nullptr); }
+void spmv_sub_dist(const CsrView& A, const double* x, double* y, const double* x2, int nsplit, const Comm& c, const HaloWait& w,
+                   const PushSpec& ps) {
+  DistSub d;
+  d.c = c; d.w = w; d.ps = ps;
+  spmv_sub_impl(A, x, y, x2, nsplit, &d);
 }
 
 static bool g_warp_attr = false;
