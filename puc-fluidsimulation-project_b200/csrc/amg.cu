@@ -427,6 +427,42 @@ __global__ void __launch_bounds__(1024) k_dense_invert(int n, double* __restrict
     __syncthreads();
   }
 }
+// The same elimination with the whole GPU: two launches per pivot (save the pivot column and scale the pivot row; update
+// all other rows).  2 n small launches (~6 ms at n = 960) instead of one CTA sweeping n^2 entries n times (256 ms).
+__global__ void __launch_bounds__(1024) k_gj_pivot(int n, int k, double* __restrict__ M, double* __restrict__ colk) {
+  __shared__ double piv;
+  if (threadIdx.x == 0) piv = 1.0 / M[(size_t)k * n + k];
+  __syncthreads();
+  const double ip = piv;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) colk[i] = M[(size_t)i * n + k];
+  __syncthreads();
+  for (int j = threadIdx.x; j < n; j += blockDim.x) M[(size_t)k * n + j] = (j == k) ? ip : M[(size_t)k * n + j] * ip;
+}
+__global__ void k_gj_update(int n, int k, double* __restrict__ M, const double* __restrict__ colk) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= n || i == k) return;
+  const double f = colk[i];
+  const double rkj = M[(size_t)k * n + j];            // already scaled; entry (k,k) holds 1/pivot
+  M[(size_t)i * n + j] = (j == k) ? -f * rkj : M[(size_t)i * n + j] - f * rkj;
+}
+static void dense_invert(int n, double* M) {
+  cudaStream_t st = stream();
+  if (n <= 64) {
+    k_dense_invert<<<1, 1024, 0, st>>>(n, M);
+    FS_LAUNCH_CHECK();
+    return;
+  }
+  DBuf<double> colk(n);
+  const dim3 grid(div_up(n, 256), n);
+  for (int k = 0; k < n; ++k) {
+    k_gj_pivot<<<1, 1024, 0, st>>>(n, k, M, colk.p);
+    k_gj_update<<<grid, 256, 0, st>>>(n, k, M, colk.p);
+  }
+  FS_CUDA(cudaGetLastError());
+  count_launch(2 * n);
+  FS_CUDA(cudaStreamSynchronize(st));
+}
+
 // x = Minv * b, one warp per row, four independent partial sums per lane (the row is a dependent
 // chain of ~n/32 loads otherwise: this kernel is pure latency)
 __global__ void k_dense_gemv(int n, const double* __restrict__ Minv, const double* __restrict__ b, double* __restrict__ x) {
@@ -649,8 +685,7 @@ Amg* amg_setup(fs_csr* fine, const AmgPartSpec* ps) {
       FS_LAUNCH_CHECK();
       k_dense_add_csr<<<div_up(n, 256), 256, 0, stream()>>>(Ac, amg->coarse_inv.p);
       FS_LAUNCH_CHECK();
-      k_dense_invert<<<1, 1024, 0, stream()>>>(n, amg->coarse_inv.p);
-      FS_LAUNCH_CHECK();
+      dense_invert(n, amg->coarse_inv.p);
       amg->coarse_n = n;
     }
   }

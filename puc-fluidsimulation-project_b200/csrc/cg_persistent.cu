@@ -72,7 +72,7 @@ struct CgPersistArgs {
   double* partA;        // gridDim
   double* partB;        // 2*gridDim
   double* scal;         // [0]=rz (in/out) [2]=bb (in) [3]=rr (out) [8..10]=ns per pass [11]=timed iterations
-  int* flags;           // [0]=converged [1]=iterations [2]=multi-GPU wait error (0 ok)
+  int* flags;           // [0]=converged [1]=iterations [2]=multi-GPU wait error (0 ok) [4],[5]=its committed copies
   int maxit;
   double tol2;
   int ntiles;
@@ -167,12 +167,17 @@ __device__ __forceinline__ double ld_sys_f64(const double* a) {
 // bounded spin: a lost peer must end in an error code, not in a hung GPU.  After a
 // time-out (or once any thread of this rank has timed out) every wait falls through, the
 // kernel runs to its end with garbage and the host reports FS_ERR_INTERNAL.
+// (FS_DIST_TIMEOUT_MS, default 20 s, measured with %globaltimer: a slow start of a peer does not trip it)
+__device__ unsigned long long g_wait_timeout_ns = 20000000000ull;
 __device__ __forceinline__ void wait_flag(const unsigned long long* a, unsigned long long want, int* err, int code) {
-  unsigned long long spins = 0;
+  unsigned spins = 0;
+  unsigned long long t0 = 0;
   while (ld_acquire_sys(a) < want) {
-    ++spins;
-    if ((spins & 1023ull) == 0 && *(volatile int*)err != 0) return;
-    if (spins > (1ull << 24)) { atomicCAS(err, 0, code); return; }
+    if ((++spins & 255u) == 0) {
+      if (*(volatile int*)err != 0) return;
+      if (t0 == 0) t0 = gtime();
+      else if (gtime() - t0 > g_wait_timeout_ns) { atomicCAS(err, 0, code); return; }
+    }
   }
 }
 
@@ -209,16 +214,17 @@ __device__ __forceinline__ void rank_allreduce(const DistArgs& d, double (&v)[K]
   if (t < d.world) {
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(d.red_local) + ((size_t)par * d.world + t) * 4;
     unsigned long long w[2 * K];
-    unsigned long long spins = 0;
+    unsigned spins = 0;
+    unsigned long long t0 = 0;
     bool ok = false;
     while (!ok) {
       ok = true;
 #pragma unroll
       for (int j = 0; j < 2 * K; ++j) { w[j] = ld_sys_u64(src + j); ok = ok && ((w[j] & 0xffffffff00000000ull) == e32); }
-      if (!ok) {
-        ++spins;
-        if ((spins & 1023ull) == 0 && *(volatile int*)err != 0) break;
-        if (spins > (1ull << 24)) { atomicCAS(err, 0, 0x200 | t); break; }
+      if (!ok && (++spins & 255u) == 0) {
+        if (*(volatile int*)err != 0) break;
+        if (t0 == 0) t0 = gtime();
+        else if (gtime() - t0 > g_wait_timeout_ns) { atomicCAS(err, 0, 0x200 | t); break; }
       }
     }
 #pragma unroll
@@ -353,7 +359,12 @@ __global__ void __launch_bounds__(kPT, 2) k_cg_persistent(CgPersistArgs a, DistA
     }
     blk_reduce<1>(accA, red);
     if (t == 0) __stcg(a.partA + b, accA[0]);
+    // A time-out must end the solve in ALL CTAs at the same barrier (a CTA that left the loop alone would leave the others
+    // hanging in the next grid.sync): CTA 0 copies the live error word into a per-iteration-parity slot BEFORE the barrier,
+    // every CTA reads that slot AFTER it -- one value for the whole grid, and a slow reader is never overtaken (two slots).
+    if (DIST && b == 0 && t == 0) __stcg(a.flags + 4 + (it & 1), *(volatile int*)(a.flags + 2));
     grid.sync();
+    if (DIST && __ldcg(a.flags + 4 + (it & 1)) != 0) break;
     if (timer) { unsigned long long t1 = gtime(); nsA += t1 - t0; t0 = t1; }
 
     // ------------------------------------------------------------------ pass B
@@ -690,7 +701,15 @@ int fs_dist_cg_run(fs_dist* d, double bb_global, double rz_global, double* x_own
   double hs[16] = {0};
   hs[0] = rz_global; hs[2] = bb_global; hs[3] = bb_global;
   FS_CUDA(cudaMemcpyAsync(scal, hs, sizeof(hs), cudaMemcpyHostToDevice, stream()));
-  FS_CUDA(cudaMemsetAsync(flags, 0, 4 * sizeof(int), stream()));
+  FS_CUDA(cudaMemsetAsync(flags, 0, 8 * sizeof(int), stream()));   // [4], [5]: committed copies of the error word (uniform exit)
+  static bool timeout_set = false;
+  if (!timeout_set) {
+    if (const char* e = std::getenv("FS_DIST_TIMEOUT_MS")) {
+      const unsigned long long ns = (unsigned long long)std::atof(e) * 1000000ull;
+      FS_CUDA(cudaMemcpyToSymbol(g_wait_timeout_ns, &ns, sizeof(ns)));
+    }
+    timeout_set = true;
+  }
   Out<double> ox(x_own, d->n_own);
   int it = 0;
   double rr = bb_global;
