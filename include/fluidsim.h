@@ -316,6 +316,14 @@ int fs_raster_points(uint8_t* rgba /* H*W*4 in/out */, int32_t W, int32_t H, dou
                      const double* pts /* (P,2) */, const int32_t* status /* P or NULL */, int64_t P,
                      const uint8_t* colors_kx3, int32_t n_colors, double radius_px);
 
+/* fs_raster_quiver: velocity arrows of ax.quiver(x, y, u, v, angles='xy', scale_units='xy', scale=s)
+ *   (code/StokesColor.py:514-527, code/StokesFood.py:517-519): shaft (x,y) -> (x+u/s, y+v/s) plus two head strokes of
+ *   head_frac x the shaft length at +-25 degrees, painted where a pixel centre is within half_width_px of a stroke.
+ *   color_rgb: 3 bytes, host. */
+int fs_raster_quiver(uint8_t* rgba /* H*W*4 in/out */, int32_t W, int32_t H, double x0, double x1, double y0, double y1,
+                     const double* pts /* (P,2) */, const double* vec /* (P,2) */, int64_t P, double scale,
+                     double half_width_px, double head_frac, const uint8_t* color_rgb);
+
 #ifdef __cplusplus
 }
 #endif

@@ -680,6 +680,46 @@ def splat_points(rgba, points, status, colors, radius_px, extent=(0.0, 1.0, 0.0,
     return rgba
 
 
+def draw_quiver(rgba, points, vectors, scale, half_width_px=0.6, head_frac=0.3, color=(0, 0, 0), extent=(0.0, 1.0, 0.0, 1.0)):
+    """ax.quiver(x, y, u, v, angles='xy', scale_units='xy', scale=scale) (code/StokesColor.py:514-527,
+    code/StokesFood.py:517-519), restated (matplotlib is absent: pinned to this restatement only): shaft from (x, y) to
+    (x + u/scale, y + v/scale), two head strokes of head_frac x the shaft length at +-25 degrees; a pixel is painted when
+    its centre is within half_width_px of a stroke.  float32 pixel arithmetic in the order of the device kernel."""
+    f = np.float32
+    h, w = rgba.shape[:2]
+    x0, x1, y0, y1 = extent
+    inv_dx, inv_dy, inv_s = w / (x1 - x0), h / (y1 - y0), 1.0 / scale
+    hw, hf = f(half_width_px), f(head_frac)
+    c, s = f(0.90630779), f(0.42261826)
+    r2 = hw * hw
+
+    def d2(px, py, ax, ay, bx, by):
+        dx, dy = bx - ax, by - ay
+        l2 = dx * dx + dy * dy
+        t = ((px - ax) * dx + (py - ay) * dy) / l2 if l2 > 0 else f(0)
+        t = min(max(t, f(0)), f(1))
+        qx, qy = ax + t * dx - px, ay + t * dy - py
+        return qx * qx + qy * qy
+
+    for (px_, py_), (vx, vy) in zip(points, vectors):
+        if np.isnan(px_) or np.isnan(py_) or np.isnan(vx) or np.isnan(vy):
+            continue
+        ax, ay = f((px_ - x0) * inv_dx), f((y1 - py_) * inv_dy)
+        bx, by = f((px_ + vx * inv_s - x0) * inv_dx), f((y1 - (py_ + vy * inv_s)) * inv_dy)
+        sx, sy = ax - bx, ay - by
+        h1x, h1y = bx + hf * (c * sx - s * sy), by + hf * (s * sx + c * sy)
+        h2x, h2y = bx + hf * (c * sx + s * sy), by + hf * (-s * sx + c * sy)
+        xl, xh = min(ax, bx, h1x, h2x) - hw, max(ax, bx, h1x, h2x) + hw
+        yl, yh = min(ay, by, h1y, h2y) - hw, max(ay, by, h1y, h2y) + hw
+        for yy in range(max(int(np.floor(yl)), 0), min(int(np.ceil(yh)), h - 1) + 1):
+            for xx in range(max(int(np.floor(xl)), 0), min(int(np.ceil(xh)), w - 1) + 1):
+                px, py = f(xx + 0.5), f(yy + 0.5)
+                if d2(px, py, ax, ay, bx, by) <= r2 or d2(px, py, bx, by, h1x, h1y) <= r2 or d2(px, py, bx, by, h2x, h2y) <= r2:
+                    rgba[yy, xx, :3] = color
+                    rgba[yy, xx, 3] = 255
+    return rgba
+
+
 # --------------------------------------------------------------------------- physics variants of the draft scripts (SURVEY 8 f4)
 def ramp_omega(step, target=5.0, ramp_up_steps=200):
     """scripts/stokes_report.py:1156-1162."""

@@ -17,7 +17,7 @@ from .hostmesh import node_block_split, sub_mesh, local_index_sets  # noqa: F401
 from .poisson import (PoissonProblem, HeatProblem, apply_periodic_bc, apply_dirichlet_rows,  # noqa: F401
                       add_identity_scaled, helmholtz_smooth)
 from .meshgen import triangulate, triangulate_poly, box_with_hole_pslg, read_poly_full  # noqa: F401
-from .raster import (raster_field, colorize, splat_points, colormap_lut, write_png, read_png, write_apng,  # noqa: F401
+from .raster import (raster_field, colorize, splat_points, draw_quiver, colormap_lut, write_png, read_png, write_apng,  # noqa: F401
                      read_apng, FrameSink)
 
 

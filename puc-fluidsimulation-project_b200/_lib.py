@@ -120,6 +120,7 @@ SIGNATURES = {
     "fs_tracer_step": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, P(c_i64)]),
     "fs_raster_field": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_dbl, c_dbl, c_dbl, c_dbl, c_vp]),
     "fs_raster_colormap": (C.c_int, [c_vp, c_i32, c_i32, c_dbl, c_dbl, c_vp, c_vp, c_vp]),
+    "fs_raster_quiver": (C.c_int, [c_vp, c_i32, c_i32, c_dbl, c_dbl, c_dbl, c_dbl, c_vp, c_vp, c_i64, c_dbl, c_dbl, c_dbl, c_vp]),
     "fs_raster_points": (C.c_int, [c_vp, c_i32, c_i32, c_dbl, c_dbl, c_dbl, c_dbl, c_vp, c_vp, c_i64, c_vp, c_i32, c_dbl]),
 }
 

@@ -505,11 +505,66 @@ __global__ void k_raster_paint(const int* __restrict__ owner, long long n, const
   rgba[i] = make_uchar4(colors[3 * k], colors[3 * k + 1], colors[3 * k + 2], 255);
 }
 
+// Velocity arrows (ax.quiver(x, y, u, v, angles='xy', scale_units='xy', scale=s), code/StokesColor.py:514-527,
+// code/StokesFood.py:517-519): shaft from (x, y) to (x + u/s, y + v/s) and two head strokes of head_frac x the shaft length
+// at +-25 degrees; a pixel is painted when its centre lies within half_width_px of one of the three segments (float32
+// pixel arithmetic, same rule in the oracle).  One thread per arrow; all arrows share one colour, so overlaps need no order.
+__device__ __forceinline__ float seg_dist2(float px, float py, float ax, float ay, float bx, float by) {
+  const float dx = bx - ax, dy = by - ay;
+  const float l2 = dx * dx + dy * dy;
+  float t = l2 > 0.f ? ((px - ax) * dx + (py - ay) * dy) / l2 : 0.f;
+  t = fminf(fmaxf(t, 0.f), 1.f);
+  const float qx = ax + t * dx - px, qy = ay + t * dy - py;
+  return qx * qx + qy * qy;
+}
+__global__ void k_raster_quiver(const double2* __restrict__ pts, const double2* __restrict__ vec, long long P, int W, int H, double x0,
+                                double inv_dx, double ytop, double inv_dy, double inv_scale, float hw, float head_frac, uchar4 color,
+                                uchar4* __restrict__ rgba) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const double2 p = pts[i], v = vec[i];
+  if (!(p.x == p.x) || !(p.y == p.y) || !(v.x == v.x) || !(v.y == v.y)) return;
+  const float ax = (float)((p.x - x0) * inv_dx), ay = (float)((ytop - p.y) * inv_dy);
+  const float bx = (float)((p.x + v.x * inv_scale - x0) * inv_dx), by = (float)((ytop - (p.y + v.y * inv_scale)) * inv_dy);
+  const float sx = ax - bx, sy = ay - by;                       // from the tip back along the shaft
+  const float c = 0.90630779f, s = 0.42261826f;                 // cos / sin of 25 degrees
+  const float h1x = bx + head_frac * (c * sx - s * sy), h1y = by + head_frac * (s * sx + c * sy);
+  const float h2x = bx + head_frac * (c * sx + s * sy), h2y = by + head_frac * (-s * sx + c * sy);
+  const float xl = fminf(fminf(ax, bx), fminf(h1x, h2x)) - hw, xh = fmaxf(fmaxf(ax, bx), fmaxf(h1x, h2x)) + hw;
+  const float yl = fminf(fminf(ay, by), fminf(h1y, h2y)) - hw, yh = fmaxf(fmaxf(ay, by), fmaxf(h1y, h2y)) + hw;
+  const int ix0 = max((int)floorf(xl), 0), ix1 = min((int)ceilf(xh), W - 1);
+  const int iy0 = max((int)floorf(yl), 0), iy1 = min((int)ceilf(yh), H - 1);
+  const float r2 = hw * hw;
+  for (int yy = iy0; yy <= iy1; ++yy)
+    for (int xx = ix0; xx <= ix1; ++xx) {
+      const float px = xx + 0.5f, py = yy + 0.5f;
+      if (seg_dist2(px, py, ax, ay, bx, by) <= r2 || seg_dist2(px, py, bx, by, h1x, h1y) <= r2 || seg_dist2(px, py, bx, by, h2x, h2y) <= r2)
+        rgba[(size_t)yy * W + xx] = color;
+    }
+}
+
 }  // namespace fs
 
 using namespace fs;
 
 extern "C" {
+
+int fs_raster_quiver(uint8_t* rgba, int32_t W, int32_t H, double x0, double x1, double y0, double y1, const double* pts,
+                     const double* vec, int64_t P, double scale, double half_width_px, double head_frac, const uint8_t* color_rgb) {
+  FS_API_BEGIN
+  FS_REQUIRE(rgba && W > 0 && H > 0 && x1 > x0 && y1 > y0 && scale > 0 && color_rgb && (P == 0 || (pts && vec)), "bad arguments");
+  if (P == 0) return FS_OK;
+  In<double> ip(pts, 2 * P), iv(vec, 2 * P);
+  Out<uint8_t> oo(rgba, (size_t)4 * W * H, true);
+  const uchar4 col = make_uchar4(color_rgb[0], color_rgb[1], color_rgb[2], 255);
+  k_raster_quiver<<<(unsigned)div_up(P, 128), 128, 0, stream()>>>((const double2*)ip.d, (const double2*)iv.d, P, W, H, x0, W / (x1 - x0), y1,
+                                                                  H / (y1 - y0), 1.0 / scale, (float)half_width_px, (float)head_frac, col,
+                                                                  (uchar4*)oo.d);
+  FS_LAUNCH_CHECK();
+  oo.commit();
+  fs::sync();
+  FS_API_END
+}
 
 int fs_locate(fs_mesh* m, const double* pts, int64_t P, int32_t* ids) {
   FS_API_BEGIN

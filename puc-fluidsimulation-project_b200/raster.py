@@ -82,6 +82,24 @@ def splat_points(rgba, points, status=None, colors=((0, 0, 255), (255, 0, 0)), r
     return rgba
 
 
+def draw_quiver(rgba, points, vectors, scale=10.0, half_width_px=0.6, head_frac=0.3, color=(0, 0, 0),
+                extent=(0.0, 1.0, 0.0, 1.0)):
+    """Velocity arrows into an RGBA picture (in place): ``ax.quiver(x, y, u, v, angles='xy', scale_units='xy', scale=scale)``
+    of code/StokesColor.py:514-527 (every 3rd node, scale 10, black) and code/StokesFood.py:517-519 (scale 40, white)."""
+    if rgba.dtype != np.uint8 or rgba.ndim != 3 or rgba.shape[2] != 4 or not rgba.flags["C_CONTIGUOUS"]:
+        raise ValueError("rgba must be a C-contiguous (H, W, 4) uint8 array")
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    vec = np.ascontiguousarray(vectors, dtype=np.float64)
+    if pts.shape != vec.shape or pts.ndim != 2 or pts.shape[1] != 2:
+        raise ValueError("points and vectors must both have shape (P, 2)")
+    col = np.ascontiguousarray(color, dtype=np.uint8)
+    h, w = rgba.shape[:2]
+    x0, x1, y0, y1 = map(float, extent)
+    call("fs_raster_quiver", ptr(rgba), int(w), int(h), x0, x1, y0, y1, ptr(pts), ptr(vec), int(len(pts)), float(scale),
+         float(half_width_px), float(head_frac), ptr(col))
+    return rgba
+
+
 def write_png(path, rgba):
     """Minimal PNG writer (8-bit RGBA, no interlace)."""
     rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
@@ -199,9 +217,13 @@ class FrameSink:
         os.makedirs(directory, exist_ok=True)
 
     def render(self, field, vmin, vmax, cmap="viridis", tracers=None, status=None, radius_px=2.0,
-               background=(0, 0, 0, 255), colors=((0, 0, 255), (255, 0, 0))):
+               background=(0, 0, 0, 255), colors=((0, 0, 255), (255, 0, 0)), quiver=None):
+        """quiver = (points, vectors, scale[, color]): velocity arrows on top of the field, under the tracers."""
         img = raster_field(self.mesh, field, self.width, self.height, self.extent)
         rgba = colorize(img, vmin, vmax, cmap, background)
+        if quiver is not None:
+            qp, qv, qs = quiver[:3]
+            draw_quiver(rgba, qp, qv, qs, color=quiver[3] if len(quiver) > 3 else (0, 0, 0), extent=self.extent)
         if tracers is not None and len(tracers):
             splat_points(rgba, tracers, status, colors, radius_px, self.extent)
         return rgba

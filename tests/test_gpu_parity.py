@@ -858,3 +858,32 @@ def test_rotating_cylinder_flow_vs_restated_oracle():
         assert rel(sim.u, ref.u) <= 1e-9, step
     speed = np.hypot(sim.u[:, 0], sim.u[:, 1])
     assert speed[sim.inner_boundary_indices].max() > 0.1 and np.abs(sim.u[sim.wall_node_indices]).max() == 0.0
+
+
+def test_quiver_overlay_matches_oracle():
+    """Output sink: the velocity arrows of code/StokesColor.py:514-527 (every 3rd node, scale 10) pixel for pixel against the
+    restated rasteriser, plus NaN / off-picture arrows."""
+    g = load_golden("mesh5_1_ops")
+    rng = np.random.default_rng(4)
+    mask = np.arange(len(g["nodes"]))[::3]
+    pts = g["nodes"][mask]
+    vec = rng.standard_normal((len(mask), 2)) * 0.8
+    vec[5] = np.nan
+    pts = np.vstack([pts, [[1.3, 0.5], [0.99, 0.99]]])
+    vec = np.vstack([vec, [[1.0, 1.0], [3.0, 3.0]]])
+    a = np.zeros((160, 200, 4), dtype=np.uint8)
+    a[..., 3] = 255
+    a[..., 0] = 90
+    b = a.copy()
+    fb.draw_quiver(a, pts, vec, scale=10.0, color=(0, 0, 0))
+    R.draw_quiver(b, pts, vec, 10.0, color=(0, 0, 0))
+    assert np.array_equal(a, b)
+    assert 200 < int((a[..., 0] == 0).sum()) < 160 * 200 // 2
+    # through the frame sink
+    m = fb.Mesh(g["nodes"], g["tris"], g["markers"])
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        sink = fb.FrameSink(d, m, 128, 128)
+        plain = sink.render(g["dye_c0"], 0.0, 1.0, cmap="plasma")
+        withq = sink.render(g["dye_c0"], 0.0, 1.0, cmap="plasma", quiver=(pts, vec, 10.0))
+    assert (plain != withq).any() and (plain == withq).mean() > 0.6
