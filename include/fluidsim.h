@@ -157,6 +157,11 @@ int fs_cg(fs_csr* a, const double* b, double* x, int nrhs, double rtol, int maxi
           int project_mean, int* iters, double* relres);
 int fs_bicgstab(fs_csr* a, const double* b, double* x, double rtol, int maxit, int precond,
                 int* iters, double* relres);
+/* One application z = M^-1 r of the smoothed-aggregation V(1,1) cycle that FS_PRECOND_AMG uses (the hierarchy is
+ * built on first use and kept in the handle).  A fixed symmetric positive definite map: what a caller needs to run
+ * its own Krylov method around the library's preconditioner.  No reference analogue (every reference solve is a
+ * dense LU, code/StokesColor.py:555). */
+int fs_precond_apply(fs_csr* a, const double* r, double* z);
 
 /* ---- the operator-split Stokes step, code/StokesColor.py:537-575 ==
  * code/StokesFood.py:441-479.  fs_stokes_create assembles K, the lumped mass,

@@ -83,6 +83,7 @@ SIGNATURES = {
     "fs_csr_sizes": (C.c_int, [c_vp, P(c_i64), P(c_i64)]),
     "fs_csr_get": (C.c_int, [c_vp, c_vp, c_vp, c_vp]),
     "fs_spmv": (C.c_int, [c_vp, c_vp, c_vp]),
+    "fs_precond_apply": (C.c_int, [c_vp, c_vp, c_vp]),
     "fs_cg": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, c_dbl, C.c_int, C.c_int, C.c_int, P(C.c_int), P(c_dbl)]),
     "fs_bicgstab": (C.c_int, [c_vp, c_vp, c_vp, c_dbl, C.c_int, C.c_int, P(C.c_int), P(c_dbl)]),
     "fs_stokes_default_opts": (C.c_int, [P(StokesOpts)]),

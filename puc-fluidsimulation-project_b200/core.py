@@ -84,6 +84,13 @@ class CsrMatrix:
 
     __matmul__ = matvec
 
+    def precond_apply(self, r):
+        """z = M^-1 r: one V(1,1) cycle of the AMG hierarchy behind PRECOND_AMG (built on first use)."""
+        r = as_f64(r)
+        z = _empty_like_buf(r, self.n, np.float64)
+        call("fs_precond_apply", self._h, ptr(r, np.float64, (self.n,)), ptr(z))
+        return z
+
     def cg(self, b, x0=None, rtol=1e-10, maxit=100000, precond=PRECOND_JACOBI, project_mean=False):
         b = as_f64(b)
         nrhs = 1 if b.ndim == 1 else b.shape[1]

@@ -35,6 +35,7 @@ struct AmgLevel {
   fs_csr U, Rt;             // folded cycle: U = [G | S P] (n x (n + n_coarse)),  Rt = (S P)^T
   fs_sell Us, Rts;          // ... and their SELL-32 copies (what the cycle streams; CSR kept on small levels)
   DBuf<double> x, b, r, t;  // work vectors of this level (level 0 uses caller buffers for b/x)
+  DBuf<float> x32;          // fp32 mirror of x, written by this level's SELL up-sweep for the fp32 gathers of the level above
   const fs_csr& mat() const { return Aref ? *Aref : A; }
 };
 
@@ -49,6 +50,8 @@ struct Amg {
   // the V-cycle as a CUDA graph (captured on its second application; one launch per cycle)
   cudaGraphExec_t graph = nullptr;
   const double* graph_r = nullptr;
+  const float* graph_r32 = nullptr;
+  const float* r32 = nullptr;   // transient: fp32 mirror of the finest right-hand side (amg_apply's r32)
   double* graph_z = nullptr;
   bool graph_x0 = false;
   bool graph_failed = false;
@@ -693,8 +696,9 @@ Amg* amg_setup(fs_csr* fine, const AmgPartSpec* ps) {
   if (std::getenv("FS_AMG_VERBOSE")) {
     std::fprintf(stderr, "[amg] levels:");
     for (auto& l : amg->L)
-      std::fprintf(stderr, " %d(nnz %lld, U %lld [sell %lld], Rt %lld [sell %lld])", l->n, (long long)l->mat().nnz, (long long)l->U.nnz,
-                   l->Us.padded, (long long)l->Rt.nnz, l->Rts.padded);
+      std::fprintf(stderr, " %d(nnz %lld, U %lld [sell %lld%s, %lld slices unpacked], Rt %lld [sell %lld%s, %lld slices unpacked])", l->n,
+                   (long long)l->mat().nnz, (long long)l->U.nnz, l->Us.padded, l->Us.pk.p ? " packed" : "", l->Us.pk_unpacked,
+                   (long long)l->Rt.nnz, l->Rts.padded, l->Rts.pk.p ? " packed" : "", l->Rts.pk_unpacked);
     std::fprintf(stderr, "  folded %d\n", (int)amg->folded);
   }
   return amg.release();
@@ -775,7 +779,11 @@ static int vcycle_folded(Amg& amg, size_t l, const double* b, double* x, double*
   const int sub_rows = amg.sub_rows;
   // down: b_c = R~ b
   if (nx.n <= sub_rows && lv.Rt.rowptr) spmv_sub(lv.Rt.view32(), b, nx.b.p, nullptr, 0);
-  else if (lv.Rts.nslices) spmv_sell(lv.Rts, b, nx.b.p, nullptr, nullptr);
+  else if (lv.Rts.nslices) {
+    SellF32 f;
+    if (l == 0) f.xf = amg.r32;                  // finest restriction: fp32 gathers from the mirror of r
+    spmv_sell(lv.Rts, b, nx.b.p, nullptr, nullptr, &f);
+  }
   else {
     const CsrView Rt = lv.Rt.view32();
     if (!spmv_warp(Rt, EPI_AX, b, nx.b.p, nullptr, nullptr, 0.0, nullptr, nullptr)) spmv_sub(Rt, b, nx.b.p, nullptr, 0);
@@ -786,7 +794,10 @@ static int vcycle_folded(Amg& amg, size_t l, const double* b, double* x, double*
   if (lv.n <= sub_rows && lv.U.rowptr) spmv_sub(lv.U.view32(), b, x, nx.x.p, lv.n);
   else if (lv.Us.nslices) {
     if (l == 0 && amg.top_ev) cudaEventRecord(amg.top_ev[0], stream());
-    g = spmv_sell(lv.Us, b, x, nx.x.p, dot_part);
+    SellF32 f;
+    if (l == 0 && amg.r32 && nx.x32.p) { f.xf = amg.r32; f.x2f = nx.x32.p; }   // finest up-sweep: fp32 gathers
+    if (l == 1 && amg.r32) f.yf = lv.x32.p;      // level 1 leaves the mirror of its result for it
+    g = spmv_sell(lv.Us, b, x, nx.x.p, dot_part, &f);
     if (l == 0 && amg.top_ev) cudaEventRecord(amg.top_ev[1], stream());
   }
   else {
@@ -854,15 +865,19 @@ void amg_presmooth_target(Amg* amg, double** x0, const double** dinv, double* om
 double amg_top_bytes(const Amg* amg) {
   if (!amg->folded || amg->L.size() < 2 || !amg->L[0]->Us.nslices) return 0.0;
   const AmgLevel& l0 = *amg->L[0];
-  const double val_bytes = l0.Us.v32.n ? 4.0 : 8.0;
-  // true nonzeros (value + column), slice pointers, b gathered + re-read for the dot, x_c gathered, y written
-  return (double)l0.Us.nnz * (val_bytes + 4.0) + 8.0 * (l0.Us.nslices + 1) + 8.0 * l0.n + 8.0 * amg->L[1]->n + 8.0 * l0.n;
+  // bytes per true nonzero: fp64 / fp32 value + 32-bit column, or one packed 32-bit word (fp16 value | 16-bit column offset)
+  const double entry_bytes = l0.Us.pk.n ? 4.0 : (l0.Us.v32.n ? 8.0 : 12.0);
+  // true nonzeros, slice pointers (+ packed: base columns), b gathered + re-read for the dot, x_c gathered, y written
+  return (double)l0.Us.nnz * entry_bytes + (l0.Us.pk.n ? 16.0 : 8.0) * (l0.Us.nslices + 1) + 8.0 * l0.n + 8.0 * amg->L[1]->n + 8.0 * l0.n;
 }
 
-int amg_apply(Amg* amg, const double* r, double* z, bool x0_ready, double* rz_part, cudaEvent_t* top_ev) {
+int amg_apply(Amg* amg, const double* r, double* z, bool x0_ready, double* rz_part, cudaEvent_t* top_ev, const float* r32) {
   static const bool use_graph = env_num("FS_AMG_GRAPH", 1) != 0;
   cudaStream_t st = stream();
   ++amg->applications;
+  amg->r32 = r32;
+  // the mirror of the level-1 result exists only when that level's up-sweep is a SELL kernel (it writes it)
+  if (r32 && amg->folded && amg->L.size() > 2 && amg->L[1]->n > amg->sub_rows && amg->L[1]->Us.nslices && !amg->L[1]->x32.p) amg->L[1]->x32.alloc((size_t)amg->L[1]->n);
   const bool fold = amg->folded && amg->L.size() > 1;
   auto cycle = [&]() -> int {
     if (fold) return vcycle_folded(*amg, 0, r, z, rz_part);
@@ -876,7 +891,7 @@ int amg_apply(Amg* amg, const double* r, double* z, bool x0_ready, double* rz_pa
     return np;
   }
   if (use_graph && amg->graph && amg->graph_r == r && amg->graph_z == z && amg->graph_x0 == x0_ready &&
-      amg->graph_part == rz_part) {
+      amg->graph_part == rz_part && amg->graph_r32 == r32) {
     FS_CUDA(cudaGraphLaunch(amg->graph, st));
     count_launch();
     return amg->graph_nparts;
@@ -893,7 +908,7 @@ int amg_apply(Amg* amg, const double* r, double* z, bool x0_ready, double* rz_pa
     if (ok && e == cudaSuccess && g) {
       cudaGraphExec_t ex = nullptr;
       if (cudaGraphInstantiate(&ex, g, 0) == cudaSuccess) {
-        amg->graph = ex; amg->graph_r = r; amg->graph_z = z; amg->graph_x0 = x0_ready;
+        amg->graph = ex; amg->graph_r = r; amg->graph_z = z; amg->graph_x0 = x0_ready; amg->graph_r32 = r32;
         amg->graph_part = rz_part; amg->graph_nparts = nparts;
         if (std::getenv("FS_AMG_VERBOSE")) std::fprintf(stderr, "[amg] V-cycle captured as a graph\n");
         cudaGraphDestroy(g);
@@ -990,11 +1005,13 @@ void amg_part_finalize(Amg* amg, const Space& space0, DistCtx& ctx) {
     {
       fs_csr loc;
       extract_rows(lv.U.view(), P.split[l][rank], P.split[l][rank + 1], sl, lv.n, sn, loc);
+      // the packed entries are rounded at the GLOBAL operator's scale: same bits as the single-GPU hierarchy
+      const double mu = (amg->part_f32 && sell_pack_enabled()) ? csr_maxabs(lv.U) : 0.0;
       drop(lv.U);
       const int nsplit = (int)(sl.n_own + sl.n_halo);
       if (l >= 1 && loc.n <= amg->sub_rows) keep_csr(lv.U, loc);
       else {
-        sell_build(loc, amg->part_f32, lv.Us, nsplit);
+        sell_build(loc, amg->part_f32, lv.Us, nsplit, 0, mu);
         sell_mark_boundary(lv.Us, loc, (int)sl.n_own, nsplit, sn->gather ? -1 : (int)sn->n_own, l >= 1 ? &sl : nullptr);
       }
       lv.part_nsplit = nsplit;
@@ -1004,11 +1021,12 @@ void amg_part_finalize(Amg* amg, const Space& space0, DistCtx& ctx) {
       const int64_t r0 = P.split[l + 1][rank], r1 = P.split[l + 1][rank + 1];
       const bool have = r1 > r0;
       if (have) extract_rows(lv.Rt.view(), r0, r1, sl, lv.n, nullptr, loc);
+      const double mr = (amg->part_f32 && sell_pack_enabled()) ? csr_maxabs(lv.Rt) : 0.0;
       drop(lv.Rt);
       if (have) {
         if (loc.n <= amg->sub_rows) keep_csr(lv.Rt, loc);
         else {
-          sell_build(loc, amg->part_f32, lv.Rts);
+          sell_build(loc, amg->part_f32, lv.Rts, -1, 0, mr);
           sell_mark_boundary(lv.Rts, loc, (int)sl.n_own, 0x7fffffff, -1, sn);
         }
       }

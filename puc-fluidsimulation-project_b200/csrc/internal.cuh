@@ -283,6 +283,14 @@ struct fs_sell {
   DBuf<int> cols;
   DBuf<float> v32;        // exactly one of v32 / v64 is filled
   DBuf<double> v64;
+  // packed form of an fp32 operator (FS_SELL_PACK, default on): one 32-bit word per entry = fp16 value (scaled by the power
+  // of two 1 / pk_inv) << 16 | 16-bit column offset from the slice's base column cbase[s] (.x first part, .y second part of a
+  // split slice).  Same element offsets as cols / v32.  A slice whose columns span more than 65535 keeps cbase[s].x = INT_MIN
+  // and is read from cols / v32, which then hold the SAME fp16-rounded values: both encodings give the same bits.
+  DBuf<unsigned> pk;
+  DBuf<int2> cbase;
+  double pk_inv = 1.0;
+  long long pk_unpacked = 0;   // slices left in the 32-bit encoding
   DBuf<int> perm;         // SELL-C-sigma: slot (32 s + lane) holds row perm[slot] (rows sorted by length inside windows
                           // of sigma rows, so a slice pads to its own longest row only); empty: identity
   // partitioned step: slices that read halo entries of their input vectors (bit per slice + list); the DIST kernel
@@ -292,8 +300,15 @@ struct fs_sell {
   int n_blist = 0;
   DBuf<int2> btab;        // per boundary slice and lane: up to two destinations (rank << 28 | slot; -1 none; .y = -2: look up)
 };
-void sell_build(const fs_csr& A, bool f32, fs_sell& out, int nsplit = -1, int sigma = 0);
-int spmv_sell(const fs_sell& S, const double* x, double* y, const double* x2, double* dot_partials);
+// pk_maxabs: largest |value| that fixes the fp16 scale of the packed form (0: take it from A; the partitioned set-up
+// passes the global operator's so that every rank rounds exactly like the single-GPU hierarchy)
+void sell_build(const fs_csr& A, bool f32, fs_sell& out, int nsplit = -1, int sigma = 0, double pk_maxabs = 0.0);
+double csr_maxabs(const fs_csr& A);
+bool sell_pack_enabled();
+// fp32 mirrors for the packed kernel with fp32 gathers: xf / x2f mirror x / x2 (both needed to select that kernel),
+// yf (optional, any kernel) receives an fp32 copy of y
+struct SellF32 { const float* xf = nullptr; const float* x2f = nullptr; float* yf = nullptr; };
+int spmv_sell(const fs_sell& S, const double* x, double* y, const double* x2, double* dot_partials, const SellF32* f32v = nullptr);
 int spmv_sell_grid(const fs_sell& S);   // grid (= dot partials per column) of spmv_sell2
 void spmv_sell2(const fs_sell& S, const double* x, double* y, double* dot_partials, const int* done);
 // any-matrix fallback: y = A [x; x2] (columns >= nsplit gather from x2; x2 null: y = A x)
@@ -305,8 +320,10 @@ Amg* amg_setup(fs_csr* fine, const AmgPartSpec* part = nullptr);   // part: row-
 // many were written by the cycle's last kernel (0: the caller computes r.z itself).
 // top_ev (optional, two events): run the cycle eagerly and bracket its largest kernel (the finest
 // level's up-sweep) with them -- the sampled roofline timing of bench.py.
+// r32 (optional): fp32 mirror of r, kept by the caller next to r -- the two finest-level kernels of the folded cycle then
+// gather in fp32 (spmv_sell.cu, FMT 4).
 int amg_apply(Amg* amg, const double* r, double* z, bool x0_ready = false, double* rz_part = nullptr,
-              cudaEvent_t* top_ev = nullptr);
+              cudaEvent_t* top_ev = nullptr, const float* r32 = nullptr);
 double amg_top_bytes(const Amg* amg);   // algorithmic bytes of one launch of that kernel (0: unfolded cycle)
 void amg_presmooth_target(Amg* amg, double** x0, const double** dinv, double* omega);
 int amg_levels(const Amg* amg, int* sizes, int cap);

@@ -824,7 +824,7 @@ __global__ void k_pcg_init(const double* __restrict__ partRZ, int nrz, double bb
 __global__ void __launch_bounds__(kBlock)
 k_pcg_xr(int64_t n, const double* __restrict__ p, const double* __restrict__ Ap, double* __restrict__ x, double* __restrict__ r,
          const double* __restrict__ partA, int nblkA, const double* __restrict__ sc, int slot, const int* __restrict__ flags,
-         double* __restrict__ partB, double* __restrict__ x0out, const double* __restrict__ dinv, double w) {
+         double* __restrict__ partB, double* __restrict__ x0out, const double* __restrict__ dinv, double w, float* __restrict__ r32) {
   __shared__ double red[32];
   __shared__ double sm[1];
   if (flags[0]) return;
@@ -837,6 +837,7 @@ k_pcg_xr(int64_t n, const double* __restrict__ p, const double* __restrict__ Ap,
     const double rn = r[i] - alpha * Ap[i];
     x[i] += alpha * p[i];
     r[i] = rn;
+    if (r32) r32[i] = (float)rn;                // fp32 mirror for the V-cycle's finest-level gathers
     if (x0out) x0out[i] = w * dinv[i] * rn;     // the unfolded V-cycle's pre-smoothed iterate, for free
     acc[0] += rn * rn;
   }
@@ -877,10 +878,22 @@ k_pcg_p(int64_t n, const double* __restrict__ z, double* __restrict__ p, const d
   }
 }
 
+// fp32 mirror of r for the gathers of the packed V-cycle kernels (FS_PCG_R32=0: fp64 gathers, the arithmetic of the
+// partitioned cycle; read at every solve so that a caller can compare the two)
+static bool pcg_use_r32() {
+  const char* e = std::getenv("FS_PCG_R32");
+  return !e || std::atoi(e) != 0;
+}
+
+__global__ void k_mirror_f32(int64_t n, const double* __restrict__ in, float* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (float)in[i];
+}
+
 static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, int maxit, int project_mean, double* relres) {
   const int64_t n = a->n;
-  ensure_ws(a, 5 * (size_t)n);
+  ensure_ws(a, 5 * (size_t)n + (size_t)(n + 1) / 2);
   double *r = a->ws.p, *p = r + n, *Ap = p + n, *z = Ap + n, *bproj = z + n;
+  float* r32 = pcg_use_r32() ? reinterpret_cast<float*>(bproj + n) : nullptr;
   if (!a->amg) a->amg = amg_setup(a);
   ensure_tiles(a);
   static const bool sell_ap = [] { const char* e = std::getenv("FS_PCG_SELL"); return !e || std::atoi(e) != 0; }();
@@ -927,7 +940,7 @@ static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, in
     if (ev) cudaEventRecord(ev[2], st);
     const bool samp_top = ev && (napply % 8 == 4);
     ++napply;
-    int nrz = amg_apply(a->amg, rin, zout, x0_ready, partRZ, samp_top ? ev + 5 : nullptr);
+    int nrz = amg_apply(a->amg, rin, zout, x0_ready, partRZ, samp_top ? ev + 5 : nullptr, r32);
     if (ev) { cudaEventRecord(ev[3], st); top_sampled.push_back(samp_top ? 1 : 0); }
     if (!nrz) {
       k_pcg_rz<<<g, kBlock, 0, st>>>(n, rin, zout, partRZ); FS_LAUNCH_CHECK();
@@ -948,6 +961,7 @@ static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, in
   int it = 0;
   bool done = rr <= tol2 * bb;
   if (!done) {
+    if (r32) { k_mirror_f32<<<g, kBlock, 0, st>>>(n, r, r32); FS_LAUNCH_CHECK(); }
     int nrz = precond(r, z, false, nullptr);
     FS_CUDA(cudaMemcpyAsync(p, z, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     k_pcg_init<<<1, kBlock, 0, st>>>(partRZ, nrz, bb, rr, tol2, sc, flags); FS_LAUNCH_CHECK();
@@ -961,7 +975,7 @@ static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, in
       if (!ga) ga = spmv_warp(A, EPI_AX, p, Ap, nullptr, nullptr, 0.0, nullptr, partA);
       if (!ga) { ga = spmv_launch_grid<1>(A); launch_spmv<1, true>(A, p, Ap, partA, nullptr, ga); }
       if (ev) cudaEventRecord(ev[1], st);
-      k_pcg_xr<<<g, kBlock, 0, st>>>(n, p, Ap, x, r, partA, ga, sc, slot, flags, partB, x0, dinv0, w0); FS_LAUNCH_CHECK();
+      k_pcg_xr<<<g, kBlock, 0, st>>>(n, p, Ap, x, r, partA, ga, sc, slot, flags, partB, x0, dinv0, w0, r32); FS_LAUNCH_CHECK();
       nrz = precond(r, z, x0 != nullptr, ev);
       k_pcg_p<<<g, kBlock, 0, st>>>(n, z, p, partB, g, partRZ, nrz, sc, slot, flags); FS_LAUNCH_CHECK();
       if (ev) cudaEventRecord(ev[4], st);
@@ -1389,6 +1403,26 @@ int fs_spmv(fs_csr* a, const double* x, double* y) {
   ensure_tiles(a);
   spmv_dev(a->view(), ix.d, oy.d);
   oy.commit();
+  fs::sync();
+  FS_API_END
+}
+
+int fs_precond_apply(fs_csr* a, const double* r, double* z) {
+  FS_API_BEGIN
+  FS_REQUIRE(a && r && z, "NULL argument");
+  FS_REQUIRE(a->n > 0, "empty matrix");
+  In<double> ir(r, a->n);
+  Out<double> oz(z, a->n);
+  if (!a->amg) a->amg = amg_setup(a);
+  ensure_tiles(a);
+  DBuf<float> r32;
+  if (pcg_use_r32()) {      // the same arithmetic as inside fs_cg
+    r32.alloc((size_t)a->n);
+    k_mirror_f32<<<vec_grid(a->n), kBlock, 0, stream()>>>(a->n, ir.d, r32.p);
+    FS_LAUNCH_CHECK();
+  }
+  amg_apply(a->amg, ir.d, oz.d, false, nullptr, nullptr, r32.p);
+  oz.commit();
   fs::sync();
   FS_API_END
 }

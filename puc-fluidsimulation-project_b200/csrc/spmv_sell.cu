@@ -14,7 +14,9 @@
 // The CSR-stream kernels measured ~1.0-1.3 nonzeros / cycle / SM whatever the value width (L1TEX
 // bound: scattered gathers + shared-memory staging), so fp32 values bought nothing there.
 // y = A x or A [x; x2] (columns >= nsplit read x2), optional per-CTA partials of x.y.
+#include <climits>
 #include <cub/cub.cuh>
+#include <cuda_fp16.h>
 
 #include "dist.cuh"
 
@@ -36,6 +38,12 @@ struct SellArgs {
   double* part;
   int l2hint;
   const int* perm;      // SELL-C-sigma row of every slot (null: identity)
+  const unsigned* pk;   // packed form (fp16 value << 16 | column offset), null: none
+  const int2* cbase;    // per slice: base column of each part, .x == INT_MIN: slice kept in cols / v32
+  double pk_inv;        // 1 / (power-of-two scale of the packed values)
+  const float* xf;      // FMT 4: fp32 mirrors of x / x2 (the gather sources of packed slices)
+  const float* x2f;
+  float* yf;            // optional fp32 mirror of y (any format)
 };
 
 // streamed once per launch: read-only path, no L1 allocation (the L1 is for the gathered vectors), and an L2
@@ -60,6 +68,11 @@ __device__ __forceinline__ double ld_stream(const double* a, uint64_t pol) {
 __device__ __forceinline__ int ld_stream(const int* a, uint64_t pol) {
   int v;
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ unsigned ld_stream(const unsigned* a, uint64_t pol) {
+  unsigned v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
   return v;
 }
 
@@ -136,6 +149,141 @@ __device__ __forceinline__ double sell_part4(const float* __restrict__ vp, const
   return acc;
 }
 
+// ---- packed entries: 4 bytes instead of 8 per nonzero ----------------------------------------------------
+// The preconditioner's operators only have to be a fixed SPD map, so their values are stored as fp16 (scaled by a power of
+// two per matrix: no iteration more than with fp32 values on the bench meshes, against +2 for bf16 --
+// scratch/proto_bf16.py) and the column as a 16-bit offset from the slice's base column: the rows of a slice are
+// neighbours in the mesh numbering, their columns sit in a narrow band.  One 32-bit stream load per entry instead of two,
+// half the bytes; xb = x + base.
+// gather x[base + 16-bit offset]: one LOP + one IMAD.WIDE.U32 + the load
+__device__ __forceinline__ double pk_gather(const double* xb, unsigned w) {
+  const double* p;
+  asm("mad.wide.u32 %0, %1, 8, %2;" : "=l"(p) : "r"(w & 0xffffu), "l"(xb));
+  return __ldg(p);
+}
+__device__ __forceinline__ double pk_mac(unsigned w, double xv, double acc) {
+  return fma((double)__half2float(__ushort_as_half((unsigned short)(w >> 16))), xv, acc);
+}
+
+template <int U>
+__device__ __forceinline__ double pk_batch(const unsigned* __restrict__ wp, const double* __restrict__ xb, double acc, uint64_t pol) {
+  unsigned ww[U];
+#pragma unroll
+  for (int j = 0; j < U; ++j) ww[j] = ld_stream(wp + (j << 5), pol);
+  double xx[U];
+#pragma unroll
+  for (int j = 0; j < U; ++j) xx[j] = pk_gather(xb, ww[j]);
+#pragma unroll
+  for (int j = 0; j < U; ++j) acc = pk_mac(ww[j], xx[j], acc);
+  return acc;
+}
+
+template <int U>
+__device__ __forceinline__ double pk_tail(const unsigned* __restrict__ wp, int rem, const double* __restrict__ xb, double acc,
+                                          uint64_t pol) {
+  unsigned ww[U];
+#pragma unroll
+  for (int j = 0; j < U; ++j) ww[j] = j < rem ? ld_stream(wp + (j << 5), pol) : 0u;   // value 0 times xb[0]
+  double xx[U];
+#pragma unroll
+  for (int j = 0; j < U; ++j) xx[j] = pk_gather(xb, ww[j]);
+#pragma unroll
+  for (int j = 0; j < U; ++j) acc = pk_mac(ww[j], xx[j], acc);
+  return acc;
+}
+
+template <int U>
+__device__ __forceinline__ double pk_part(const unsigned* __restrict__ wp, int W, const double* __restrict__ xb, double acc,
+                                          uint64_t pol) {
+  int k = 0;
+  for (; k + U <= W; k += U, wp += U * 32) acc = pk_batch<U>(wp, xb, acc, pol);
+  if (U == 8) {
+    if (k + 4 <= W) { acc = pk_batch<4>(wp, xb, acc, pol); k += 4; wp += 128; }
+  }
+  if (k < W) acc = pk_tail<3>(wp, W - k, xb, acc, pol);
+  return acc;
+}
+
+// fp32 gathers (FMT 4).  The gathered vector costs two registers per entry in flight as fp64 and one as fp32, and half the
+// L1 / L2 sectors: with an fp32 mirror of the input vectors (written by their producers) a batch of 8 entries fits the
+// 32-register budget of 64 resident warps.  Products and the row sum are fp32 (13 terms, operators already rounded to
+// fp16); the row result is widened and scaled in fp64.  The preconditioner stays a fixed map to 1e-7.
+__device__ __forceinline__ float pk_gather32(const float* xb, unsigned w) {
+  const float* p;
+  asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(p) : "r"(w & 0xffffu), "l"(xb));
+  return __ldg(p);
+}
+
+template <int U, bool GUARD>
+__device__ __forceinline__ float pk32_batch(const unsigned* __restrict__ wp, int rem, const float* __restrict__ xb, float acc, uint64_t pol) {
+  unsigned ww[U];
+#pragma unroll
+  for (int j = 0; j < U; ++j) ww[j] = (!GUARD || j < rem) ? ld_stream(wp + (j << 5), pol) : 0u;
+  float xx[U];
+#pragma unroll
+  for (int j = 0; j < U; ++j) xx[j] = pk_gather32(xb, ww[j]);
+#pragma unroll
+  for (int j = 0; j < U; ++j) acc = fmaf(__half2float(__ushort_as_half((unsigned short)(ww[j] >> 16))), xx[j], acc);
+  return acc;
+}
+
+__device__ __forceinline__ float pk32_part(const unsigned* __restrict__ wp, int W, const float* __restrict__ xb, float acc, uint64_t pol) {
+  int k = 0;
+  for (; k + 8 <= W; k += 8, wp += 256) acc = pk32_batch<8, false>(wp, 8, xb, acc, pol);
+  if (k < W) acc = pk32_batch<8, true>(wp, W - k, xb, acc, pol);     // the last 1..7 entries as one guarded batch
+  return acc;
+}
+
+// These kernels are latency bound, not bandwidth bound: a warp walks its slice as a chain of dependent memory rounds
+// (slice header -> stream loads -> gathers -> next batch ...), and the time is (rounds per slice) / (resident warps)
+// -- measured: the same code at 48 instead of 64 warps per SM runs 1.4x longer.  The packed words are small enough to
+// put a whole slice in flight at once: the first 8 words of BOTH parts (or 16 of a one-part slice) are loaded in one
+// round, then gathered in two groups of 8; rows longer than that continue in batches of 4.  Sums stay in ascending
+// column order, part 1 before part 2 -- the same bits as the batch-of-4 kernel and as the 32-bit encoding.
+template <int U>
+__device__ __forceinline__ void pk_load_guarded(unsigned (&ww)[U], const unsigned* __restrict__ wp, int cnt, uint64_t pol) {
+#pragma unroll
+  for (int j = 0; j < U; ++j) ww[j] = j < cnt ? ld_stream(wp + (j << 5), pol) : 0u;   // word 0: value 0 times xb[0]
+}
+
+template <int U>
+__device__ __forceinline__ double pk_consume(const unsigned (&ww)[U], const double* __restrict__ xb, double acc) {
+  double xx[U];
+#pragma unroll
+  for (int j = 0; j < U; ++j) xx[j] = pk_gather(xb, ww[j]);
+#pragma unroll
+  for (int j = 0; j < U; ++j) acc = pk_mac(ww[j], xx[j], acc);
+  return acc;
+}
+
+template <bool SPLIT>
+__device__ __forceinline__ double pk_slice_wide(const unsigned* __restrict__ wp, int W, int Wg, const double* __restrict__ xb,
+                                                const double* __restrict__ xb2, uint64_t pol) {
+  double acc = 0.0;
+  if (SPLIT) {
+    const unsigned* __restrict__ wp2 = wp + ((long long)Wg << 5);
+    const int W2 = W - Wg;
+    unsigned wa[8], wb[8];
+    pk_load_guarded<8>(wa, wp, Wg, pol);
+    pk_load_guarded<8>(wb, wp2, W2, pol);
+    asm volatile("" ::: "memory");      // all 16 stream loads are issued before the first gather
+    acc = pk_consume<8>(wa, xb, acc);
+    if (Wg > 8) acc = pk_part<4>(wp + 256, Wg - 8, xb, acc, pol);
+    acc = pk_consume<8>(wb, xb2, acc);
+    if (W2 > 8) acc = pk_part<4>(wp2 + 256, W2 - 8, xb2, acc, pol);
+  } else {
+    for (int k = 0; k < W; k += 16, wp += 512) {
+      unsigned wa[8], wb[8];
+      pk_load_guarded<8>(wa, wp, W - k, pol);
+      pk_load_guarded<8>(wb, wp + 256, W - k - 8, pol);
+      asm volatile("" ::: "memory");
+      acc = pk_consume<8>(wa, xb, acc);
+      acc = pk_consume<8>(wb, xb, acc);
+    }
+  }
+  return acc;
+}
+
 // DIST (partitioned step, pstokes.cu): x / x2 are [own | halo] vectors whose halo entries are written by the
 // neighbouring ranks; the kernel returns at once when the running solve has converged and otherwise
 // waits for the halo flags of its input channels before the first gather (dist.cuh).
@@ -157,8 +305,20 @@ struct DistSell {
   int tag = 0;
 };
 
-template <bool SPLIT, bool DOT, bool F32, bool DIST>
-__global__ void __launch_bounds__(kST, (SPLIT && F32 && DOT && !DIST) ? 8 : 6) k_spmv_sell(SellArgs a, DistSell d) {
+// FMT: 0 fp64 values, 1 fp32 values, 2 packed entries in batches of 4 (32 registers, 64 warps per SM), 3 packed entries
+// with a whole slice in flight and the next slice's header prefetched (5 CTAs = 40 warps per SM), 4 packed entries with
+// fp32 gathers in batches of 8; slices that could not be packed take the fp32-value path (fp64 gathers)
+struct SliceHdr {
+  int s;            // slice, -1: skip
+  int W, Wg;
+  long long off;
+  int2 cb, dst;
+};
+
+template <bool SPLIT, bool DOT, int FMT, bool DIST>
+__global__ void __launch_bounds__(kST, ((SPLIT && FMT == 1 && DOT && !DIST) || FMT == 2 || FMT == 4) ? 8 : (FMT == 3 ? 5 : 6)) k_spmv_sell(SellArgs a, DistSell d) {
+  constexpr bool F32 = FMT >= 1;
+  constexpr bool PREFETCH = FMT == 3;
   __shared__ double red[kSW];
   if (DIST) {
     if (d.c.done && *d.c.done) return;
@@ -180,25 +340,57 @@ __global__ void __launch_bounds__(kST, (SPLIT && F32 && DOT && !DIST) ? 8 : 6) k
   const int first = (bcta ? blockIdx.x : blockIdx.x - nb) * kSW + warp;
   const int nwarps = (bcta ? nb : (int)gridDim.x - nb) * kSW;
   {
-  for (int si = first; si < count; si += nwarps) {
+  auto fetch = [&](int si) -> SliceHdr {
+    SliceHdr h;
+    h.s = -1; h.W = h.Wg = 0; h.off = 0; h.cb = make_int2(INT_MIN, 0); h.dst = make_int2(-1, -1);
+    if (si >= count) return h;
     int s = si;
-    int2 dst = make_int2(-1, -1);
     if (two) {
       if (bcta) {
         s = __ldg(d.blist + si);
-        if (d.btab) dst = __ldg(d.btab + ((size_t)si << 5) + lane);
-      } else if ((__ldg(d.bmask + (si >> 5)) >> (si & 31)) & 1u) continue;
+        if (d.btab) h.dst = __ldg(d.btab + ((size_t)si << 5) + lane);
+      } else if ((__ldg(d.bmask + (si >> 5)) >> (si & 31)) & 1u) return h;
     }
-    const long long off = __ldg(a.sptr + s);
-    const int W = (int)((__ldg(a.sptr + s + 1) - off) >> 5);
-    const int Wg = SPLIT ? __ldg(a.wg + s) : W;
+    h.s = s;
+    h.off = __ldg(a.sptr + s);
+    h.W = (int)((__ldg(a.sptr + s + 1) - h.off) >> 5);
+    h.Wg = SPLIT ? __ldg(a.wg + s) : h.W;
+    if (FMT >= 2) h.cb = __ldg(a.cbase + s);
+    return h;
+  };
+  SliceHdr hcur;
+  if (PREFETCH) hcur = fetch(first);
+  for (int si = first; si < count; si += nwarps) {
+    SliceHdr h;
+    if (PREFETCH) { h = hcur; hcur = fetch(si + nwarps); }      // the next header is in flight while this slice is streamed
+    else h = fetch(si);
+    if (h.s < 0) continue;
+    const int s = h.s;
+    const int2 dst = h.dst;
+    const long long off = h.off;
+    const int W = h.W, Wg = h.Wg;
     const int* __restrict__ cp = a.cols + off + lane;
     double acc = 0.0;
-    if (F32) {
+    const int2 cb = h.cb;
+    if (FMT >= 2 && cb.x != INT_MIN) {
+      const unsigned* __restrict__ wp = a.pk + off + lane;
+      const double* xb = a.x + cb.x;
+      const double* xb2 = SPLIT ? a.x2 + cb.y : nullptr;
+      if (FMT == 4) {
+        float f = pk32_part(wp, Wg, a.xf + cb.x, 0.0f, pol);
+        if (SPLIT) f = pk32_part(wp + ((long long)Wg << 5), W - Wg, a.x2f + cb.y, f, pol);
+        acc = (double)f;
+      } else if (FMT == 3) acc = pk_slice_wide<SPLIT>(wp, W, Wg, xb, xb2, pol);
+      else {
+        acc = pk_part<4>(wp, Wg, xb, acc, pol);
+        if (SPLIT) acc = pk_part<4>(wp + ((long long)Wg << 5), W - Wg, xb2, acc, pol);
+      }
+      acc *= a.pk_inv;
+    } else if (F32) {
       const float* __restrict__ vp = a.v32 + off + lane;
-      if (SPLIT && DOT) {   // the finest up-sweep
+      if ((SPLIT && DOT) || FMT >= 2) {   // the finest up-sweep; unpackable slices of a packed matrix
         acc = sell_part4(vp, cp, Wg, a.x, acc, pol);
-        acc = sell_part4(vp + ((long long)Wg << 5), cp + ((long long)Wg << 5), W - Wg, a.x2, acc, pol);
+        if (SPLIT) acc = sell_part4(vp + ((long long)Wg << 5), cp + ((long long)Wg << 5), W - Wg, a.x2, acc, pol);
       } else {
         acc = sell_part<float>(vp, cp, Wg, a.x, acc, pol);
         if (SPLIT) acc = sell_part<float>(vp + ((long long)Wg << 5), cp + ((long long)Wg << 5), W - Wg, a.x2, acc, pol);
@@ -212,6 +404,7 @@ __global__ void __launch_bounds__(kST, (SPLIT && F32 && DOT && !DIST) ? 8 : 6) k
     if (slot < a.n) {
       const int row = a.perm ? __ldg(a.perm + slot) : slot;
       a.y[row] = acc;
+      if (a.yf) a.yf[row] = (float)acc;
       if (DOT) dacc += __ldg(a.x + row) * acc;
       if (DIST && d.ps.enabled) {
         if (d.ps.gather) pushed |= push_row(d.ps, row, acc);
@@ -479,6 +672,82 @@ __global__ void k_sell_fill(CsrView A, int nslices, int nsplit, const int* __res
   }
 }
 
+// ---- packed form ---------------------------------------------------------------------------------------
+__global__ void k_maxabs_bits(const double* __restrict__ v, int64_t n, unsigned long long* __restrict__ out) {
+  unsigned long long m = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double a = fabs(v[i]);
+    if (a == a) m = max(m, (unsigned long long)__double_as_longlong(a));   // non-negative doubles order like their bits
+  }
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+double csr_maxabs(const fs_csr& A) {
+  if (!A.nnz || !A.vals.p) return 0.0;
+  DBuf<unsigned long long> m(1);
+  m.zero();
+  k_maxabs_bits<<<(int)std::min<int64_t>(div_up(A.nnz, 256), 2048), 256, 0, stream()>>>(A.vals.p, A.nnz, m.p);
+  FS_LAUNCH_CHECK();
+  const unsigned long long bits = m.to_host()[0];
+  double r;
+  std::memcpy(&r, &bits, sizeof r);
+  return r;
+}
+
+static int sell_pack_mode() {  // read at every set-up (not cached): tests switch it between hierarchies
+  const char* e = std::getenv("FS_SELL_PACK");
+  return e ? std::atoi(e) : 1;
+}
+// FS_SELL_PACK=0: fp32 value + 32-bit column per entry; 1 (default): packed; 2: the packed form's rounding with every
+// slice left in the 32-bit encoding (test: both encodings must give the same bits)
+bool sell_pack_enabled() { return sell_pack_mode() != 0; }
+
+// One warp per slice.  Rounds the slice's fp32 values to fp16 at the matrix scale (v32 keeps the rounded value, so the
+// 32-bit encoding of an unpackable slice gives the same products), finds the column range of each part over the real
+// entries and, if both ranges fit 16 bits, writes the packed words.  Padding (value 0) becomes word 0: 0 * x[base].
+__global__ void k_sell_pack(int nslices, const long long* __restrict__ sptr, const int* __restrict__ wg, const int* __restrict__ cols,
+                            float* __restrict__ v32, float scale, float inv_scale, unsigned* __restrict__ pk, int2* __restrict__ cbase,
+                            unsigned long long* __restrict__ n_unpacked, int force_unpacked) {
+  const int s = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (s >= nslices) return;
+  const long long off = sptr[s];
+  const int W = (int)((sptr[s + 1] - off) >> 5);
+  const int Wg = wg ? wg[s] : W;
+  int lo1 = INT_MAX, hi1 = INT_MIN, lo2 = INT_MAX, hi2 = INT_MIN;
+  for (int k = 0; k < W; ++k) {
+    const long long idx = off + ((long long)k << 5) + lane;
+    const float h = __half2float(__float2half_rn(v32[idx] * scale));
+    v32[idx] = h * inv_scale;
+    if (h != 0.0f) {
+      const int c = cols[idx];
+      if (k < Wg) { lo1 = min(lo1, c); hi1 = max(hi1, c); }
+      else { lo2 = min(lo2, c); hi2 = max(hi2, c); }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lo1 = min(lo1, __shfl_xor_sync(0xffffffffu, lo1, o)); hi1 = max(hi1, __shfl_xor_sync(0xffffffffu, hi1, o));
+    lo2 = min(lo2, __shfl_xor_sync(0xffffffffu, lo2, o)); hi2 = max(hi2, __shfl_xor_sync(0xffffffffu, hi2, o));
+  }
+  if (hi1 < lo1) lo1 = hi1 = 0;     // a part without real entries
+  if (hi2 < lo2) lo2 = hi2 = 0;
+  const bool ok = !force_unpacked && (long long)hi1 - lo1 <= 65535 && (long long)hi2 - lo2 <= 65535;
+  if (lane == 0) {
+    cbase[s] = ok ? make_int2(lo1, lo2) : make_int2(INT_MIN, 0);
+    if (!ok) atomicAdd(n_unpacked, 1ull);
+  }
+  for (int k = 0; k < W; ++k) {
+    const long long idx = off + ((long long)k << 5) + lane;
+    unsigned w = 0;
+    if (ok) {
+      const __half h = __float2half_rn(v32[idx] * scale);     // exact: v32 is already an fp16 value / scale
+      const unsigned hb = __half_as_ushort(h);
+      if (hb & 0x7fffu) w = (hb << 16) | (unsigned)(cols[idx] - (k < Wg ? lo1 : lo2));
+    }
+    pk[idx] = w;
+  }
+}
+
 void sell_free(fs_sell* s) { delete s; }
 
 // nsplit >= 0: two-part slices (columns < nsplit first, padded per slice; the second part's columns
@@ -491,7 +760,7 @@ __global__ void k_sigma_keys(const int* __restrict__ rowptr, int n, int sigma, u
   rows[i] = i;
 }
 
-void sell_build(const fs_csr& A, bool f32, fs_sell& out, int nsplit, int sigma) {
+void sell_build(const fs_csr& A, bool f32, fs_sell& out, int nsplit, int sigma, double pk_maxabs) {
   cudaStream_t st = stream();
   const int n = (int)A.n;
   const int nslices = div_up(n, 32);
@@ -537,6 +806,23 @@ void sell_build(const fs_csr& A, bool f32, fs_sell& out, int nsplit, int sigma) 
   else k_sell_fill<false><<<g, 256, 0, st>>>(A.view(), nslices, ns, perm, out.sptr.p, out.wg.p, out.cols.p, nullptr, out.v64.p);
   FS_LAUNCH_CHECK();
   FS_CUDA(cudaStreamSynchronize(st));
+  if (f32 && sell_pack_enabled() && total > 0) {
+    const double m = pk_maxabs > 0.0 ? pk_maxabs : csr_maxabs(A);
+    if (m > 0.0 && m < 1e30 && m > 1e-30) {
+      // largest value lands in [2^14, 2^15): inside fp16's range, 24 binades above its smallest subnormal
+      const double scale = std::ldexp(1.0, 14 - std::ilogb(m));
+      out.pk.alloc((size_t)total);
+      out.cbase.alloc((size_t)nslices);
+      DBuf<unsigned long long> cnt(1);
+      cnt.zero();
+      k_sell_pack<<<(int)div_up((int64_t)nslices * 32, 256), 256, 0, st>>>(nslices, out.sptr.p, split ? out.wg.p : nullptr, out.cols.p,
+                                                                           out.v32.p, (float)scale, (float)(1.0 / scale), out.pk.p,
+                                                                           out.cbase.p, cnt.p, sell_pack_mode() == 2 ? 1 : 0);
+      FS_LAUNCH_CHECK();
+      out.pk_inv = 1.0 / scale;
+      out.pk_unpacked = (long long)cnt.to_host()[0];
+    }
+  }
 }
 
 static int l2_hint() {
@@ -544,15 +830,24 @@ static int l2_hint() {
   return v;
 }
 
+static int pk_mode() {   // FS_PK_MODE: kernel for packed matrices (2 / 3 / 4, see k_spmv_sell); 4 needs the fp32 mirrors
+  static const int v = [] { const char* e = std::getenv("FS_PK_MODE"); return e ? std::atoi(e) : 4; }();
+  return v;
+}
+
 template <bool SPLIT, bool DOT>
 static void launch_sell(const SellArgs& args, int grid, const DistSell* d) {
   static const DistSell none{};
   if (d) {
-    if (args.v32) k_spmv_sell<SPLIT, DOT, true, true><<<grid, kST, 0, stream()>>>(args, *d);
-    else k_spmv_sell<SPLIT, DOT, false, true><<<grid, kST, 0, stream()>>>(args, *d);
+    if (args.pk) k_spmv_sell<SPLIT, DOT, 2, true><<<grid, kST, 0, stream()>>>(args, *d);
+    else if (args.v32) k_spmv_sell<SPLIT, DOT, 1, true><<<grid, kST, 0, stream()>>>(args, *d);
+    else k_spmv_sell<SPLIT, DOT, 0, true><<<grid, kST, 0, stream()>>>(args, *d);
   } else {
-    if (args.v32) k_spmv_sell<SPLIT, DOT, true, false><<<grid, kST, 0, stream()>>>(args, none);
-    else k_spmv_sell<SPLIT, DOT, false, false><<<grid, kST, 0, stream()>>>(args, none);
+    if (args.pk && args.xf) k_spmv_sell<SPLIT, DOT, 4, false><<<grid, kST, 0, stream()>>>(args, none);
+    else if (args.pk && pk_mode() == 3) k_spmv_sell<SPLIT, DOT, 3, false><<<grid, kST, 0, stream()>>>(args, none);
+    else if (args.pk) k_spmv_sell<SPLIT, DOT, 2, false><<<grid, kST, 0, stream()>>>(args, none);
+    else if (args.v32) k_spmv_sell<SPLIT, DOT, 1, false><<<grid, kST, 0, stream()>>>(args, none);
+    else k_spmv_sell<SPLIT, DOT, 0, false><<<grid, kST, 0, stream()>>>(args, none);
   }
 }
 
@@ -591,11 +886,12 @@ static int sell_tma_mode() {
 }
 
 static int spmv_sell_impl(const fs_sell& S, const double* x, double* y, const double* x2, double* dot_partials,
-                          DistSell* d) {
+                          DistSell* d, const SellF32* f32v = nullptr) {
   if (!S.nslices) return 0;
   FS_REQUIRE((S.nsplit >= 0) == (x2 != nullptr), "spmv_sell: split form and second vector must come together");
   if (!d && sell_tma_mode() && S.nslices >= 4096) {
-    SellArgs args{S.n, S.nslices, S.sptr.p, S.wg.p, S.cols.p, S.v32.p, S.v64.p, x, x2, y, dot_partials, 1, S.perm.p};
+    SellArgs args{S.n, S.nslices, S.sptr.p, S.wg.p, S.cols.p, S.v32.p, S.v64.p, x, x2, y, dot_partials, 1, S.perm.p, nullptr, nullptr, 1.0,
+                  nullptr, nullptr, nullptr};
     const bool f32 = S.v32.p != nullptr;
     if (x2) {
       if (dot_partials) return f32 ? launch_bulk<true, true, true>(args) : launch_bulk<true, true, false>(args);
@@ -604,9 +900,13 @@ static int spmv_sell_impl(const fs_sell& S, const double* x, double* y, const do
     if (dot_partials) return f32 ? launch_bulk<false, true, true>(args) : launch_bulk<false, true, false>(args);
     return f32 ? launch_bulk<false, false, true>(args) : launch_bulk<false, false, false>(args);
   }
-  const int per_sm = (x2 && S.v32.p && dot_partials && !d) ? 8 : 6;   // the finest up-sweep runs at 32 registers
+  // fp32 gathers: every gather source needs its mirror (and the kernel is only built for the single-GPU path)
+  const bool g32 = S.pk.p && !d && pk_mode() == 4 && f32v && f32v->xf && (!x2 || f32v->x2f);
+  const bool wide = S.pk.p && !d && !g32 && pk_mode() == 3;
+  const int per_sm = ((x2 && S.v32.p && dot_partials && !d) || (S.pk.p && !wide)) ? 8 : (wide ? 5 : 6);   // 8: kernels that fit 32 registers
   int grid = std::max(1, std::min(div_up(S.nslices, kSW), sm_count() * per_sm));
-  SellArgs args{S.n, S.nslices, S.sptr.p, S.wg.p, S.cols.p, S.v32.p, S.v64.p, x, x2, y, dot_partials, l2_hint(), S.perm.p};
+  SellArgs args{S.n, S.nslices, S.sptr.p, S.wg.p, S.cols.p, S.v32.p, S.v64.p, x, x2, y, dot_partials, l2_hint(), S.perm.p,
+                S.pk.p, S.cbase.p, S.pk_inv, g32 ? f32v->xf : nullptr, g32 ? f32v->x2f : nullptr, f32v ? f32v->yf : nullptr};
   FS_REQUIRE(!(d && S.perm.p), "SELL-C-sigma matrices are not used by the partitioned kernels");
   int grid_add = 0;
   if (d && (d->w.nch || (d->ps.enabled && !d->ps.gather)) && S.n_blist > 0) {
@@ -631,8 +931,8 @@ static int spmv_sell_impl(const fs_sell& S, const double* x, double* y, const do
   return grid;
 }
 
-int spmv_sell(const fs_sell& S, const double* x, double* y, const double* x2, double* dot_partials) {
-  return spmv_sell_impl(S, x, y, x2, dot_partials, nullptr);
+int spmv_sell(const fs_sell& S, const double* x, double* y, const double* x2, double* dot_partials, const SellF32* f32v) {
+  return spmv_sell_impl(S, x, y, x2, dot_partials, nullptr, f32v);
 }
 
 int spmv_sell_dist(const fs_sell& S, const double* x, double* y, const double* x2, double* dot_partials, const Comm& c,
@@ -700,7 +1000,7 @@ int spmv_sell_grid(const fs_sell& S) { return std::max(1, std::min(div_up(S.nsli
 void spmv_sell2(const fs_sell& S, const double* x, double* y, double* dot_partials, const int* done) {
   FS_REQUIRE(S.nslices && S.v64.p && S.nsplit < 0, "spmv_sell2: needs a one-part fp64 SELL matrix");
   const int grid = spmv_sell_grid(S);
-  SellArgs args{S.n, S.nslices, S.sptr.p, nullptr, S.cols.p, nullptr, S.v64.p, x, nullptr, y, dot_partials, l2_hint(), nullptr};
+  SellArgs args{S.n, S.nslices, S.sptr.p, nullptr, S.cols.p, nullptr, S.v64.p, x, nullptr, y, dot_partials, l2_hint(), nullptr, nullptr, nullptr, 1.0, nullptr, nullptr, nullptr};
   static const DistSell none{};
   if (dot_partials) k_spmv_sell2<true, false><<<grid, kST, 0, stream()>>>(args, done, none);
   else k_spmv_sell2<false, false><<<grid, kST, 0, stream()>>>(args, done, none);
@@ -711,7 +1011,7 @@ void spmv_sell2_dist(const fs_sell& S, const double* x, double* y, double* dot_p
                      const HaloWait& w) {
   FS_REQUIRE(S.nslices && S.v64.p && S.nsplit < 0, "spmv_sell2: needs a one-part fp64 SELL matrix");
   const int grid = spmv_sell_grid(S);
-  SellArgs args{S.n, S.nslices, S.sptr.p, nullptr, S.cols.p, nullptr, S.v64.p, x, nullptr, y, dot_partials, l2_hint(), nullptr};
+  SellArgs args{S.n, S.nslices, S.sptr.p, nullptr, S.cols.p, nullptr, S.v64.p, x, nullptr, y, dot_partials, l2_hint(), nullptr, nullptr, nullptr, 1.0, nullptr, nullptr, nullptr};
   DistSell d;
   d.c = c;
   d.w = w;

@@ -52,4 +52,10 @@ if has 6; then   # A/B: the bulk-async (TMA) staged SELL kernel against the regi
       -o $out/${tag}_spmv_sell_bulk -f python scripts/prof_amg.py 6 > $out/${tag}_ncu_spmv_tma.log 2>&1
   tail -2 $out/${tag}_ncu_spmv_tma.log
 fi
+if has 7; then   # the five k_spmv_sell launches of one AMG-PCG iteration (A*p, finest / level-1 restriction, level-1 / finest up-sweep)
+  python scripts/prof_amg.py 6 > $out/${tag}_plain_amg_pk.log 2>&1 || { echo "plain amg (packed) failed"; exit 1; }
+  ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"k_spmv_sell<" --launch-skip 9 -c 5 \
+      -o $out/${tag}_spmv_pk -f python scripts/prof_amg.py 6 > $out/${tag}_ncu_spmv_pk.log 2>&1
+  tail -2 $out/${tag}_ncu_spmv_pk.log
+fi
 echo "profile.sh done: $steps"

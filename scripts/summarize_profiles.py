@@ -171,3 +171,17 @@ if os.path.exists(f"{G}/{tag}_spmv_sell_bulk.ncu-rep"):
 
 json.dump(traffic, open(TRAFFIC, "w"), indent=1)
 print(open(TRAFFIC).read())
+
+# 7) the five k_spmv_sell launches of one AMG-PCG iteration with the packed (fp16 | 16-bit offset) V-cycle operators
+if os.path.exists(f"{G}/{tag}_spmv_pk.ncu-rep"):
+    h, u, rs = raw_page(f"{G}/{tag}_spmv_pk.ncu-rep")
+    with open(f"{P}/{tag}_spmv_pk_ncu_full.txt", "w") as f:
+        f.write("# ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'k_spmv_sell<' "
+                "--launch-skip 9 -c 5 python scripts/prof_amg.py 6\n"
+                "# (one AMG-PCG iteration at 4M triangles: A*p <0,1,0,0> fp64 values; finest restriction <0,0,4,0>, level-1 restriction\n"
+                "#  <0,0,2,0>, level-1 up-sweep <1,0,2,0>, finest up-sweep <1,1,4,0>; template arguments <SPLIT, DOT, FMT, DIST>,\n"
+                "#  FMT 2 = packed entries with fp64 gathers, 4 = packed entries with fp32 gathers; cold cache, one launch each)\n")
+        for r in rs:
+            write_full(h, u, r, f)
+            f.write("\n")
+    print(open(f"{P}/{tag}_spmv_pk_ncu_full.txt").read())

@@ -427,10 +427,10 @@ def test_amg_pcg_matches_oracle_and_is_mesh_independent():
 
 
 def test_amg_cycle_forms_agree(monkeypatch):
-    """The folded two-SpMV-per-level V-cycle (SELL-32 on the large levels, lanes-per-row CSR kernel on the
-    small ones) is the same operator as the unfolded smoother/residual/transfer sequence: same iteration
-    counts (+-1), same solution; 131k rows so that the SELL kernels, the fp64 SELL A*p and the split-form
-    up-sweep all run."""
+    """The folded two-SpMV-per-level V-cycle (SELL-32 on the large levels -- packed fp16 | 16-bit-offset entries by
+    default, 32-bit value + column with FS_SELL_PACK=0 -- lanes-per-row CSR kernel on the small ones) is the same
+    operator as the unfolded smoother/residual/transfer sequence: same iteration counts (+-1), same solution; 131k
+    rows so that the SELL kernels, the fp64 SELL A*p and the split-form up-sweep all run."""
     nodes, markers, tris = fb.square_with_hole(512, 256)
     mm = fb.Mesh(nodes, tris, markers)
     rowptr, colidx = mm.csr_pattern()
@@ -439,8 +439,9 @@ def test_amg_cycle_forms_agree(monkeypatch):
     b -= b.mean()
     out = {}
     for name, env in (("folded_sell", {}), ("folded_csr", {"FS_AMG_SELL": "0"}), ("folded_all_sell", {"FS_AMG_SUB_ROWS": "0"}),
-                      ("unfolded", {"FS_AMG_FOLD": "0"}), ("folded_fp64", {"FS_AMG_FP32": "0"})):
-        for k in ("FS_AMG_SELL", "FS_AMG_FOLD", "FS_AMG_SUB_ROWS", "FS_AMG_FP32"):
+                      ("unfolded", {"FS_AMG_FOLD": "0"}), ("folded_fp64", {"FS_AMG_FP32": "0"}),
+                      ("folded_sell_32bit_entries", {"FS_SELL_PACK": "0"})):
+        for k in ("FS_AMG_SELL", "FS_AMG_FOLD", "FS_AMG_SUB_ROWS", "FS_AMG_FP32", "FS_SELL_PACK"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -454,6 +455,41 @@ def test_amg_cycle_forms_agree(monkeypatch):
         assert abs(it - it_ref) <= 1, (name, it, it_ref)
         assert rel(x, ref) <= 1e-9, name
         assert rel(x, xj) <= 1e-8 and it * 4 < itj, name
+
+
+def test_packed_sell_entries_same_bits_as_32bit_encoding(monkeypatch):
+    """The V-cycle operators of the large levels are streamed as packed 32-bit entries (fp16 value at a power-of-two
+    scale | 16-bit column offset from the slice's base column).  A slice whose columns do not fit 16 bits stays in the
+    value + column encoding with the same rounded values: with fp64 gathers (FS_PCG_R32=0, the arithmetic of the
+    partitioned cycle) one application of the cycle must give the SAME BITS with every slice packed and with every
+    slice unpacked (FS_SELL_PACK=2), and stay within fp16 rounding of the fp32-valued operators (FS_SELL_PACK=0).
+    The default single-GPU cycle gathers the two finest-level kernels' inputs from fp32 mirrors and sums those rows in
+    fp32: equal to the fp64-gather result to fp32 rounding.  Every variant is a symmetric positive map (PCG needs that)."""
+    nodes, markers, tris = fb.square_with_hole(512, 256)
+    mm = fb.Mesh(nodes, tris, markers)
+    vals = mm.stiffness_values()
+    rng = np.random.default_rng(21)
+    r = rng.standard_normal(mm.N)
+    r -= r.mean()
+    s = rng.standard_normal(mm.N)
+    s -= s.mean()
+    z = {}
+    for name, env in (("packed", {"FS_SELL_PACK": "1", "FS_PCG_R32": "0"}), ("unpacked", {"FS_SELL_PACK": "2", "FS_PCG_R32": "0"}),
+                      ("fp32_values", {"FS_SELL_PACK": "0", "FS_PCG_R32": "0"}), ("default", {})):
+        for k in ("FS_SELL_PACK", "FS_PCG_R32"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        A = mm.matrix(vals)
+        z[name] = (A.precond_apply(r), A.precond_apply(s))
+    for k in ("FS_SELL_PACK", "FS_PCG_R32"):
+        monkeypatch.delenv(k, raising=False)
+    assert np.array_equal(z["packed"][0], z["unpacked"][0]) and np.array_equal(z["packed"][1], z["unpacked"][1])
+    assert 0 < rel(z["packed"][0], z["fp32_values"][0]) <= 2e-3
+    assert rel(z["default"][0], z["packed"][0]) <= 1e-5
+    for name, (zr, zs) in z.items():
+        assert abs(s @ zr - r @ zs) <= 1e-5 * np.linalg.norm(s) * np.linalg.norm(zr), name      # symmetric map
+        assert r @ zr > 0 and s @ zs > 0
 
 
 def test_two_rhs_cg_large_matches_single_rhs():
