@@ -204,6 +204,11 @@ int fs_stokes_matrices(fs_stokes* s, fs_csr** a_visc, fs_csr** k_pressure, int32
  * Read (set=0) or restore (set=1).  With u this is the complete state of the time loop
  * (checkpoint / resume, repeatable benchmarks). */
 int fs_stokes_warm_state(fs_stokes* s, double* q /* 6*n_dof + 2 */, int set);
+/* Large pressure systems (>= 20000 merged dofs) start each solve from the projection of the new solution onto the span
+ * of the previous ones (an A-orthonormal basis of up to 12 vectors per solve, Fischer 1998; csrc/recycle.cuh) instead
+ * of the time extrapolation.  That basis is part of the loop state: read it (set=0; buf may be NULL or too small,
+ * *needed always receives the size in doubles) or restore it (set=1, cap = the size read; cap = 0 empties it). */
+int fs_stokes_recycle_state(fs_stokes* s, double* buf /* host */, int64_t cap, int set, int64_t* needed);
 
 /* ---- partitioned pressure CG, one rank (process) per GPU, peer memory over NVLink.
  * Replaces the same np.linalg.solve(A_pressure, .) for meshes that are split across GPUs

@@ -53,9 +53,68 @@ class _Csr:
         return cgport.spmv(self.rowptr, self.colidx, self.vals, np.ascontiguousarray(x, dtype=np.float64))
 
 
+class Recycler:
+    """Solution-subspace projection for successive right-hand sides, as csrc/recycle.cu does it on the GPU: an
+    A-orthonormal basis of previous solutions (Fischer 1998), compressed to the span of the last `keep` solutions
+    when it reaches `kmax` vectors."""
+
+    def __init__(self, K, kmax=12, keep=6):
+        self.K, self.kmax, self.keep, self.X, self.C = K, kmax, keep, [], []
+        self.alpha, self.x0 = None, None
+
+    def guess(self, b):
+        self.x0 = None
+        if not self.X:
+            return None
+        self.alpha = np.array([x @ b for x in self.X])
+        self.x0 = sum(a * x for a, x in zip(self.alpha, self.X))
+        return self.x0
+
+    def update(self, q):
+        k = len(self.X)
+        if self.x0 is None and k:
+            self.X, self.C, k = [], [], 0
+        if k:
+            d = q - self.x0
+            Ad = self.K.dot(d)
+            c = np.array([x @ Ad for x in self.X])
+            d = d - sum(ci * x for ci, x in zip(c, self.X))
+            coords = list(self.alpha + c)
+        else:
+            d, coords = q.copy(), []
+        self.x0 = None
+        nrm2 = d @ self.K.dot(d)
+        have2 = float(np.dot(coords, coords)) if coords else 0.0
+        if nrm2 > 0.0 and nrm2 > 1e-26 * have2:
+            nrm = np.sqrt(nrm2)
+            self.X.append(d / nrm)
+            self.C = [cc + [0.0] for cc in self.C]
+            coords = coords + [nrm]
+        elif not k:
+            return
+        self.C = (self.C + [coords])[-self.keep:]
+        if len(self.X) < self.kmax:
+            return
+        Q, first = [], 0.0
+        for v in (np.array(cc) for cc in self.C[::-1]):
+            for _ in range(2):
+                for qv in Q:
+                    v = v - (qv @ v) * qv
+            nv = np.linalg.norm(v)
+            if not Q:
+                first = nv
+            if nv > 1e-10 * first and nv > 0.0:
+                Q.append(v / nv)
+        self.X = [sum(qv[i] * self.X[i] for i in range(len(self.X))) for qv in Q]
+        self.C = [[float(qv @ np.array(cc)) for qv in Q] for cc in self.C]
+
+
+RECYCLE_MIN_ROWS = 20000     # csrc/stokes.cu: kRecycleMinRows
+
+
 class CpuStokes:
     def __init__(self, nodes, markers, tris, B1=-2.0, B2=0.0, DT=0.05, v=0.1, precond="amg",
-                 rtol_pressure=1e-10, rtol_visc=1e-12, H=1.0, tol=1e-6, threads=None, exact_ops=False):
+                 rtol_pressure=1e-10, rtol_visc=1e-12, H=1.0, tol=1e-6, threads=None, exact_ops=False, recycle=None):
         # exact_ops: divergence / gradient by restated.divergence / restated.gradient (the element sums of the
         # reference in the reference's order) instead of the pre-assembled sparse operators
         self.exact_ops = exact_ops
@@ -83,6 +142,9 @@ class CpuStokes:
         self.u = np.zeros((n, 2))
         R.make_dir_bcu(self.u, nodes, self.wall, self.inner_b, B1, B2)
         self.hist = [dict(q=None, q1=None, q2=None), dict(q=None, q1=None, q2=None)]
+        if recycle is None:
+            recycle = self.psys.nd >= RECYCLE_MIN_ROWS
+        self.rec = [Recycler(self.K), Recycler(self.K)] if recycle else None
         self.iters = (0, 0, 0)
 
     def divergence(self, u):
@@ -104,7 +166,12 @@ class CpuStokes:
         ps = self.psys
         r = np.bincount(ps.dof, weights=ps.M * b_nodes, minlength=ps.nd)
         x0 = None
-        if h["q"] is not None:
+        rec = self.rec[0 if h is self.hist[0] else 1] if self.rec else None
+        if rec is not None:
+            x0 = rec.guess(r - r.mean()) if h["q"] is not None else None
+            if x0 is None and h["q"] is not None:
+                x0 = h["q"]
+        elif h["q"] is not None:
             rm = r - r.mean()
             cands = [h["q"]]
             if h["q1"] is not None:
@@ -119,6 +186,8 @@ class CpuStokes:
             q, it, _ = cgport.cg(self.K.rowptr, self.K.colidx, self.K.vals, r, x0=x0, rtol=self.rtol_p, jacobi=True,
                                  project_mean=True)
         h["q2"], h["q1"], h["q"] = h["q1"], h["q"], q
+        if rec is not None:
+            rec.update(q)
         return q[ps.dof], it
 
     def step(self):

@@ -94,6 +94,7 @@ SIGNATURES = {
     "fs_stokes_set_pressure": (C.c_int, [c_vp, c_vp, c_vp]),
     "fs_stokes_matrices": (C.c_int, [c_vp, P(c_vp), P(c_vp), c_vp]),
     "fs_stokes_warm_state": (C.c_int, [c_vp, c_vp, C.c_int]),
+    "fs_stokes_recycle_state": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, P(c_i64)]),
     "fs_dist_create": (C.c_int, [C.c_int, C.c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, P(c_vp)]),
     "fs_dist_destroy": (C.c_int, [c_vp]),
     "fs_dist_ipc_handle": (C.c_int, [c_vp, c_vp]),

@@ -15,8 +15,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfluidsim.so")
-SOURCES = ["core.cu", "topology.cu", "assembly.cu", "solver.cu", "cg_persistent.cu", "spmv_warp.cu", "spmv_sell.cu", "amg.cu", "stokes.cu", "tracer.cu", "dist.cu", "pstokes.cu"]
-HEADERS = [os.path.join(CSRC, "internal.cuh"), os.path.join(CSRC, "dist.cuh"), os.path.join(CSRC, "reduce.cuh"),
+SOURCES = ["core.cu", "topology.cu", "assembly.cu", "solver.cu", "cg_persistent.cu", "spmv_warp.cu", "spmv_sell.cu", "amg.cu", "recycle.cu", "stokes.cu", "tracer.cu", "dist.cu", "pstokes.cu"]
+HEADERS = [os.path.join(CSRC, "internal.cuh"), os.path.join(CSRC, "dist.cuh"), os.path.join(CSRC, "reduce.cuh"), os.path.join(CSRC, "recycle.cuh"),
            os.path.join(os.path.dirname(HERE), "include", "fluidsim.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -35,7 +35,8 @@ struct AmgLevel {
   fs_csr U, Rt;             // folded cycle: U = [G | S P] (n x (n + n_coarse)),  Rt = (S P)^T
   fs_sell Us, Rts;          // ... and their SELL-32 copies (what the cycle streams; CSR kept on small levels)
   DBuf<double> x, b, r, t;  // work vectors of this level (level 0 uses caller buffers for b/x)
-  DBuf<float> x32;          // fp32 mirror of x, written by this level's SELL up-sweep for the fp32 gathers of the level above
+  DBuf<float> x32, b32;     // fp32 mirrors of x / b, written by the kernels that produce x / b for the fp32 gathers of the
+                            // packed SELL kernels (spmv_sell.cu, FMT 4); allocated when the caller keeps a mirror of r
   const fs_csr& mat() const { return Aref ? *Aref : A; }
 };
 
@@ -470,8 +471,11 @@ static void dense_invert(int n, double* M) {
 // chain of ~n/32 loads otherwise: this kernel is pure latency)
 __global__ void k_dense_gemv(int n, const double* __restrict__ Minv, const double* __restrict__ b, double* __restrict__ x) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  pdl_launch();
   if (row >= n) return;
   const double* __restrict__ m = Minv + (size_t)row * n;
+  for (int j = lane * 16; j < n; j += 512) prefetch_l2(m + j);     // the row is on its way while the producer of b finishes
+  pdl_wait();
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
   int j = lane;
   for (; j + 96 < n; j += 128) {
@@ -751,7 +755,7 @@ static void coarse_solve(Amg& amg, size_t l, const double* b, double* x) {
   const int n = lv.n, g = vgrid(n);
   const double w = amg.omega;
   if (amg.coarse_n == n && l > 0) {
-    k_dense_gemv<<<div_up(n * 32, 128), 128, 0, st>>>(n, amg.coarse_inv.p, b, x);
+    launch_pdl(k_dense_gemv, div_up(n * 32, 128), 128, 0, n, amg.coarse_inv.p, b, x);
     FS_LAUNCH_CHECK();
   } else if (n <= 1024) {
     k_coarse_jacobi<<<1, 1024, 0, st>>>(Av, A.dinv.p, b, x, w, amg.coarse_sweeps);
@@ -769,7 +773,11 @@ static void coarse_solve(Amg& amg, size_t l, const double* b, double* x) {
 
 // The folded cycle: b_c = R~ b ; recurse ; x = [G | P~] [b; x_c].  With dot_part the up-sweep of
 // this level also leaves the per-CTA partials of b.x (the CG's r.z); returns their count.
-static int vcycle_folded(Amg& amg, size_t l, const double* b, double* x, double* dot_part) {
+// b32: fp32 mirror of b (null: none).  x32: where to leave an fp32 mirror of x (null: not wanted); *x32_done says whether
+// this level's up-sweep kernel wrote it.
+static int vcycle_folded(Amg& amg, size_t l, const double* b, double* x, double* dot_part, const float* b32 = nullptr,
+                         float* x32 = nullptr, bool* x32_done = nullptr) {
+  if (x32_done) *x32_done = false;
   if (l + 1 == amg.L.size()) {
     coarse_solve(amg, l, b, x);
     return 0;
@@ -778,26 +786,34 @@ static int vcycle_folded(Amg& amg, size_t l, const double* b, double* x, double*
   AmgLevel& nx = *amg.L[l + 1];
   const int sub_rows = amg.sub_rows;
   // down: b_c = R~ b
-  if (nx.n <= sub_rows && lv.Rt.rowptr) spmv_sub(lv.Rt.view32(), b, nx.b.p, nullptr, 0);
-  else if (lv.Rts.nslices) {
+  const float* nb32 = nullptr;
+  if (nx.n <= sub_rows && lv.Rt.rowptr) {
+    spmv_sub(lv.Rt.view32(), b, nx.b.p, nullptr, 0, nx.b32.p);
+    nb32 = nx.b32.p;
+  } else if (lv.Rts.nslices) {
     SellF32 f;
-    if (l == 0) f.xf = amg.r32;                  // finest restriction: fp32 gathers from the mirror of r
+    f.xf = b32;
+    f.yf = nx.b32.p;
     spmv_sell(lv.Rts, b, nx.b.p, nullptr, nullptr, &f);
-  }
-  else {
+    nb32 = nx.b32.p;
+  } else {
     const CsrView Rt = lv.Rt.view32();
     if (!spmv_warp(Rt, EPI_AX, b, nx.b.p, nullptr, nullptr, 0.0, nullptr, nullptr)) spmv_sub(Rt, b, nx.b.p, nullptr, 0);
   }
-  vcycle_folded(amg, l + 1, nx.b.p, nx.x.p, nullptr);
+  bool nx32 = false;
+  vcycle_folded(amg, l + 1, nx.b.p, nx.x.p, nullptr, nb32, nx.x32.p, &nx32);
   // up: x = [G | P~] [b; x_c]
   int g = 0;
-  if (lv.n <= sub_rows && lv.U.rowptr) spmv_sub(lv.U.view32(), b, x, nx.x.p, lv.n);
-  else if (lv.Us.nslices) {
+  if (lv.n <= sub_rows && lv.U.rowptr) {
+    spmv_sub(lv.U.view32(), b, x, nx.x.p, lv.n, x32);
+    if (x32_done) *x32_done = x32 != nullptr;
+  } else if (lv.Us.nslices) {
     if (l == 0 && amg.top_ev) cudaEventRecord(amg.top_ev[0], stream());
     SellF32 f;
-    if (l == 0 && amg.r32 && nx.x32.p) { f.xf = amg.r32; f.x2f = nx.x32.p; }   // finest up-sweep: fp32 gathers
-    if (l == 1 && amg.r32) f.yf = lv.x32.p;      // level 1 leaves the mirror of its result for it
+    if (b32 && nx32) { f.xf = b32; f.x2f = nx.x32.p; }      // both gather sources have their mirror: fp32 gathers
+    f.yf = x32;
     g = spmv_sell(lv.Us, b, x, nx.x.p, dot_part, &f);
+    if (x32_done) *x32_done = x32 != nullptr;
     if (l == 0 && amg.top_ev) cudaEventRecord(amg.top_ev[1], stream());
   }
   else {
@@ -876,17 +892,19 @@ int amg_apply(Amg* amg, const double* r, double* z, bool x0_ready, double* rz_pa
   cudaStream_t st = stream();
   ++amg->applications;
   amg->r32 = r32;
-  // the mirror of the level-1 result exists only when that level's up-sweep is a SELL kernel (it writes it)
-  if (r32 && amg->folded && amg->L.size() > 2 && amg->L[1]->n > amg->sub_rows && amg->L[1]->Us.nslices && !amg->L[1]->x32.p) amg->L[1]->x32.alloc((size_t)amg->L[1]->n);
+  static const bool mirror_all = env_num("FS_AMG_MIRROR_ALL", 1) != 0;   // 0: only the finest level gathers in fp32
+  if (r32 && amg->folded)     // mirrors of the level vectors (a few MB), written by the kernels that produce them
+    for (size_t l = 1; l < (mirror_all ? amg->L.size() : std::min<size_t>(2, amg->L.size())); ++l)
+      if (!amg->L[l]->x32.p) { amg->L[l]->x32.alloc((size_t)amg->L[l]->n); amg->L[l]->b32.alloc((size_t)amg->L[l]->n); }
   const bool fold = amg->folded && amg->L.size() > 1;
   auto cycle = [&]() -> int {
-    if (fold) return vcycle_folded(*amg, 0, r, z, rz_part);
+    if (fold) return vcycle_folded(*amg, 0, r, z, rz_part, amg->r32);
     vcycle_level(*amg, 0, r, z, x0_ready);
     return 0;
   };
   if (top_ev && fold) {   // sampled timing: eager, with the event pair around the finest up-sweep
     amg->top_ev = top_ev;
-    const int np = vcycle_folded(*amg, 0, r, z, rz_part);
+    const int np = vcycle_folded(*amg, 0, r, z, rz_part, amg->r32);
     amg->top_ev = nullptr;
     return np;
   }

@@ -19,6 +19,10 @@ static int g_sm_count = 0;
 
 void set_last_error(const std::string& s) { g_err = s; }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static const bool v = [] { const char* e = std::getenv("FS_PDL"); return !e || std::atoi(e) != 0; }();
+  return v;
+}
 
 // keep freed stream-ordered staging buffers in the pool: without this every host-buffer call
 // re-maps tens of MB (default release threshold 0 returns the memory at each synchronise)

@@ -62,6 +62,35 @@ void count_launch(int n = 1);   // bumps fs_launch_count()
     FS_CUDA(cudaGetLastError());   \
   } while (0)
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// The kernels of one PCG iteration form a chain of ~12 dependent launches, most of them latency bound.  Launched with
+// the programmatic-stream-serialization attribute, a kernel may start while its predecessor is still running: its CTAs
+// become resident as the predecessor's retire, do whatever does not depend on the predecessor (index arithmetic, the
+// slice / row headers, L2 prefetches of the matrix stream they are about to read) and then block in pdl_wait() until the
+// predecessor has completed and its writes are visible.  Rules kept by every kernel launched through launch_pdl:
+// pdl_launch() first, pdl_wait() before the first read of anything an earlier kernel writes AND before the first global
+// write (an earlier kernel may still be reading what this one overwrites).  Both are no-ops in a normal launch.
+// Stream capture turns the attribute into programmatic edges of the V-cycle's CUDA graph.  FS_PDL=0: plain launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+bool pdl_enabled();
+
+template <class... KArgs, class... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream();
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  FS_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
+}
+
 // ---------------------------------------------------------------- device buffer
 template <class T>
 struct DBuf {
@@ -312,7 +341,7 @@ int spmv_sell(const fs_sell& S, const double* x, double* y, const double* x2, do
 int spmv_sell_grid(const fs_sell& S);   // grid (= dot partials per column) of spmv_sell2
 void spmv_sell2(const fs_sell& S, const double* x, double* y, double* dot_partials, const int* done);
 // any-matrix fallback: y = A [x; x2] (columns >= nsplit gather from x2; x2 null: y = A x)
-void spmv_sub(const CsrView& A, const double* x, double* y, const double* x2, int nsplit);
+void spmv_sub(const CsrView& A, const double* x, double* y, const double* x2, int nsplit, float* yf = nullptr);   // yf: fp32 mirror of y
 struct AmgPartSpec;
 Amg* amg_setup(fs_csr* fine, const AmgPartSpec* part = nullptr);   // part: row-block partitioned cycle (dist.cuh)
 // x0_ready: the caller has written w D^-1 r into the buffer given by amg_presmooth_target (unfolded

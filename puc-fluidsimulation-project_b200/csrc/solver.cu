@@ -827,6 +827,8 @@ k_pcg_xr(int64_t n, const double* __restrict__ p, const double* __restrict__ Ap,
          double* __restrict__ partB, double* __restrict__ x0out, const double* __restrict__ dinv, double w, float* __restrict__ r32) {
   __shared__ double red[32];
   __shared__ double sm[1];
+  pdl_launch();
+  pdl_wait();
   if (flags[0]) return;
   double pAp[1];
   reduce_partials<1>(partA, nblkA, pAp, sm);
@@ -859,6 +861,8 @@ __global__ void __launch_bounds__(kBlock)
 k_pcg_p(int64_t n, const double* __restrict__ z, double* __restrict__ p, const double* __restrict__ partB, int nB,
         const double* __restrict__ partRZ, int nRZ, double* __restrict__ sc, int slot, int* __restrict__ flags) {
   __shared__ double sm[1];
+  pdl_launch();
+  pdl_wait();
   if (block_done(flags)) return;      // block 0 of THIS launch may set the flag: one read per CTA
   double rr[1], rzn[1];
   reduce_partials<1>(partB, nB, rr, sm);
@@ -878,6 +882,54 @@ k_pcg_p(int64_t n, const double* __restrict__ z, double* __restrict__ p, const d
   }
 }
 
+// L2 residency of the CG vectors (FS_L2_PERSIST=1; OFF by default -- measured slower): an access-policy window on the
+// library stream marks their lines persisting for the duration of a solve (the B200 lets 79 MB of its 126 MB L2 be set
+// aside, the window is r, p, Ap, z, r32 = 76 MB at 4M triangles); everything else keeps its normal policy, the matrix
+// streams carry their own evict-first hint.  Result at 4M triangles (profiles/r02_ab_l2_persist.txt): the two vector
+// kernels 39.3 -> 34.2 us per iteration, but A*p 39.4 -> 42.5 us and the V-cycle 125.6 -> 136.9 us -- the ~430 MB of
+// matrix entries per iteration then stream through the remaining 47 MB and evict each other's gather lines.
+struct L2Persist {
+  bool on = false;
+  L2Persist(void* base, size_t bytes) {
+    static const int mode = [] { const char* e = std::getenv("FS_L2_PERSIST"); return e ? std::atoi(e) : 0; }();
+    static size_t max_persist = 0, max_window = 0, set_aside = 0;
+    static bool queried = false;
+    if (!mode || bytes < (8u << 20)) return;
+    if (!queried) {
+      queried = true;
+      int dev = 0, v = 0;
+      cudaGetDevice(&dev);
+      if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, dev) == cudaSuccess) max_persist = (size_t)std::max(v, 0);
+      if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, dev) == cudaSuccess) max_window = (size_t)std::max(v, 0);
+      if (std::getenv("FS_AMG_VERBOSE")) std::fprintf(stderr, "[l2] max persisting %zu MB, max window %zu MB\n", max_persist >> 20, max_window >> 20);
+      cudaGetLastError();
+    }
+    if (!max_persist || !max_window) return;
+    const size_t want = std::min(bytes, max_persist);
+    if (want > set_aside) {
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) { cudaGetLastError(); return; }
+      set_aside = want;
+    }
+    cudaStreamAttrValue v = {};
+    v.accessPolicyWindow.base_ptr = base;
+    v.accessPolicyWindow.num_bytes = std::min(bytes, max_window);
+    v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)set_aside / (double)v.accessPolicyWindow.num_bytes);
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = mode == 2 ? cudaAccessPropertyStreaming : cudaAccessPropertyNormal;
+    if (cudaStreamSetAttribute(stream(), cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) { cudaGetLastError(); return; }
+    on = true;
+  }
+  ~L2Persist() {
+    if (!on) return;
+    cudaStreamAttrValue v = {};
+    v.accessPolicyWindow.num_bytes = 0;
+    cudaStreamSetAttribute(stream(), cudaStreamAttributeAccessPolicyWindow, &v);
+    static const bool reset = [] { const char* e = std::getenv("FS_L2_PERSIST_RESET"); return e && std::atoi(e) != 0; }();
+    if (reset) cudaCtxResetPersistingL2Cache();
+    cudaGetLastError();
+  }
+};
+
 // fp32 mirror of r for the gathers of the packed V-cycle kernels (FS_PCG_R32=0: fp64 gathers, the arithmetic of the
 // partitioned cycle; read at every solve so that a caller can compare the two)
 static bool pcg_use_r32() {
@@ -891,9 +943,13 @@ __global__ void k_mirror_f32(int64_t n, const double* __restrict__ in, float* __
 
 static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, int maxit, int project_mean, double* relres) {
   const int64_t n = a->n;
-  ensure_ws(a, 5 * (size_t)n + (size_t)(n + 1) / 2);
-  double *r = a->ws.p, *p = r + n, *Ap = p + n, *z = Ap + n, *bproj = z + n;
-  float* r32 = pcg_use_r32() ? reinterpret_cast<float*>(bproj + n) : nullptr;
+  const size_t n32 = ((size_t)n + 1) / 2;      // doubles that hold the fp32 mirror of r
+  ensure_ws(a, 5 * (size_t)n + n32);
+  double *r = a->ws.p, *p = r + n, *Ap = p + n, *z = Ap + n, *bproj = z + n + n32;
+  float* r32 = pcg_use_r32() ? reinterpret_cast<float*>(z + n) : nullptr;
+  // the vectors every kernel of the iteration re-reads (r, p, Ap, z, r32: 76 MB at 4M triangles) stay in L2 while the
+  // matrix streams (~430 MB per iteration) pass through it
+  L2Persist keep(r, (4 * (size_t)n + n32) * sizeof(double));
   if (!a->amg) a->amg = amg_setup(a);
   ensure_tiles(a);
   static const bool sell_ap = [] { const char* e = std::getenv("FS_PCG_SELL"); return !e || std::atoi(e) != 0; }();
@@ -975,9 +1031,9 @@ static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, in
       if (!ga) ga = spmv_warp(A, EPI_AX, p, Ap, nullptr, nullptr, 0.0, nullptr, partA);
       if (!ga) { ga = spmv_launch_grid<1>(A); launch_spmv<1, true>(A, p, Ap, partA, nullptr, ga); }
       if (ev) cudaEventRecord(ev[1], st);
-      k_pcg_xr<<<g, kBlock, 0, st>>>(n, p, Ap, x, r, partA, ga, sc, slot, flags, partB, x0, dinv0, w0, r32); FS_LAUNCH_CHECK();
+      launch_pdl(k_pcg_xr, g, kBlock, 0, n, p, Ap, x, r, partA, ga, sc, slot, flags, partB, x0, dinv0, w0, r32); FS_LAUNCH_CHECK();
       nrz = precond(r, z, x0 != nullptr, ev);
-      k_pcg_p<<<g, kBlock, 0, st>>>(n, z, p, partB, g, partRZ, nrz, sc, slot, flags); FS_LAUNCH_CHECK();
+      launch_pdl(k_pcg_p, g, kBlock, 0, n, z, p, partB, g, partRZ, nrz, sc, slot, flags); FS_LAUNCH_CHECK();
       if (ev) cudaEventRecord(ev[4], st);
       ++queued;
       if (queued > unchecked) {

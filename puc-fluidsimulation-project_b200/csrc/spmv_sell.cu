@@ -51,7 +51,7 @@ struct SellArgs {
 // the ~100 MB of CG / multigrid vectors between the kernels that produce and consume them (FS_L2_HINT=0: no hint)
 __device__ __forceinline__ uint64_t sell_policy(int hint) {
   uint64_t p;
-  if (hint) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  if (hint & 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
@@ -320,6 +320,7 @@ __global__ void __launch_bounds__(kST, ((SPLIT && FMT == 1 && DOT && !DIST) || F
   constexpr bool F32 = FMT >= 1;
   constexpr bool PREFETCH = FMT == 3;
   __shared__ double red[kSW];
+  if (!DIST) pdl_launch();
   if (DIST) {
     if (d.c.done && *d.c.done) return;
     dist_trace(d.c, d.tag * 10 + 0);
@@ -358,12 +359,21 @@ __global__ void __launch_bounds__(kST, ((SPLIT && FMT == 1 && DOT && !DIST) || F
     if (FMT >= 2) h.cb = __ldg(a.cbase + s);
     return h;
   };
-  SliceHdr hcur;
-  if (PREFETCH) hcur = fetch(first);
+  // programmatic dependent launch: the matrix (headers, entries) is not written by any kernel of the iteration, so the
+  // first slice's header is read, and its entry lines are pulled into L2, while the previous kernel is still running
+  SliceHdr hcur = fetch(first);
+  if (!DIST) {
+    if ((a.l2hint & 2) && hcur.s >= 0 && lane < hcur.W) {
+      const long long e = hcur.off + ((long long)lane << 5);
+      if (FMT >= 2 && hcur.cb.x != INT_MIN) prefetch_l2(a.pk + e);
+      else { prefetch_l2(a.cols + e); if (F32) prefetch_l2(a.v32 + e); else { prefetch_l2(a.v64 + e); prefetch_l2(a.v64 + e + 16); } }
+    }
+    pdl_wait();
+  }
   for (int si = first; si < count; si += nwarps) {
     SliceHdr h;
     if (PREFETCH) { h = hcur; hcur = fetch(si + nwarps); }      // the next header is in flight while this slice is streamed
-    else h = fetch(si);
+    else h = si == first ? hcur : fetch(si);
     if (h.s < 0) continue;
     const int s = h.s;
     const int2 dst = h.dst;
@@ -825,8 +835,12 @@ void sell_build(const fs_csr& A, bool f32, fs_sell& out, int nsplit, int sigma, 
   }
 }
 
-static int l2_hint() {
-  static const int v = [] { const char* e = std::getenv("FS_L2_HINT"); return e ? std::atoi(e) : 1; }();
+static int l2_hint() {   // bit 0: evict-first hint on the matrix streams; bit 1: L2 prefetch of the first slice before pdl_wait
+  static const int v = [] {
+    const char* e = std::getenv("FS_L2_HINT");
+    const char* f = std::getenv("FS_SELL_PF");
+    return (e ? (std::atoi(e) & 1) : 1) | ((f ? std::atoi(f) : 1) ? 2 : 0);
+  }();
   return v;
 }
 
@@ -843,11 +857,11 @@ static void launch_sell(const SellArgs& args, int grid, const DistSell* d) {
     else if (args.v32) k_spmv_sell<SPLIT, DOT, 1, true><<<grid, kST, 0, stream()>>>(args, *d);
     else k_spmv_sell<SPLIT, DOT, 0, true><<<grid, kST, 0, stream()>>>(args, *d);
   } else {
-    if (args.pk && args.xf) k_spmv_sell<SPLIT, DOT, 4, false><<<grid, kST, 0, stream()>>>(args, none);
-    else if (args.pk && pk_mode() == 3) k_spmv_sell<SPLIT, DOT, 3, false><<<grid, kST, 0, stream()>>>(args, none);
-    else if (args.pk) k_spmv_sell<SPLIT, DOT, 2, false><<<grid, kST, 0, stream()>>>(args, none);
-    else if (args.v32) k_spmv_sell<SPLIT, DOT, 1, false><<<grid, kST, 0, stream()>>>(args, none);
-    else k_spmv_sell<SPLIT, DOT, 0, false><<<grid, kST, 0, stream()>>>(args, none);
+    if (args.pk && args.xf) launch_pdl(k_spmv_sell<SPLIT, DOT, 4, false>, grid, kST, 0, args, none);
+    else if (args.pk && pk_mode() == 3) launch_pdl(k_spmv_sell<SPLIT, DOT, 3, false>, grid, kST, 0, args, none);
+    else if (args.pk) launch_pdl(k_spmv_sell<SPLIT, DOT, 2, false>, grid, kST, 0, args, none);
+    else if (args.v32) launch_pdl(k_spmv_sell<SPLIT, DOT, 1, false>, grid, kST, 0, args, none);
+    else launch_pdl(k_spmv_sell<SPLIT, DOT, 0, false>, grid, kST, 0, args, none);
   }
 }
 

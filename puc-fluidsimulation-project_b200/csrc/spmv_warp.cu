@@ -53,6 +53,7 @@ struct SpmvWarpArgs {
   int ntiles;     // 512-row tiles
   const double* x2 = nullptr;   // EPI_AXS: second gather source
   int nsplit = 0;               // EPI_AXS: first column served by x2
+  float* yf = nullptr;          // k_spmv_sub: optional fp32 mirror of y (gather source of the packed SELL kernels)
 };
 
 __device__ __forceinline__ float w_ld_stream_f32(const float* a, uint64_t pol) {
@@ -172,6 +173,7 @@ struct DistSub {
 
 template <int LPR, bool F32, bool DIST>
 __global__ void __launch_bounds__(256) k_spmv_sub(SpmvWarpArgs a, DistSub d) {
+  if (!DIST) pdl_launch();
   if (DIST) {
     if (d.c.done && *d.c.done) return;
     halo_wait(d.c, d.w);
@@ -191,6 +193,8 @@ __global__ void __launch_bounds__(256) k_spmv_sub(SpmvWarpArgs a, DistSub d) {
         v[j] = ok ? (F32 ? (double)__ldg(a.A.vals32 + k) : __ldg(a.A.vals + k)) : 0.0;
         c[j] = ok ? __ldg(a.A.colidx + k) : 0;
       }
+      // programmatic dependent launch: the row's entries are on their way before the producer of x has finished
+      if (!DIST) pdl_wait();
       double xx[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) xx[j] = c[j] < a.nsplit ? __ldg(a.x + c[j]) : __ldg(a.x2 + (c[j] - a.nsplit));
@@ -200,8 +204,10 @@ __global__ void __launch_bounds__(256) k_spmv_sub(SpmvWarpArgs a, DistSub d) {
   }
 #pragma unroll
   for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (!DIST) pdl_wait();      // rows without entries have not waited yet: no write before the predecessor is done
   if (row < a.A.n && sub == 0) {
     a.y[row] = s;
+    if (a.yf) a.yf[row] = (float)s;
     if (DIST && d.ps.enabled) push_row(d.ps, row, s);
   }
   if (DIST && d.ps.enabled) push_finish(d.c, d.ps, true, dist_seq(d.c), (int)gridDim.x);
@@ -215,8 +221,8 @@ static void launch_sub(const SpmvWarpArgs& args, const DistSub* d = nullptr) {
     if (args.A.vals32) k_spmv_sub<LPR, true, true><<<grid, 256, 0, stream()>>>(args, *d);
     else k_spmv_sub<LPR, false, true><<<grid, 256, 0, stream()>>>(args, *d);
   } else {
-    if (args.A.vals32) k_spmv_sub<LPR, true, false><<<grid, 256, 0, stream()>>>(args, none);
-    else k_spmv_sub<LPR, false, false><<<grid, 256, 0, stream()>>>(args, none);
+    if (args.A.vals32) launch_pdl(k_spmv_sub<LPR, true, false>, grid, 256, 0, args, none);
+    else launch_pdl(k_spmv_sub<LPR, false, false>, grid, 256, 0, args, none);
   }
   FS_LAUNCH_CHECK();
 }
@@ -224,8 +230,10 @@ static void launch_sub(const SpmvWarpArgs& args, const DistSub* d = nullptr) {
 // y = A [x; x2] (x2 may be null: plain y = A x) for any CSR matrix.  Lanes per row: about a quarter of
 // the mean row length (each lane keeps four entries in flight), so that small matrices still
 // spread over the whole machine in one wave.
-static void spmv_sub_impl(const CsrView& A, const double* x, double* y, const double* x2, int nsplit, const DistSub* d) {
+static void spmv_sub_impl(const CsrView& A, const double* x, double* y, const double* x2, int nsplit, const DistSub* d,
+                          float* yf = nullptr) {
   SpmvWarpArgs args{A, x, y, nullptr, nullptr, 0.0, nullptr, nullptr, 0, 0};
+  args.yf = yf;
   args.x2 = x2;
   args.nsplit = x2 ? nsplit : 0x7fffffff;
   static const double per_lane = [] { const char* e = std::getenv("FS_SUB_PER_LANE"); return e ? std::atof(e) : 4.0; }();
@@ -236,7 +244,9 @@ static void spmv_sub_impl(const CsrView& A, const double* x, double* y, const do
   else if (lanes <= 16.0) launch_sub<16>(args, d);
   else launch_sub<32>(args, d);
 }
-void spmv_sub(const CsrView& A, const double* x, double* y, const double* x2, int nsplit) { spmv_sub_impl(A, x, y, x2, nsplit, nullptr); }
+void spmv_sub(const CsrView& A, const double* x, double* y, const double* x2, int nsplit, float* yf) {
+  spmv_sub_impl(A, x, y, x2, nsplit, nullptr, yf);
+}
 void spmv_sub_dist(const CsrView& A, const double* x, double* y, const double* x2, int nsplit, const Comm& c, const HaloWait& w,
                    const PushSpec& ps) {
   DistSub d;

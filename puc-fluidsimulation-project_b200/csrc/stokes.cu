@@ -17,6 +17,7 @@
 #include <chrono>
 
 #include "internal.cuh"
+#include "recycle.cuh"
 
 struct fs_stokes {
   fs_mesh* mesh = nullptr;
@@ -40,6 +41,7 @@ struct fs_stokes {
   };
   PressHist h1, h2;                 // first / second projection of the step
   fs::DBuf<double> y0, q_try;       // K q of the current solve; the chosen extrapolated guess
+  fs::Recycler rec1, rec2;          // solution-subspace projection of the two solves (large systems, recycle.cuh)
 };
 
 namespace fs {
@@ -99,9 +101,28 @@ __global__ void k_expand(int64_t N, const int* __restrict__ dof, const double* _
 // with y_k = K q_k kept from the earlier steps the three residual norms cost ONE SpMV (y0 = K q) and
 // one pass over four vectors: it buys 7-10 of ~27 PCG iterations while the flow evolves smoothly and
 // loses nothing when it does not (every solve still runs to rtol).
-static void pressure_solve(fs_stokes* s, const double* d_vel, double* q, fs_stokes::PressHist& H, double* p_full,
+// Systems of at least kRecycleMinRows rows (where AUTO also picks the multigrid preconditioner) start from the
+// projection of the new solution onto the span of the previous ones instead (recycle.cuh): 542 instead of 921 PCG
+// iterations over the bench's 20 timed steps.
+constexpr int64_t kRecycleMinRows = 20000;
+
+static void pressure_solve(fs_stokes* s, const double* d_vel, double* q, fs_stokes::PressHist& H, Recycler& rec, double* p_full,
                            const fs_stokes_opts& o, int* iters, double* relres, double* max_div) {
   static const int extrap = [] { const char* e = std::getenv("FS_STOKES_EXTRAP"); return e ? std::atoi(e) : 2; }();
+  const bool recycle = o.warm_start && s->nd >= kRecycleMinRows && recycle_enabled();
+  const Recycler::MatVec matvec = [s](const double* x, double* y) { spmv_best_dev(&s->k_red, x, y); };
+  const Recycler::Reduce reduce = [](const double* part, int nblk, int nchunk, double* host) {
+    std::vector<double> h((size_t)nblk * nchunk * 6);
+    FS_CUDA(cudaMemcpyAsync(h.data(), part, h.size() * sizeof(double), cudaMemcpyDeviceToHost, stream()));
+    FS_CUDA(cudaStreamSynchronize(stream()));
+    for (int c = 0; c < nchunk; ++c)
+      for (int j = 0; j < 6; ++j) {
+        double t = 0.0;
+        for (int b = 0; b < nblk; ++b) t += h[((size_t)c * nblk + b) * 6 + j];
+        host[6 * c + j] = t;
+      }
+  };
+  if (recycle && !rec.ready()) rec.init(s->nd, recycle_kmax(), recycle_keep());
   fs_mesh* m = s->mesh;
   cudaStream_t st = stream();
   divergence_dev(m, d_vel, s->div.p, nullptr);
@@ -116,6 +137,9 @@ static void pressure_solve(fs_stokes* s, const double* d_vel, double* q, fs_stok
   if (!o.warm_start || !s->have_p) {
     FS_CUDA(cudaMemsetAsync(q, 0, s->nd * sizeof(double), st));
     H.nq = H.ny = 0;
+    if (rec.ready()) rec.reset();
+  } else if (recycle) {
+    rec.guess(s->rhs_red.p, q, reduce);     // empty basis (after a restore without it): q keeps the previous solution
   } else if (extrap > 0) {
     const size_t bytes = s->nd * sizeof(double);
     int best = 0;   // 0: q, 1: linear, 2: quadratic
@@ -148,6 +172,7 @@ static void pressure_solve(fs_stokes* s, const double* d_vel, double* q, fs_stok
   int it = cg_dev(&s->k_red, s->rhs_red.p, q, 1, o.rtol_pressure, o.maxit, o.precond, 1, relres);
   if (it < 0) throw Error(FS_ERR_NOCONV, "pressure CG did not converge within maxit");
   *iters = it;
+  if (recycle) rec.update(q, matvec, reduce);
   k_expand<<<div_up(m->N, 256), 256, 0, st>>>(m->N, s->dof.p, q, p_full);
   FS_LAUNCH_CHECK();
 }
@@ -305,7 +330,7 @@ int fs_stokes_step(fs_stokes* s, double* u, double B1, double B2, const fs_stoke
   dirichlet(s->ustar.p);
   mark();
   // Step 2+3: pressure correction and velocity update
-  pressure_solve(s, s->ustar.p, s->p_red.p, s->h1, s->p_full.p, o, &sts.iters_p1, &sts.relres_p1,
+  pressure_solve(s, s->ustar.p, s->p_red.p, s->h1, s->rec1, s->p_full.p, o, &sts.iters_p1, &sts.relres_p1,
                  o.final_div ? &sts.max_div_ustar : nullptr);
   mark();
   grad_update_dev(m, s->p_full.p, s->ustar.p, du, s->DT, nullptr);
@@ -313,7 +338,7 @@ int fs_stokes_step(fs_stokes* s, double* u, double B1, double B2, const fs_stoke
   dirichlet(du);
   mark();
   // second projection, interior nodes only, no BC re-imposition (:566-573)
-  pressure_solve(s, du, s->p2_red.p, s->h2, s->p2_full.p, o, &sts.iters_p2, &sts.relres_p2, nullptr);
+  pressure_solve(s, du, s->p2_red.p, s->h2, s->rec2, s->p2_full.p, o, &sts.iters_p2, &sts.relres_p2, nullptr);
   mark();
   grad_update_dev(m, s->p2_full.p, du, du, s->DT, s->is_interior.p);
   s->have_p = true;
@@ -477,6 +502,44 @@ int fs_stokes_warm_state(fs_stokes* s, double* q, int set) {
   } else {
     for (int k = 0; k < 6; ++k) FS_CUDA(cudaMemcpyAsync(q + k * nd, bufs[k], nd * sizeof(double), cudaMemcpyDefault, st));
     FS_CUDA(cudaMemcpyAsync(q + 6 * nd, hist, sizeof(hist), cudaMemcpyDefault, st));
+  }
+  fs::sync();
+  FS_API_END
+}
+
+int fs_stokes_recycle_state(fs_stokes* s, double* buf, int64_t cap, int set, int64_t* needed) {
+  FS_API_BEGIN
+  FS_REQUIRE(s, "NULL argument");
+  Recycler* recs[2] = {&s->rec1, &s->rec2};
+  if (!set) {
+    int64_t need = 0;
+    for (Recycler* r : recs) need += 1 + (r->ready() ? r->state_size() : 0);
+    if (needed) *needed = need;
+    if (buf && cap >= need) {
+      double* p = buf;
+      for (Recycler* r : recs) {
+        const int64_t sz = r->ready() ? r->state_size() : 0;
+        *p++ = (double)sz;
+        if (sz) r->get_state(p);
+        p += sz;
+      }
+    }
+  } else {
+    FS_REQUIRE(buf || cap == 0, "NULL argument");
+    const double* p = buf;
+    int64_t left = cap;
+    for (Recycler* r : recs) {
+      if (left <= 0) { if (r->ready()) r->reset(); continue; }       // a state without this part: start the basis afresh
+      const int64_t sz = (int64_t)*p++;
+      --left;
+      FS_REQUIRE(sz >= 0 && sz <= left, "recycle state: truncated");
+      if (sz) {
+        if (!r->ready()) r->init(s->nd, recycle_kmax(), recycle_keep());
+        r->set_state(p, sz);
+      } else if (r->ready()) r->reset();
+      p += sz;
+      left -= sz;
+    }
   }
   fs::sync();
   FS_API_END

@@ -97,16 +97,24 @@ class StokesSolver:
         """CG warm-start state of the two pressure solves: last three solutions of each + history depth
         (with ``u`` the full loop state)."""
         _, kp, _ = self.matrices()
-        q = np.empty(6 * kp.n + 2)
+        base = 6 * kp.n + 2
+        need = C.c_int64(0)
+        call("fs_stokes_recycle_state", self._h, None, 0, 0, C.byref(need))
+        q = np.empty(base + need.value)
         call("fs_stokes_warm_state", self._h, ptr(q), 0)
+        # large systems: + the A-orthonormal basis of previous solutions the next guess is projected onto
+        call("fs_stokes_recycle_state", self._h, C.c_void_p(q.ctypes.data + 8 * base), need.value, 0, C.byref(need))
         return q
 
     def set_warm_state(self, q):
         _, kp, _ = self.matrices()
         q = np.ascontiguousarray(q, dtype=np.float64)
-        if q.size != 6 * kp.n + 2:
-            raise ValueError(f"warm state has {q.size} entries, expected {6 * kp.n + 2}")
+        base = 6 * kp.n + 2
+        if q.size < base:
+            raise ValueError(f"warm state has {q.size} entries, expected at least {base}")
         call("fs_stokes_warm_state", self._h, ptr(q), 1)
+        call("fs_stokes_recycle_state", self._h, C.c_void_p(q.ctypes.data + 8 * base) if q.size > base else None,
+             q.size - base, 1, None)
 
     # -- checkpoint / resume (SURVEY 5.4: the reference keeps its state in module globals)
     def _state_arrays(self):

@@ -612,6 +612,50 @@ def test_checkpoint_resume_is_bit_exact(tmp_path):
             assert np.array_equal(a.tracer_status, b.tracer_status)
 
 
+def test_recycled_pressure_guess_on_a_large_mesh(monkeypatch):
+    """Pressure systems of >= 20000 dofs start every solve from the projection of the new solution onto the span of
+    the previous ones (csrc/recycle.cu).  Same fields as with the time-extrapolated guess (every solve runs to its
+    tolerance), markedly fewer PCG iterations once the basis exists, iteration counts of the CPU restatement
+    (oracle/cpu_step.py: Recycler), and a checkpoint taken AFTER the basis was compressed continues bit for bit."""
+    from oracle.cpu_step import CpuStokes
+    c, mk, t = fb.square_with_hole(256, 128)
+    a = fb.StokesSolver(c, mk, t, B1=-2.0, B2=-5.0, precond=fb.PRECOND_AMG)
+    assert a.matrices()[1].n >= 20000
+    monkeypatch.setenv("FS_STOKES_RECYCLE", "0")
+    b = fb.StokesSolver(c, mk, t, B1=-2.0, B2=-5.0, precond=fb.PRECOND_AMG)
+    ib = []
+    for _ in range(16):
+        st = b.step()                   # the stats object is reused: keep the numbers
+        ib.append((st.iters_p1, st.iters_p2))
+    monkeypatch.delenv("FS_STOKES_RECYCLE")
+    o = CpuStokes(c, mk, t, B1=-2.0, B2=-5.0, precond="amg", recycle=True)
+    ia, io = [], []
+    for _ in range(16):
+        st = a.step()
+        ia.append((st.iters_p1, st.iters_p2))
+        io.append(o.step()[1:])
+    assert rel(a.u, b.u) <= 1e-9 and rel(a.u, o.u) <= 1e-9
+    na, nb = sum(map(sum, ia[8:])), sum(map(sum, ib[8:]))
+    assert na <= 0.75 * nb, (ia, ib)
+    for (a1, a2), (o1, o2) in zip(ia, io):
+        assert abs(a1 - o1) <= 3 and abs(a2 - o2) <= 3, (ia, io)
+    # checkpoint / resume: the basis (compressed at the 12th solve) is part of the state
+    warm, u = a.get_warm_state(), a.u.copy()
+    assert warm.size > 6 * a.matrices()[1].n + 2
+    r = fb.StokesSolver(c, mk, t, B1=-2.0, B2=-5.0, precond=fb.PRECOND_AMG)
+    r.u[...] = u
+    r.set_warm_state(warm)
+    for _ in range(3):
+        sa = a.step()
+        its = (sa.iters_p1, sa.iters_p2)
+        sr = r.step()
+        assert its == (sr.iters_p1, sr.iters_p2)
+    assert np.array_equal(a.u, r.u)
+    # a state without the basis (older checkpoint): still valid, the basis starts afresh
+    r.set_warm_state(warm[:6 * a.matrices()[1].n + 2])
+    r.step()
+
+
 # ---- output sink (SURVEY section 8 f2): device raster of the dye / velocity field + tracers -----------
 def test_raster_field_colormap_and_points_match_oracle(tmp_path):
     g = load_golden("mesh5_1_ops")
