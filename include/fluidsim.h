@@ -286,6 +286,8 @@ int fs_pstokes_profile_pcg(fs_pstokes* s, int iters, double* us_per_iter);
  * this copies them out (pairs of uint64) and resets the log */
 int fs_pstokes_trace(fs_pstokes* s, uint64_t* out /* 2*cap */, int64_t cap, int64_t* n);
 int fs_pstokes_state(fs_pstokes* s, double* buf, int set);
+/* the projection bases of the two pressure solves, this rank's rows (see fs_stokes_recycle_state) */
+int fs_pstokes_recycle_state(fs_pstokes* s, double* buf /* host */, int64_t cap, int set, int64_t* needed);
 
 /* ---- tracers and dye.
  * fs_locate: PointLocator.find, code/StokesColor.py:314-345 -- the 10 nearest

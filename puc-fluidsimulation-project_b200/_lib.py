@@ -113,6 +113,7 @@ SIGNATURES = {
     "fs_pstokes_step": (C.c_int, [c_vp, c_vp, c_dbl, c_dbl, c_vp, c_vp]),
     "fs_pstokes_pressure": (C.c_int, [c_vp, c_vp, c_vp]),
     "fs_pstokes_state": (C.c_int, [c_vp, c_vp, C.c_int]),
+    "fs_pstokes_recycle_state": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, P(c_i64)]),
     "fs_pstokes_profile_pcg": (C.c_int, [c_vp, C.c_int, P(c_dbl)]),
     "fs_pstokes_trace": (C.c_int, [c_vp, c_vp, c_i64, P(c_i64)]),
     "fs_locate": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),

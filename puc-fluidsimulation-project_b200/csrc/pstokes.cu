@@ -16,6 +16,7 @@
 // Setup is replicated: every rank builds the global operators and hierarchy once (so the partitioned
 // solver has exactly the single-GPU hierarchy), keeps its blocks and frees the rest.
 #include "dist.cuh"
+#include "recycle.cuh"
 #include "reduce.cuh"
 
 namespace fs {
@@ -395,6 +396,8 @@ struct fs_pstokes {
   fs::DVec P, R, Q1, Q2, QTRY;
   fs::DBuf<double> Ap, z, bproj, rhs, y0;
   struct Hist { fs::DBuf<double> q1, q2, y1, y2; int nq = 0, ny = 0; } h1, h2;
+  fs::Recycler rec1, rec2;          // solution-subspace projection of the two pressure solves (recycle.cuh), own rows
+  fs::DBuf<double> rec_red;         // its dot products, summed over the ranks
   bool have_p = false;
   fs::DBuf<double> partials, scal, red_out;
   int hint = 0, hint_prev = 0;
@@ -568,9 +571,25 @@ static void barrier_dev(fs_pstokes* s) {   // a reduction of nothing: separates 
 }
 
 // divergence -> mass-weighted merged right-hand side -> warm start -> PCG -> nodal pressure on [own | halo] nodes
-static void pressure_solve(fs_pstokes* s, DVec& VEL, DVec& Q, fs_pstokes::Hist& H, double* p_loc, const fs_stokes_opts& o,
-                           int* iters, double* relres) {
+static void pressure_solve(fs_pstokes* s, DVec& VEL, DVec& Q, fs_pstokes::Hist& H, Recycler& rec, double* p_loc,
+                           const fs_stokes_opts& o, int* iters, double* relres) {
   static const int extrap = [] { const char* e = std::getenv("FS_STOKES_EXTRAP"); return e ? std::atoi(e) : 2; }();
+  // the same rule as the single-GPU step (stokes.cu), on the GLOBAL system size: every rank decides alike
+  const bool recycle = o.warm_start && s->nd_glob >= 20000 && recycle_enabled();
+  // K d: through the scratch arena vector (halo exchange inside); a reduction separates two pushes of its channel
+  const Recycler::MatVec matvec = [s](const double* x, double* y) {
+    barrier_dev(s);
+    FS_CUDA(cudaMemcpyAsync(s->QTRY.p, x, (size_t)s->dofs.n_own * sizeof(double), cudaMemcpyDeviceToDevice, stream()));
+    kmul(s, s->QTRY, y);
+  };
+  // sums over this rank's CTAs and over the ranks, six at a time: identical on every rank, so the bases stay consistent
+  const Recycler::Reduce reduce = [s](const double* part, int nblk, int nchunk, double* host) {
+    if (!s->rec_red.p) s->rec_red.alloc(kRecCap);
+    for (int c = 0; c < nchunk; ++c) allreduce_k(s, part + (size_t)c * nblk * 6, nblk, 6, s->rec_red.p + 6 * c);
+    FS_CUDA(cudaMemcpyAsync(host, s->rec_red.p, (size_t)6 * nchunk * sizeof(double), cudaMemcpyDeviceToHost, stream()));
+    FS_CUDA(cudaStreamSynchronize(stream()));
+  };
+  if (recycle && !rec.ready()) rec.init(s->dofs.n_own, recycle_kmax(), recycle_keep());
   DistCtx& ctx = s->ctx;
   fs_mesh* m = s->lmesh;
   cudaStream_t st = stream();
@@ -587,6 +606,9 @@ static void pressure_solve(fs_pstokes* s, DVec& VEL, DVec& Q, fs_pstokes::Hist& 
   if (!o.warm_start || !s->have_p) {
     FS_CUDA(cudaMemsetAsync(Q.p, 0, nd * sizeof(double), st));
     H.nq = H.ny = 0;
+    if (rec.ready()) rec.reset();
+  } else if (recycle) {
+    rec.guess(s->rhs.p, Q.p, reduce);
   } else if (extrap > 0) {
     const size_t bytes = nd * sizeof(double);
     int best = 0;
@@ -630,6 +652,8 @@ static void pressure_solve(fs_pstokes* s, DVec& VEL, DVec& Q, fs_pstokes::Hist& 
   if (it < 0) throw Error(FS_ERR_NOCONV, "partitioned pressure CG did not converge within maxit");
   *iters = it;
   ctx.wait(Q);                                          // ppcg_amg pushed the final solution
+  // (a halo flag carries the sequence number of its push: it has to be consumed before the next reduction bumps it)
+  if (recycle) rec.update(Q.p, matvec, reduce);
   k_expand_l<<<div_up(m->N, 256), 256, 0, st>>>(m->N, s->ldof.p, Q.p, p_loc); FS_LAUNCH_CHECK();
 }
 
@@ -837,12 +861,12 @@ int fs_pstokes_step(fs_pstokes* s, double* u_own, double B1, double B2, const fs
   per_bcu_dev(m, s->USTAR.p);
   dirichlet(s->USTAR.p);
   ctx.push(s->USTAR);
-  pressure_solve(s, s->USTAR, s->Q1, s->h1, s->p_loc.p, o, &sts.iters_p1, &sts.relres_p1);
+  pressure_solve(s, s->USTAR, s->Q1, s->h1, s->rec1, s->p_loc.p, o, &sts.iters_p1, &sts.relres_p1);
   grad_update_dev(m, s->p_loc.p, s->USTAR.p, s->U.p, s->DT, nullptr);
   per_bcu_dev(m, s->U.p);
   dirichlet(s->U.p);
   ctx.push(s->U);
-  pressure_solve(s, s->U, s->Q2, s->h2, s->p2_loc.p, o, &sts.iters_p2, &sts.relres_p2);
+  pressure_solve(s, s->U, s->Q2, s->h2, s->rec2, s->p2_loc.p, o, &sts.iters_p2, &sts.relres_p2);
   grad_update_dev(m, s->p2_loc.p, s->U.p, s->U.p, s->DT, s->is_interior.p);
   s->have_p = true;
   // the next step pushes U again: separate the two pushes of that channel by a reduction
@@ -931,6 +955,45 @@ int fs_pstokes_state(fs_pstokes* s, double* buf, int set) {
   } else {
     for (int k = 0; k < 10; ++k) FS_CUDA(cudaMemcpyAsync(buf + k * nd, bufs[k], nd * sizeof(double), cudaMemcpyDefault, st));
     FS_CUDA(cudaMemcpyAsync(buf + 10 * nd, meta, sizeof(meta), cudaMemcpyDefault, st));
+  }
+  fs::sync();
+  FS_API_END
+}
+
+// the projection bases of the two pressure solves (own rows); same protocol as fs_stokes_recycle_state
+int fs_pstokes_recycle_state(fs_pstokes* s, double* buf, int64_t cap, int set, int64_t* needed) {
+  FS_API_BEGIN
+  FS_REQUIRE(s, "NULL argument");
+  Recycler* recs[2] = {&s->rec1, &s->rec2};
+  if (!set) {
+    int64_t need = 0;
+    for (Recycler* r : recs) need += 1 + (r->ready() ? r->state_size() : 0);
+    if (needed) *needed = need;
+    if (buf && cap >= need) {
+      double* p = buf;
+      for (Recycler* r : recs) {
+        const int64_t sz = r->ready() ? r->state_size() : 0;
+        *p++ = (double)sz;
+        if (sz) r->get_state(p);
+        p += sz;
+      }
+    }
+  } else {
+    FS_REQUIRE(buf || cap == 0, "NULL argument");
+    const double* p = buf;
+    int64_t left = cap;
+    for (Recycler* r : recs) {
+      if (left <= 0) { if (r->ready()) r->reset(); continue; }
+      const int64_t sz = (int64_t)*p++;
+      --left;
+      FS_REQUIRE(sz >= 0 && sz <= left, "recycle state: truncated");
+      if (sz) {
+        if (!r->ready()) r->init(s->dofs.n_own, recycle_kmax(), recycle_keep());
+        r->set_state(p, sz);
+      } else if (r->ready()) r->reset();
+      p += sz;
+      left -= sz;
+    }
   }
   fs::sync();
   FS_API_END

@@ -51,7 +51,7 @@ struct SellArgs {
 // the ~100 MB of CG / multigrid vectors between the kernels that produce and consume them (FS_L2_HINT=0: no hint)
 __device__ __forceinline__ uint64_t sell_policy(int hint) {
   uint64_t p;
-  if (hint & 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  if (hint) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
@@ -235,54 +235,11 @@ __device__ __forceinline__ float pk32_part(const unsigned* __restrict__ wp, int 
 }
 
 // These kernels are latency bound, not bandwidth bound: a warp walks its slice as a chain of dependent memory rounds
-// (slice header -> stream loads -> gathers -> next batch ...), and the time is (rounds per slice) / (resident warps)
-// -- measured: the same code at 48 instead of 64 warps per SM runs 1.4x longer.  The packed words are small enough to
-// put a whole slice in flight at once: the first 8 words of BOTH parts (or 16 of a one-part slice) are loaded in one
-// round, then gathered in two groups of 8; rows longer than that continue in batches of 4.  Sums stay in ascending
-// column order, part 1 before part 2 -- the same bits as the batch-of-4 kernel and as the 32-bit encoding.
-template <int U>
-__device__ __forceinline__ void pk_load_guarded(unsigned (&ww)[U], const unsigned* __restrict__ wp, int cnt, uint64_t pol) {
-#pragma unroll
-  for (int j = 0; j < U; ++j) ww[j] = j < cnt ? ld_stream(wp + (j << 5), pol) : 0u;   // word 0: value 0 times xb[0]
-}
-
-template <int U>
-__device__ __forceinline__ double pk_consume(const unsigned (&ww)[U], const double* __restrict__ xb, double acc) {
-  double xx[U];
-#pragma unroll
-  for (int j = 0; j < U; ++j) xx[j] = pk_gather(xb, ww[j]);
-#pragma unroll
-  for (int j = 0; j < U; ++j) acc = pk_mac(ww[j], xx[j], acc);
-  return acc;
-}
-
-template <bool SPLIT>
-__device__ __forceinline__ double pk_slice_wide(const unsigned* __restrict__ wp, int W, int Wg, const double* __restrict__ xb,
-                                                const double* __restrict__ xb2, uint64_t pol) {
-  double acc = 0.0;
-  if (SPLIT) {
-    const unsigned* __restrict__ wp2 = wp + ((long long)Wg << 5);
-    const int W2 = W - Wg;
-    unsigned wa[8], wb[8];
-    pk_load_guarded<8>(wa, wp, Wg, pol);
-    pk_load_guarded<8>(wb, wp2, W2, pol);
-    asm volatile("" ::: "memory");      // all 16 stream loads are issued before the first gather
-    acc = pk_consume<8>(wa, xb, acc);
-    if (Wg > 8) acc = pk_part<4>(wp + 256, Wg - 8, xb, acc, pol);
-    acc = pk_consume<8>(wb, xb2, acc);
-    if (W2 > 8) acc = pk_part<4>(wp2 + 256, W2 - 8, xb2, acc, pol);
-  } else {
-    for (int k = 0; k < W; k += 16, wp += 512) {
-      unsigned wa[8], wb[8];
-      pk_load_guarded<8>(wa, wp, W - k, pol);
-      pk_load_guarded<8>(wb, wp + 256, W - k - 8, pol);
-      asm volatile("" ::: "memory");
-      acc = pk_consume<8>(wa, xb, acc);
-      acc = pk_consume<8>(wb, xb, acc);
-    }
-  }
-  return acc;
-}
+// (slice header -> stream loads -> gathers -> next batch ...), and the time is (rounds per slice) / (resident warps) --
+// measured: the same code at 48 instead of 64 warps per SM runs 1.4x longer.  Tried and dropped: all 16 packed words of a
+// slice loaded at once with the next header prefetched (48 registers, 40 warps per SM): ptxas sinks the second group of
+// loads behind the first group's gathers whatever the source order, 46.9 us against 43.0 us for the finest up-sweep
+// (profiles/r02_ab_l2_persist.txt, FS_PK_MODE=3).  What helps is a smaller footprint per entry in flight: fp32 gathers.
 
 // DIST (partitioned step, pstokes.cu): x / x2 are [own | halo] vectors whose halo entries are written by the
 // neighbouring ranks; the kernel returns at once when the running solve has converged and otherwise
@@ -305,20 +262,11 @@ struct DistSell {
   int tag = 0;
 };
 
-// FMT: 0 fp64 values, 1 fp32 values, 2 packed entries in batches of 4 (32 registers, 64 warps per SM), 3 packed entries
-// with a whole slice in flight and the next slice's header prefetched (5 CTAs = 40 warps per SM), 4 packed entries with
-// fp32 gathers in batches of 8; slices that could not be packed take the fp32-value path (fp64 gathers)
-struct SliceHdr {
-  int s;            // slice, -1: skip
-  int W, Wg;
-  long long off;
-  int2 cb, dst;
-};
-
+// FMT: 0 fp64 values, 1 fp32 values, 2 packed entries in batches of 4 with fp64 gathers, 4 packed entries in batches of 8
+// with fp32 gathers (both 32 registers, 64 warps per SM); slices that could not be packed take the fp32-value path
 template <bool SPLIT, bool DOT, int FMT, bool DIST>
-__global__ void __launch_bounds__(kST, ((SPLIT && FMT == 1 && DOT && !DIST) || FMT == 2 || FMT == 4) ? 8 : (FMT == 3 ? 5 : 6)) k_spmv_sell(SellArgs a, DistSell d) {
+__global__ void __launch_bounds__(kST, ((SPLIT && FMT == 1 && DOT && !DIST) || FMT == 2 || FMT == 4) ? 8 : 6) k_spmv_sell(SellArgs a, DistSell d) {
   constexpr bool F32 = FMT >= 1;
-  constexpr bool PREFETCH = FMT == 3;
   __shared__ double red[kSW];
   if (!DIST) pdl_launch();
   if (DIST) {
@@ -341,47 +289,26 @@ __global__ void __launch_bounds__(kST, ((SPLIT && FMT == 1 && DOT && !DIST) || F
   const int first = (bcta ? blockIdx.x : blockIdx.x - nb) * kSW + warp;
   const int nwarps = (bcta ? nb : (int)gridDim.x - nb) * kSW;
   {
-  auto fetch = [&](int si) -> SliceHdr {
-    SliceHdr h;
-    h.s = -1; h.W = h.Wg = 0; h.off = 0; h.cb = make_int2(INT_MIN, 0); h.dst = make_int2(-1, -1);
-    if (si >= count) return h;
+  // programmatic dependent launch: everything above ran while the previous kernel was finishing.  (Reading the first
+  // header and prefetching its entry lines into L2 before the wait was measured: no gain, and the header kept live
+  // across the loop cost registers -- spills at the 32 / 40 register budgets.)
+  if (!DIST) pdl_wait();
+  for (int si = first; si < count; si += nwarps) {
     int s = si;
+    int2 dst = make_int2(-1, -1);
     if (two) {
       if (bcta) {
         s = __ldg(d.blist + si);
-        if (d.btab) h.dst = __ldg(d.btab + ((size_t)si << 5) + lane);
-      } else if ((__ldg(d.bmask + (si >> 5)) >> (si & 31)) & 1u) return h;
+        if (d.btab) dst = __ldg(d.btab + ((size_t)si << 5) + lane);
+      } else if ((__ldg(d.bmask + (si >> 5)) >> (si & 31)) & 1u) continue;
     }
-    h.s = s;
-    h.off = __ldg(a.sptr + s);
-    h.W = (int)((__ldg(a.sptr + s + 1) - h.off) >> 5);
-    h.Wg = SPLIT ? __ldg(a.wg + s) : h.W;
-    if (FMT >= 2) h.cb = __ldg(a.cbase + s);
-    return h;
-  };
-  // programmatic dependent launch: the matrix (headers, entries) is not written by any kernel of the iteration, so the
-  // first slice's header is read, and its entry lines are pulled into L2, while the previous kernel is still running
-  SliceHdr hcur = fetch(first);
-  if (!DIST) {
-    if ((a.l2hint & 2) && hcur.s >= 0 && lane < hcur.W) {
-      const long long e = hcur.off + ((long long)lane << 5);
-      if (FMT >= 2 && hcur.cb.x != INT_MIN) prefetch_l2(a.pk + e);
-      else { prefetch_l2(a.cols + e); if (F32) prefetch_l2(a.v32 + e); else { prefetch_l2(a.v64 + e); prefetch_l2(a.v64 + e + 16); } }
-    }
-    pdl_wait();
-  }
-  for (int si = first; si < count; si += nwarps) {
-    SliceHdr h;
-    if (PREFETCH) { h = hcur; hcur = fetch(si + nwarps); }      // the next header is in flight while this slice is streamed
-    else h = si == first ? hcur : fetch(si);
-    if (h.s < 0) continue;
-    const int s = h.s;
-    const int2 dst = h.dst;
-    const long long off = h.off;
-    const int W = h.W, Wg = h.Wg;
+    const long long off = __ldg(a.sptr + s);
+    const int W = (int)((__ldg(a.sptr + s + 1) - off) >> 5);
+    const int Wg = SPLIT ? __ldg(a.wg + s) : W;
     const int* __restrict__ cp = a.cols + off + lane;
     double acc = 0.0;
-    const int2 cb = h.cb;
+    int2 cb = make_int2(INT_MIN, 0);
+    if (FMT >= 2) cb = __ldg(a.cbase + s);
     if (FMT >= 2 && cb.x != INT_MIN) {
       const unsigned* __restrict__ wp = a.pk + off + lane;
       const double* xb = a.x + cb.x;
@@ -390,8 +317,7 @@ __global__ void __launch_bounds__(kST, ((SPLIT && FMT == 1 && DOT && !DIST) || F
         float f = pk32_part(wp, Wg, a.xf + cb.x, 0.0f, pol);
         if (SPLIT) f = pk32_part(wp + ((long long)Wg << 5), W - Wg, a.x2f + cb.y, f, pol);
         acc = (double)f;
-      } else if (FMT == 3) acc = pk_slice_wide<SPLIT>(wp, W, Wg, xb, xb2, pol);
-      else {
+      } else {
         acc = pk_part<4>(wp, Wg, xb, acc, pol);
         if (SPLIT) acc = pk_part<4>(wp + ((long long)Wg << 5), W - Wg, xb2, acc, pol);
       }
@@ -835,16 +761,12 @@ void sell_build(const fs_csr& A, bool f32, fs_sell& out, int nsplit, int sigma, 
   }
 }
 
-static int l2_hint() {   // bit 0: evict-first hint on the matrix streams; bit 1: L2 prefetch of the first slice before pdl_wait
-  static const int v = [] {
-    const char* e = std::getenv("FS_L2_HINT");
-    const char* f = std::getenv("FS_SELL_PF");
-    return (e ? (std::atoi(e) & 1) : 1) | ((f ? std::atoi(f) : 1) ? 2 : 0);
-  }();
+static int l2_hint() {
+  static const int v = [] { const char* e = std::getenv("FS_L2_HINT"); return e ? std::atoi(e) : 1; }();
   return v;
 }
 
-static int pk_mode() {   // FS_PK_MODE: kernel for packed matrices (2 / 3 / 4, see k_spmv_sell); 4 needs the fp32 mirrors
+static int pk_mode() {   // FS_PK_MODE: kernel for packed matrices (2 / 4, see k_spmv_sell); 4 needs the fp32 mirrors
   static const int v = [] { const char* e = std::getenv("FS_PK_MODE"); return e ? std::atoi(e) : 4; }();
   return v;
 }
@@ -858,7 +780,6 @@ static void launch_sell(const SellArgs& args, int grid, const DistSell* d) {
     else k_spmv_sell<SPLIT, DOT, 0, true><<<grid, kST, 0, stream()>>>(args, *d);
   } else {
     if (args.pk && args.xf) launch_pdl(k_spmv_sell<SPLIT, DOT, 4, false>, grid, kST, 0, args, none);
-    else if (args.pk && pk_mode() == 3) launch_pdl(k_spmv_sell<SPLIT, DOT, 3, false>, grid, kST, 0, args, none);
     else if (args.pk) launch_pdl(k_spmv_sell<SPLIT, DOT, 2, false>, grid, kST, 0, args, none);
     else if (args.v32) launch_pdl(k_spmv_sell<SPLIT, DOT, 1, false>, grid, kST, 0, args, none);
     else launch_pdl(k_spmv_sell<SPLIT, DOT, 0, false>, grid, kST, 0, args, none);
@@ -916,8 +837,7 @@ static int spmv_sell_impl(const fs_sell& S, const double* x, double* y, const do
   }
   // fp32 gathers: every gather source needs its mirror (and the kernel is only built for the single-GPU path)
   const bool g32 = S.pk.p && !d && pk_mode() == 4 && f32v && f32v->xf && (!x2 || f32v->x2f);
-  const bool wide = S.pk.p && !d && !g32 && pk_mode() == 3;
-  const int per_sm = ((x2 && S.v32.p && dot_partials && !d) || (S.pk.p && !wide)) ? 8 : (wide ? 5 : 6);   // 8: kernels that fit 32 registers
+  const int per_sm = ((x2 && S.v32.p && dot_partials && !d) || S.pk.p) ? 8 : 6;   // 8: kernels that fit 32 registers
   int grid = std::max(1, std::min(div_up(S.nslices, kSW), sm_count() * per_sm));
   SellArgs args{S.n, S.nslices, S.sptr.p, S.wg.p, S.cols.p, S.v32.p, S.v64.p, x, x2, y, dot_partials, l2_hint(), S.perm.p,
                 S.pk.p, S.cbase.p, S.pk_inv, g32 ? f32v->xf : nullptr, g32 ? f32v->x2f : nullptr, f32v ? f32v->yf : nullptr};

@@ -91,15 +91,24 @@ class PartitionedStokes:
         return p, p2
 
     def get_state(self):
-        q = np.empty(10 * self.n_own_dofs + 4)
+        """Warm-start state of this rank: the solution history of the two pressure solves, then (large systems) the
+        bases the next guesses are projected onto."""
+        base = 10 * self.n_own_dofs + 4
+        need = C.c_int64(0)
+        call("fs_pstokes_recycle_state", self._h, None, 0, 0, C.byref(need))
+        q = np.empty(base + need.value)
         call("fs_pstokes_state", self._h, ptr(q), 0)
+        call("fs_pstokes_recycle_state", self._h, C.c_void_p(q.ctypes.data + 8 * base), need.value, 0, C.byref(need))
         return q
 
     def set_state(self, q):
         q = np.ascontiguousarray(q, dtype=np.float64)
-        if q.size != 10 * self.n_own_dofs + 4:
+        base = 10 * self.n_own_dofs + 4
+        if q.size < base:
             raise ValueError("state size mismatch")
         call("fs_pstokes_state", self._h, ptr(q), 1)
+        call("fs_pstokes_recycle_state", self._h, C.c_void_p(q.ctypes.data + 8 * base) if q.size > base else None,
+             q.size - base, 1, None)
 
     def profile_pcg(self, iters=40):
         """µs per AMG-PCG iteration on the last pressure right-hand side (fixed iteration count; collective)."""
