@@ -200,12 +200,13 @@ def workload_config(args, world=1, **extra):
     nt, nr = (args.n_theta, args.n_r) if world == 1 else weak_shape(args, world)
     cfg = {"workload": f"stokes_step square-with-hole n_theta={nt} n_r={nr} "
                        f"(T={2 * nt * nr}, N={nt * (nr + 1)}), pusher B1=-2 B2=-5, nu=0.1, DT=0.05",
-           "solver": f"pressure: fp64 CG preconditioned by a smoothed-aggregation AMG V(1,1) cycle whose operators are stored in "
-                     f"fp32 (vectors, sums and the CG itself fp64), cycle folded to two SELL-32 SpMVs per level "
-                     f"[--precond amg] or Jacobi persistent CG [--precond jacobi], rtol_pressure={RTOL_P:g}; "
-                     f"viscous: 2-RHS Jacobi CG rtol={RTOL_V:g}; pressure warm start = best of the previous solution and its "
-                     f"linear / quadratic extrapolation in time (every solve still runs to rtol)",
-           "l2": "inputs larger than L2 (per PCG iteration: A 190 MB fp64 SELL + V-cycle operators ~440 MB fp32 SELL "
+           "solver": f"pressure: fp64 CG (A, vectors, dot products, convergence test fp64) preconditioned by a smoothed-aggregation "
+                     f"AMG V(1,1) cycle folded to two SELL-32 SpMVs per level; the cycle's operators are stored as packed 32-bit "
+                     f"entries (fp16 value | 16-bit column offset), its two finest levels gather from fp32 mirrors on one GPU "
+                     f"[--precond amg], or Jacobi persistent CG [--precond jacobi]; rtol_pressure={RTOL_P:g}; "
+                     f"viscous: 2-RHS Jacobi CG rtol={RTOL_V:g}; every pressure solve starts from the projection of its solution "
+                     f"onto the span of the previous ones (A-orthonormal basis of <= 12 vectors, csrc/recycle.cu) and runs to rtol",
+           "l2": "inputs larger than L2 (per PCG iteration: A 190 MB fp64 SELL + V-cycle operators ~200 MB packed SELL "
                  "+ 5 vectors 84 MB > 126 MB per GPU), no flush needed",
            "steps_from": "t=0 (u=0 + squirmer BC); warm-up steps advance the same trajectory"}
     cfg.update(extra)
@@ -383,8 +384,8 @@ def run_ours(args):
     out_extra = {}
     if partitioned:
         # per-rank algorithmic bytes of one AMG-PCG iteration at 4M triangles per GPU: A*p (SELL fp64)
-        # 210 MB + folded V-cycle operators and vectors ~440 MB + the two PCG vector kernels 151 MB
-        it_bytes = 801e6
+        # 210 MB + folded V-cycle with packed operators and fp64 gathers ~300 MB + the two PCG vector kernels 151 MB
+        it_bytes = 661e6
         roof = {"bound": "hbm", "kernel": "whole AMG-PCG iteration per rank (k_spmv_sell A*p + folded V-cycle SpMVs + k_ppcg_xr / k_ppcg_p, "
                                           "halo pushes and all-reduces inside the kernels), fixed-count run timed with CUDA events",
                 "achieved": it_bytes / (us_iter_part * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
@@ -409,8 +410,8 @@ def run_ours(args):
                    "traffic": traffic.get("sell_ap_dram_bytes_per_launch")}
         if top_n.value > 0:
             t_top = top_ms.value / top_n.value / 1e3
-            roof = {"bound": "hbm", "kernel": "k_spmv_sell<split,DOT,f32> (finest up-sweep of the folded AMG V-cycle: "
-                                              "z = [G | SP] [r; x_c], fused r.z)",
+            roof = {"bound": "hbm", "kernel": "k_spmv_sell<split,DOT,packed> (finest up-sweep of the folded AMG V-cycle: "
+                                              "z = [G | SP] [r; x_c], fused r.z; packed fp16 | 16-bit-offset entries, fp32 gathers)",
                     "achieved": top_bytes.value / t_top / 1e9, "peak": peak, "unit": "GB/s",
                     "frac": top_bytes.value / t_top / 1e9 / peak, "traffic": traffic.get("sell_up0_dram_bytes_per_launch"),
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": top_bytes.value, "us_per_launch": 1e6 * t_top,
@@ -422,6 +423,15 @@ def run_ours(args):
         us_it = {"A*p": 1e6 * t_spmv, "V-cycle": 1e3 * pms[1] / samples, "vector ops + dots": 1e3 * pms[2] / samples}
         us_it["total"] = sum(us_it.values())
         roof["us_per_pcg_iteration"] = us_it
+        # the whole iteration against the same peak: A*p + the cycle's algorithmic bytes (library figure) + the two vector
+        # kernels (k_pcg_xr: p, Ap, x, r read, x, r, r32 written; k_pcg_p: z, p read, p written)
+        cyc = C.c_double(0)
+        _lib.call("fs_precond_bytes", kp._h, C.byref(cyc))
+        it_bytes = ap_bytes + cyc.value + 9.5 * 8.0 * nd
+        roof["whole_pcg_iteration"] = {"algorithmic_bytes": it_bytes, "us": us_it["total"],
+                                       "achieved": it_bytes / (us_it["total"] * 1e-6) / 1e9,
+                                       "frac": it_bytes / (us_it["total"] * 1e-6) / 1e9 / peak,
+                                       "bytes": {"A*p": ap_bytes, "V-cycle": cyc.value, "vector kernels": 9.5 * 8.0 * nd}}
         roof["note"] = "timed in a separate sampled pass over the same K steps (events inside the solver); value is timed without them"
     if args.precond == "amg" and not args.no_extra and world == 1:
         # the Jacobi-preconditioned persistent CG kernel on the same operator: the path's HBM-roofline kernel

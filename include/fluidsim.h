@@ -162,6 +162,9 @@ int fs_bicgstab(fs_csr* a, const double* b, double* x, double rtol, int maxit, i
  * its own Krylov method around the library's preconditioner.  No reference analogue (every reference solve is a
  * dense LU, code/StokesColor.py:555). */
 int fs_precond_apply(fs_csr* a, const double* r, double* z);
+/* algorithmic bytes one application of that cycle moves (operator entries once, gather sources and results once):
+ * the denominator of bench.py's whole-iteration roofline figure */
+int fs_precond_bytes(fs_csr* a, double* bytes_per_apply);
 
 /* ---- the operator-split Stokes step, code/StokesColor.py:537-575 ==
  * code/StokesFood.py:441-479.  fs_stokes_create assembles K, the lumped mass,

@@ -84,6 +84,7 @@ SIGNATURES = {
     "fs_csr_get": (C.c_int, [c_vp, c_vp, c_vp, c_vp]),
     "fs_spmv": (C.c_int, [c_vp, c_vp, c_vp]),
     "fs_precond_apply": (C.c_int, [c_vp, c_vp, c_vp]),
+    "fs_precond_bytes": (C.c_int, [c_vp, P(c_dbl)]),
     "fs_cg": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, c_dbl, C.c_int, C.c_int, C.c_int, P(C.c_int), P(c_dbl)]),
     "fs_bicgstab": (C.c_int, [c_vp, c_vp, c_vp, c_dbl, C.c_int, C.c_int, P(C.c_int), P(c_dbl)]),
     "fs_stokes_default_opts": (C.c_int, [P(StokesOpts)]),

@@ -887,6 +887,31 @@ double amg_top_bytes(const Amg* amg) {
   return (double)l0.Us.nnz * entry_bytes + (l0.Us.pk.n ? 16.0 : 8.0) * (l0.Us.nslices + 1) + 8.0 * l0.n + 8.0 * amg->L[1]->n + 8.0 * l0.n;
 }
 
+// Algorithmic bytes of one application of the folded cycle: every operator entry once (packed word 4 B, fp32 value +
+// column 8 B, fp64 value + column 12 B; CSR levels + 4 B per row), the dense coarse inverse, and per operator its gather
+// sources and its result once (fp32 where a mirror is gathered, + the mirror writes, + r re-read for the fused dot).
+double amg_cycle_bytes(const Amg* amg, bool mirrors) {
+  if (!amg->folded || amg->L.size() < 2) return 0.0;
+  auto entry = [](const fs_sell& S) { return S.pk.n ? 4.0 : (S.v32.n ? 8.0 : 12.0); };
+  double bytes = 0.0;
+  const size_t nl = amg->L.size();
+  for (size_t l = 0; l + 1 < nl; ++l) {
+    const AmgLevel& lv = *amg->L[l];
+    const AmgLevel& nx = *amg->L[l + 1];
+    const bool rt_sell = !(nx.n <= amg->sub_rows && lv.Rt.rowptr) && lv.Rts.nslices;
+    const bool u_sell = !(lv.n <= amg->sub_rows && lv.U.rowptr) && lv.Us.nslices;
+    const double g_in = (mirrors && rt_sell && lv.Rts.pk.n) ? 4.0 : 8.0;       // gather width of b_l in the restriction
+    bytes += rt_sell ? (double)lv.Rts.nnz * entry(lv.Rts) + 16.0 * lv.Rts.nslices : (double)lv.Rt.nnz * 8.0 + 4.0 * nx.n;
+    bytes += g_in * lv.n + (mirrors ? 12.0 : 8.0) * nx.n;
+    const double g_up = (mirrors && u_sell && lv.Us.pk.n) ? 4.0 : 8.0;
+    bytes += u_sell ? (double)lv.Us.nnz * entry(lv.Us) + 16.0 * lv.Us.nslices : (double)lv.U.nnz * 8.0 + 4.0 * lv.n;
+    bytes += g_up * (lv.n + nx.n) + ((mirrors && l > 0) ? 12.0 : 8.0) * lv.n + (l == 0 ? 8.0 * lv.n : 0.0);
+  }
+  const double nc = (double)amg->L.back()->n;
+  bytes += amg->coarse_n ? nc * nc * 8.0 + 16.0 * nc : 0.0;
+  return bytes;
+}
+
 int amg_apply(Amg* amg, const double* r, double* z, bool x0_ready, double* rz_part, cudaEvent_t* top_ev, const float* r32) {
   static const bool use_graph = env_num("FS_AMG_GRAPH", 1) != 0;
   cudaStream_t st = stream();

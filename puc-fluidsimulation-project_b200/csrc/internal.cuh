@@ -354,6 +354,7 @@ Amg* amg_setup(fs_csr* fine, const AmgPartSpec* part = nullptr);   // part: row-
 int amg_apply(Amg* amg, const double* r, double* z, bool x0_ready = false, double* rz_part = nullptr,
               cudaEvent_t* top_ev = nullptr, const float* r32 = nullptr);
 double amg_top_bytes(const Amg* amg);   // algorithmic bytes of one launch of that kernel (0: unfolded cycle)
+double amg_cycle_bytes(const Amg* amg, bool mirrors);   // ... of one application of the whole folded cycle
 void amg_presmooth_target(Amg* amg, double** x0, const double** dinv, double* omega);
 int amg_levels(const Amg* amg, int* sizes, int cap);
 bool cg_persistent_supported(const CsrView& A, size_t* smem_out);

@@ -1463,6 +1463,14 @@ int fs_spmv(fs_csr* a, const double* x, double* y) {
   FS_API_END
 }
 
+int fs_precond_bytes(fs_csr* a, double* bytes_per_apply) {
+  FS_API_BEGIN
+  FS_REQUIRE(a && bytes_per_apply, "NULL argument");
+  if (!a->amg) a->amg = amg_setup(a);
+  *bytes_per_apply = amg_cycle_bytes(a->amg, pcg_use_r32());
+  FS_API_END
+}
+
 int fs_precond_apply(fs_csr* a, const double* r, double* z) {
   FS_API_BEGIN
   FS_REQUIRE(a && r && z, "NULL argument");

@@ -49,7 +49,7 @@ SETUP = ("cub::", "k_spgemm", "k_pick", "k_match", "k_leftover", "k_is_leader", 
          "k_prolongator", "k_transpose", "k_split_keys", "k_rowptr", "k_make_keys", "k_fill_pattern", "k_head_flags",
          "k_assemble", "k_element", "k_inc_", "k_check_tris", "k_tile_nnz", "k_diag_inv", "k_dense_from", "k_dense_add",
          "k_dense_invert", "k_rowsum", "k_flag", "k_visc_vals", "k_inner_trig", "k_elem_thirds", "k_node_sum", "k_iota",
-         "k_ptr_from", "k_fold_coo", "k_sell_", "k_to_f32")
+         "k_ptr_from", "k_fold_coo", "k_sell_", "k_to_f32", "k_gj_", "k_maxabs_bits", "k_sigma_keys")
 if os.path.exists(f"{G}/{tag}_launches.csv"):
     rows = [r for r in csv.reader(open(f"{G}/{tag}_launches.csv")) if len(r) > 5]
     hdr = rows[0]; ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
@@ -184,4 +184,7 @@ if os.path.exists(f"{G}/{tag}_spmv_pk.ncu-rep"):
         for r in rs:
             write_full(h, u, r, f)
             f.write("\n")
+            name = r[h.index("Kernel Name")]
+            if "<1, 1, 4, 0>" in name: traffic["sell_up0_dram_bytes_per_launch"] = dram_bytes(h, u, r)
+            if "<0, 1, 0, 0>" in name: traffic["sell_ap_dram_bytes_per_launch"] = dram_bytes(h, u, r)
     print(open(f"{P}/{tag}_spmv_pk_ncu_full.txt").read())
