@@ -946,7 +946,11 @@ static int pcg_amg_impl(fs_csr* a, const double* d_b, double* x, double rtol, in
   const size_t n32 = ((size_t)n + 1) / 2;      // doubles that hold the fp32 mirror of r
   ensure_ws(a, 5 * (size_t)n + n32);
   double *r = a->ws.p, *p = r + n, *Ap = p + n, *z = Ap + n, *bproj = z + n + n32;
-  float* r32 = pcg_use_r32() ? reinterpret_cast<float*>(z + n) : nullptr;
+  // fp32 gathers in the cycle's finest kernels perturb the preconditioner by ~1e-7 of the gathered terms per application;
+  // on smooth residuals those terms cancel, and below a relative residual of ~1e-12 the perturbation shows: 133 instead
+  // of 66 iterations to 1e-13 at 4M triangles, no difference at 1e-12 and above (scripts/exp_tight_rtol.py).  Tighter
+  // solves gather in fp64.
+  float* r32 = (pcg_use_r32() && rtol >= 1e-12) ? reinterpret_cast<float*>(z + n) : nullptr;
   // the vectors every kernel of the iteration re-reads (r, p, Ap, z, r32: 76 MB at 4M triangles) stay in L2 while the
   // matrix streams (~430 MB per iteration) pass through it
   L2Persist keep(r, (4 * (size_t)n + n32) * sizeof(double));

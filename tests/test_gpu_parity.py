@@ -336,7 +336,7 @@ def test_synthetic_mesh_vs_oracle():
         o.flow_step()
     p, _ = s.pressure()
     assert rel(s.u, o.u) <= 1e-9 and rel(p, o.p) <= 1e-9
-    assert st.iters_p1 > 50
+    assert st.iters_p1 > 20             # a real iterative solve (AMG-PCG from the projected guess), not a fallback
 
 
 def test_large_mesh_properties():
