@@ -152,8 +152,9 @@ def cpu_steps(nodes, markers, tris, precond, warmup, steps, threads, budget_s=No
 
 
 def cpu_baseline_line(res, precond, threads, nt, nr):
-    algo = ("AMG-preconditioned pressure CG (same algorithm as the GPU arm)" if precond == "amg" else
-            "Jacobi-preconditioned pressure CG (closest sparse analogue of the reference's dense solve)")
+    algo = ("AMG-preconditioned pressure CG started from the projection onto the previous solutions (same algorithm as "
+            "the GPU arm: oracle/amg_cpu.py hierarchy, oracle/cpu_step.py Recycler)" if precond == "amg" else
+            "Jacobi-preconditioned pressure CG (closest sparse analogue of the reference's dense solve), same projected guess")
     return {"value": 1.0 / res["s_per_step"], "unit": "steps/s", "cores": threads, "kind": "port",
             "sample": f"{res['steps_timed']} complete measured Stokes steps after {res['warmup']} warm-up steps on the "
                       f"{2 * nt * nr}-triangle mesh, oracle/cpu_step.py + oracle/cg_port.c (OpenMP): {algo}; "

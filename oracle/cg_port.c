@@ -226,3 +226,25 @@ void cgport_set_threads(int n) {
   (void)n;
 #endif
 }
+
+/* ---- vector kernels of the solution-subspace projection (oracle/cpu_step.py: Recycler; GPU: csrc/recycle.cu).
+ * X: k vectors of length n, row-major with leading dimension ld. */
+void cgport_multidot(int64_t n, int k, const double* X, int64_t ld, const double* a, double* out) {
+  for (int j = 0; j < k; ++j) {
+    const double* x = X + (int64_t)j * ld;
+    double s = 0.0;
+#pragma omp parallel for reduction(+ : s) schedule(static)
+    for (int64_t i = 0; i < n; ++i) s += x[i] * a[i];
+    out[j] = s;
+  }
+}
+
+/* out = beta * in + sum_j coef[j] X_j  (in may be NULL; out may alias in) */
+void cgport_comb(int64_t n, int k, const double* X, int64_t ld, const double* coef, double beta, const double* in, double* out) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    double v = in ? beta * in[i] : 0.0;
+    for (int j = 0; j < k; ++j) v += coef[j] * X[(int64_t)j * ld + i];
+    out[i] = v;
+  }
+}

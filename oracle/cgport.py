@@ -15,6 +15,8 @@ def load():
     lib = C.CDLL(_LIB)
     lib.cgport_threads.restype = C.c_int
     lib.cgport_spmv.argtypes = [C.c_int64] + [C.c_void_p] * 5
+    lib.cgport_multidot.argtypes = [C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.cgport_comb.argtypes = [C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
     lib.cgport_cg.restype = C.c_int
     lib.cgport_cg.argtypes = [C.c_int64] + [C.c_void_p] * 5 + [C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
     return lib
@@ -40,3 +42,22 @@ def cg(rowptr, colidx, vals, b, x0=None, rtol=1e-10, maxit=100000, jacobi=True, 
     it = load().cgport_cg(len(rowptr) - 1, rowptr.ctypes.data, colidx.ctypes.data, vals.ctypes.data, b.ctypes.data,
                           x.ctypes.data, rtol, maxit, 1 if jacobi else 0, 1 if project_mean else 0, C.byref(rr))
     return x, it, rr.value
+
+
+def multidot(X, k, a):
+    """X[:k] @ a with the OpenMP loops of the port (X: 2-D C-contiguous)."""
+    out = np.zeros(max(k, 1))
+    if k:
+        load().cgport_multidot(X.shape[1], k, X.ctypes.data, X.shape[1], a.ctypes.data, out.ctypes.data)
+    return out[:k]
+
+
+def comb(X, k, coef, beta=0.0, vin=None, out=None):
+    """beta * vin + coef @ X[:k]"""
+    n = X.shape[1]
+    if out is None:
+        out = np.empty(n)
+    coef = np.ascontiguousarray(coef, dtype=np.float64)
+    load().cgport_comb(n, k, X.ctypes.data, n, coef.ctypes.data, float(beta), None if vin is None else vin.ctypes.data,
+                       out.ctypes.data)
+    return out

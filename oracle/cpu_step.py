@@ -56,44 +56,50 @@ class _Csr:
 class Recycler:
     """Solution-subspace projection for successive right-hand sides, as csrc/recycle.cu does it on the GPU: an
     A-orthonormal basis of previous solutions (Fischer 1998), compressed to the span of the last `keep` solutions
-    when it reaches `kmax` vectors."""
+    when it reaches `kmax` vectors.  The basis is one (kmax + keep, n) array; the multi-dot and combination loops are
+    the OpenMP ones of oracle/cg_port.c, so that the CPU arm of bench.py pays for the algorithm, not for numpy."""
 
     def __init__(self, K, kmax=12, keep=6):
-        self.K, self.kmax, self.keep, self.X, self.C = K, kmax, keep, [], []
+        self.K, self.kmax, self.keep = K, kmax, keep
+        self.X, self.k, self.C = None, 0, []
         self.alpha, self.x0 = None, None
 
     def guess(self, b):
         self.x0 = None
-        if not self.X:
+        if not self.k:
             return None
-        self.alpha = np.array([x @ b for x in self.X])
-        self.x0 = sum(a * x for a, x in zip(self.alpha, self.X))
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        self.alpha = cgport.multidot(self.X, self.k, b)
+        self.x0 = cgport.comb(self.X, self.k, self.alpha)
         return self.x0
 
     def update(self, q):
-        k = len(self.X)
-        if self.x0 is None and k:
-            self.X, self.C, k = [], [], 0
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        if self.X is None:
+            self.X = np.zeros((self.kmax + self.keep, q.size))
+        if self.x0 is None and self.k:
+            self.k, self.C = 0, []
+        k = self.k
         if k:
             d = q - self.x0
-            Ad = self.K.dot(d)
-            c = np.array([x @ Ad for x in self.X])
-            d = d - sum(ci * x for ci, x in zip(c, self.X))
+            c = cgport.multidot(self.X, k, self.K.dot(d))
+            d = cgport.comb(self.X, k, -c, 1.0, d)
             coords = list(self.alpha + c)
         else:
             d, coords = q.copy(), []
         self.x0 = None
-        nrm2 = d @ self.K.dot(d)
+        nrm2 = float(d @ self.K.dot(d))
         have2 = float(np.dot(coords, coords)) if coords else 0.0
         if nrm2 > 0.0 and nrm2 > 1e-26 * have2:
             nrm = np.sqrt(nrm2)
-            self.X.append(d / nrm)
+            self.X[k] = d / nrm
+            self.k = k = k + 1
             self.C = [cc + [0.0] for cc in self.C]
             coords = coords + [nrm]
         elif not k:
             return
         self.C = (self.C + [coords])[-self.keep:]
-        if len(self.X) < self.kmax:
+        if k < self.kmax:
             return
         Q, first = [], 0.0
         for v in (np.array(cc) for cc in self.C[::-1]):
@@ -105,8 +111,11 @@ class Recycler:
                 first = nv
             if nv > 1e-10 * first and nv > 0.0:
                 Q.append(v / nv)
-        self.X = [sum(qv[i] * self.X[i] for i in range(len(self.X))) for qv in Q]
+        for j, qv in enumerate(Q):
+            cgport.comb(self.X, k, qv, out=self.X[self.kmax + j])
+        self.X[:len(Q)] = self.X[self.kmax:self.kmax + len(Q)]
         self.C = [[float(qv @ np.array(cc)) for qv in Q] for cc in self.C]
+        self.k = len(Q)
 
 
 RECYCLE_MIN_ROWS = 20000     # csrc/stokes.cu: kRecycleMinRows

@@ -359,6 +359,28 @@ def test_cpu_step_matches_restated_oracle():
     assert sims["amg"].iters[1] < 60 < sims["jacobi"].iters[1]
 
 
+def test_cpu_recycler_projection_matches_direct_solves_with_fewer_iterations():
+    """oracle/cpu_step.py: Recycler (the CPU restatement of csrc/recycle.cu): starting every pressure solve from the
+    projection onto the span of the previous solutions leaves the fields where the restated oracle's direct solves put
+    them and needs fewer PCG iterations than the time-extrapolated guess once the basis exists; the run passes through
+    a compression of the basis (12 -> <= 6 vectors at the 12th solve)."""
+    from oracle import cpu_step
+    nodes, markers, tris = fb.square_with_hole(128, 32)
+    ref = R.RestatedStokes(nodes, markers, tris, B1=-2.0, B2=-5.0)
+    a = cpu_step.CpuStokes(nodes, markers, tris, B1=-2.0, B2=-5.0, precond="amg", recycle=True)
+    b = cpu_step.CpuStokes(nodes, markers, tris, B1=-2.0, B2=-5.0, precond="amg", recycle=False)
+    ia, ib, sizes = [], [], []
+    for _ in range(16):
+        ref.flow_step()
+        ia.append(a.step()[1:])
+        ib.append(b.step()[1:])
+        sizes.append(a.rec[0].k)
+    assert np.linalg.norm(a.u - ref.u) <= 1e-9 * np.linalg.norm(ref.u)
+    assert np.linalg.norm(a.u - b.u) <= 1e-9 * np.linalg.norm(b.u)
+    assert max(sizes) == 11 and sizes[11] <= 6 and sizes[-1] > sizes[11]        # grew, was compressed, grows again
+    assert sum(map(sum, ia[8:])) <= 0.8 * sum(map(sum, ib[8:])), (ia, ib)
+
+
 def test_bench_reference_arm_runs_without_the_product():
     import json, subprocess, sys
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--n-theta", "128", "--n-r", "32",
