@@ -885,7 +885,7 @@ k_pcg_p(int64_t n, const double* __restrict__ z, double* __restrict__ p, const d
 // L2 residency of the CG vectors (FS_L2_PERSIST=1; OFF by default -- measured slower): an access-policy window on the
 // library stream marks their lines persisting for the duration of a solve (the B200 lets 79 MB of its 126 MB L2 be set
 // aside, the window is r, p, Ap, z, r32 = 76 MB at 4M triangles); everything else keeps its normal policy, the matrix
-// streams carry their own evict-first hint.  Result at 4M triangles (profiles/r02_ab_l2_persist.txt): the two vector
+// streams carry their own evict-first hint.  Result at 4M triangles (profiles/r02_ab_round2b.txt): the two vector
 // kernels 39.3 -> 34.2 us per iteration, but A*p 39.4 -> 42.5 us and the V-cycle 125.6 -> 136.9 us -- the ~430 MB of
 // matrix entries per iteration then stream through the remaining 47 MB and evict each other's gather lines.
 struct L2Persist {

@@ -239,7 +239,7 @@ __device__ __forceinline__ float pk32_part(const unsigned* __restrict__ wp, int 
 // measured: the same code at 48 instead of 64 warps per SM runs 1.4x longer.  Tried and dropped: all 16 packed words of a
 // slice loaded at once with the next header prefetched (48 registers, 40 warps per SM): ptxas sinks the second group of
 // loads behind the first group's gathers whatever the source order, 46.9 us against 43.0 us for the finest up-sweep
-// (profiles/r02_ab_l2_persist.txt, FS_PK_MODE=3).  What helps is a smaller footprint per entry in flight: fp32 gathers.
+// (profiles/r02_ab_round2b.txt, FS_PK_MODE=3).  What helps is a smaller footprint per entry in flight: fp32 gathers.
 
 // DIST (partitioned step, pstokes.cu): x / x2 are [own | halo] vectors whose halo entries are written by the
 // neighbouring ranks; the kernel returns at once when the running solve has converged and otherwise
