@@ -169,8 +169,6 @@ if os.path.exists(f"{G}/{tag}_spmv_sell_bulk.ncu-rep"):
             f.write("\n")
     print(open(f"{P}/{tag}_spmv_sell_bulk_ncu_full.txt").read())
 
-json.dump(traffic, open(TRAFFIC, "w"), indent=1)
-print(open(TRAFFIC).read())
 
 # 7) the five k_spmv_sell launches of one AMG-PCG iteration with the packed (fp16 | 16-bit offset) V-cycle operators
 if os.path.exists(f"{G}/{tag}_spmv_pk.ncu-rep"):
@@ -188,3 +186,6 @@ if os.path.exists(f"{G}/{tag}_spmv_pk.ncu-rep"):
             if "<1, 1, 4, 0>" in name: traffic["sell_up0_dram_bytes_per_launch"] = dram_bytes(h, u, r)
             if "<0, 1, 0, 0>" in name: traffic["sell_ap_dram_bytes_per_launch"] = dram_bytes(h, u, r)
     print(open(f"{P}/{tag}_spmv_pk_ncu_full.txt").read())
+
+json.dump(traffic, open(TRAFFIC, "w"), indent=1)
+print(open(TRAFFIC).read())
