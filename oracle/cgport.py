@@ -10,7 +10,8 @@ _LIB = os.path.join(_HERE, "_ref", "libcgport.so")
 
 
 def load():
-    if not os.path.exists(_LIB):
+    src = os.path.join(_HERE, "cg_port.c")
+    if not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):     # missing or older than its source
         subprocess.run(["make", "-s", "-C", _HERE], check=True)
     lib = C.CDLL(_LIB)
     lib.cgport_threads.restype = C.c_int
