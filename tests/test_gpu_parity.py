@@ -475,7 +475,8 @@ def test_packed_sell_entries_same_bits_as_32bit_encoding(monkeypatch):
     s -= s.mean()
     z = {}
     for name, env in (("packed", {"FS_SELL_PACK": "1", "FS_PCG_R32": "0"}), ("unpacked", {"FS_SELL_PACK": "2", "FS_PCG_R32": "0"}),
-                      ("fp32_values", {"FS_SELL_PACK": "0", "FS_PCG_R32": "0"}), ("default", {})):
+                      ("fp32_values", {"FS_SELL_PACK": "0", "FS_PCG_R32": "0"}), ("default", {}),
+                      ("unpacked_in_the_fp32_gather_kernel", {"FS_SELL_PACK": "2"})):
         for k in ("FS_SELL_PACK", "FS_PCG_R32"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
@@ -487,9 +488,36 @@ def test_packed_sell_entries_same_bits_as_32bit_encoding(monkeypatch):
     assert np.array_equal(z["packed"][0], z["unpacked"][0]) and np.array_equal(z["packed"][1], z["unpacked"][1])
     assert 0 < rel(z["packed"][0], z["fp32_values"][0]) <= 2e-3
     assert rel(z["default"][0], z["packed"][0]) <= 1e-5
+    assert np.array_equal(z["unpacked_in_the_fp32_gather_kernel"][0], z["unpacked"][0])      # its fallback path gathers in fp64
     for name, (zr, zs) in z.items():
         assert abs(s @ zr - r @ zs) <= 1e-5 * np.linalg.norm(s) * np.linalg.norm(zr), name      # symmetric map
         assert r @ zr > 0 and s @ zs > 0
+
+
+def test_packed_entries_fall_back_per_slice_on_a_scrambled_numbering():
+    """Node numbering with far-apart neighbours: 300 node pairs (i, i + 70000) of a 131k-node mesh are swapped, so the
+    slices that hold or reference them span more than 16 bits of column offsets and stay in the value + column encoding
+    while the rest of each operator is packed.  The Stokes step on the renumbered mesh gives the renumbered fields."""
+    c, mk, t = fb.square_with_hole(512, 256)
+    n = len(c)
+    rng = np.random.default_rng(5)
+    perm = np.arange(n)
+    lo = rng.choice(n - 70000, size=300, replace=False)
+    perm[lo], perm[lo + 70000] = perm[lo + 70000].copy(), perm[lo].copy()      # new node k = old node perm[k]
+    inv = np.empty(n, dtype=np.int64)
+    inv[perm] = np.arange(n)
+    c2, mk2, t2 = np.ascontiguousarray(c[perm]), np.ascontiguousarray(mk[perm]), np.ascontiguousarray(inv[t]).astype(t.dtype)
+    a = fb.StokesSolver(c, mk, t, B1=-2.0, B2=-5.0, precond=fb.PRECOND_AMG)
+    b = fb.StokesSolver(c2, mk2, t2, B1=-2.0, B2=-5.0, precond=fb.PRECOND_AMG)
+    for _ in range(3):
+        sa = a.step()
+        ia = (sa.iters_p1, sa.iters_p2)
+        sb = b.step()
+        assert abs(sb.iters_p1 - ia[0]) <= 8 and abs(sb.iters_p2 - ia[1]) <= 8      # another aggregation, same quality
+    assert rel(b.u[inv], a.u) <= 1e-9
+    pa, _ = a.pressure()
+    pb, _ = b.pressure()
+    assert rel(pb[inv], pa) <= 1e-7
 
 
 def test_two_rhs_cg_large_matches_single_rhs():
