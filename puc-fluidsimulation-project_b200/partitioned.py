@@ -11,6 +11,7 @@ and frees the rest); the time loop is fully partitioned.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -43,6 +44,8 @@ class PartitionedStokes:
         self.mesh.set_bc(wall, inner, pairs, interior)
         h = C.c_void_p()
         split = np.ascontiguousarray(self.split, dtype=np.int64)
+        # FS_GATHER_ROWS: experiment switch for the level from which the hierarchy is replicated (global rows)
+        gather_rows = int(os.environ.get("FS_GATHER_ROWS", gather_rows))
         call("fs_pstokes_create", glob._h, self.mesh._h, rank, world, ptr(split), ptr(l2g, np.int32), int(gather_rows), C.byref(h))
         self._h = h
         self.u = np.ascontiguousarray(glob.u[self.lo:self.hi])      # this rank's rows of the velocity
