@@ -64,12 +64,21 @@ class Recycler:
         self.X, self.k, self.C = None, 0, []
         self.alpha, self.x0 = None, None
 
+    # the three operations a row-partitioned variant replaces (tests/test_parallel_gloo.py: sums all-reduced, K on row blocks)
+    def _dots(self, v):
+        return cgport.multidot(self.X, self.k, np.ascontiguousarray(v, dtype=np.float64))
+
+    def _dot(self, a, b):
+        return float(a @ b)
+
+    def _Kdot(self, d):
+        return self.K.dot(d)
+
     def guess(self, b):
         self.x0 = None
         if not self.k:
             return None
-        b = np.ascontiguousarray(b, dtype=np.float64)
-        self.alpha = cgport.multidot(self.X, self.k, b)
+        self.alpha = self._dots(b)
         self.x0 = cgport.comb(self.X, self.k, self.alpha)
         return self.x0
 
@@ -82,13 +91,13 @@ class Recycler:
         k = self.k
         if k:
             d = q - self.x0
-            c = cgport.multidot(self.X, k, self.K.dot(d))
+            c = self._dots(self._Kdot(d))
             d = cgport.comb(self.X, k, -c, 1.0, d)
             coords = list(self.alpha + c)
         else:
             d, coords = q.copy(), []
         self.x0 = None
-        nrm2 = float(d @ self.K.dot(d))
+        nrm2 = self._dot(d, self._Kdot(d))
         have2 = float(np.dot(coords, coords)) if coords else 0.0
         if nrm2 > 0.0 and nrm2 > 1e-26 * have2:
             nrm = np.sqrt(nrm2)

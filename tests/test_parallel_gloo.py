@@ -137,3 +137,85 @@ def test_shard_helpers():
     p1 = par.row_block_partition(rp, ci, 1, 2, align=100)
     assert p0["hi"] == p1["lo"] and p1["hi"] == 1000 and p0["lo"] == 0
     assert len(p0["halo_global"]) == 0 and list(p1["halo_global"]) == [0, 1, 2, 3]
+
+
+# ---- the projected pressure guesses on a row-partitioned system (csrc/pstokes.cu keeps one basis block per rank) ----------
+def _recycler_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from fluidsim_b200.mesh import square_with_hole, find_boundary_pairs, filter_wall_pairs
+    from oracle import restated as R
+    from oracle.cpu_step import Recycler
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    nodes, markers, tris = square_with_hole(64, 48)
+    ps = R.PressureSystem(nodes, tris, filter_wall_pairs(nodes, find_boundary_pairs(nodes)))
+    K = ps.K.tocsr()
+    n = K.shape[0]
+    lo, hi = rank * n // world, (rank + 1) * n // world
+    lu = spla.splu((K + sp.identity(n) * 1e-3).tocsc())          # SPD stand-in with a unique solution, same on both ranks
+    A = (K + sp.identity(n) * 1e-3).tocsr()
+
+    def allsum(v):
+        t = torch.from_numpy(np.atleast_1d(np.asarray(v, dtype=np.float64)).copy())
+        dist.all_reduce(t)
+        return t.numpy()
+
+    class RowBlockRecycler(Recycler):
+        """vectors hold the rows [lo, hi) only; dots are all-reduced, A d gathers the blocks of d first"""
+        def _dots(self, v):
+            return allsum(super()._dots(v))
+
+        def _dot(self, a, b):
+            return float(allsum(a @ b)[0])
+
+        def _Kdot(self, d):
+            parts = [None] * world
+            dist.all_gather_object(parts, d)
+            return (A @ np.concatenate(parts))[lo:hi]
+
+    class _Op:                                                   # the whole-system twin's operator
+        def dot(self, x):
+            return A @ x
+
+    part, whole = RowBlockRecycler(None, kmax=6, keep=3), Recycler(_Op(), kmax=6, keep=3)
+    rng = np.random.default_rng(3)
+    modes = rng.standard_normal((7, n))
+    sizes, x_prev = [], None
+    anorm = lambda e: float(np.sqrt(e @ (A @ e)))
+    for step in range(14):
+        t = 0.1 * step
+        b = sum(np.cos(0.7 * j * t + j) * m for j, m in enumerate(modes))      # slowly varying right-hand side, 7 modes
+        x = lu.solve(b)
+        g_part, g_whole = part.guess(b[lo:hi]), whole.guess(b)
+        if step:
+            assert np.abs(g_part - g_whole[lo:hi]).max() <= 1e-10 * np.abs(g_whole).max()
+            # the projection is the A-norm best approximation in a span that contains the previous solution
+            assert anorm(g_whole - x) <= anorm(x_prev - x) * (1 + 1e-9)
+        x_prev = x
+        part.update(x[lo:hi])
+        whole.update(x)
+        sizes.append(part.k)
+        assert part.k == whole.k and np.allclose(part.C, whole.C, rtol=0, atol=1e-9 * np.abs(whole.C).max())
+    # the same coordinates on every rank (they decide the compression): exchanged and compared
+    got = [None] * world
+    dist.all_gather_object(got, (part.k, [list(c) for c in part.C]))
+    assert all(g == got[0] for g in got)
+    assert max(sizes) <= 5 and any(b < a for a, b in zip(sizes, sizes[1:]))      # at least one compression happened
+    dist.destroy_process_group()
+    q.put((rank, "ok"))
+
+
+def test_world2_recycler_row_blocks():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 200
+    procs = [ctx.Process(target=_recycler_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert sorted(q.get(timeout=5)[0] for _ in range(2)) == [0, 1]
