@@ -10,7 +10,7 @@
 // while the basis grows again), the basis here is COMPRESSED: the last `keep` solutions are known through their
 // coordinates in the basis, a QR factorisation of those coordinate vectors (on the host, k x keep numbers) gives an
 // orthonormal basis of their span as combinations of the old vectors, and the solver continues from there without a
-// jump in the iteration counts.  Measured on the bench trajectory (scratch/proto_fischer.py, CPU restatement, 262k
+// jump in the iteration counts.  Measured on the bench trajectory (scripts/proto_projected_guess.py, CPU restatement, 262k
 // triangles, steps 6-25): 921 PCG iterations with the time-extrapolated warm start, 630 with Fischer's restart
 // (k = 12), 542 with compression (k = 12, keep = 6).  Every solve still runs to its tolerance: only the starting point
 // changes.

@@ -152,7 +152,7 @@ __device__ __forceinline__ double sell_part4(const float* __restrict__ vp, const
 // ---- packed entries: 4 bytes instead of 8 per nonzero ----------------------------------------------------
 // The preconditioner's operators only have to be a fixed SPD map, so their values are stored as fp16 (scaled by a power of
 // two per matrix: no iteration more than with fp32 values on the bench meshes, against +2 for bf16 --
-// scratch/proto_bf16.py) and the column as a 16-bit offset from the slice's base column: the rows of a slice are
+// scripts/proto_operator_precision.py) and the column as a 16-bit offset from the slice's base column: the rows of a slice are
 // neighbours in the mesh numbering, their columns sit in a narrow band.  One 32-bit stream load per entry instead of two,
 // half the bytes; xb = x + base.
 // gather x[base + 16-bit offset]: one LOP + one IMAD.WIDE.U32 + the load
