@@ -1,5 +1,7 @@
-"""Iteration counts of the pressure solves over the bench trajectory: time-extrapolated warm start (current) against
-Fischer's A-orthonormal projection onto previous solutions.  CPU prototype on oracle/cpu_step.py."""
+"""Iteration counts of the pressure solves over the bench trajectory: time-extrapolated warm start (round 1) against
+Fischer's A-orthonormal projection onto previous solutions with a restart, a sliding-window Gram formulation, and the
+compressed basis that csrc/recycle.cu implements.  CPU prototype on oracle/cpu_step.py.
+    python scripts/proto_projected_guess.py 512 256 25"""
 import sys, time
 sys.path.insert(0, ".")
 import numpy as np
@@ -97,7 +99,7 @@ class Gram:
 
 def run(nt, nr, steps, mode, kmax=8, drop="restart"):
     nodes, markers, tris = hm.square_with_hole(nt, nr)
-    s = CS.CpuStokes(nodes, markers, tris, B1=-2.0, B2=-5.0, precond="amg")
+    s = CS.CpuStokes(nodes, markers, tris, B1=-2.0, B2=-5.0, precond="amg", recycle=False)    # the variants below replace the guess
     if mode == "fischer":
         F = [(Gram if drop.startswith('gram') else FischerC if drop.startswith('compress') else Fischer)(s.K, kmax, drop) for _ in range(2)]
         def pressure(b_nodes, h):
@@ -117,6 +119,8 @@ def run(nt, nr, steps, mode, kmax=8, drop="restart"):
     return its
 
 nt, nr, steps = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
-for k, drop in ((8, "compress3"), (8, "compress4"), (12, "compress4"), (12, "compress6"), (16, "compress8")):
+a = run(nt, nr, steps, "extrap")
+print("time-extrapolated guess   :", [(i[1], i[2]) for i in a], "sum over steps 6..", sum(i[1] + i[2] for i in a[5:]), flush=True)
+for k, drop in ((12, "restart"), (12, "gram"), (12, "compress6"), (16, "compress8")):
     b = run(nt, nr, steps, "fischer", k, drop)
-    print(f"k={k} {drop}:", [(i[1], i[2]) for i in b], "sum", sum(i[1] + i[2] for i in b[5:25]), sum(i[1] + i[2] for i in b[5:]), flush=True)
+    print(f"k={k:2d} {drop:10s}           :", [(i[1], i[2]) for i in b], "sum over steps 6..", sum(i[1] + i[2] for i in b[5:]), flush=True)
